@@ -1,0 +1,143 @@
+"""Pin the oracle (oracle/*.py) against outputs of the REAL reference (tests/golden/*.npz, made by
+tests/golden/make_golden.py in the build container). Tolerances are fp32 round-off only: the oracle
+and the reference call the same torch CPU kernels, but the GPU box may have a different CPU/ISA."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import diffusion as odiff
+from oracle import mdm as omdm
+from oracle import pose as opose
+from oracle import rvq as orvq
+from syntalker_b200 import synth
+
+torch.set_grad_enabled(False)
+
+
+def maxabs(a, b):
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))))
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return {v: synth.mdm_state_dict(v, seed=0) for v in synth.VARIANTS}
+
+
+def y_of(inp):
+    return {k: inp[k] for k in ("audio", "word", "seed", "style_feature") if k in inp}
+
+
+@pytest.mark.parametrize("tag,spec", [("ddim50", "ddim50"), ("ddpm1000", [1000]), ("ddim10", "ddim10"), ("sec20", [20])])
+def test_schedule_tables_bit_exact(golden, tag, spec):
+    g = golden("schedule")
+    s = odiff.Schedule(odiff.space_timesteps(1000, spec))
+    assert list(g[f"{tag}.timestep_map"]) == s.timestep_map
+    for k in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod",
+              "sqrt_recipm1_alphas_cumprod", "posterior_log_variance_clipped", "posterior_mean_coef1",
+              "posterior_mean_coef2"):
+        assert np.array_equal(g[f"{tag}.{k}"], getattr(s, k)), k     # fp64, same numpy ops => identical
+
+
+@pytest.mark.parametrize("variant", synth.VARIANTS)
+def test_mdm_forward(golden, weights, variant):
+    g = golden(f"mdm_{variant}")
+    inp = synth.make_inputs(2, seed=1, variant=variant)
+    y = y_of(inp)
+    if variant == "h3d":
+        y["style_feature"] = inp["style_upper"]
+    t = torch.from_numpy(g["t"])
+    taps = {}
+    out = omdm.mdm_forward(weights[variant], inp["noise"], t, y, variant, taps)
+    assert maxabs(out, g["out"]) < 2e-5
+    if variant == "beatx":
+        assert maxabs(taps["block0"], g["block0"]) < 2e-5
+        assert maxabs(taps["block7"], g["block7"]) < 2e-5
+        assert maxabs(omdm.wav_encoder(weights[variant], inp["audio"])[:, ::8], g["wav"]) < 1e-5
+    else:
+        yu = dict(y); yu["uncond"] = True
+        assert maxabs(omdm.mdm_forward(weights[variant], inp["noise"], t, yu, variant), g["out_uncond"]) < 2e-5
+    if variant == "h3d":
+        ya = dict(y); ya["uncond_audio"] = True
+        assert maxabs(omdm.mdm_forward(weights[variant], inp["noise"], t, ya, variant), g["out_uncond_audio"]) < 2e-5
+
+
+def test_cfg_text(golden, weights):
+    W = weights["beatx_motionclip"]
+    inp = synth.make_inputs(2, seed=1, variant="beatx_motionclip")
+    y = y_of(inp); y["scale"] = torch.ones(1) * 2.0
+    fn = lambda x, t, yy: omdm.mdm_forward(W, x, t, yy, "beatx_motionclip")
+    out = omdm.cfg_text(fn, inp["noise"], torch.tensor([500, 500]), y)
+    assert maxabs(out, golden("cfg_text")["out"]) < 5e-5
+
+
+def test_cfg_identity_without_motionclip(weights):
+    """ClassifierFreeSampleModel over denoiser.MDM without motionclip is an exact no-op."""
+    W = weights["beatx"]
+    inp = synth.make_inputs(1, seed=3, variant="beatx")
+    y = y_of(inp); y["scale"] = torch.ones(1) * 2.0
+    fn = lambda x, t, yy: omdm.mdm_forward(W, x, t, yy, "beatx")
+    t = torch.tensor([700])
+    assert torch.equal(omdm.cfg_text(fn, inp["noise"], t, y), fn(inp["noise"], t, y))
+
+
+def test_cfg_bodypart(golden, weights):
+    W = weights["h3d"]
+    inp = synth.make_inputs(1, seed=2, variant="h3d")
+    y = y_of(inp)
+    y["style_feature"] = {"upper_mask": inp["style_upper"], "hands_mask": None, "lower_mask": inp["style_lower"]}
+    fn = lambda x, t, yy: omdm.mdm_forward(W, x, t, yy, "h3d")
+    out = omdm.cfg_bodypart(fn, inp["noise"], torch.tensor([300]), y)
+    assert maxabs(out, golden("cfg_bodypart")["out"]) < 1e-4
+
+
+def test_loops(golden, weights):
+    W = weights["beatx"]
+    g = golden("loops")
+    inp = synth.make_inputs(1, seed=1, variant="beatx")
+    fn = lambda x, t, yy: omdm.mdm_forward(W, x, t, yy, "beatx")
+    s10 = odiff.ddim_sample_loop(odiff.make_schedule(respacing="ddim10"), fn, inp["noise"], y_of(inp))
+    assert maxabs(s10, g["ddim10"]) < 1e-4
+    torch.manual_seed(123)
+    p20 = odiff.p_sample_loop(odiff.make_schedule(respacing=[20]), fn, inp["noise"], y_of(inp),
+                              lambda k, x: torch.randn_like(x))
+    assert maxabs(p20, g["ddpm_sec20"]) < 1e-4
+
+
+def test_rvq_and_pose(golden):
+    g = golden("rvq")
+    recs = []
+    for d in synth.PART_DIMS_BEATX:
+        W = synth.rvq_state_dict(d, seed=0)
+        lat = torch.from_numpy(g[f"lat{d}"])
+        rec, idx = orvq.latent2origin(W, lat)
+        assert np.array_equal(idx.numpy(), g[f"idx{d}"])
+        assert maxabs(rec, g[f"rec{d}"]) < 2e-5
+        xq, _, _ = orvq.residual_quantize(W, lat.permute(0, 2, 1))
+        assert maxabs(xq[:, ::8], g[f"xq{d}"]) < 1e-5
+        recs.append(torch.from_numpy(g[f"rec{d}"]))
+    gp = golden("pose")
+    ms = {k: torch.from_numpy(v) for k, v in np.load(synth_data("beatx_mean_std.npz")).items()}
+    pose, trans = opose.assemble_330(recs[0], recs[1], recs[2], ms, torch.from_numpy(gp["jaw"]))
+    assert maxabs(trans, gp["rec_trans"]) < 1e-5
+    d = np.abs(pose.numpy() - gp["rec_pose"])
+    assert d.max() < 1e-3 and np.mean(d > 1e-5) < 1e-3      # rotation round trip is ill-conditioned near pi
+
+
+def synth_data(name):
+    import os
+    return os.path.join(os.path.dirname(synth.__file__), "data", name)
+
+
+def test_e2e_config1(golden, weights):
+    """BASELINE config 1: B=1, DDIM-10 -> x5 -> latent2origin x3 -> 330-d."""
+    W = weights["beatx"]
+    inp = synth.make_inputs(1, seed=1, variant="beatx")
+    fn = lambda x, t, yy: omdm.mdm_forward(W, x, t, yy, "beatx")
+    s = odiff.ddim_sample_loop(odiff.make_schedule(respacing="ddim10"), fn, inp["noise"], y_of(inp))
+    lats = opose.sample_to_parts(s, 5.0)
+    recs = [orvq.latent2origin(synth.rvq_state_dict(d, seed=0), l)[0] for d, l in zip(synth.PART_DIMS_BEATX, lats)]
+    ms = {k: torch.from_numpy(v) for k, v in np.load(synth_data("beatx_mean_std.npz")).items()}
+    pose, trans = opose.assemble_330(recs[0], recs[1], recs[2], ms, None)
+    g = golden("e2e_config1")
+    assert maxabs(trans, g["rec_trans"]) < 1e-4
+    assert maxabs(pose, g["rec_pose"]) < 1e-3
