@@ -1,0 +1,205 @@
+/*
+ * syntalker_b200 -- C ABI of the B200-native SynTalker sampling hot path.
+ *
+ * The reference (RobinWitch/SynTalker) has no FFI: its boundary for this path is four Python call
+ * sites.  Each entry point below names the reference interface it replaces; the
+ * Python shim in syntalker_b200/ keeps those Python signatures and forwards here through ctypes
+ * (INTEGRATION.md shows the binding).  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative ST_E* code; st_last_error() gives the text
+ *     (thread-local).  Nothing throws across the boundary.
+ *   - pointers documented "device" are CUDA device pointers on the device the handle was created on;
+ *     the caller owns them; the library never frees caller memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     stream-ordered; no entry point synchronises the host except the *_host ones and *_create.
+ *   - handles own their weights and a workspace that grows (cudaMalloc) only when a larger batch
+ *     than ever before is seen -- never in steady state.
+ *   - all floating point data is IEEE fp32 unless stated; code indices are int64 like torch.argmax.
+ */
+#ifndef SYNTALKER_B200_H_
+#define SYNTALKER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ST_ABI_VERSION 1
+
+/* error codes */
+#define ST_OK 0
+#define ST_EINVAL (-1)   /* bad argument (shape, null pointer, unknown tensor name, t out of range) */
+#define ST_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define ST_ENOMEM (-3)   /* device allocation failed */
+#define ST_ESTATE (-4)   /* call order violated (e.g. sample before cond encode) */
+#define ST_EUNSUPPORTED (-5)
+
+/* fixed geometry of the path (models/denoiser.py:19-22,36-37; diffusion_rvqvae_trainer.py:422) */
+#define ST_TOKENS 32          /* latent tokens per window = 128 frames / vqvae_squeeze_scale 4 */
+#define ST_FRAMES 128
+#define ST_LATENT 1536        /* 3 body parts x 512 */
+#define ST_DMODEL 512
+#define ST_AUDIO_LEN 68224    /* 16000/30*128 samples, 2 channels (amplitude, onset) */
+#define ST_SEED_FRAMES 4
+#define ST_MAX_T 1000         /* original diffusion steps */
+#define ST_MAX_EVALS 4
+
+/* model variants: which MDM the weights came from */
+#define ST_VARIANT_BEATX 0             /* models/denoiser.py MDM, use_motionclip=False */
+#define ST_VARIANT_BEATX_MOTIONCLIP 1  /* models/denoiser.py MDM, use_motionclip=True (512-d style) */
+#define ST_VARIANT_H3D 2               /* models/denoiser_h3d.py MDM (256-d prompt style, null embedding) */
+
+/* GEMM engines (st_set_engine): SIMT = exact-fp32 FMA kernels; TC = tcgen05 split-fp16 (3 MMAs/product) */
+#define ST_ENGINE_SIMT 0
+#define ST_ENGINE_TC 1
+
+typedef struct st_model st_model;
+typedef struct st_vq st_vq;
+typedef struct st_schedule st_schedule;
+
+/* A named host tensor (fp32 unless the name is documented otherwise). */
+typedef struct {
+  const char* name;
+  const void* data;   /* host pointer */
+  int64_t numel;
+} st_tensor;
+
+const char* st_last_error(void);
+int st_abi_version(void);
+/* Number of kernels this library has launched on the calling thread's device since load (bench.py's
+ * gpu_launches claim is read from here). */
+int64_t st_launch_count(void);
+int st_set_engine(int engine);
+int st_get_engine(void);
+
+/* ---- weights -------------------------------------------------------------------------------------
+ * Replaces: MDM(args) construction + load_checkpoints (train.py:85-94, utils/other_tools.py:771-790).
+ * `packed` are the tensors syntalker_b200/packer.py derives from the reference state dict
+ * (BatchNorm folded into the WavEncoder convs, input_process/2/3 folded into one 1536->512 matrix,
+ * the timestep MLP tabulated for t = 0..999).  Names are checked; a missing or
+ * mis-sized tensor is ST_EINVAL. */
+int st_model_create(const st_tensor* packed, int n, int variant, st_model** out);
+void st_model_destroy(st_model* m);
+
+/* Replaces: RVQVAE(args, D, 512, 512, 512, 2, 2, 512, 3, 3, 'relu', None) + load 'net'
+ * (diffusion_rvqvae_trainer.py:106-155).  Decoder side only: 6 codebooks + conv decoder. */
+int st_vq_create(const st_tensor* packed, int n, int out_dim, st_vq** out);
+void st_vq_destroy(st_vq* v);
+int st_vq_out_dim(const st_vq* v);
+
+/* ---- schedule ------------------------------------------------------------------------------------
+ * Replaces: create_gaussian_diffusion()/SpacedDiffusion.__init__ tables (diffusion/model_util.py:8-50,
+ * respace.py:73-87, gaussian_diffusion.py:160-197) and the per-step _extract_into_tensor gathers
+ * (gaussian_diffusion.py:1606-1619).  The host computes the fp64 tables and rounds the per-step
+ * coefficients to fp32 in the reference's operation order (syntalker_b200/schedule.py); here they
+ * are only uploaded.
+ *   mode ST_MODE_DDPM: coef[k] = {coef1, coef2, sigma, 0, 0}:  x <- coef1*x0 + coef2*x + sigma*eps_k
+ *   mode ST_MODE_DDIM: coef[k] = {a, b, c1, c2, sigma}:        e = (a*x - x0)/b; x <- x0*c1 + c2*e + sigma*eps_k
+ * k runs S-1 .. 0;  t_model[k] is the ORIGINAL timestep fed to the denoiser (respace.py:124-129). */
+#define ST_MODE_DDPM 0
+#define ST_MODE_DDIM 1
+#define ST_COEF_STRIDE 5
+int st_schedule_create(int S, int mode, const int32_t* t_model, const float* coef, st_schedule** out);
+void st_schedule_destroy(st_schedule* s);
+
+/* ---- conditioning --------------------------------------------------------------------------------
+ * The y dict of the reference (diffusion_rvqvae_trainer.py:433-443, h3d_diffusion_new_trainer.py:548-556). */
+typedef struct {
+  const float* audio;     /* device [B, ST_AUDIO_LEN, 2] */
+  const int32_t* word;    /* device [B, 128] */
+  const float* seed;      /* device [B, 4, 1536] */
+  const float* style[3];  /* device [B, style_dim] or NULL.  BEATX_MOTIONCLIP: style[0] (512-d).
+                             H3D: {upper, hands, lower} prompt vectors (256-d); NULL = no prompt */
+} st_cond;
+
+/* Guidance = which reference wrapper is around the model (diffusion/cfg_sampler.py). */
+#define ST_CFG_NONE 0       /* bare MDM; `flags` may force uncond / uncond_audio (y['uncond'], y['uncond_audio']) */
+#define ST_CFG_TEXT 1       /* ClassifierFreeSampleModel            :17-28   scale[B] */
+#define ST_CFG_TWO 2        /* TwoClassifierFreeSampleModel          :38-54   scale_audio[B], scale_prompt[B]; style[0] is the prompt */
+#define ST_CFG_BODYPART 3   /* TwoClassifierFreeSampleModel_Bodypart :67-117  audio_scale 1, prompt_scale 4 unless overridden */
+#define ST_FLAG_UNCOND 1
+#define ST_FLAG_UNCOND_AUDIO 2
+typedef struct {
+  int mode;
+  int flags;                 /* ST_CFG_NONE only */
+  const float* scale;        /* host [B]: TEXT scale / TWO scale_audio */
+  const float* scale2;       /* host [B]: TWO scale_prompt */
+  float audio_scale;         /* BODYPART (cfg_sampler.py:64)  default 1 */
+  float prompt_scale;        /* BODYPART (cfg_sampler.py:65)  default 4 */
+} st_guidance;
+
+/* Encode the step-invariant conditioning once (D2, D3, D3b, D3c of SURVEY.md §8a) into the model's
+ * cache.  The reference recomputes this inside every MDM.forward (denoiser.py:147-157). */
+int st_cond_encode(st_model* m, const st_cond* cond, int B, void* stream);
+
+/* ---- denoiser ------------------------------------------------------------------------------------
+ * Replaces: model(x, timesteps, y=dict) -- MDM.forward (models/denoiser.py:132, denoiser_h3d.py:148)
+ * optionally inside a CFG wrapper.  x, out: device [B,1536,1,32];  t: device int64 [B] original
+ * timesteps (0..999).  Uses the cache of the last st_cond_encode with the same B. */
+int st_denoise(st_model* m, const float* x, const int64_t* t, const st_guidance* g, float* out, int B, void* stream);
+
+/* ---- sampler -------------------------------------------------------------------------------------
+ * Replaces: diffusion.p_sample_loop / ddim_sample_loop (gaussian_diffusion.py:607,888) with
+ * clip_denoised=False, no cond_fn -- the only way the trainers call it.  x_init: device [B,1536,1,32]
+ * (the `noise` argument or th.randn(shape)).  noise_tape: device [S,B,1536,1,32] eps_k for k = S-1..0
+ * stored in draw order (tape[0] is used at k=S-1), required when any sigma != 0, else may be NULL.
+ * x_out may alias x_init.  Uses the cache of the last st_cond_encode. */
+int st_sample(st_model* m, const st_schedule* s, const st_guidance* g, const float* x_init, const float* noise_tape,
+              int B, float* x_out, void* stream);
+
+/* ---- RVQ-VAE decode ------------------------------------------------------------------------------
+ * Replaces: vq.latent2origin(x)[0] (models/vq/model.py:102-109).  lat: device [B,T4,512] already
+ * multiplied by vqvae_latent_scale; rec: device [B,4*T4,D]; idx_out: device int64 [B,T4,6] or NULL.
+ * lat_stride = floats between consecutive tokens (512 when contiguous; 1536 to read one body part
+ * straight out of a [B,T4,1536] sample).  If residual_out != NULL the final residual is written there
+ * [B,T4,512] (the reference leaves it in its input tensor, residual_vq.py:146). */
+int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, float lat_scale, int B, int T4, float* rec,
+                  int64_t* idx_out, float* residual_out, void* stream);
+
+/* ---- 330-d assembly ------------------------------------------------------------------------------
+ * Replaces: diffusion_rvqvae_trainer.py:484-531.  rec_*: device decoder outputs [B,n,78|180|57];
+ * mean/std: device [330]; trans_mean/std: device [3]; jaw_aa: device [B,n,3] or NULL (zeros).
+ * rec_pose: device [B,n,330]; rec_trans: device [B,n,3]. */
+int st_pose_assemble_330(const float* rec_upper, const float* rec_hands, const float* rec_lower, const float* mean,
+                         const float* std, const float* trans_mean, const float* trans_std, const float* jaw_aa, int B,
+                         int n, float* rec_pose, float* rec_trans, void* stream);
+/* h3d: scatter the three decoder outputs [B,n,156|360|107] into [B,n,623]
+ * (h3d_diffusion_new_trainer.py:194-221,604-607). */
+int st_pose_assemble_623(const float* rec_upper, const float* rec_hands, const float* rec_lower, int B, int n,
+                         float* rec_pose, void* stream);
+
+/* ---- layout helpers ------------------------------------------------------------------------------ */
+/* sample [B,1536,1,T] -> token-major [B,T,1536] * scale (trainer:457 `squeeze().permute(1,0)` batched). */
+int st_sample_to_tokens(const float* sample, int B, int T, float scale, float* tokens, void* stream);
+
+/* ---- whole window, host buffers ------------------------------------------------------------------
+ * One call a trainer's _g_test makes per window batch: H2D(cond, noise) -> cond encode -> sample ->
+ * x latent_scale -> latent2origin x3 -> 330-d -> D2H.  All pointers are HOST (ideally pinned).
+ * Synchronises `stream` before returning.  noise_tape_host may be NULL when all sigma == 0. */
+typedef struct {
+  const float* audio; const int32_t* word; const float* seed; const float* style[3];
+  const float* x_init; const float* noise_tape; const float* jaw_aa;
+  const float* mean; const float* std; const float* trans_mean; const float* trans_std;
+} st_host_inputs;
+int st_generate_330_host(st_model* m, const st_schedule* s, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
+                         st_vq* vq_lower, const st_host_inputs* in, int B, float latent_scale, float* rec_pose_host,
+                         float* rec_trans_host, float* sample_host /* nullable [B,1536,1,32] */, void* stream);
+
+/* ---- GEMM-engine profiling (bench.py roofline leg) -------------------------------------------------
+ * Between begin and end every GEMM-engine launch is bracketed by CUDA events on its stream.  end()
+ * synchronises and returns the summed device time (ms), the summed algorithmic FLOPs (2*M*N*K per
+ * launch, K counting every tap of a conv) and the launch count.  Slows the run slightly; never on
+ * during timed throughput runs. */
+int st_profile_begin(void);
+int st_profile_end(double* ms_total, double* flops_total, int64_t* launches);
+
+/* ---- self test (no oracle involved): split-fp16 tcgen05 GEMM vs the SIMT fp32 GEMM on device ----- */
+int st_selftest_gemm(int M, int N, int K, int engine, const float* A, const float* W, const float* bias, float* out,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYNTALKER_B200_H_ */

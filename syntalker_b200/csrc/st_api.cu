@@ -1,0 +1,733 @@
+// C-ABI entry points (include/syntalker_b200.h): handles, weight upload, conditioning cache, the denoiser
+// evaluation, the sampling loop, RVQ decode, pose assembly and the host-buffer pipeline.
+#include "st_internal.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace st {
+
+thread_local char g_err[1024] = "";
+thread_local int64_t g_launches = 0;
+static int g_engine = ST_ENGINE_SIMT;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int Arena::reserve(size_t bytes) {
+  off = 0;
+  if (bytes <= cap) return ST_OK;
+  if (base) { cudaDeviceSynchronize(); cudaFree(base); base = nullptr; cap = 0; }
+  size_t want = bytes + (bytes >> 3) + (1 << 20);
+  cudaError_t e = cudaMalloc(&base, want);
+  if (e != cudaSuccess) {
+    set_error("workspace cudaMalloc(%zu MiB) failed: %s", want >> 20, cudaGetErrorString(e));
+    base = nullptr;
+    return ST_ENOMEM;
+  }
+  cap = want;
+  return ST_OK;
+}
+void Arena::release() {
+  if (base) cudaFree(base);
+  base = nullptr; cap = 0; off = 0;
+}
+
+int Weights::upload(const st_tensor* t, int n) {
+  for (int i = 0; i < n; ++i) {
+    ST_REQUIRE(t[i].name && t[i].data && t[i].numel > 0, "tensor %d is empty", i);
+    float* d = nullptr;
+    size_t bytes = (size_t)t[i].numel * sizeof(float);
+    if (cudaMalloc(&d, (bytes + 255) & ~size_t(255)) != cudaSuccess) { set_error("cudaMalloc for %s failed", t[i].name); return ST_ENOMEM; }
+    ST_CHECK_CUDA(cudaMemcpy(d, t[i].data, bytes, cudaMemcpyHostToDevice));
+    dev[t[i].name] = d;
+    numel[t[i].name] = t[i].numel;
+  }
+  return ST_OK;
+}
+const float* Weights::get(const std::string& name, int64_t expect, int* err) const {
+  auto it = dev.find(name);
+  if (it == dev.end()) { set_error("packed tensor '%s' is missing", name.c_str()); *err = ST_EINVAL; return nullptr; }
+  if (expect > 0 && numel.at(name) != expect) {
+    set_error("packed tensor '%s' has %lld elements, expected %lld", name.c_str(), (long long)numel.at(name), (long long)expect);
+    *err = ST_EINVAL;
+    return nullptr;
+  }
+  return it->second;
+}
+void Weights::release() {
+  for (auto& kv : dev) cudaFree(kv.second);
+  dev.clear(); numel.clear();
+}
+
+static bool g_prof = false;
+static std::vector<cudaEvent_t> g_prof_ev;
+static double g_prof_flops = 0.0;
+
+int gemm(const GemmP& p, cudaStream_t s) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof) {
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, s);
+  }
+  const int r = (g_engine == ST_ENGINE_TC && tc_supported(p)) ? gemm_tc(p, s) : gemm_simt(p, s);
+  if (g_prof) {
+    cudaEventRecord(e1, s);
+    g_prof_ev.push_back(e0); g_prof_ev.push_back(e1);
+    g_prof_flops += 2.0 * (double)p.M * (double)p.N * (double)p.K;
+  }
+  return r;
+}
+
+int profile_begin() {
+  for (auto e : g_prof_ev) cudaEventDestroy(e);
+  g_prof_ev.clear();
+  g_prof_flops = 0.0;
+  g_prof = true;
+  return ST_OK;
+}
+int profile_end(double* ms, double* flops, int64_t* n) {
+  g_prof = false;
+  ST_CHECK_CUDA(cudaDeviceSynchronize());
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < g_prof_ev.size(); i += 2) {
+    float t = 0.f;
+    ST_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof_ev[i], g_prof_ev[i + 1]));
+    tot += t;
+  }
+  if (ms) *ms = tot;
+  if (flops) *flops = g_prof_flops;
+  if (n) *n = (int64_t)(g_prof_ev.size() / 2);
+  for (auto e : g_prof_ev) cudaEventDestroy(e);
+  g_prof_ev.clear();
+  return ST_OK;
+}
+
+}  // namespace st
+
+using namespace st;
+
+// WavEncoder geometry (models/denoiser.py:308-315): C_in, C_out, stride, pad of the first conv, conv shortcut
+static const int kWav[6][5] = {{2, 64, 5, 1700, 1}, {64, 64, 6, 0, 1}, {64, 64, 1, 7, 0}, {64, 128, 6, 0, 1}, {128, 128, 1, 7, 0}, {128, 256, 3, 0, 1}};
+static const int kWavLen[7] = {68224, 14322, 2385, 2385, 396, 396, 128};
+static const int kCondChunk = 32;
+
+struct ConvW { const float* w; const float* b; int ldw; };
+struct BlkW { const float *ln1g, *ln1b, *qkv, *projw, *projb, *ln2g, *ln2b, *fc1w, *fc1b, *fc2w, *fc2b; };
+struct EvalSpec { int cst_null; int sv_src; };   // sv_src: -1 none, 0..2 = style k, 3 = null embedding
+
+struct st_model {
+  int variant = 0, device = 0, style_dim = 0;
+  Weights w;
+  ConvW wav[6][3];   // conv1, conv2, ds
+  const float *word_table = nullptr, *w_cm = nullptr, *w_seed = nullptr, *bias_all = nullptr, *w_x = nullptr, *vt_table = nullptr;
+  const float *w_style = nullptr, *null_sv = nullptr, *rope_cos = nullptr, *rope_sin = nullptr, *out_w = nullptr, *out_b = nullptr;
+  BlkW blk[8];
+  // constants for audio-masked evaluations (h3d): computed lazily
+  float* cst_null = nullptr;   // [32,512]
+  bool null_ready = false;
+  // workspace
+  Arena ws, io;
+  int ws_B = 0;
+  float *cst_real = nullptr, *g2 = nullptr, *sv[3] = {nullptr, nullptr, nullptr};
+  bool have_style[3] = {false, false, false};
+  int cond_B = 0;
+  float *xs = nullptr, *comb = nullptr, *z = nullptr, *X = nullptr, *H = nullptr, *ATT = nullptr, *QKV = nullptr, *G = nullptr, *O = nullptr;
+  float *wavbuf[4] = {nullptr, nullptr, nullptr, nullptr}, *atcat = nullptr, *pooled = nullptr;
+  float *scale_dev = nullptr, *scale2_dev = nullptr;
+  int64_t* t_tmp = nullptr;
+};
+
+struct st_schedule {
+  int S = 0, mode = 0;
+  std::vector<int32_t> t_model;
+  std::vector<float> coef;
+};
+
+struct st_vq {
+  int out_dim = 0, ldw_last = 0;
+  Weights w;
+  const float *cb[6], *cnorm[6];
+  ConvW c0, res1[2][3], res2[2][3], up[2], c4, c6;
+  Arena ws;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" const char* st_last_error(void) { return g_err; }
+extern "C" int st_abi_version(void) { return ST_ABI_VERSION; }
+extern "C" int64_t st_launch_count(void) { return g_launches; }
+extern "C" int st_set_engine(int engine) {
+  ST_REQUIRE(engine == ST_ENGINE_SIMT || engine == ST_ENGINE_TC, "unknown engine %d", engine);
+  g_engine = engine;
+  return ST_OK;
+}
+extern "C" int st_get_engine(void) { return g_engine; }
+extern "C" int st_profile_begin(void) { return st::profile_begin(); }
+extern "C" int st_profile_end(double* ms_total, double* flops_total, int64_t* launches) { return st::profile_end(ms_total, flops_total, launches); }
+
+// ---------------------------------------------------------------------------------------------------------
+static int model_resolve(st_model* m) {
+  int err = ST_OK;
+  char nm[96];
+  const char* cname[3] = {"conv1", "conv2", "ds"};
+  for (int i = 0; i < 6; ++i) {
+    const int cin = kWav[i][0], cout = kWav[i][1];
+    for (int c = 0; c < 3; ++c) {
+      m->wav[i][c] = ConvW{nullptr, nullptr, 0};
+      if (c == 2 && !kWav[i][4]) continue;
+      const int cc = (c == 1) ? cout : cin;
+      const int K = 15 * cc, ldw = (K + 3) & ~3;
+      snprintf(nm, sizeof nm, "wav.%d.%s.w", i, cname[c]);
+      m->wav[i][c].w = m->w.get(nm, (int64_t)cout * ldw, &err);
+      snprintf(nm, sizeof nm, "wav.%d.%s.b", i, cname[c]);
+      m->wav[i][c].b = m->w.get(nm, cout, &err);
+      m->wav[i][c].ldw = ldw;
+    }
+  }
+  m->word_table = m->w.get("word_table", 0, &err);
+  m->w_cm = m->w.get("w_cm", 512 * 512, &err);
+  m->w_seed = m->w.get("w_seed", 512 * 6144, &err);
+  m->bias_all = m->w.get("bias_all", 512, &err);
+  m->w_x = m->w.get("w_x", 512 * 1536, &err);
+  m->vt_table = m->w.get("vt_table", ST_MAX_T * 512, &err);
+  m->rope_cos = m->w.get("rope_cos", 32 * 32, &err);
+  m->rope_sin = m->w.get("rope_sin", 32 * 32, &err);
+  m->out_w = m->w.get("out.w", 1536 * 512, &err);
+  m->out_b = m->w.get("out.b", 1536, &err);
+  m->style_dim = m->variant == ST_VARIANT_BEATX_MOTIONCLIP ? 512 : m->variant == ST_VARIANT_H3D ? 256 : 0;
+  if (m->style_dim) m->w_style = m->w.get("w_style", 512 * m->style_dim, &err);
+  if (m->variant == ST_VARIANT_H3D) m->null_sv = m->w.get("null_sv", 512, &err);
+  for (int i = 0; i < 8; ++i) {
+    BlkW& b = m->blk[i];
+    auto g = [&](const char* suffix, int64_t n) { snprintf(nm, sizeof nm, "blk.%d.%s", i, suffix); return m->w.get(nm, n, &err); };
+    b.ln1g = g("ln1.g", 512); b.ln1b = g("ln1.b", 512); b.qkv = g("qkv.w", 1536 * 512);
+    b.projw = g("proj.w", 512 * 512); b.projb = g("proj.b", 512);
+    b.ln2g = g("ln2.g", 512); b.ln2b = g("ln2.b", 512);
+    b.fc1w = g("fc1.w", 1024 * 512); b.fc1b = g("fc1.b", 1024);
+    b.fc2w = g("fc2.w", 512 * 1024); b.fc2b = g("fc2.b", 512);
+  }
+  return err;
+}
+
+extern "C" int st_model_create(const st_tensor* packed, int n, int variant, st_model** out) {
+  ST_REQUIRE(packed && out && n > 0, "st_model_create: null argument");
+  ST_REQUIRE(variant >= 0 && variant <= 2, "st_model_create: unknown variant %d", variant);
+  st_model* m = new st_model();
+  m->variant = variant;
+  cudaGetDevice(&m->device);
+  int r = m->w.upload(packed, n);
+  if (r == ST_OK) r = model_resolve(m);
+  if (r != ST_OK) { m->w.release(); delete m; return r; }
+  *out = m;
+  return ST_OK;
+}
+
+extern "C" void st_model_destroy(st_model* m) {
+  if (!m) return;
+  cudaDeviceSynchronize();
+  m->w.release(); m->ws.release(); m->io.release();
+  if (m->cst_null) cudaFree(m->cst_null);
+  delete m;
+}
+
+static int model_workspace(st_model* m, int B) {
+  if (B <= m->ws_B) return ST_OK;
+  const size_t rows = (size_t)B * 32, nE = ST_MAX_EVALS;
+  const int cb = B < kCondChunk ? B : kCondChunk;
+  size_t f = 0;   // floats
+  f += rows * 512 + (size_t)B * 512 * 4;                       // cst_real, g2, sv[3]
+  f += rows * 1536 * 2 + rows * 512;                           // xs, comb, z
+  f += nE * rows * (512 * 3 + 1536 * 2 + 1024);                // X,H,ATT,QKV,O,G
+  f += 4 * (size_t)cb * kWavLen[1] * 64 + (size_t)cb * 128 * 512 + (size_t)cb * 32 * 512;
+  f += 2 * (size_t)B + 64;
+  size_t bytes = f * sizeof(float) + (size_t)B * sizeof(int64_t) + 64 * 256;
+  ST_TRY(m->ws.reserve(bytes));
+  Arena& a = m->ws;
+  m->cst_real = a.take<float>(rows * 512);
+  m->g2 = a.take<float>((size_t)B * 512);
+  for (int k = 0; k < 3; ++k) m->sv[k] = a.take<float>((size_t)B * 512);
+  m->xs = a.take<float>(rows * 1536);
+  m->comb = a.take<float>(rows * 1536);
+  m->z = a.take<float>(rows * 512);
+  m->X = a.take<float>(nE * rows * 512);
+  m->H = a.take<float>(nE * rows * 512);
+  m->ATT = a.take<float>(nE * rows * 512);
+  m->QKV = a.take<float>(nE * rows * 1536);
+  m->G = a.take<float>(nE * rows * 1024);
+  m->O = a.take<float>(nE * rows * 1536);
+  for (int k = 0; k < 4; ++k) m->wavbuf[k] = a.take<float>((size_t)cb * kWavLen[1] * 64);
+  m->atcat = a.take<float>((size_t)cb * 128 * 512);
+  m->pooled = a.take<float>((size_t)cb * 32 * 512);
+  m->scale_dev = a.take<float>(B);
+  m->scale2_dev = a.take<float>(B);
+  m->t_tmp = a.take<int64_t>(B);
+  m->ws_B = B;
+  m->cond_B = 0;   // the cache lived in the old block
+  return ST_OK;
+}
+
+// WavEncoder + word path + mix + pool for `cb` clips -> pooled [cb*32, 512]   (denoiser.py:151-157)
+static int encode_audio_words(st_model* m, const float* audio, const int32_t* word, int cb, int null_inputs, cudaStream_t s) {
+  const float* in = audio;
+  int in_buf = -1;
+  for (int i = 0; i < 6; ++i) {
+    const int cin = kWav[i][0], cout = kWav[i][1], stride = kWav[i][2], pad = kWav[i][3], ds = kWav[i][4];
+    const int Lin = kWavLen[i], Lout = kWavLen[i + 1];
+    int free_b[3], nf = 0;
+    for (int k = 0; k < 4 && nf < 3; ++k) if (k != in_buf) free_b[nf++] = k;
+    float* h1 = m->wavbuf[free_b[0]];
+    float* sc = m->wavbuf[free_b[1]];
+    const bool last = (i == 5);
+    float* outb = last ? m->atcat : m->wavbuf[free_b[2]];
+    GemmP p;
+    p.A = in; p.W = m->wav[i][0].w; p.bias = m->wav[i][0].b; p.out = h1;
+    p.M = cb * Lout; p.N = cout; p.K = 15 * cin; p.ldw = m->wav[i][0].ldw;
+    p.Lout = Lout; p.Lin = Lin; p.C = cin; p.stride = stride; p.pad = pad; p.dil = 1;
+    p.a_batch = (long long)Lin * cin; p.lda = cin; p.ldo = cout; p.act = ACT_LRELU;
+    ST_TRY(gemm(p, s));
+    const float* shortcut = in;
+    if (ds) {
+      GemmP q = p;
+      q.W = m->wav[i][2].w; q.bias = m->wav[i][2].b; q.ldw = m->wav[i][2].ldw; q.out = sc; q.act = ACT_NONE;
+      ST_TRY(gemm(q, s));
+      shortcut = sc;
+    }
+    GemmP c2;
+    c2.A = h1; c2.W = m->wav[i][1].w; c2.bias = m->wav[i][1].b; c2.out = outb;
+    c2.M = cb * Lout; c2.N = cout; c2.K = 15 * cout; c2.ldw = m->wav[i][1].ldw;
+    c2.Lout = Lout; c2.Lin = Lout; c2.C = cout; c2.stride = 1; c2.pad = 7; c2.dil = 1;
+    c2.a_batch = (long long)Lout * cout; c2.lda = cout; c2.ldo = last ? 512 : cout;
+    c2.res = shortcut; c2.res_mode = RES_PRE; c2.ldr = cout; c2.res_div = 1; c2.act = ACT_LRELU;
+    ST_TRY(gemm(c2, s));
+    in = outb;
+    in_buf = last ? -1 : free_b[2];
+  }
+  ST_TRY(gather_words(word, m->word_table, m->atcat + 256, 512, cb * 128, null_inputs, s));
+  ST_TRY(avgpool4(m->atcat, m->pooled, cb * 32, 512, s));
+  return ST_OK;
+}
+
+static int ensure_null_consts(st_model* m, cudaStream_t s) {
+  if (m->null_ready) return ST_OK;
+  // audio := 0 before the WavEncoder and word ids := 0 (denoiser_h3d.py:173-179): a per-model constant [32,512]
+  if (!m->cst_null) ST_CHECK_CUDA(cudaMalloc(&m->cst_null, 32 * 512 * sizeof(float)));
+  float* zeros = m->wavbuf[3];   // not touched by block 0 when in_buf == -1 (uses buffers 0,1,2)
+  ST_CHECK_CUDA(cudaMemsetAsync(zeros, 0, (size_t)ST_AUDIO_LEN * 2 * sizeof(float), s));
+  ST_TRY(encode_audio_words(m, zeros, nullptr, 1, 1, s));
+  GemmP p = linear(m->pooled, 32, 512, m->w_cm, m->bias_all, m->cst_null, 512);
+  ST_TRY(gemm(p, s));
+  m->null_ready = true;
+  return ST_OK;
+}
+
+extern "C" int st_cond_encode(st_model* m, const st_cond* c, int B, void* stream) {
+  ST_REQUIRE(m && c && B > 0, "st_cond_encode: null argument or B <= 0");
+  ST_REQUIRE(c->audio && c->word && c->seed, "st_cond_encode: audio, word and seed are required");
+  cudaStream_t s = (cudaStream_t)stream;
+  ST_TRY(model_workspace(m, B));
+  if (m->variant == ST_VARIANT_H3D) ST_TRY(ensure_null_consts(m, s));
+  for (int b0 = 0; b0 < B; b0 += kCondChunk) {
+    const int cb = (B - b0) < kCondChunk ? (B - b0) : kCondChunk;
+    ST_TRY(encode_audio_words(m, c->audio + (size_t)b0 * ST_AUDIO_LEN * 2, c->word + (size_t)b0 * 128, cb, 0, s));
+    GemmP p = linear(m->pooled, cb * 32, 512, m->w_cm, m->bias_all, m->cst_real + (size_t)b0 * 32 * 512, 512);
+    ST_TRY(gemm(p, s));
+  }
+  GemmP ps = linear(c->seed, B, 6144, m->w_seed, nullptr, m->g2, 512);
+  ST_TRY(gemm(ps, s));
+  for (int k = 0; k < 3; ++k) {
+    m->have_style[k] = false;
+    if (m->style_dim && c->style[k]) {
+      GemmP pv = linear(c->style[k], B, m->style_dim, m->w_style, nullptr, m->sv[k], 512);
+      ST_TRY(gemm(pv, s));
+      m->have_style[k] = true;
+    }
+  }
+  m->cond_B = B;
+  return ST_OK;
+}
+
+// ---- guidance -> evaluation list ---------------------------------------------------------------------
+struct Plan {
+  int nE = 1;
+  EvalSpec ev[ST_MAX_EVALS];
+  int cfg_mode = ST_CFG_NONE;
+  float part_sa[3] = {0, 0, 0}, part_sp[3] = {0, 0, 0};
+  int part_ua[3] = {-1, -1, -1};
+};
+
+static int make_plan(const st_model* m, const st_guidance* g, Plan* pl) {
+  const int mode = g ? g->mode : ST_CFG_NONE;
+  const int flags = g ? g->flags : 0;
+  const int v = m->variant;
+  Plan& p = *pl;
+  p = Plan();
+  auto need_style = [&](int k) -> int {
+    if (!m->have_style[k]) { set_error("guidance needs style[%d] but st_cond_encode did not receive it", k); return ST_ESTATE; }
+    return ST_OK;
+  };
+  if (mode == ST_CFG_NONE || v == ST_VARIANT_BEATX) {
+    // bare model; denoiser.MDM without motionclip never reads y['uncond'] (denoiser.py:144,172-174), so any
+    // CFG wrapper around it degenerates to the conditional output exactly.
+    ST_REQUIRE(mode == ST_CFG_NONE || mode == ST_CFG_TEXT, "variant beatx supports CFG_NONE / CFG_TEXT only");
+    p.nE = 1; p.cfg_mode = ST_CFG_NONE;
+    p.ev[0].cst_null = (v == ST_VARIANT_H3D) && (flags & ST_FLAG_UNCOND_AUDIO);
+    if (v == ST_VARIANT_BEATX) p.ev[0].sv_src = -1;
+    else if (flags & ST_FLAG_UNCOND) p.ev[0].sv_src = (v == ST_VARIANT_H3D) ? 3 : -1;
+    else { ST_TRY(need_style(0)); p.ev[0].sv_src = 0; }
+    return ST_OK;
+  }
+  if (mode == ST_CFG_TEXT) {
+    ST_REQUIRE(g->scale, "CFG_TEXT needs scale[B]");
+    ST_TRY(need_style(0));
+    p.nE = 2; p.cfg_mode = ST_CFG_TEXT;
+    const int an = (v == ST_VARIANT_H3D);          // the wrapper sets uncond_audio on both passes (cfg_sampler.py:18,22)
+    p.ev[0] = EvalSpec{an, 0};
+    p.ev[1] = EvalSpec{an, v == ST_VARIANT_H3D ? 3 : -1};
+    return ST_OK;
+  }
+  ST_REQUIRE(v == ST_VARIANT_H3D, "CFG_TWO / CFG_BODYPART are defined for the h3d model only");
+  p.ev[0] = EvalSpec{1, 3};    // uu: prompt null, audio null
+  p.ev[1] = EvalSpec{0, 3};    // ut: prompt null, audio real
+  if (mode == ST_CFG_TWO) {
+    ST_REQUIRE(g->scale && g->scale2, "CFG_TWO needs scale (audio) and scale2 (prompt)");
+    ST_TRY(need_style(0));
+    p.nE = 3; p.cfg_mode = ST_CFG_TWO;
+    p.ev[2] = EvalSpec{1, 0};
+    return ST_OK;
+  }
+  ST_REQUIRE(mode == ST_CFG_BODYPART, "unknown guidance mode %d", mode);
+  p.cfg_mode = ST_CFG_BODYPART;
+  p.nE = 2;
+  const float a_s = g->audio_scale, p_s = g->prompt_scale;
+  for (int k = 0; k < 3; ++k) {
+    if (!m->have_style[k]) { p.part_sa[k] = a_s; p.part_sp[k] = 0.f; p.part_ua[k] = -1; continue; }
+    p.part_sa[k] = (k == 0) ? 1.0f : 0.0f;         // cfg_sampler.py:100-105
+    p.part_sp[k] = p_s;
+    if (p_s != 0.f) { p.ev[p.nE] = EvalSpec{1, k}; p.part_ua[k] = p.nE; p.nE++; }
+  }
+  return ST_OK;
+}
+
+// ---- one trunk pass over the state m->xs for all planned evaluations -> m->O ---------------------------
+static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, int t_scalar, cudaStream_t s) {
+  const int rows = B * 32, R = pl.nE * rows;
+  GemmP pz = linear(m->xs, rows, 1536, m->w_x, nullptr, m->z, 512);
+  ST_TRY(gemm(pz, s));
+  TokensInP tp;
+  tp.z = m->z; tp.vt_table = m->vt_table; tp.t_dev = t_dev; tp.t_scalar = t_scalar; tp.g2 = m->g2;
+  tp.rope_cos = m->rope_cos; tp.rope_sin = m->rope_sin; tp.x = m->X; tp.B = B; tp.nE = pl.nE;
+  for (int e = 0; e < ST_MAX_EVALS; ++e) { tp.cst[e] = m->cst_real; tp.cst_bcast[e] = 0; tp.sv[e] = nullptr; tp.sv_bcast[e] = 0; }
+  for (int e = 0; e < pl.nE; ++e) {
+    if (pl.ev[e].cst_null) { tp.cst[e] = m->cst_null; tp.cst_bcast[e] = 1; }
+    const int sv = pl.ev[e].sv_src;
+    if (sv >= 0 && sv <= 2) tp.sv[e] = m->sv[sv];
+    else if (sv == 3) { tp.sv[e] = m->null_sv; tp.sv_bcast[e] = 1; }
+  }
+  ST_TRY(tokens_in(tp, s));
+  for (int i = 0; i < 8; ++i) {
+    const BlkW& b = m->blk[i];
+    ST_TRY(layernorm512(m->X, b.ln1g, b.ln1b, m->H, R, s));
+    GemmP pq = linear(m->H, R, 512, b.qkv, nullptr, m->QKV, 1536);
+    ST_TRY(gemm(pq, s));
+    ST_TRY(attention32(m->QKV, m->ATT, pl.nE * B, s));
+    GemmP pp = linear(m->ATT, R, 512, b.projw, b.projb, m->X, 512);
+    pp.res = m->X; pp.res_mode = RES_POST; pp.ldr = 512;
+    ST_TRY(gemm(pp, s));
+    ST_TRY(layernorm512(m->X, b.ln2g, b.ln2b, m->H, R, s));
+    GemmP p1 = linear(m->H, R, 512, b.fc1w, b.fc1b, m->G, 1024);
+    p1.act = ACT_GELU;
+    ST_TRY(gemm(p1, s));
+    GemmP p2 = linear(m->G, R, 1024, b.fc2w, b.fc2b, m->X, 512);
+    p2.res = m->X; p2.res_mode = RES_POST; p2.ldr = 512;
+    ST_TRY(gemm(p2, s));
+  }
+  GemmP po = linear(m->X, R, 512, m->out_w, m->out_b, m->O, 1536);
+  ST_TRY(gemm(po, s));
+  return ST_OK;
+}
+
+static int upload_scales(st_model* m, const Plan& pl, const st_guidance* g, int B, StepP* sp, cudaStream_t s) {
+  sp->cfg_mode = pl.cfg_mode;
+  sp->nE = pl.nE;
+  sp->B = B;
+  sp->o = m->O;
+  sp->scale = nullptr; sp->scale2 = nullptr;
+  for (int k = 0; k < 3; ++k) { sp->part_sa[k] = pl.part_sa[k]; sp->part_sp[k] = pl.part_sp[k]; sp->part_ua[k] = pl.part_ua[k]; }
+  if (pl.cfg_mode == ST_CFG_TEXT || pl.cfg_mode == ST_CFG_TWO) {
+    ST_CHECK_CUDA(cudaMemcpyAsync(m->scale_dev, g->scale, B * sizeof(float), cudaMemcpyHostToDevice, s));
+    sp->scale = m->scale_dev;
+    if (pl.cfg_mode == ST_CFG_TWO) {
+      ST_CHECK_CUDA(cudaMemcpyAsync(m->scale2_dev, g->scale2, B * sizeof(float), cudaMemcpyHostToDevice, s));
+      sp->scale2 = m->scale2_dev;
+    }
+  }
+  return ST_OK;
+}
+
+extern "C" int st_denoise(st_model* m, const float* x, const int64_t* t, const st_guidance* g, float* out, int B, void* stream) {
+  ST_REQUIRE(m && x && t && out && B > 0, "st_denoise: null argument or B <= 0");
+  if (m->cond_B != B) { set_error("st_denoise: B=%d but the conditioning cache holds B=%d (call st_cond_encode first)", B, m->cond_B); return ST_ESTATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  Plan pl;
+  ST_TRY(make_plan(m, g, &pl));
+  ST_TRY(transpose_to_tokens(x, m->xs, B, 1536, 32, 1.0f, s));
+  ST_TRY(run_trunk(m, pl, B, t, 0, s));
+  StepP sp;
+  ST_TRY(upload_scales(m, pl, g, B, &sp, s));
+  sp.xs = m->comb; sp.eps = nullptr; sp.mode = -1;
+  ST_TRY(step_update(sp, s));
+  ST_TRY(transpose_from_tokens(m->comb, out, B, 1536, 32, s));
+  return ST_OK;
+}
+
+extern "C" int st_schedule_create(int S, int mode, const int32_t* t_model, const float* coef, st_schedule** out) {
+  ST_REQUIRE(S > 0 && t_model && coef && out, "st_schedule_create: null argument or S <= 0");
+  ST_REQUIRE(mode == ST_MODE_DDPM || mode == ST_MODE_DDIM, "st_schedule_create: unknown mode %d", mode);
+  for (int k = 0; k < S; ++k) ST_REQUIRE(t_model[k] >= 0 && t_model[k] < ST_MAX_T, "t_model[%d]=%d out of [0,%d)", k, t_model[k], ST_MAX_T);
+  st_schedule* sc = new st_schedule();
+  sc->S = S; sc->mode = mode;
+  sc->t_model.assign(t_model, t_model + S);
+  sc->coef.assign(coef, coef + (size_t)S * ST_COEF_STRIDE);
+  *out = sc;
+  return ST_OK;
+}
+extern "C" void st_schedule_destroy(st_schedule* s) { delete s; }
+
+extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* g, const float* x_init, const float* noise_tape,
+                         int B, float* x_out, void* stream) {
+  ST_REQUIRE(m && sc && x_init && x_out && B > 0, "st_sample: null argument or B <= 0");
+  if (m->cond_B != B) { set_error("st_sample: B=%d but the conditioning cache holds B=%d (call st_cond_encode first)", B, m->cond_B); return ST_ESTATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  Plan pl;
+  ST_TRY(make_plan(m, g, &pl));
+  bool any_sigma = false;
+  for (int k = 0; k < sc->S; ++k) any_sigma |= sc->coef[(size_t)k * ST_COEF_STRIDE + (sc->mode == ST_MODE_DDPM ? 2 : 4)] != 0.f;
+  ST_REQUIRE(!any_sigma || noise_tape, "st_sample: schedule has sigma != 0 but noise_tape is NULL");
+  StepP sp;
+  ST_TRY(upload_scales(m, pl, g, B, &sp, s));
+  ST_TRY(transpose_to_tokens(x_init, m->xs, B, 1536, 32, 1.0f, s));
+  const size_t per = (size_t)B * ST_LATENT * ST_TOKENS;
+  for (int k = sc->S - 1; k >= 0; --k) {
+    ST_TRY(run_trunk(m, pl, B, nullptr, sc->t_model[k], s));
+    sp.xs = m->xs; sp.mode = sc->mode;
+    sp.eps = noise_tape ? noise_tape + (size_t)(sc->S - 1 - k) * per : nullptr;
+    for (int q = 0; q < ST_COEF_STRIDE; ++q) sp.c[q] = sc->coef[(size_t)k * ST_COEF_STRIDE + q];
+    ST_TRY(step_update(sp, s));
+  }
+  ST_TRY(transpose_from_tokens(m->xs, x_out, B, 1536, 32, s));
+  return ST_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static int vq_resolve(st_vq* v) {
+  int err = ST_OK;
+  char nm[96];
+  auto conv = [&](const char* name, int cout, int K) {
+    ConvW c;
+    c.ldw = (K + 3) & ~3;
+    snprintf(nm, sizeof nm, "dec.%s.w", name);
+    c.w = v->w.get(nm, (int64_t)cout * c.ldw, &err);
+    snprintf(nm, sizeof nm, "dec.%s.b", name);
+    c.b = v->w.get(nm, cout, &err);
+    return c;
+  };
+  for (int q = 0; q < 6; ++q) {
+    snprintf(nm, sizeof nm, "cb.%d", q);
+    v->cb[q] = v->w.get(nm, 512 * 512, &err);
+    snprintf(nm, sizeof nm, "cnorm.%d", q);
+    v->cnorm[q] = v->w.get(nm, 512, &err);
+  }
+  v->c0 = conv("0", 512, 1536);
+  for (int i = 0; i < 2; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      char n2[32];
+      snprintf(n2, sizeof n2, "%d.0.%d.conv1", i + 2, j);
+      v->res1[i][j] = conv(n2, 512, 1536);
+      snprintf(n2, sizeof n2, "%d.0.%d.conv2", i + 2, j);
+      v->res2[i][j] = conv(n2, 512, 512);
+    }
+    char n3[32];
+    snprintf(n3, sizeof n3, "%d.2", i + 2);
+    v->up[i] = conv(n3, 512, 1536);
+  }
+  v->c4 = conv("4", 512, 1536);
+  v->c6 = conv("6", v->out_dim, 1536);
+  return err;
+}
+
+extern "C" int st_vq_create(const st_tensor* packed, int n, int out_dim, st_vq** out) {
+  ST_REQUIRE(packed && out && n > 0 && out_dim > 0, "st_vq_create: null argument");
+  st_vq* v = new st_vq();
+  v->out_dim = out_dim;
+  int r = v->w.upload(packed, n);
+  if (r == ST_OK) r = vq_resolve(v);
+  if (r != ST_OK) { v->w.release(); delete v; return r; }
+  *out = v;
+  return ST_OK;
+}
+extern "C" void st_vq_destroy(st_vq* v) {
+  if (!v) return;
+  cudaDeviceSynchronize();
+  v->w.release(); v->ws.release();
+  delete v;
+}
+extern "C" int st_vq_out_dim(const st_vq* v) { return v ? v->out_dim : 0; }
+
+static GemmP conv3(const float* in, const ConvW& w, float* out, int B, int Lin, int Lout, int N, int dil, int ups) {
+  GemmP p;
+  p.A = in; p.W = w.w; p.bias = w.b; p.out = out;
+  p.M = B * Lout; p.N = N; p.K = 1536; p.ldw = w.ldw;
+  p.Lout = Lout; p.Lin = Lin; p.C = 512; p.stride = 1; p.pad = dil; p.dil = dil; p.ups = ups;
+  p.a_batch = (long long)Lin * 512; p.lda = 512; p.ldo = N;
+  return p;
+}
+
+extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, float lat_scale, int B, int T4, float* rec,
+                             int64_t* idx_out, float* residual_out, void* stream) {
+  ST_REQUIRE(v && lat && rec && B > 0 && T4 > 0, "st_rvq_decode: null argument or empty batch");
+  ST_REQUIRE(lat_stride >= 512 && (lat_stride & 3) == 0, "st_rvq_decode: lat_stride=%lld", (long long)lat_stride);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t rows = (size_t)B * T4;
+  const size_t big = rows * 4 * 512;
+  ST_TRY(v->ws.reserve((rows * 512 * 3 + big * 3) * sizeof(float) + 16 * 256));
+  float* r = v->ws.take<float>(rows * 512);
+  float* dot = v->ws.take<float>(rows * 512);
+  float* qsum = v->ws.take<float>(rows * 512);
+  float* hA = v->ws.take<float>(big);
+  float* hB = v->ws.take<float>(big);
+  float* hC = v->ws.take<float>(big);
+  ST_TRY(copy_strided_scale(lat, lat_stride, lat_scale, r, (int)rows, 512, s));
+  // residual quantisation, 6 layers (residual_vq.py:132-152)
+  for (int q = 0; q < 6; ++q) {
+    GemmP p = linear(r, (int)rows, 512, v->cb[q], nullptr, dot, 512);
+    ST_TRY(gemm_simt(p, s));   // code ranking always on the exact-fp32 engine
+    ST_TRY(vq_select(dot, v->cnorm[q], v->cb[q], r, qsum, idx_out ? idx_out + q : nullptr, 6, (int)rows, q == 0, s));
+  }
+  if (residual_out) ST_CHECK_CUDA(cudaMemcpyAsync(residual_out, r, rows * 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  // decoder (encdec.py:51-68)
+  int T = T4;
+  GemmP p0 = conv3(qsum, v->c0, hA, B, T, T, 512, 1, 0);
+  p0.act = ACT_RELU;
+  ST_TRY(gemm(p0, s));
+  float* h = hA; float* tmp = hB; float* nxt = hC;
+  const int dils[3] = {9, 3, 1};
+  for (int i = 0; i < 2; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      GemmP p1 = conv3(h, v->res1[i][j], tmp, B, T, T, 512, dils[j], 0);
+      p1.a_relu = 1;
+      ST_TRY(gemm(p1, s));
+      GemmP p2 = linear(tmp, B * T, 512, v->res2[i][j].w, v->res2[i][j].b, h, 512);
+      p2.a_relu = 1; p2.res = h; p2.res_mode = RES_POST; p2.ldr = 512;
+      ST_TRY(gemm(p2, s));
+    }
+    GemmP pu = conv3(h, v->up[i], nxt, B, T, 2 * T, 512, 1, 1);
+    ST_TRY(gemm(pu, s));
+    T *= 2;
+    float* o = h; h = nxt; nxt = o;
+  }
+  GemmP p4 = conv3(h, v->c4, tmp, B, T, T, 512, 1, 0);
+  p4.act = ACT_RELU;
+  ST_TRY(gemm(p4, s));
+  GemmP p6 = conv3(tmp, v->c6, rec, B, T, T, v->out_dim, 1, 0);
+  ST_TRY(gemm(p6, s));
+  return ST_OK;
+}
+
+extern "C" int st_pose_assemble_330(const float* rec_upper, const float* rec_hands, const float* rec_lower, const float* mean,
+                                    const float* std, const float* trans_mean, const float* trans_std, const float* jaw_aa, int B,
+                                    int n, float* rec_pose, float* rec_trans, void* stream) {
+  ST_REQUIRE(rec_upper && rec_hands && rec_lower && mean && std && rec_pose && B > 0 && n > 0, "st_pose_assemble_330: null argument");
+  ST_REQUIRE(!rec_trans || (trans_mean && trans_std), "st_pose_assemble_330: rec_trans needs trans_mean/std");
+  return pose330(rec_upper, rec_hands, rec_lower, mean, std, trans_mean, trans_std, jaw_aa, B, n, rec_pose, rec_trans, (cudaStream_t)stream);
+}
+extern "C" int st_pose_assemble_623(const float* rec_upper, const float* rec_hands, const float* rec_lower, int B, int n,
+                                    float* rec_pose, void* stream) {
+  ST_REQUIRE(rec_upper && rec_hands && rec_lower && rec_pose && B > 0 && n > 0, "st_pose_assemble_623: null argument");
+  return pose623(rec_upper, rec_hands, rec_lower, B, n, rec_pose, (cudaStream_t)stream);
+}
+extern "C" int st_sample_to_tokens(const float* sample, int B, int T, float scale, float* tokens, void* stream) {
+  ST_REQUIRE(sample && tokens && B > 0 && T > 0, "st_sample_to_tokens: null argument");
+  return transpose_to_tokens(sample, tokens, B, 1536, T, scale, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int st_generate_330_host(st_model* m, const st_schedule* sc, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
+                                    st_vq* vq_lower, const st_host_inputs* in, int B, float latent_scale, float* rec_pose_host,
+                                    float* rec_trans_host, float* sample_host, void* stream) {
+  ST_REQUIRE(m && sc && vq_upper && vq_hands && vq_lower && in && rec_pose_host && B > 0, "st_generate_330_host: null argument");
+  ST_REQUIRE(in->audio && in->word && in->seed && in->x_init && in->mean && in->std, "st_generate_330_host: missing host input");
+  ST_REQUIRE(vq_upper->out_dim == 78 && vq_hands->out_dim == 180 && vq_lower->out_dim == 57, "st_generate_330_host: decoders must be 78/180/57 wide");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nx = (size_t)B * ST_LATENT * ST_TOKENS;
+  const int sdim = m->style_dim;
+  bool any_sigma = false;
+  for (int k = 0; k < sc->S; ++k) any_sigma |= sc->coef[(size_t)k * ST_COEF_STRIDE + (sc->mode == ST_MODE_DDPM ? 2 : 4)] != 0.f;
+  ST_REQUIRE(!any_sigma || in->noise_tape, "st_generate_330_host: schedule has sigma != 0 but noise_tape is NULL");
+  size_t f = (size_t)B * ST_AUDIO_LEN * 2 + (size_t)B * 128 + (size_t)B * 6144 + 3 * (size_t)B * (sdim ? sdim : 1) + nx * 2 +
+             (any_sigma ? nx * sc->S : 0) + (size_t)B * 128 * (3 + 78 + 180 + 57 + 330 + 3) + 666 + 64 * 16;
+  ST_TRY(m->io.reserve(f * sizeof(float) + 32 * 256));
+  Arena& a = m->io;
+  float* d_audio = a.take<float>((size_t)B * ST_AUDIO_LEN * 2);
+  int32_t* d_word = a.take<int32_t>((size_t)B * 128);
+  float* d_seed = a.take<float>((size_t)B * 6144);
+  float* d_style[3] = {nullptr, nullptr, nullptr};
+  float* d_x = a.take<float>(nx);
+  float* d_tok = a.take<float>(nx);
+  float* d_tape = any_sigma ? a.take<float>(nx * sc->S) : nullptr;
+  float* d_jaw = in->jaw_aa ? a.take<float>((size_t)B * 128 * 3) : nullptr;
+  float* d_up = a.take<float>((size_t)B * 128 * 78);
+  float* d_ha = a.take<float>((size_t)B * 128 * 180);
+  float* d_lo = a.take<float>((size_t)B * 128 * 57);
+  float* d_pose = a.take<float>((size_t)B * 128 * 330);
+  float* d_trans = a.take<float>((size_t)B * 128 * 3);
+  float* d_ms = a.take<float>(666);
+  auto h2d = [&](void* d, const void* h, size_t bytes) { return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s); };
+  ST_CHECK_CUDA(h2d(d_audio, in->audio, (size_t)B * ST_AUDIO_LEN * 2 * sizeof(float)));
+  ST_CHECK_CUDA(h2d(d_word, in->word, (size_t)B * 128 * sizeof(int32_t)));
+  ST_CHECK_CUDA(h2d(d_seed, in->seed, (size_t)B * 6144 * sizeof(float)));
+  for (int k = 0; k < 3; ++k)
+    if (sdim && in->style[k]) {
+      d_style[k] = a.take<float>((size_t)B * sdim);
+      ST_CHECK_CUDA(h2d(d_style[k], in->style[k], (size_t)B * sdim * sizeof(float)));
+    }
+  ST_CHECK_CUDA(h2d(d_x, in->x_init, nx * sizeof(float)));
+  if (d_tape) ST_CHECK_CUDA(h2d(d_tape, in->noise_tape, nx * sc->S * sizeof(float)));
+  if (d_jaw) ST_CHECK_CUDA(h2d(d_jaw, in->jaw_aa, (size_t)B * 128 * 3 * sizeof(float)));
+  ST_CHECK_CUDA(h2d(d_ms, in->mean, 330 * sizeof(float)));
+  ST_CHECK_CUDA(h2d(d_ms + 330, in->std, 330 * sizeof(float)));
+  const bool want_trans = rec_trans_host && in->trans_mean && in->trans_std;
+  if (want_trans) {
+    ST_CHECK_CUDA(h2d(d_ms + 660, in->trans_mean, 3 * sizeof(float)));
+    ST_CHECK_CUDA(h2d(d_ms + 663, in->trans_std, 3 * sizeof(float)));
+  }
+  st_cond c;
+  c.audio = d_audio; c.word = d_word; c.seed = d_seed;
+  for (int k = 0; k < 3; ++k) c.style[k] = d_style[k];
+  ST_TRY(st_cond_encode(m, &c, B, stream));
+  ST_TRY(st_sample(m, sc, g, d_x, d_tape, B, d_x, stream));
+  if (sample_host) ST_CHECK_CUDA(cudaMemcpyAsync(sample_host, d_x, nx * sizeof(float), cudaMemcpyDeviceToHost, s));
+  ST_TRY(transpose_to_tokens(d_x, d_tok, B, 1536, 32, 1.0f, s));
+  ST_TRY(st_rvq_decode(vq_upper, d_tok, 1536, latent_scale, B, 32, d_up, nullptr, nullptr, stream));
+  ST_TRY(st_rvq_decode(vq_hands, d_tok + 512, 1536, latent_scale, B, 32, d_ha, nullptr, nullptr, stream));
+  ST_TRY(st_rvq_decode(vq_lower, d_tok + 1024, 1536, latent_scale, B, 32, d_lo, nullptr, nullptr, stream));
+  ST_TRY(pose330(d_up, d_ha, d_lo, d_ms, d_ms + 330, d_ms + 660, d_ms + 663, d_jaw, B, 128, d_pose, want_trans ? d_trans : nullptr, s));
+  ST_CHECK_CUDA(cudaMemcpyAsync(rec_pose_host, d_pose, (size_t)B * 128 * 330 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (want_trans) ST_CHECK_CUDA(cudaMemcpyAsync(rec_trans_host, d_trans, (size_t)B * 128 * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  ST_CHECK_CUDA(cudaStreamSynchronize(s));
+  return ST_OK;
+}
+
+extern "C" int st_selftest_gemm(int M, int N, int K, int engine, const float* A, const float* W, const float* bias, float* out,
+                                void* stream) {
+  ST_REQUIRE(A && W && out && M > 0 && N > 0 && K > 0, "st_selftest_gemm: null argument");
+  GemmP p = linear(A, M, K, W, bias, out, N);
+  if (engine == ST_ENGINE_TC) {
+    if (!tc_supported(p)) { set_error("st_selftest_gemm: shape M=%d N=%d K=%d not supported by the tcgen05 engine", M, N, K); return ST_EUNSUPPORTED; }
+    return gemm_tc(p, (cudaStream_t)stream);
+  }
+  return gemm_simt(p, (cudaStream_t)stream);
+}

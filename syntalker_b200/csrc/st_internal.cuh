@@ -1,0 +1,152 @@
+// Internal declarations shared by the translation units of libsyntalker_b200.so (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <map>
+#include <vector>
+
+#include "../../include/syntalker_b200.h"
+
+namespace st {
+
+// ---- error plumbing -----------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern thread_local int64_t g_launches;
+
+#define ST_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      st::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));       \
+      return ST_ECUDA;                                                                           \
+    }                                                                                            \
+  } while (0)
+
+#define ST_CHECK_LAUNCH()                                                                        \
+  do {                                                                                           \
+    st::g_launches++;                                                                            \
+    cudaError_t _e = cudaPeekAtLastError();                                                      \
+    if (_e != cudaSuccess) {                                                                     \
+      st::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e));   \
+      return ST_ECUDA;                                                                           \
+    }                                                                                            \
+  } while (0)
+
+#define ST_TRY(expr)              \
+  do {                            \
+    int _r = (expr);              \
+    if (_r != ST_OK) return _r;   \
+  } while (0)
+
+#define ST_REQUIRE(cond, ...)      \
+  do {                             \
+    if (!(cond)) {                 \
+      st::set_error(__VA_ARGS__);  \
+      return ST_EINVAL;            \
+    }                              \
+  } while (0)
+
+// ---- generic implicit-GEMM descriptor ------------------------------------------------------------------
+// out[m, n] = act( sum_k A(m,k) * W[n,k] + bias[n] + res_pre[m/res_div, n] ) + res_post[m/res_div, n]
+// A(m,k): m -> (b = m / Lout, t = m % Lout);  k -> (j = k / C, c = k % C);  l = t*stride - pad + j*dil;
+//         ups: valid iff 0 <= l < 2*Lin, then l >>= 1;  else valid iff 0 <= l < Lin;
+//         value = A[b*a_batch + l*lda + c] (0 when invalid), optionally max(.,0) (a_relu).
+// A plain Linear is Lout = Lin = M, C = K, stride 1, pad 0.  Conv1d over channels-last activations is the rest.
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_LRELU = 3 };
+enum { RES_NONE = 0, RES_PRE = 1, RES_POST = 2 };
+
+struct GemmP {
+  const float* A = nullptr;
+  const float* W = nullptr;      // [N, ldw] row-major, zero padded to ldw (multiple of 4)
+  const float* bias = nullptr;   // [N] or null
+  const float* res = nullptr;    // [M/res_div, ldr] or null
+  float* out = nullptr;          // [M, ldo]
+  int M = 0, N = 0, K = 0, ldw = 0;
+  int Lout = 1, Lin = 1, C = 1, stride = 1, pad = 0, dil = 1, ups = 0;
+  long long a_batch = 0;
+  int lda = 0;
+  int a_relu = 0, act = ACT_NONE, res_mode = RES_NONE, ldr = 0, res_div = 1, ldo = 0;
+  float out_scale = 1.0f;        // applied to the accumulator before bias (used by nothing exact-critical)
+};
+
+GemmP linear(const float* A, int M, int K, const float* W, const float* bias, float* out, int N);
+
+int gemm_simt(const GemmP& p, cudaStream_t s);
+int gemm(const GemmP& p, cudaStream_t s);   // dispatches on the engine (TC falls back to SIMT for shapes it does not take)
+bool tc_supported(const GemmP& p);
+int gemm_tc(const GemmP& p, cudaStream_t s);
+int profile_begin();
+int profile_end(double* ms, double* flops, int64_t* n);
+
+// ---- other kernels --------------------------------------------------------------------------------------
+int layernorm512(const float* x, const float* gamma, const float* beta, float* y, int rows, cudaStream_t s);
+int attention32(const float* qkv, float* out, int nseq, cudaStream_t s);   // qkv [nseq*32,1536] -> out [nseq*32,512]
+struct TokensInP {
+  const float* z;            // [B*32,512] = x_t . Wx^T
+  const float* vt_table;     // [1000,512]
+  const int64_t* t_dev;      // [B] or null
+  int t_scalar;              // used when t_dev == null
+  const float* cst[ST_MAX_EVALS];   // per eval: [B*32,512] or [32,512] (cst_bcast) conditioning constant
+  int cst_bcast[ST_MAX_EVALS];
+  const float* g2;           // [B,512] seed term (always added)
+  const float* sv[ST_MAX_EVALS];    // per eval: [B,512], [1,512] (sv_bcast) or null: style term
+  int sv_bcast[ST_MAX_EVALS];
+  const float* rope_cos;     // [32,32]
+  const float* rope_sin;
+  float* x;                  // [nE*B*32,512]
+  int B, nE;
+};
+int tokens_in(const TokensInP& p, cudaStream_t s);
+
+struct StepP {
+  const float* o;            // [nE*B*32,1536] eval outputs, eval-major
+  float* xs;                 // [B*32,1536] state, updated in place (or x0 written when mode<0)
+  const float* eps;          // [B,1536,1,32] caller layout noise or null
+  int B, nE;
+  int cfg_mode;              // ST_CFG_*
+  const float* scale;        // device [B] (TEXT: scale; TWO: scale_audio)
+  const float* scale2;       // device [B] (TWO: scale_prompt)
+  float part_sa[3], part_sp[3];  // BODYPART
+  int part_ua[3];                // eval index of the part's prompt evaluation or -1
+  int mode;                  // ST_MODE_DDPM / ST_MODE_DDIM / -1 = write combined model output only
+  float c[ST_COEF_STRIDE];
+};
+int step_update(const StepP& p, cudaStream_t s);
+
+int transpose_to_tokens(const float* x, float* tok, int B, int C, int T, float scale, cudaStream_t s);     // [B,C,T]->[B,T,C]
+int transpose_from_tokens(const float* tok, float* x, int B, int C, int T, cudaStream_t s);                // [B,T,C]->[B,C,T]
+int gather_words(const int32_t* word, const float* table, float* out, int ldo, int rows, int force_zero, cudaStream_t s);
+int avgpool4(const float* in, float* out, int rows_out, int cols, cudaStream_t s);                         // rows_out x cols, in has 4x rows
+int vq_select(const float* dot, const float* cnorm, const float* codebook, float* residual, float* qsum, int64_t* idx,
+              int idx_stride, int rows, int first, cudaStream_t s);
+int copy_strided_scale(const float* in, long long in_stride, float scale, float* out, int rows, int cols, cudaStream_t s);
+int pose330(const float* up, const float* ha, const float* lo, const float* mean, const float* std, const float* tmean,
+            const float* tstd, const float* jaw, int B, int n, float* pose, float* trans, cudaStream_t s);
+int pose623(const float* up, const float* ha, const float* lo, int B, int n, float* pose, cudaStream_t s);
+
+// ---- device memory helpers ------------------------------------------------------------------------------
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  int reserve(size_t bytes);   // (re)allocates when cap < bytes; resets the bump pointer
+  void reset() { off = 0; }
+  template <typename T>
+  T* take(size_t n) {
+    size_t a = (off + 255) & ~size_t(255);
+    off = a + n * sizeof(T);
+    return reinterpret_cast<T*>(base + a);
+  }
+  void release();
+};
+
+struct Weights {
+  std::map<std::string, float*> dev;
+  std::map<std::string, int64_t> numel;
+  int upload(const st_tensor* t, int n);
+  const float* get(const std::string& name, int64_t expect_numel, int* err) const;
+  void release();
+};
+
+}  // namespace st

@@ -1,0 +1,795 @@
+// Exact-fp32 kernels of the SynTalker sampling path for sm_100a: the implicit-GEMM SIMT engine (Linear and
+// channels-last Conv1d in one kernel), LayerNorm, the 32-token attention core, RoPE + conditioning add,
+// CFG combine + DDIM/DDPM update, the RVQ code selection and the 330-d pose assembly.
+// Reference arithmetic each kernel reproduces is cited at the kernel.
+#include "st_internal.cuh"
+
+#include <math.h>
+
+namespace st {
+
+// =========================================================================================================
+// 1. Implicit-GEMM SIMT engine.  128x64 CTA tile, BK=16, 256 threads, 8x4 register tile, double-buffered
+//    shared memory with register prefetch.  A is gathered through the (b,t,j,c) map of GemmP so the same
+//    kernel does nn.Linear (denoiser.py, transformer.py), the k=15 strided WavEncoder convs
+//    (denoiser.py:304-322, layer.py:144-184) and the dilated / upsampled k=3 decoder convs
+//    (encdec.py:37-68, resnet.py:12-69) over channels-last activations.
+// =========================================================================================================
+constexpr int BM = 128, BN = 64, BK = 16, GEMM_THREADS = 256;
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_GELU: return v * 0.5f * (1.0f + erff(v * 0.70710678118654752440f));   // exact-erf GELU (transformer.py:131 nn.GELU)
+    case ACT_RELU: return fmaxf(v, 0.0f);
+    case ACT_LRELU: return v > 0.0f ? v : v * 0.01f;                                 // nn.LeakyReLU default slope (layer.py:146)
+    default: return v;
+  }
+}
+
+template <bool VEC_A>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_simt_kernel(GemmP p) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  // ---- A gather bookkeeping: two (row, k4) slots per thread ----
+  int a_row[2], a_k4[2], a_basel[2];
+  const float* a_ptr[2];
+  bool a_ok[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int slot = tid + i * GEMM_THREADS;
+    a_row[i] = slot >> 2;
+    a_k4[i] = slot & 3;
+    const int m = m0 + a_row[i];
+    a_ok[i] = m < p.M;
+    const int mm = a_ok[i] ? m : 0;
+    const int b = mm / p.Lout;
+    const int t = mm - b * p.Lout;
+    a_basel[i] = t * p.stride - p.pad;
+    a_ptr[i] = p.A + (long long)b * p.a_batch;
+  }
+  const int b_n = tid >> 2, b_k4 = tid & 3;
+  const bool b_ok = (n0 + b_n) < p.N;
+  const float* b_ptr = p.W + (long long)(n0 + (b_ok ? b_n : 0)) * p.ldw;
+  const int lim = p.ups ? 2 * p.Lin : p.Lin;
+
+  float4 ra[2], rb;
+  auto load_tile = [&](int kt) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = kt * BK + a_k4[i] * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (VEC_A) {
+        if (a_ok[i] && k < p.K) {
+          const int j = k / p.C;
+          const int c = k - j * p.C;
+          int l = a_basel[i] + j * p.dil;
+          if (l >= 0 && l < lim) {
+            if (p.ups) l >>= 1;
+            v = __ldg(reinterpret_cast<const float4*>(a_ptr[i] + (long long)l * p.lda + c));
+          }
+        }
+      } else {
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a_ok[i]) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int kk = k + q;
+            if (kk < p.K) {
+              const int j = kk / p.C;
+              const int c = kk - j * p.C;
+              int l = a_basel[i] + j * p.dil;
+              if (l >= 0 && l < lim) {
+                if (p.ups) l >>= 1;
+                e[q] = __ldg(a_ptr[i] + (long long)l * p.lda + c);
+              }
+            }
+          }
+        }
+        v = make_float4(e[0], e[1], e[2], e[3]);
+      }
+      if (p.a_relu) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      }
+      ra[i] = v;
+    }
+    const int kb = kt * BK + b_k4 * 4;
+    rb = (b_ok && kb < p.ldw) ? __ldg(reinterpret_cast<const float4*>(b_ptr + kb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int kk = a_k4[i] * 4;
+      As[buf][kk + 0][a_row[i]] = ra[i].x;
+      As[buf][kk + 1][a_row[i]] = ra[i].y;
+      As[buf][kk + 2][a_row[i]] = ra[i].z;
+      As[buf][kk + 3][a_row[i]] = ra[i].w;
+    }
+    const int kk = b_k4 * 4;
+    Bs[buf][kk + 0][b_n] = rb.x;
+    Bs[buf][kk + 1][b_n] = rb.y;
+    Bs[buf][kk + 2][b_n] = rb.z;
+    Bs[buf][kk + 3][b_n] = rb.w;
+  };
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nkt = (p.K + BK - 1) / BK;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nkt) load_tile(kt + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nkt) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue ----
+  const int nb = n0 + tx * 4;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (nb + j < p.N) bias[j] = __ldg(p.bias + nb + j);
+  }
+  const bool vec_out = ((p.ldo & 3) == 0) && (nb + 3 < p.N);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= p.M) continue;
+    float v[4];
+    const float* rrow = p.res ? p.res + (long long)(m / p.res_div) * p.ldr : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = acc[i][j] * p.out_scale + bias[j];
+      const float r = (rrow && nb + j < p.N) ? rrow[nb + j] : 0.f;
+      if (p.res_mode == RES_PRE) x += r;
+      x = apply_act(x, p.act);
+      if (p.res_mode == RES_POST) x += r;
+      v[j] = x;
+    }
+    float* orow = p.out + (long long)m * p.ldo;
+    if (vec_out) {
+      *reinterpret_cast<float4*>(orow + nb) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (nb + j < p.N) orow[nb + j] = v[j];
+    }
+  }
+}
+
+GemmP linear(const float* A, int M, int K, const float* W, const float* bias, float* out, int N) {
+  GemmP p;
+  p.A = A; p.W = W; p.bias = bias; p.out = out;
+  p.M = M; p.N = N; p.K = K; p.ldw = K;
+  p.Lout = M; p.Lin = M; p.C = K; p.lda = K; p.ldo = N;
+  return p;
+}
+
+int gemm_simt(const GemmP& p, cudaStream_t s) {
+  ST_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  ST_REQUIRE((p.ldw & 3) == 0 && p.ldw >= p.K, "gemm: ldw=%d must be a multiple of 4 and >= K=%d", p.ldw, p.K);
+  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
+  const bool vec = ((p.C & 3) == 0) && ((p.lda & 3) == 0) && ((p.a_batch & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+  if (vec) gemm_simt_kernel<true><<<grid, GEMM_THREADS, 0, s>>>(p);
+  else gemm_simt_kernel<false><<<grid, GEMM_THREADS, 0, s>>>(p);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+// =========================================================================================================
+// 2. LayerNorm over 512 channels, eps 1e-5, affine (transformer.py:172,185).  One warp per row.
+// =========================================================================================================
+__global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                           const float* __restrict__ b, float* __restrict__ y, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * 512);
+  float4 v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / 512.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q * (1.0f / 512.0f) + 1e-5f);
+  float4* yr = reinterpret_cast<float4*>(y + (long long)row * 512);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 gg = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * gg.x + bb.x;
+    o.y = (v[i].y - mean) * rstd * gg.y + bb.y;
+    o.z = (v[i].z - mean) * rstd * gg.z + bb.z;
+    o.w = (v[i].w - mean) * rstd * gg.w + bb.w;
+    yr[lane + 32 * i] = o;
+  }
+}
+
+int layernorm512(const float* x, const float* gamma, const float* beta, float* y, int rows, cudaStream_t s) {
+  layernorm512_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, gamma, beta, y, rows);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+// =========================================================================================================
+// 3. Attention core for one (sequence, head): 32 tokens x 128 dims, softmax(q k^T / sqrt(128)) v, no mask
+//    (transformer.py:83-104; qkv channel = which*512 + head*128 + d).  256 threads, fp32 throughout.
+// =========================================================================================================
+constexpr int ATT_LD = 132;   // padded row stride (floats) -> conflict-free float4 reads
+
+__global__ void __launch_bounds__(256) attention32_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
+  extern __shared__ __align__(16) float att_smem[];
+  float (*q)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem);
+  float (*k)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 32 * ATT_LD);
+  float (*v)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 64 * ATT_LD);
+  float (*pr)[33] = reinterpret_cast<float (*)[33]>(att_smem + 96 * ATT_LD);
+  const int seq = blockIdx.x, head = blockIdx.y, tid = threadIdx.x;
+  const float* base = qkv + (long long)seq * 32 * 1536 + head * 128;
+  for (int i = tid; i < 32 * 32; i += 256) {           // 32 rows x 32 float4 per matrix
+    const int r = i >> 5, c4 = i & 31;
+    const float* src = base + (long long)r * 1536 + c4 * 4;
+    *reinterpret_cast<float4*>(&q[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(src));
+    *reinterpret_cast<float4*>(&k[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(src + 512));
+    *reinterpret_cast<float4*>(&v[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(src + 1024));
+  }
+  __syncthreads();
+  const int i = tid >> 3, u = tid & 7;                 // row i, 8 threads per row
+  float sc[4] = {0.f, 0.f, 0.f, 0.f};                  // scores for j = u + 8*jj
+#pragma unroll 8
+  for (int d = 0; d < 128; d += 4) {
+    const float4 qa = *reinterpret_cast<const float4*>(&q[i][d]);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float4 kb = *reinterpret_cast<const float4*>(&k[u + 8 * jj][d]);
+      sc[jj] = fmaf(qa.x, kb.x, sc[jj]);
+      sc[jj] = fmaf(qa.y, kb.y, sc[jj]);
+      sc[jj] = fmaf(qa.z, kb.z, sc[jj]);
+      sc[jj] = fmaf(qa.w, kb.w, sc[jj]);
+    }
+  }
+  const float scale = 0.08838834764831845f;            // 128^-0.5
+  float mx = -INFINITY;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) { sc[jj] *= scale; mx = fmaxf(mx, sc[jj]); }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) { sc[jj] = expf(sc[jj] - mx); sum += sc[jj]; }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) pr[i][u + 8 * jj] = sc[jj] * inv;
+  __syncthreads();
+  // out[i][d]: thread owns d = u*4 + 32*dd, dd = 0..3 (float4 each)
+  float4 o4[4];
+#pragma unroll
+  for (int dd = 0; dd < 4; ++dd) o4[dd] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < 32; ++j) {
+    const float pj = pr[i][j];
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd) {
+      const float4 vv = *reinterpret_cast<const float4*>(&v[j][u * 4 + 32 * dd]);
+      o4[dd].x = fmaf(pj, vv.x, o4[dd].x);
+      o4[dd].y = fmaf(pj, vv.y, o4[dd].y);
+      o4[dd].z = fmaf(pj, vv.z, o4[dd].z);
+      o4[dd].w = fmaf(pj, vv.w, o4[dd].w);
+    }
+  }
+  float* orow = out + ((long long)seq * 32 + i) * 512 + head * 128;
+#pragma unroll
+  for (int dd = 0; dd < 4; ++dd) *reinterpret_cast<float4*>(orow + u * 4 + 32 * dd) = o4[dd];
+}
+
+int attention32(const float* qkv, float* out, int nseq, cudaStream_t s) {
+  constexpr int smem = (96 * ATT_LD + 32 * 33) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ST_CHECK_CUDA(cudaFuncSetAttribute(attention32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  attention32_kernel<<<dim3(nseq, 4), 256, smem, s>>>(qkv, out);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+// =========================================================================================================
+// 4. Token prologue: x_e[b,tau,:] = RoPE( z[b,tau,:] + vt[t_b,:] + cst_e[b,tau,:] + g2[b,:] + sv_e[b,:] )
+//    = input_process / input_process2 / input_process3 with the step-invariant terms hoisted
+//    (denoiser.py:160-174) followed by the rotary embedding on 8 groups of 64 (denoiser.py:178-186,324-343).
+//    One thread per (eval, row, pair j<256): columns g*64 + j' and g*64 + j' + 32.
+// =========================================================================================================
+__global__ void __launch_bounds__(256) tokens_in_kernel(TokensInP p) {
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long per_eval = (long long)p.B * 32 * 256;
+  if (gid >= per_eval * p.nE) return;
+  const int e = (int)(gid / per_eval);
+  const long long r = gid - e * per_eval;
+  const int row = (int)(r >> 8);              // b*32 + tau
+  const int pj = (int)(r & 255);
+  const int grp = pj >> 5, j = pj & 31;
+  const int c1 = grp * 64 + j, c2 = c1 + 32;
+  const int b = row >> 5, tau = row & 31;
+  const int t = p.t_dev ? (int)p.t_dev[b] : p.t_scalar;
+  const float* vt = p.vt_table + (long long)t * 512;
+  const float* cst = p.cst[e] + (long long)(p.cst_bcast[e] ? tau : row) * 512;
+  const float* g2 = p.g2 + (long long)b * 512;
+  const float* zr = p.z + (long long)row * 512;
+  float x1 = zr[c1] + vt[c1] + cst[c1] + g2[c1];
+  float x2 = zr[c2] + vt[c2] + cst[c2] + g2[c2];
+  if (p.sv[e]) {
+    const float* sv = p.sv[e] + (p.sv_bcast[e] ? 0 : (long long)b * 512);
+    x1 += sv[c1];
+    x2 += sv[c2];
+  }
+  const float cs = p.rope_cos[tau * 32 + j], sn = p.rope_sin[tau * 32 + j];
+  float* xo = p.x + ((long long)e * p.B * 32 + row) * 512;
+  xo[c1] = __fadd_rn(__fmul_rn(x1, cs), __fmul_rn(-x2, sn));
+  xo[c2] = __fadd_rn(__fmul_rn(x2, cs), __fmul_rn(x1, sn));
+}
+
+int tokens_in(const TokensInP& p, cudaStream_t s) {
+  const long long n = (long long)p.nE * p.B * 32 * 256;
+  tokens_in_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+// =========================================================================================================
+// 5. CFG combine + sampler update on the token-major state [B*32,1536].
+//    CFG: cfg_sampler.py:28 / :54 / :67-117.   DDIM: gaussian_diffusion.py:772-790 (eps re-derived from x0).
+//    DDPM: gaussian_diffusion.py:383 (posterior mean) + :556.  Intrinsics keep the reference's
+//    separate fp32 roundings (no FMA contraction), so given equal inputs the update is bit-identical.
+// =========================================================================================================
+__global__ void __launch_bounds__(256) step_update_kernel(StepP p) {
+  const long long n4 = (long long)p.B * 32 * 1536 / 4;
+  const long long i4 = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i4 >= n4) return;
+  const long long e0 = i4 * 4;
+  const int row = (int)(e0 / 1536);
+  const int col = (int)(e0 - (long long)row * 1536);
+  const int b = row >> 5, tau = row & 31;
+  const long long per_eval = (long long)p.B * 32 * 1536;
+  auto ld = [&](int e) { return *reinterpret_cast<const float4*>(p.o + e * per_eval + e0); };
+  float x0[4];
+  if (p.cfg_mode == ST_CFG_NONE) {
+    const float4 a = ld(0);
+    x0[0] = a.x; x0[1] = a.y; x0[2] = a.z; x0[3] = a.w;
+  } else if (p.cfg_mode == ST_CFG_TEXT) {
+    const float4 c = ld(0), u = ld(1);                  // eval 0 = conditional, eval 1 = unconditional
+    const float sc = p.scale[b];
+    const float cv[4] = {c.x, c.y, c.z, c.w}, uv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x0[q] = __fadd_rn(uv[q], __fmul_rn(sc, __fsub_rn(cv[q], uv[q])));
+  } else {
+    // eval 0 = uu (no prompt, no audio), eval 1 = ut (no prompt, audio), eval >= 2 = ua (prompt, no audio)
+    const float4 uu = ld(0), ut = ld(1);
+    float sa, sp;
+    int ua_e;
+    if (p.cfg_mode == ST_CFG_TWO) { sa = p.scale[b]; sp = p.scale2[b]; ua_e = 2; }
+    else { const int part = col / 512; sa = p.part_sa[part]; sp = p.part_sp[part]; ua_e = p.part_ua[part]; }
+    const float uuv[4] = {uu.x, uu.y, uu.z, uu.w}, utv[4] = {ut.x, ut.y, ut.z, ut.w};
+    float uav[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ua_e >= 0) { const float4 ua = ld(ua_e); uav[0] = ua.x; uav[1] = ua.y; uav[2] = ua.z; uav[3] = ua.w; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float acc = __fadd_rn(uuv[q], __fmul_rn(sa, __fsub_rn(utv[q], uuv[q])));
+      if (ua_e >= 0) acc = __fadd_rn(acc, __fmul_rn(sp, __fsub_rn(uav[q], uuv[q])));
+      x0[q] = acc;
+    }
+  }
+  float4* xs4 = reinterpret_cast<float4*>(p.xs + e0);
+  if (p.mode < 0) { *xs4 = make_float4(x0[0], x0[1], x0[2], x0[3]); return; }
+  const float4 xv4 = *xs4;
+  const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+  float nz[4] = {0.f, 0.f, 0.f, 0.f};
+  const float sigma = p.mode == ST_MODE_DDPM ? p.c[2] : p.c[4];
+  if (p.eps && sigma != 0.f) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) nz[q] = p.eps[((long long)b * 1536 + col + q) * 32 + tau];   // caller layout [B,1536,1,32]
+  }
+  float o[4];
+  if (p.mode == ST_MODE_DDPM) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float mean = __fadd_rn(__fmul_rn(p.c[0], x0[q]), __fmul_rn(p.c[1], xv[q]));
+      o[q] = sigma != 0.f ? __fadd_rn(mean, __fmul_rn(sigma, nz[q])) : mean;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(p.c[0], xv[q]), x0[q]), p.c[1]);
+      const float mean = __fadd_rn(__fmul_rn(x0[q], p.c[2]), __fmul_rn(p.c[3], eps));
+      o[q] = sigma != 0.f ? __fadd_rn(mean, __fmul_rn(sigma, nz[q])) : mean;
+    }
+  }
+  *xs4 = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+int step_update(const StepP& p, cudaStream_t s) {
+  const long long n4 = (long long)p.B * 32 * 1536 / 4;
+  step_update_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(p);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+// =========================================================================================================
+// 6. Layout: [B,C,T] <-> [B,T,C] tile transposes (trainer:457 squeeze().permute(1,0); OutputProcess permute).
+// =========================================================================================================
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc,
+                                                        float scale) {
+  // in: [B, R, Cc] -> out: [B, Cc, R]
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* ib = in + (long long)b * R * Cc;
+  float* ob = out + (long long)b * R * Cc;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    if (r < R && c < Cc) tile[i][tx] = ib[(long long)r * Cc + c];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < R && c < Cc) ob[(long long)c * R + r] = tile[tx][i] * scale;
+  }
+}
+
+int transpose_to_tokens(const float* x, float* tok, int B, int C, int T, float scale, cudaStream_t s) {
+  transpose_kernel<<<dim3((T + 31) / 32, (C + 31) / 32, B), 256, 0, s>>>(x, tok, C, T, scale);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+int transpose_from_tokens(const float* tok, float* x, int B, int C, int T, cudaStream_t s) {
+  transpose_kernel<<<dim3((C + 31) / 32, (T + 31) / 32, B), 256, 0, s>>>(tok, x, T, C, 1.0f);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+// =========================================================================================================
+// 7. Conditioning helpers: word-embedding gather (Embedding + Linear folded into one table,
+//    denoiser.py:152-153) and the 4-frame average pool (denoiser.py:157).
+// =========================================================================================================
+__global__ void __launch_bounds__(256) gather_words_kernel(const int32_t* __restrict__ word, const float* __restrict__ table,
+                                                           float* __restrict__ out, int ldo, int rows, int force_zero) {
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;    // rows x 64 float4
+  if (gid >= (long long)rows * 64) return;
+  const int r = (int)(gid >> 6), c4 = (int)(gid & 63);
+  const int w = force_zero ? 0 : word[r];
+  const float4 v = __ldg(reinterpret_cast<const float4*>(table + (long long)w * 256) + c4);
+  *reinterpret_cast<float4*>(out + (long long)r * ldo + c4 * 4) = v;
+}
+int gather_words(const int32_t* word, const float* table, float* out, int ldo, int rows, int force_zero, cudaStream_t s) {
+  const long long n = (long long)rows * 64;
+  gather_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(word, table, out, ldo, rows, force_zero);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+__global__ void __launch_bounds__(256) avgpool4_kernel(const float* __restrict__ in, float* __restrict__ out, long long n4,
+                                                       int cols4) {
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (gid >= n4) return;
+  const long long r = gid / cols4;
+  const int c = (int)(gid - r * cols4);
+  const float4* src = reinterpret_cast<const float4*>(in) + (r * 4) * cols4 + c;
+  const float4 a = src[0], b = src[cols4], d = src[2 * (long long)cols4], e = src[3 * (long long)cols4];
+  float4 o;
+  o.x = (((a.x + b.x) + d.x) + e.x) * 0.25f;
+  o.y = (((a.y + b.y) + d.y) + e.y) * 0.25f;
+  o.z = (((a.z + b.z) + d.z) + e.z) * 0.25f;
+  o.w = (((a.w + b.w) + d.w) + e.w) * 0.25f;
+  reinterpret_cast<float4*>(out)[gid] = o;
+}
+int avgpool4(const float* in, float* out, int rows_out, int cols, cudaStream_t s) {
+  const long long n4 = (long long)rows_out * cols / 4;
+  avgpool4_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(in, out, n4, cols / 4);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+__global__ void __launch_bounds__(256) copy_strided_scale_kernel(const float* __restrict__ in, long long in_stride, float scale,
+                                                                 float* __restrict__ out, long long n4, int cols4) {
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (gid >= n4) return;
+  const long long r = gid / cols4;
+  const int c = (int)(gid - r * cols4);
+  float4 v = *(reinterpret_cast<const float4*>(in + r * in_stride) + c);
+  v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+  reinterpret_cast<float4*>(out)[gid] = v;
+}
+int copy_strided_scale(const float* in, long long in_stride, float scale, float* out, int rows, int cols, cudaStream_t s) {
+  const long long n4 = (long long)rows * cols / 4;
+  copy_strided_scale_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(in, in_stride, scale, out, n4, cols / 4);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+// =========================================================================================================
+// 8. RVQ code selection for one quantizer layer (quantizer.py:67-80,132-158; residual_vq.py:143-147).
+//    dot[r,j] = residual_r . c_j comes from the GEMM engine.  dist = (|r|^2 - 2 dot) + |c_j|^2 in fp32 like
+//    the reference, argmin with first-index ties (= argmax(-dist)), then x_q = r + (c - r),
+//    residual -= x_q, qsum += x_q.  One warp per row.
+// =========================================================================================================
+__global__ void __launch_bounds__(256) vq_select_kernel(const float* __restrict__ dot, const float* __restrict__ cnorm,
+                                                        const float* __restrict__ codebook, float* __restrict__ residual,
+                                                        float* __restrict__ qsum, int64_t* __restrict__ idx, int idx_stride,
+                                                        int rows, int first) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float4* rr = reinterpret_cast<float4*>(residual + (long long)row * 512);
+  float4 r[4];
+  float x2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r[i] = rr[lane + 32 * i];
+    x2 += (r[i].x * r[i].x + r[i].y * r[i].y) + (r[i].z * r[i].z + r[i].w * r[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+  const float* dr = dot + (long long)row * 512;
+  float best = INFINITY;
+  int bi = 0x7fffffff;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int j = lane + 32 * i;
+    const float d = __fadd_rn(__fsub_rn(x2, __fmul_rn(2.0f, dr[j])), __ldg(cnorm + j));
+    if (d < best) { best = d; bi = j; }        // ascending j per lane: strict < keeps the first index
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0 && idx) idx[(long long)row * idx_stride] = bi;
+  const float4* cb = reinterpret_cast<const float4*>(codebook + (long long)bi * 512);
+  float4* qs = reinterpret_cast<float4*>(qsum + (long long)row * 512);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 c = __ldg(cb + lane + 32 * i);
+    float4 xq, nr, acc;
+    xq.x = __fadd_rn(r[i].x, __fsub_rn(c.x, r[i].x));
+    xq.y = __fadd_rn(r[i].y, __fsub_rn(c.y, r[i].y));
+    xq.z = __fadd_rn(r[i].z, __fsub_rn(c.z, r[i].z));
+    xq.w = __fadd_rn(r[i].w, __fsub_rn(c.w, r[i].w));
+    nr.x = __fsub_rn(r[i].x, xq.x); nr.y = __fsub_rn(r[i].y, xq.y);
+    nr.z = __fsub_rn(r[i].z, xq.z); nr.w = __fsub_rn(r[i].w, xq.w);
+    rr[lane + 32 * i] = nr;
+    if (first) acc = make_float4(0.f + xq.x, 0.f + xq.y, 0.f + xq.z, 0.f + xq.w);
+    else {
+      const float4 old = qs[lane + 32 * i];
+      acc = make_float4(__fadd_rn(old.x, xq.x), __fadd_rn(old.y, xq.y), __fadd_rn(old.z, xq.z), __fadd_rn(old.w, xq.w));
+    }
+    qs[lane + 32 * i] = acc;
+  }
+}
+
+int vq_select(const float* dot, const float* cnorm, const float* codebook, float* residual, float* qsum, int64_t* idx,
+              int idx_stride, int rows, int first, cudaStream_t s) {
+  vq_select_kernel<<<(rows + 7) / 8, 256, 0, s>>>(dot, cnorm, codebook, residual, qsum, idx, idx_stride, rows, first);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+// =========================================================================================================
+// 9. 330-d assembly (diffusion_rvqvae_trainer.py:484-531; utils/rotation_conversions.py:39-64,96-118,
+//    432-508,511-550).  One thread per (b, frame, joint): de-normalise the 6d, Gram-Schmidt, matrix ->
+//    quaternion -> axis-angle -> quaternion -> matrix, keep the first two rows.  Jaw (joint 22) comes from
+//    the caller, eyes (23, 24) are zero rotations.  Root translation: v*std+mean, cumsum over frames for
+//    x/z, y kept as is.
+// =========================================================================================================
+__constant__ int c_upper_j[13] = {3, 6, 9, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21};
+__constant__ int c_lower_j[9] = {0, 1, 2, 4, 5, 7, 8, 10, 11};
+
+__device__ __forceinline__ float sqrt_pos(float x) { return x > 0.f ? sqrtf(x) : 0.f; }
+__device__ __forceinline__ float copysign_ref(float a, float b) { return ((a < 0.f) != (b < 0.f)) ? -a : a; }
+__device__ __forceinline__ float half_sinc(float angle, float half) {
+  return fabsf(angle) < 1e-6f ? 0.5f - angle * angle / 48.0f : sinf(half) / angle;
+}
+
+__device__ void aa_to_6d(const float aa[3], float out[6]) {
+  const float angle = sqrtf(aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2]);
+  const float half = 0.5f * angle;
+  const float s = half_sinc(angle, half);
+  const float r = cosf(half), i = aa[0] * s, j = aa[1] * s, k = aa[2] * s;
+  const float two_s = 2.0f / (r * r + i * i + j * j + k * k);
+  out[0] = 1.0f - two_s * (j * j + k * k);
+  out[1] = two_s * (i * j - k * r);
+  out[2] = two_s * (i * k + j * r);
+  out[3] = two_s * (i * j + k * r);
+  out[4] = 1.0f - two_s * (i * i + k * k);
+  out[5] = two_s * (j * k - i * r);
+}
+
+__device__ void sixd_roundtrip(const float d6[6], float out[6]) {
+  // rotation_6d_to_matrix
+  const float n1 = fmaxf(sqrtf(d6[0] * d6[0] + d6[1] * d6[1] + d6[2] * d6[2]), 1e-12f);
+  const float b1[3] = {d6[0] / n1, d6[1] / n1, d6[2] / n1};
+  const float dp = b1[0] * d6[3] + b1[1] * d6[4] + b1[2] * d6[5];
+  float b2[3] = {d6[3] - dp * b1[0], d6[4] - dp * b1[1], d6[5] - dp * b1[2]};
+  const float n2 = fmaxf(sqrtf(b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2]), 1e-12f);
+  b2[0] /= n2; b2[1] /= n2; b2[2] /= n2;
+  const float b3[3] = {b1[1] * b2[2] - b1[2] * b2[1], b1[2] * b2[0] - b1[0] * b2[2], b1[0] * b2[1] - b1[1] * b2[0]};
+  // matrix_to_quaternion (rows b1,b2,b3)
+  const float m00 = b1[0], m11 = b2[1], m22 = b3[2];
+  const float o0 = 0.5f * sqrt_pos(1.f + m00 + m11 + m22);
+  const float qx = 0.5f * sqrt_pos(1.f + m00 - m11 - m22);
+  const float qy = 0.5f * sqrt_pos(1.f - m00 + m11 - m22);
+  const float qz = 0.5f * sqrt_pos(1.f - m00 - m11 + m22);
+  const float o1 = copysign_ref(qx, b3[1] - b2[2]);
+  const float o2 = copysign_ref(qy, b1[2] - b3[0]);
+  const float o3 = copysign_ref(qz, b2[0] - b1[1]);
+  // quaternion_to_axis_angle
+  const float nrm = sqrtf(o1 * o1 + o2 * o2 + o3 * o3);
+  const float half = atan2f(nrm, o0);
+  const float angle = 2.0f * half;
+  const float s = half_sinc(angle, half);
+  const float aa[3] = {o1 / s, o2 / s, o3 / s};
+  aa_to_6d(aa, out);
+}
+
+__global__ void __launch_bounds__(256) pose330_kernel(const float* __restrict__ up, const float* __restrict__ ha,
+                                                      const float* __restrict__ lo, const float* __restrict__ mean,
+                                                      const float* __restrict__ std, const float* __restrict__ jaw, int BN_,
+                                                      float* __restrict__ pose) {
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (gid >= (long long)BN_ * 55) return;
+  const int f = (int)(gid / 55), j = (int)(gid - (long long)f * 55);
+  float out[6];
+  const float* src = nullptr;
+  if (j >= 25) src = ha + (long long)f * 180 + (j - 25) * 6;
+  else if (j == 22) {
+    float aa[3] = {0.f, 0.f, 0.f};
+    if (jaw) { aa[0] = jaw[(long long)f * 3]; aa[1] = jaw[(long long)f * 3 + 1]; aa[2] = jaw[(long long)f * 3 + 2]; }
+    aa_to_6d(aa, out);
+  } else if (j == 23 || j == 24) {
+    const float aa[3] = {0.f, 0.f, 0.f};
+    aa_to_6d(aa, out);
+  } else {
+    for (int q = 0; q < 13; ++q) if (c_upper_j[q] == j) src = up + (long long)f * 78 + q * 6;
+    for (int q = 0; q < 9; ++q) if (c_lower_j[q] == j) src = lo + (long long)f * 57 + q * 6;
+  }
+  if (src) {
+    float d6[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) d6[q] = __fadd_rn(__fmul_rn(src[q], std[j * 6 + q]), mean[j * 6 + q]);
+    sixd_roundtrip(d6, out);
+  }
+  float* o = pose + (long long)f * 330 + j * 6;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) o[q] = out[q];
+}
+
+__global__ void trans_kernel(const float* __restrict__ lo, const float* __restrict__ tmean, const float* __restrict__ tstd,
+                             int B, int n, float* __restrict__ trans) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * 3) return;
+  const int b = gid / 3, c = gid - b * 3;
+  float run = 0.f;
+  for (int f = 0; f < n; ++f) {
+    const float v = __fadd_rn(__fmul_rn(lo[((long long)b * n + f) * 57 + 54 + c], tstd[c]), tmean[c]);
+    run = (f == 0) ? v : __fadd_rn(run, v);
+    trans[((long long)b * n + f) * 3 + c] = (c == 1) ? v : run;
+  }
+}
+
+int pose330(const float* up, const float* ha, const float* lo, const float* mean, const float* std, const float* tmean,
+            const float* tstd, const float* jaw, int B, int n, float* pose, float* trans, cudaStream_t s) {
+  const long long tot = (long long)B * n * 55;
+  pose330_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(up, ha, lo, mean, std, jaw, B * n, pose);
+  ST_CHECK_LAUNCH();
+  if (trans) {
+    trans_kernel<<<(B * 3 + 127) / 128, 128, 0, s>>>(lo, tmean, tstd, B, n, trans);
+    ST_CHECK_LAUNCH();
+  }
+  return ST_OK;
+}
+
+// h3d 623-d scatter (h3d_diffusion_new_trainer.py:194-221,604-607): column c of the output belongs to one body
+// part at a fixed position; enumerate the masks exactly like the reference builds them.
+__device__ int h3d_lookup(int c, int* part) {
+  // returns position inside the part's decoder output, sets *part (0 upper, 1 hands, 2 lower), or -1 (stays zero)
+  const int uj[13] = {3, 6, 9, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21};
+  const int lj[9] = {0, 1, 2, 4, 5, 7, 8, 10, 11};
+  int pos = 0;
+  for (int q = 0; q < 13; ++q) {
+    const int i = uj[q];
+    for (int k = 0; k < 3; ++k, ++pos) if (c == 4 + (i - 1) * 3 + k) { *part = 0; return pos; }
+    for (int k = 0; k < 6; ++k, ++pos) if (c == 4 + 51 * 3 + (i - 1) * 6 + k) { *part = 0; return pos; }
+    for (int k = 0; k < 3; ++k, ++pos) if (c == 4 + 51 * 9 + i * 3 + k) { *part = 0; return pos; }
+  }
+  pos = 0;
+  for (int i = 22; i < 52; ++i) {
+    for (int k = 0; k < 3; ++k, ++pos) if (c == 4 + (i - 1) * 3 + k) { *part = 1; return pos; }
+    for (int k = 0; k < 6; ++k, ++pos) if (c == 4 + 51 * 3 + (i - 1) * 6 + k) { *part = 1; return pos; }
+    for (int k = 0; k < 3; ++k, ++pos) if (c == 4 + 51 * 9 + i * 3 + k) { *part = 1; return pos; }
+  }
+  pos = 0;
+  for (int k = 0; k < 4; ++k, ++pos) if (c == k) { *part = 2; return pos; }
+  for (int k = 619; k < 623; ++k, ++pos) if (c == k) { *part = 2; return pos; }
+  for (int q = 0; q < 9; ++q) {
+    const int i = lj[q];
+    if (i > 0) {
+      for (int k = 0; k < 3; ++k, ++pos) if (c == 4 + (i - 1) * 3 + k) { *part = 2; return pos; }
+      for (int k = 0; k < 6; ++k, ++pos) if (c == 4 + 51 * 3 + (i - 1) * 6 + k) { *part = 2; return pos; }
+    }
+    for (int k = 0; k < 3; ++k, ++pos) if (c == 4 + 51 * 9 + i * 3 + k) { *part = 2; return pos; }
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(256) pose623_kernel(const float* __restrict__ up, const float* __restrict__ ha,
+                                                      const float* __restrict__ lo, int frames, float* __restrict__ pose) {
+  __shared__ int s_part[623], s_pos[623];
+  for (int c = threadIdx.x; c < 623; c += 256) {
+    int part = -1;
+    s_pos[c] = h3d_lookup(c, &part);
+    s_part[c] = part;
+  }
+  __syncthreads();
+  for (int f = blockIdx.x; f < frames; f += gridDim.x) {
+    for (int c = threadIdx.x; c < 623; c += 256) {
+      float v = 0.f;
+      const int pos = s_pos[c];
+      if (pos >= 0) {
+        const int part = s_part[c];
+        v = part == 0 ? up[(long long)f * 156 + pos] : part == 1 ? ha[(long long)f * 360 + pos] : lo[(long long)f * 107 + pos];
+      }
+      pose[(long long)f * 623 + c] = v;
+    }
+  }
+}
+
+int pose623(const float* up, const float* ha, const float* lo, int B, int n, float* pose, cudaStream_t s) {
+  const int frames = B * n;
+  pose623_kernel<<<frames < 1184 ? frames : 1184, 256, 0, s>>>(up, ha, lo, frames, pose);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+}  // namespace st

@@ -1,0 +1,206 @@
+"""Drop-in for models/denoiser.py `MDM` (and, via denoiser_h3d.py, models/denoiser_h3d.py `MDM`).
+
+Same call boundary as the reference: `MDM(args)`, `load_state_dict(state_dict)`, `model(x, timesteps, y=dict)`
+with x [B,1536,1,32] fp32 on the GPU, timesteps [B] int64 (original 0..999 ids), y holding 'audio'
+[B,68224,2], 'word' [B,128] int, 'seed' [B,4,1536], optional 'style_feature', 'uncond', 'uncond_audio'
+(models/denoiser.py:132-196). The arithmetic runs in libsyntalker_b200.so; without it every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib, packer
+from .synth import AUDIO_LEN, LATENT_C, N_FRAMES, N_TOKENS
+
+
+def _dev_f32(t: torch.Tensor, name: str, device) -> torch.Tensor:
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class CondKey:
+    """Identity of the y tensors last encoded, so a Python-side step loop (the reference's own
+    gaussian_diffusion loop calling model(x,t,y) once per step) pays for the conditioning once."""
+
+    def __init__(self):
+        self.key = None
+
+    @staticmethod
+    def of(*tensors):
+        return tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None for t in tensors)
+
+
+class MDM:
+    variant_default = "beatx"
+
+    def __init__(self, args=None, state_dict=None, device: Optional[torch.device] = None):
+        self.args = args
+        use_mc = bool(getattr(args, "use_motionclip", False)) if args is not None else False
+        self.variant = "beatx_motionclip" if (use_mc and self.variant_default == "beatx") else self.variant_default
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) \
+            if torch.cuda.is_available() else torch.device("cpu")
+        self.use_motionclip = self.variant != "beatx"
+        self.training = False
+        self._h = None
+        self._cond_key = CondKey()
+        self._keep = None
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # ---- nn.Module-like surface the trainers touch (train.py:85-94, other_tools.py:771-790) ----
+    def load_state_dict(self, state_dict, strict: bool = True):
+        if self.device.type != "cuda":
+            raise _lib.StError("syntalker_b200.MDM needs a CUDA device: there is no CPU path")
+        sd = packer.strip_module_prefix(state_dict)
+        found = packer.detect_variant(sd)
+        if found != self.variant:
+            if strict and self.args is not None:
+                raise RuntimeError(f"state dict is for variant '{found}' but the model was built as '{self.variant}'")
+            self.variant = found
+        packed = packer.pack_mdm(sd, self.variant)
+        arr, keep = _lib.tensor_array(packed)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().st_model_create(arr, len(packed), _lib.ST_VARIANT[self.variant], C.byref(h)))
+        self._free()
+        self._h = h
+        self._cond_key = CondKey()
+        return self
+
+    def _free(self):
+        if getattr(self, "_h", None):
+            _lib.lib().st_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self._free()
+        except Exception:
+            pass
+
+    def parameters(self):
+        yield torch.empty(0, device=self.device)
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("syntalker_b200.MDM is the sampling path only (SURVEY.md §8: training is out of scope)")
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def cuda(self, *a, **k):
+        return self
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise _lib.StError("MDM has no weights: call load_state_dict() first")
+        return self._h
+
+    # ---- conditioning ----
+    def encode_cond(self, y, styles=None, force: bool = False):
+        """st_cond_encode on y['audio'], y['word'], y['seed'] (+ style vectors). Cached on tensor identity."""
+        dev = self.device
+        audio = _dev_f32(y["audio"], "audio", dev)
+        B = audio.shape[0]
+        if tuple(audio.shape) != (B, AUDIO_LEN, 2):
+            raise ValueError(f"y['audio'] must be [B,{AUDIO_LEN},2], got {tuple(audio.shape)}")
+        word = y["word"]
+        if tuple(word.shape) != (B, N_FRAMES):
+            raise ValueError(f"y['word'] must be [B,{N_FRAMES}], got {tuple(word.shape)}")
+        word = word.to(dev, non_blocking=True).to(torch.int32).contiguous()
+        seed = _dev_f32(y["seed"], "seed", dev)
+        if seed.numel() != B * 4 * LATENT_C:
+            raise ValueError(f"y['seed'] must be [B,4,{LATENT_C}], got {tuple(seed.shape)}")
+        if styles is None:
+            sf = y.get("style_feature") if self.variant != "beatx" else None
+            styles = [sf, None, None] if not isinstance(sf, dict) else \
+                [sf.get("upper_mask"), sf.get("hands_mask"), sf.get("lower_mask")]
+        sdim = 512 if self.variant == "beatx_motionclip" else 256
+        st = []
+        for s in styles:
+            if s is None or self.variant == "beatx":
+                st.append(None)
+                continue
+            s = _dev_f32(s, "style", dev)
+            if s.shape[0] == 1 and B > 1:
+                s = s.expand(B, -1).contiguous()
+            if tuple(s.shape) != (B, sdim):
+                raise ValueError(f"style vector must be [B,{sdim}], got {tuple(s.shape)}")
+            st.append(s)
+        key = CondKey.of(y["audio"], y["word"], y["seed"], *st) + (B,)
+        if not force and key == self._cond_key.key:
+            return B
+        c = _lib.StCond()
+        c.audio, c.word, c.seed = audio.data_ptr(), word.data_ptr(), seed.data_ptr()
+        for k in range(3):
+            c.style[k] = st[k].data_ptr() if st[k] is not None else None
+        self._keep = (audio, word, seed, st)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().st_cond_encode(self.handle, C.byref(c), B, _lib.stream_ptr()))
+        self._cond_key.key = key
+        return B
+
+    # ---- the model call ----
+    def __call__(self, x, timesteps, y=None, uncond_info=False):
+        return self.forward(x, timesteps, y)
+
+    def forward(self, x, timesteps, y=None, _guidance=None):
+        y = dict(y or {})
+        B = self.encode_cond(y)
+        if tuple(x.shape) != (B, LATENT_C, 1, N_TOKENS):
+            raise ValueError(f"x must be [{B},{LATENT_C},1,{N_TOKENS}], got {tuple(x.shape)}")
+        xs = _dev_f32(x, "x", self.device)
+        t = timesteps.to(self.device).to(torch.int64).contiguous()
+        if t.numel() != B or int(t.min()) < 0 or int(t.max()) >= 1000:
+            raise ValueError("timesteps must be [B] with values in [0,1000)")
+        g = _guidance
+        if g is None:
+            g = Guidance(_lib.ST_CFG_NONE, flags=(_lib.ST_FLAG_UNCOND if y.get("uncond", False) else 0) |
+                         (_lib.ST_FLAG_UNCOND_AUDIO if y.get("uncond_audio", False) else 0))
+        out = torch.empty_like(xs)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().st_denoise(self.handle, xs.data_ptr(), t.data_ptr(), C.byref(g.struct(B)), out.data_ptr(),
+                                            B, _lib.stream_ptr()))
+        return out
+
+
+class Guidance:
+    """Host description of the CFG wrapper around the model (diffusion/cfg_sampler.py) -> st_guidance."""
+
+    def __init__(self, mode, flags=0, scale=None, scale2=None, audio_scale=1.0, prompt_scale=4.0):
+        self.mode, self.flags, self.scale, self.scale2 = mode, flags, scale, scale2
+        self.audio_scale, self.prompt_scale = float(audio_scale), float(prompt_scale)
+        self._keep = None
+
+    @staticmethod
+    def _host(v, B):
+        if v is None:
+            return None
+        v = torch.as_tensor(v, dtype=torch.float32).detach().cpu().reshape(-1)
+        if v.numel() == 1:
+            v = v.expand(B)
+        if v.numel() != B:
+            raise ValueError(f"guidance scale must have 1 or B={B} entries, got {v.numel()}")
+        return v.contiguous()
+
+    def struct(self, B):
+        s, s2 = self._host(self.scale, B), self._host(self.scale2, B)
+        self._keep = (s, s2)
+        g = _lib.StGuidance()
+        g.mode, g.flags = self.mode, self.flags
+        g.scale = s.data_ptr() if s is not None else None
+        g.scale2 = s2.data_ptr() if s2 is not None else None
+        g.audio_scale, g.prompt_scale = self.audio_scale, self.prompt_scale
+        return g

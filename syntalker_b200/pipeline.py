@@ -1,0 +1,111 @@
+"""The window pipeline a trainer's `_g_test` runs per 128-frame window batch, as one native call with HOST
+buffers: H2D -> conditioning -> sampling loop (+CFG) -> x latent_scale -> latent2origin x3 -> 330-d -> D2H
+(diffusion_rvqvae_trainer.py:433-531). This is the call bench.py times for the end-to-end number.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .cfg_sampler import _Wrapper
+from .denoiser import Guidance
+
+
+def load_mean_std():
+    """mean_std/beatx_2_330_{mean,std}.npy and beatx_2_trans_{mean,std}.npy (fixtures of the reference)."""
+    d = np.load(os.path.join(os.path.dirname(__file__), "data", "beatx_mean_std.npz"))
+    return {k: torch.from_numpy(d[k].astype(np.float32)) for k in d.files}
+
+
+def pose_assemble_330(rec_upper, rec_hands, rec_lower, ms, jaw_aa=None):
+    """Device tensors in, device tensors out (st_pose_assemble_330)."""
+    dev = rec_upper.device
+    B, n, _ = rec_upper.shape
+    f = lambda t: t.to(dev).float().contiguous()
+    up, ha, lo = f(rec_upper), f(rec_hands), f(rec_lower)
+    mean, std, tm, ts = f(ms["mean"]), f(ms["std"]), f(ms["trans_mean"]), f(ms["trans_std"])
+    jaw = f(jaw_aa) if jaw_aa is not None else None
+    pose = torch.empty((B, n, 330), device=dev)
+    trans = torch.empty((B, n, 3), device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().st_pose_assemble_330(up.data_ptr(), ha.data_ptr(), lo.data_ptr(), mean.data_ptr(), std.data_ptr(),
+                                                  tm.data_ptr(), ts.data_ptr(), jaw.data_ptr() if jaw is not None else None,
+                                                  B, n, pose.data_ptr(), trans.data_ptr(), _lib.stream_ptr()))
+    return pose, trans
+
+
+def pose_assemble_623(rec_upper, rec_hands, rec_lower):
+    dev = rec_upper.device
+    B, n, _ = rec_upper.shape
+    f = lambda t: t.to(dev).float().contiguous()
+    up, ha, lo = f(rec_upper), f(rec_hands), f(rec_lower)
+    pose = torch.empty((B, n, 623), device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().st_pose_assemble_623(up.data_ptr(), ha.data_ptr(), lo.data_ptr(), B, n, pose.data_ptr(), _lib.stream_ptr()))
+    return pose
+
+
+class Window330:
+    """Pinned host staging + one st_generate_330_host call per window batch."""
+
+    def __init__(self, model, diffusion, vq_upper, vq_hands, vq_lower, B, use_ddim=True, eta=0.0, latent_scale=5.0, ms=None):
+        self.base = model.base if isinstance(model, _Wrapper) else model
+        self.wrapper = model if isinstance(model, _Wrapper) else None
+        self.diffusion, self.B = diffusion, B
+        self.vqs = (vq_upper, vq_hands, vq_lower)
+        self.mode = _lib.ST_MODE_DDIM if use_ddim else _lib.ST_MODE_DDPM
+        self.eta, self.latent_scale = eta, float(latent_scale)
+        self.ms = ms or load_mean_std()
+        pin = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype).pin_memory()
+        sdim = 512 if self.base.variant == "beatx_motionclip" else 256
+        self.h = {
+            "audio": pin(B, 68224, 2), "word": pin(B, 128, dtype=torch.int32), "seed": pin(B, 4, 1536),
+            "style": [pin(B, sdim) for _ in range(3)], "x_init": pin(B, 1536, 1, 32), "jaw": pin(B, 128, 3),
+            "pose": pin(B, 128, 330), "trans": pin(B, 128, 3), "sample": pin(B, 1536, 1, 32),
+        }
+        self.h_ms = {k: v.clone().contiguous() for k, v in self.ms.items()}
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def run(self, audio, word, seed, x_init, y=None, styles=None, jaw_aa=None, noise_tape=None, want_sample=False):
+        """All inputs are CPU tensors. Returns (rec_pose [B,128,330], rec_trans [B,128,3]) pinned CPU tensors."""
+        B, h = self.B, self.h
+        h["audio"].copy_(audio); h["word"].copy_(word.to(torch.int32)); h["seed"].copy_(seed.reshape(B, 4, 1536)); h["x_init"].copy_(x_init)
+        y = dict(y or {})
+        if styles is None and self.base.variant != "beatx":
+            sf = y.get("style_feature")
+            styles = [sf.get("upper_mask"), sf.get("hands_mask"), sf.get("lower_mask")] if isinstance(sf, dict) else [sf, None, None]
+        styles = styles or [None, None, None]
+        inp = _lib.StHostInputs()
+        inp.audio, inp.word, inp.seed, inp.x_init = h["audio"].data_ptr(), h["word"].data_ptr(), h["seed"].data_ptr(), h["x_init"].data_ptr()
+        nb = h["audio"].numel() * 4 + h["word"].numel() * 4 + h["seed"].numel() * 4 + h["x_init"].numel() * 4 + 666 * 4
+        for k in range(3):
+            if styles[k] is not None and self.base.variant != "beatx":
+                s = styles[k]
+                h["style"][k].copy_(s.expand(B, -1) if s.shape[0] == 1 else s)
+                inp.style[k] = h["style"][k].data_ptr()
+                nb += h["style"][k].numel() * 4
+            else:
+                inp.style[k] = None
+        if jaw_aa is not None:
+            h["jaw"].copy_(jaw_aa); inp.jaw_aa = h["jaw"].data_ptr(); nb += h["jaw"].numel() * 4
+        if noise_tape is not None:
+            noise_tape = noise_tape.contiguous()
+            inp.noise_tape = noise_tape.data_ptr(); nb += noise_tape.numel() * 4
+        m = self.h_ms
+        inp.mean, inp.std, inp.trans_mean, inp.trans_std = m["mean"].data_ptr(), m["std"].data_ptr(), m["trans_mean"].data_ptr(), m["trans_std"].data_ptr()
+        g = self.wrapper.guidance(y) if self.wrapper is not None else Guidance(_lib.ST_CFG_NONE)
+        sched, _ = self.diffusion._native(self.mode, self.eta)
+        with torch.cuda.device(self.base.device):
+            _lib.check(_lib.lib().st_generate_330_host(
+                self.base.handle, sched, C.byref(g.struct(B)), self.vqs[0].handle, self.vqs[1].handle, self.vqs[2].handle,
+                C.byref(inp), B, self.latent_scale, h["pose"].data_ptr(), h["trans"].data_ptr(),
+                h["sample"].data_ptr() if want_sample else None, _lib.stream_ptr()))
+        self.base._cond_key.key = None          # the native call re-encoded the cache from its own staging buffers
+        self.h2d_bytes = nb
+        self.d2h_bytes = (h["pose"].numel() + h["trans"].numel() + (h["sample"].numel() if want_sample else 0)) * 4
+        return h["pose"], h["trans"]

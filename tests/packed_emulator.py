@@ -1,0 +1,69 @@
+"""TEST INFRASTRUCTURE: a torch-CPU walk through the *packed* dataflow the CUDA library executes
+(syntalker_b200/packer.py tensors), used only to validate the packer's algebra on a box
+without a GPU. It is never imported by the product."""
+import torch
+import torch.nn.functional as F
+
+WAV = ((2, 64, 5, 1700, True), (64, 64, 6, 0, True), (64, 64, 1, 7, False), (64, 128, 6, 0, True),
+       (128, 128, 1, 7, False), (128, 256, 3, 0, True))
+
+
+def _conv(P, name, h, cin, k, stride=1, pad=0, dil=1):
+    w = P[name + ".w"][:, :k * cin].reshape(-1, k, cin).permute(0, 2, 1).contiguous()
+    return F.conv1d(h, w, P[name + ".b"], stride=stride, padding=pad, dilation=dil)
+
+
+def wav(P, audio):
+    h = audio.transpose(1, 2)
+    for i, (cin, cout, s, p, ds) in enumerate(WAV):
+        h1 = F.leaky_relu(_conv(P, f"wav.{i}.conv1", h, cin, 15, s, p), 0.01)
+        sc = _conv(P, f"wav.{i}.ds", h, cin, 15, s, p) if ds else h
+        h = F.leaky_relu(_conv(P, f"wav.{i}.conv2", h1, cout, 15, 1, 7) + sc, 0.01)
+    return h.transpose(1, 2)                                   # [B,128,256]
+
+
+def cond(P, audio, word, seed, null_audio=False):
+    B = audio.shape[0]
+    if null_audio:
+        audio, word = torch.zeros_like(audio), torch.zeros_like(word)
+    at = torch.cat([wav(P, audio), P["word_table"][word.long()]], dim=-1)          # [B,128,512]
+    pooled = at.reshape(B, 32, 4, 512).mean(dim=2)
+    cst = pooled @ P["w_cm"].t() + P["bias_all"]
+    g2 = seed.reshape(B, -1) @ P["w_seed"].t()
+    return cst, g2
+
+
+def trunk(P, x, t, cst, g2, sv=None):
+    """x [B,1536,1,32] -> model output [B,1536,1,32] for one evaluation."""
+    B = x.shape[0]
+    xs = x[:, :, 0, :].permute(0, 2, 1)                                            # [B,32,1536]
+    z = xs @ P["w_x"].t() + P["vt_table"][t][:, None, :] + cst + g2[:, None, :]
+    if sv is not None:
+        z = z + sv[:, None, :]
+    zz = z.reshape(B, 32, 8, 64)
+    cos, sin = P["rope_cos"][None, :, None, :], P["rope_sin"][None, :, None, :]
+    x1, x2 = zz[..., :32], zz[..., 32:]
+    h = torch.cat([x1 * cos - x2 * sin, x2 * cos + x1 * sin], dim=-1).reshape(B, 32, 512)
+    for i in range(8):
+        p = f"blk.{i}."
+        a = F.layer_norm(h, (512,), P[p + "ln1.g"], P[p + "ln1.b"], 1e-5)
+        qkv = (a @ P[p + "qkv.w"].t()).reshape(B, 32, 3, 4, 128).permute(2, 0, 3, 1, 4)
+        att = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2) * 128 ** -0.5, dim=-1) @ qkv[2]
+        h = h + att.transpose(1, 2).reshape(B, 32, 512) @ P[p + "proj.w"].t() + P[p + "proj.b"]
+        a = F.layer_norm(h, (512,), P[p + "ln2.g"], P[p + "ln2.b"], 1e-5)
+        h = h + F.gelu(a @ P[p + "fc1.w"].t() + P[p + "fc1.b"]) @ P[p + "fc2.w"].t() + P[p + "fc2.b"]
+    o = h @ P["out.w"].t() + P["out.b"]                                            # [B,32,1536]
+    return o.permute(0, 2, 1).unsqueeze(2)
+
+
+def rvq_decoder(P, xq, out_dim):
+    """xq [B,512,T] -> [B,4T,D] through the packed decoder convs."""
+    c3 = lambda n, h, dil=1: _conv(P, "dec." + n, h, 512, 3, 1, dil, dil)
+    h = F.relu(c3("0", xq))
+    for i in (2, 3):
+        for j, dil in enumerate((9, 3, 1)):
+            r = c3(f"{i}.0.{j}.conv1", F.relu(h), dil)
+            h = _conv(P, f"dec.{i}.0.{j}.conv2", F.relu(r), 512, 1) + h
+        h = c3(f"{i}.2", F.interpolate(h, scale_factor=2, mode="nearest"))
+    h = F.relu(c3("4", h))
+    return c3("6", h).permute(0, 2, 1)

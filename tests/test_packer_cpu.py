@@ -1,0 +1,55 @@
+"""The packer's folding algebra, checked on CPU: packed dataflow (tests/packed_emulator.py) vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import packed_emulator as emu
+from oracle import mdm as omdm
+from oracle import rvq as orvq
+from syntalker_b200 import packer, synth
+
+torch.set_grad_enabled(False)
+
+
+@pytest.mark.parametrize("variant", synth.VARIANTS)
+def test_packed_forward_matches_oracle(variant):
+    W = synth.mdm_state_dict(variant, seed=0)
+    P = packer.pack_mdm(W)
+    assert packer.detect_variant(W) == variant
+    inp = synth.make_inputs(2, seed=4, variant=variant)
+    t = torch.tensor([980, 0])
+    y = {k: inp[k] for k in ("audio", "word", "seed")}
+    style = inp.get("style_feature", inp.get("style_upper"))
+    y["style_feature"] = style
+    cst, g2 = emu.cond(P, inp["audio"], inp["word"], inp["seed"])
+    sv = None if variant == "beatx" else style @ P["w_style"].t()
+    ref = omdm.mdm_forward(W, inp["noise"], t, y, variant)
+    got = emu.trunk(P, inp["noise"], t, cst, g2, sv)
+    assert float((ref - got).abs().max()) < 1e-4
+    if variant != "beatx":
+        yu = dict(y); yu["uncond"] = True
+        ref_u = omdm.mdm_forward(W, inp["noise"], t, yu, variant)
+        svu = P["null_sv"][None].expand(2, -1) if variant == "h3d" else None
+        assert float((ref_u - emu.trunk(P, inp["noise"], t, cst, g2, svu)).abs().max()) < 1e-4
+    if variant == "h3d":
+        ya = dict(y); ya["uncond_audio"] = True
+        cstn, _ = emu.cond(P, inp["audio"], inp["word"], inp["seed"], null_audio=True)
+        assert float((cstn[0] - cstn[1]).abs().max()) < 1e-7          # a per-model constant
+        ref_a = omdm.mdm_forward(W, inp["noise"], t, ya, variant)
+        assert float((ref_a - emu.trunk(P, inp["noise"], t, cstn, g2, sv)).abs().max()) < 1e-4
+
+
+def test_module_prefix_is_stripped():
+    W = synth.mdm_state_dict("beatx", seed=0)
+    Wm = {"module." + k: v for k, v in W.items()}
+    a, b = packer.pack_mdm(W), packer.pack_mdm(Wm)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+@pytest.mark.parametrize("dim", synth.PART_DIMS_BEATX)
+def test_packed_rvq_decoder(dim):
+    W = synth.rvq_state_dict(dim, seed=0)
+    P = packer.pack_rvq(W)
+    xq = torch.randn(2, 512, 32, generator=torch.Generator().manual_seed(3))
+    assert float((orvq.decoder(W, xq) - emu.rvq_decoder(P, xq, dim)).abs().max()) < 1e-5
+    assert P[f"dec.6.w"].shape == (dim, 1536)
