@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py -- denoised motion-frames/s of the SynTalker sampling hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--engine simt|tc] [--batch 32]
+
+One "step" = one pass of the hot path over one batch of synthetic windows: conditioning encode ->
+DDIM-50 sampling with classifier-free guidance 2.0 (2 denoiser evaluations per diffusion step) ->
+x5 -> RVQ latent2origin x3 -> 330-d pose features  (BASELINE config 2: diffusion_rvqvae_128, batch 32).
+`value` times that with inputs resident in HBM (st_generate_330); `e2e` times the same through the
+host-buffer C-ABI call (st_generate_330_host: pinned host inputs, H2D, compute, D2H of the poses).
+N > 1 (torchrun): every rank runs its own 32 clips (weak scaling, no data-path collective) and the ranks
+all-gather the poses at the end of each step over NCCL.
+`--impl reference` times the reference's own algorithm as written (audio encoder re-run in every
+evaluation, 2 evaluations per step) through the CPU oracle port on the host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "denoised motion-frames/sec (128-frame seq, 1000->50 DDIM)"
+UNIT = "frames/s"
+S_STEPS = 50
+CFG_SCALE = 2.0
+# algorithmic FLOPs per clip: cond encoder once, trunk per evaluation (+512-d style branch), decode once
+E_COND, E_TRUNK, E_DEC = 4.677e9, 1.2342e9 + 0.0336e9, 3.899e9
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": d.get("bf16_tflops_sustained", 1385.6), "hbm": d.get("hbm_gbs", 6534.1), "src": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        mx = max([float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in self.rows if len(r) > 4 + i)]
+        # under load = upper half of the samples (the sampler also sees the idle gaps between steps)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_sample(B_s, S_s, threads, reps=1):
+    """The reference's algorithm as written, on the CPU oracle port: S_s of the 50 DDIM steps with the
+    ClassifierFreeSampleModel wrapper (2 full MDM.forward per step, WavEncoder inside each), then x5 ->
+    latent2origin x3 -> 330-d. Per-step cost is constant in t, so the 50-step time is extrapolated."""
+    import torch
+    from oracle import diffusion as odiff, mdm as omdm, pose as opose, rvq as orvq
+    from syntalker_b200 import synth
+    from syntalker_b200.pipeline import load_mean_std
+    torch.set_num_threads(threads)
+    torch.set_grad_enabled(False)
+    W = synth.mdm_state_dict("beatx_motionclip", seed=0)
+    vqw = [synth.rvq_state_dict(d, seed=0) for d in synth.PART_DIMS_BEATX]
+    inp = synth.make_inputs(B_s, seed=1, variant="beatx_motionclip")
+    y = {k: inp[k] for k in ("audio", "word", "seed", "style_feature")}
+    y["scale"] = torch.ones(1) * CFG_SCALE
+    sched = odiff.make_schedule(use_ddim=True)
+    fn = lambda x, t, yy: omdm.cfg_text(lambda a, b, c: omdm.mdm_forward(W, a, b, c, "beatx_motionclip"), x, t, yy)
+    ms = load_mean_std()
+    best = None
+    for _ in range(reps):
+        x = inp["noise"]
+        t0 = time.perf_counter()
+        for k in range(S_STEPS - 1, S_STEPS - 1 - S_s, -1):
+            t = torch.full((B_s,), sched.timestep_map[k], dtype=torch.int64)
+            x0 = fn(x, t, y)
+            eps = (float(sched.sqrt_recip_alphas_cumprod[k]) * x - x0) / float(sched.sqrt_recipm1_alphas_cumprod[k])
+            x = x0 * float(sched.alphas_cumprod_prev[k]) ** 0.5 + (1 - float(sched.alphas_cumprod_prev[k])) ** 0.5 * eps
+        t_loop = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        lats = opose.sample_to_parts(x, 5.0)
+        recs = [orvq.latent2origin(w, l)[0] for w, l in zip(vqw, lats)]
+        opose.assemble_330(recs[0], recs[1], recs[2], ms, None)
+        t_dec = time.perf_counter() - t0
+        full = t_loop * S_STEPS / S_s + t_dec
+        best = full if best is None else min(best, full)
+    return B_s * 128 / best, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    B_s, S_s = 16, 2
+    for _ in range(args.warmup):
+        cpu_reference_sample(2, 1, threads)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, _full = cpu_reference_sample(B_s, S_s, threads)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    v = sum(vals) / len(vals)
+    sample = (f"B={B_s} clips x {S_s} of {S_STEPS} DDIM steps with CFG (2 full MDM.forward per step incl. WavEncoder, as the reference "
+              f"is written) + decode + 330-d; 50-step time extrapolated (per-step cost constant in t)")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "diffusion_rvqvae_128 + use_motionclip, batch=32, 50 DDIM steps, CFG scale 2.0 (BASELINE config 2)",
+                                            "global_batch": 32 * args.gpus, "frames": 128},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default=os.environ.get("ST_ENGINE", "simt"), choices=["simt", "tc"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from syntalker_b200 import _lib, synth
+    from syntalker_b200.cfg_sampler import ClassifierFreeSampleModel
+    from syntalker_b200.denoiser import MDM
+    from syntalker_b200.diffusion import create_gaussian_diffusion
+    from syntalker_b200.pipeline import Window330
+    from syntalker_b200.vq import RVQVAE
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.set_grad_enabled(False)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.set_engine(args.engine)
+    B = args.batch
+    model = MDM(None).load_state_dict(synth.mdm_state_dict("beatx_motionclip", seed=0))
+    wrapped = ClassifierFreeSampleModel(model)
+    vqs = [RVQVAE(None, d).load_state_dict(synth.rvq_state_dict(d, seed=0)) for d in synth.PART_DIMS_BEATX]
+    diff = create_gaussian_diffusion(use_ddim=True)
+    inp = synth.make_inputs(B, seed=1 + 1000 * rank, variant="beatx_motionclip")
+    y_host = {"scale": torch.ones(1) * CFG_SCALE, "style_feature": inp["style_feature"]}
+    win = Window330(wrapped, diff, *vqs, B=B, use_ddim=True)
+    d_in = {k: inp[k].to(dev).contiguous() for k in ("audio", "word", "seed", "noise", "style_feature")}
+    y_dev = {"scale": torch.ones(1) * CFG_SCALE, "style_feature": d_in["style_feature"]}
+    outs = (torch.empty((B, 128, 330), device=dev), torch.empty((B, 128, 3), device=dev), torch.empty((B, 1536, 1, 32), device=dev))
+    gathered = torch.empty((world * B, 128, 330), device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def step_device():
+        pose, _, _ = win.run_device(d_in["audio"], d_in["word"], d_in["seed"], d_in["noise"], y=y_dev, out=outs)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, pose)
+
+    def step_host():
+        win.run(inp["audio"], inp["word"], inp["seed"], inp["noise"], y=y_host)
+
+    def timed(fn, n):
+        evs = []
+        for _ in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launch_count()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    ms = timed(step_device, args.steps)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - w0
+    launches = _lib.launch_count() - n0
+    clocks = sampler.summary()
+    tot = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    tot_ms = float(tot.item())
+    value = world * B * 128 * args.steps / (tot_ms / 1000)
+
+    # ---- end to end through the host-buffer call ----
+    for _ in range(2):
+        step_host()
+    ms_h = timed(step_host, args.steps)
+    toth = torch.tensor([sum(ms_h)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(toth, op=dist.ReduceOp.MAX)
+    e2e = world * B * 128 * args.steps / (float(toth.item()) / 1000)
+
+    # ---- roofline of the dominant kernel class (the GEMM engine), CUDA events around every launch ----
+    pk = peaks()
+    _lib.profile_begin()
+    step_device()
+    g_ms, g_flops, g_n = _lib.profile_end()
+    torch.cuda.synchronize()
+    achieved = g_flops / (g_ms / 1000) / 1e12 if g_ms > 0 else 0.0
+    alg = B * (E_COND + S_STEPS * 2 * E_TRUNK + E_DEC)
+    step_ms = tot_ms / args.steps
+    roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+            "kernel": "gemm_tc_kernel (tcgen05 split-fp16)" if args.engine == "tc" else "gemm_simt_kernel (exact fp32 FMA)",
+            "launches_profiled": g_n, "kernel_ms_per_step": g_ms, "kernel_share_of_step": g_ms / step_ms if step_ms else None,
+            "executed_flops_per_step": g_flops, "algorithmic_flops_per_step": alg,
+            "whole_step_tflops": alg / (step_ms / 1000) / 1e12, "peak_source": pk["src"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.engine == "simt" else "f32 via split-fp16 (3 tcgen05 MMAs per product, fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": "diffusion_rvqvae_128 + use_motionclip, batch=32 per GPU, 50 DDIM steps, CFG scale 2.0 (BASELINE config 2)",
+                       "global_batch": world * B, "frames": 128, "parallelism": f"dp{world} (clips sharded, weights replicated)",
+                       "engine": args.engine, "l2": "256 MiB buffer written between timed steps (flush)", "wall_s": wall},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(win.h2d_bytes), "d2h_bytes_per_step": int(win.d2h_bytes),
+                    "ms_per_step": float(toth.item()) / args.steps},
+            "roofline": roof}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cpu_reference_sample(2, 1, threads)
+        v, full = cpu_reference_sample(8, 2, threads)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"oracle port, B=8 clips x 2 of 50 DDIM steps with CFG as the reference is written (WavEncoder inside every "
+                                          f"evaluation) + decode + 330-d, 50-step time extrapolated: {full:.1f} s per 8 clips"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

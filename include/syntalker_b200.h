@@ -174,6 +174,15 @@ int st_pose_assemble_623(const float* rec_upper, const float* rec_hands, const f
 /* sample [B,1536,1,T] -> token-major [B,T,1536] * scale (trainer:457 `squeeze().permute(1,0)` batched). */
 int st_sample_to_tokens(const float* sample, int B, int T, float scale, float* tokens, void* stream);
 
+/* ---- whole window, device buffers ----------------------------------------------------------------
+ * cond encode -> sample -> x latent_scale -> latent2origin x3 -> 330-d, everything resident in HBM.
+ * ms: device [666] = mean[330] | std[330] | trans_mean[3] | trans_std[3].  sample_out (nullable) receives
+ * the final latent [B,1536,1,32]; x_init is not modified.  No host synchronisation. */
+int st_generate_330(st_model* m, const st_schedule* s, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
+                    st_vq* vq_lower, const st_cond* cond, const float* x_init, const float* noise_tape, const float* jaw_aa,
+                    const float* ms, int B, float latent_scale, float* rec_pose, float* rec_trans /* nullable */,
+                    float* sample_out /* nullable */, void* stream);
+
 /* ---- whole window, host buffers ------------------------------------------------------------------
  * One call a trainer's _g_test makes per window batch: H2D(cond, noise) -> cond encode -> sample ->
  * x latent_scale -> latent2origin x3 -> 330-d -> D2H.  All pointers are HOST (ideally pinned).

@@ -24,7 +24,7 @@ SYMBOLS = [
     "st_model_create", "st_model_destroy", "st_vq_create", "st_vq_destroy", "st_vq_out_dim",
     "st_schedule_create", "st_schedule_destroy", "st_cond_encode", "st_denoise", "st_sample",
     "st_rvq_decode", "st_pose_assemble_330", "st_pose_assemble_623", "st_sample_to_tokens",
-    "st_generate_330_host", "st_selftest_gemm", "st_profile_begin", "st_profile_end",
+    "st_generate_330", "st_generate_330_host", "st_selftest_gemm", "st_profile_begin", "st_profile_end",
 ]
 
 
@@ -86,6 +86,7 @@ def lib():
     L.st_pose_assemble_330.argtypes = [vp] * 8 + [i32, i32, vp, vp, vp]
     L.st_pose_assemble_623.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.st_sample_to_tokens.argtypes = [vp, i32, i32, f32, vp, vp]
+    L.st_generate_330.argtypes = [vp, vp, C.POINTER(StGuidance), vp, vp, vp, C.POINTER(StCond), vp, vp, vp, vp, i32, f32, vp, vp, vp, vp]
     L.st_generate_330_host.argtypes = [vp, vp, C.POINTER(StGuidance), vp, vp, vp, C.POINTER(StHostInputs), i32, f32,
                                        vp, vp, vp, vp]
     L.st_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]

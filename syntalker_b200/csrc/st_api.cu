@@ -131,7 +131,7 @@ struct st_model {
   float* cst_null = nullptr;   // [32,512]
   bool null_ready = false;
   // workspace
-  Arena ws, io;
+  Arena ws, io, stage;
   int ws_B = 0;
   float *cst_real = nullptr, *g2 = nullptr, *sv[3] = {nullptr, nullptr, nullptr};
   bool have_style[3] = {false, false, false};
@@ -229,7 +229,7 @@ extern "C" int st_model_create(const st_tensor* packed, int n, int variant, st_m
 extern "C" void st_model_destroy(st_model* m) {
   if (!m) return;
   cudaDeviceSynchronize();
-  m->w.release(); m->ws.release(); m->io.release();
+  m->w.release(); m->ws.release(); m->io.release(); m->stage.release();
   if (m->cst_null) cudaFree(m->cst_null);
   delete m;
 }
@@ -655,33 +655,55 @@ extern "C" int st_sample_to_tokens(const float* sample, int B, int T, float scal
 }
 
 // ---------------------------------------------------------------------------------------------------------
+extern "C" int st_generate_330(st_model* m, const st_schedule* sc, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
+                               st_vq* vq_lower, const st_cond* cond, const float* x_init, const float* noise_tape,
+                               const float* jaw_aa, const float* ms, int B, float latent_scale, float* rec_pose, float* rec_trans,
+                               float* sample_out, void* stream) {
+  ST_REQUIRE(m && sc && vq_upper && vq_hands && vq_lower && cond && x_init && ms && rec_pose && B > 0, "st_generate_330: null argument");
+  ST_REQUIRE(vq_upper->out_dim == 78 && vq_hands->out_dim == 180 && vq_lower->out_dim == 57, "st_generate_330: decoders must be 78/180/57 wide");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nx = (size_t)B * ST_LATENT * ST_TOKENS;
+  ST_TRY(m->io.reserve((nx * 2 + (size_t)B * 128 * (78 + 180 + 57)) * sizeof(float) + 16 * 256));
+  float* d_x = m->io.take<float>(nx);
+  float* d_tok = m->io.take<float>(nx);
+  float* d_up = m->io.take<float>((size_t)B * 128 * 78);
+  float* d_ha = m->io.take<float>((size_t)B * 128 * 180);
+  float* d_lo = m->io.take<float>((size_t)B * 128 * 57);
+  ST_TRY(st_cond_encode(m, cond, B, stream));
+  float* xo = sample_out ? sample_out : d_x;
+  ST_TRY(st_sample(m, sc, g, x_init, noise_tape, B, xo, stream));
+  ST_TRY(transpose_to_tokens(xo, d_tok, B, 1536, 32, 1.0f, s));
+  ST_TRY(st_rvq_decode(vq_upper, d_tok, 1536, latent_scale, B, 32, d_up, nullptr, nullptr, stream));
+  ST_TRY(st_rvq_decode(vq_hands, d_tok + 512, 1536, latent_scale, B, 32, d_ha, nullptr, nullptr, stream));
+  ST_TRY(st_rvq_decode(vq_lower, d_tok + 1024, 1536, latent_scale, B, 32, d_lo, nullptr, nullptr, stream));
+  ST_TRY(pose330(d_up, d_ha, d_lo, ms, ms + 330, ms + 660, ms + 663, jaw_aa, B, 128, rec_pose, rec_trans, s));
+  return ST_OK;
+}
+
 extern "C" int st_generate_330_host(st_model* m, const st_schedule* sc, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
                                     st_vq* vq_lower, const st_host_inputs* in, int B, float latent_scale, float* rec_pose_host,
                                     float* rec_trans_host, float* sample_host, void* stream) {
-  ST_REQUIRE(m && sc && vq_upper && vq_hands && vq_lower && in && rec_pose_host && B > 0, "st_generate_330_host: null argument");
+  ST_REQUIRE(m && sc && in && rec_pose_host && B > 0, "st_generate_330_host: null argument");
   ST_REQUIRE(in->audio && in->word && in->seed && in->x_init && in->mean && in->std, "st_generate_330_host: missing host input");
-  ST_REQUIRE(vq_upper->out_dim == 78 && vq_hands->out_dim == 180 && vq_lower->out_dim == 57, "st_generate_330_host: decoders must be 78/180/57 wide");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t nx = (size_t)B * ST_LATENT * ST_TOKENS;
   const int sdim = m->style_dim;
   bool any_sigma = false;
   for (int k = 0; k < sc->S; ++k) any_sigma |= sc->coef[(size_t)k * ST_COEF_STRIDE + (sc->mode == ST_MODE_DDPM ? 2 : 4)] != 0.f;
   ST_REQUIRE(!any_sigma || in->noise_tape, "st_generate_330_host: schedule has sigma != 0 but noise_tape is NULL");
+  // staging lives in its own arena (m->io is used by st_generate_330)
   size_t f = (size_t)B * ST_AUDIO_LEN * 2 + (size_t)B * 128 + (size_t)B * 6144 + 3 * (size_t)B * (sdim ? sdim : 1) + nx * 2 +
-             (any_sigma ? nx * sc->S : 0) + (size_t)B * 128 * (3 + 78 + 180 + 57 + 330 + 3) + 666 + 64 * 16;
-  ST_TRY(m->io.reserve(f * sizeof(float) + 32 * 256));
-  Arena& a = m->io;
+             (any_sigma ? nx * sc->S : 0) + (size_t)B * 128 * (3 + 330 + 3) + 666 + 64 * 16;
+  ST_TRY(m->stage.reserve(f * sizeof(float) + 32 * 256));
+  Arena& a = m->stage;
   float* d_audio = a.take<float>((size_t)B * ST_AUDIO_LEN * 2);
   int32_t* d_word = a.take<int32_t>((size_t)B * 128);
   float* d_seed = a.take<float>((size_t)B * 6144);
   float* d_style[3] = {nullptr, nullptr, nullptr};
   float* d_x = a.take<float>(nx);
-  float* d_tok = a.take<float>(nx);
+  float* d_s = a.take<float>(nx);
   float* d_tape = any_sigma ? a.take<float>(nx * sc->S) : nullptr;
   float* d_jaw = in->jaw_aa ? a.take<float>((size_t)B * 128 * 3) : nullptr;
-  float* d_up = a.take<float>((size_t)B * 128 * 78);
-  float* d_ha = a.take<float>((size_t)B * 128 * 180);
-  float* d_lo = a.take<float>((size_t)B * 128 * 57);
   float* d_pose = a.take<float>((size_t)B * 128 * 330);
   float* d_trans = a.take<float>((size_t)B * 128 * 3);
   float* d_ms = a.take<float>(666);
@@ -697,6 +719,7 @@ extern "C" int st_generate_330_host(st_model* m, const st_schedule* sc, const st
   ST_CHECK_CUDA(h2d(d_x, in->x_init, nx * sizeof(float)));
   if (d_tape) ST_CHECK_CUDA(h2d(d_tape, in->noise_tape, nx * sc->S * sizeof(float)));
   if (d_jaw) ST_CHECK_CUDA(h2d(d_jaw, in->jaw_aa, (size_t)B * 128 * 3 * sizeof(float)));
+  ST_CHECK_CUDA(cudaMemsetAsync(d_ms, 0, 666 * sizeof(float), s));
   ST_CHECK_CUDA(h2d(d_ms, in->mean, 330 * sizeof(float)));
   ST_CHECK_CUDA(h2d(d_ms + 330, in->std, 330 * sizeof(float)));
   const bool want_trans = rec_trans_host && in->trans_mean && in->trans_std;
@@ -707,14 +730,9 @@ extern "C" int st_generate_330_host(st_model* m, const st_schedule* sc, const st
   st_cond c;
   c.audio = d_audio; c.word = d_word; c.seed = d_seed;
   for (int k = 0; k < 3; ++k) c.style[k] = d_style[k];
-  ST_TRY(st_cond_encode(m, &c, B, stream));
-  ST_TRY(st_sample(m, sc, g, d_x, d_tape, B, d_x, stream));
-  if (sample_host) ST_CHECK_CUDA(cudaMemcpyAsync(sample_host, d_x, nx * sizeof(float), cudaMemcpyDeviceToHost, s));
-  ST_TRY(transpose_to_tokens(d_x, d_tok, B, 1536, 32, 1.0f, s));
-  ST_TRY(st_rvq_decode(vq_upper, d_tok, 1536, latent_scale, B, 32, d_up, nullptr, nullptr, stream));
-  ST_TRY(st_rvq_decode(vq_hands, d_tok + 512, 1536, latent_scale, B, 32, d_ha, nullptr, nullptr, stream));
-  ST_TRY(st_rvq_decode(vq_lower, d_tok + 1024, 1536, latent_scale, B, 32, d_lo, nullptr, nullptr, stream));
-  ST_TRY(pose330(d_up, d_ha, d_lo, d_ms, d_ms + 330, d_ms + 660, d_ms + 663, d_jaw, B, 128, d_pose, want_trans ? d_trans : nullptr, s));
+  ST_TRY(st_generate_330(m, sc, g, vq_upper, vq_hands, vq_lower, &c, d_x, d_tape, d_jaw, d_ms, B, latent_scale, d_pose,
+                         want_trans ? d_trans : nullptr, d_s, stream));
+  if (sample_host) ST_CHECK_CUDA(cudaMemcpyAsync(sample_host, d_s, nx * sizeof(float), cudaMemcpyDeviceToHost, s));
   ST_CHECK_CUDA(cudaMemcpyAsync(rec_pose_host, d_pose, (size_t)B * 128 * 330 * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (want_trans) ST_CHECK_CUDA(cudaMemcpyAsync(rec_trans_host, d_trans, (size_t)B * 128 * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
   ST_CHECK_CUDA(cudaStreamSynchronize(s));

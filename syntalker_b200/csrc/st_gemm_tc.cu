@@ -1,10 +1,498 @@
-// tcgen05 split-fp16 GEMM engine (placeholder until the kernel lands; the dispatcher then never selects it).
+// tcgen05 GEMM engine for sm_100a: fp32-class accuracy from fp16 tensor cores by operand splitting.
+//
+//   a = a_hi + a_lo,  w = w_hi + w_lo   (fp16 pairs of the pre-scaled fp32 values, 22 significand bits)
+//   a.w ~= a_hi.w_hi + a_hi.w_lo + a_lo.w_hi     (three tcgen05.mma per K step, fp32 accumulation in TMEM;
+//                                                  the dropped a_lo.w_lo term is 2^-24 relative)
+//
+// Data path per CTA (one 128 x BN output tile): a single elected thread streams K-blocks of the four operand
+// planes with TMA (cp.async.bulk.tensor, 128B swizzle, both planes of an operand in one 3-D box) into a
+// STAGES-deep shared-memory ring; a second elected thread issues the MMAs from shared-memory descriptors into
+// a TMEM accumulator and releases ring slots with tcgen05.commit; four epilogue warps read the accumulator
+// back with tcgen05.ld (lane = output row), apply scale/bias/activation/residual and store fp32 -- and, when
+// asked, the fp16 hi/lo planes of the result so that the next GEMM can TMA them directly.
 #include "st_internal.cuh"
 
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <mutex>
+#include <unordered_map>
+
 namespace st {
-bool tc_supported(const GemmP&) { return false; }
-int gemm_tc(const GemmP&, cudaStream_t) {
-  set_error("tcgen05 engine not built");
-  return ST_EUNSUPPORTED;
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must end in a trap (launch failure), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start address >> 4 | LBO (ignored for swizzled K-major, 1) << 16 | SBO = 1024 B between 8-row groups << 32 |
+// version 1 << 46 | layout SWIZZLE_128B (2) << 61.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (InstrDescriptor): D = F32 (1 << 4), A = B = F16 (0), K-major both, N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Kernel
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
+constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;   // bytes of one A plane tile (128 rows x 128 B)
+
+struct TcEpi {
+  float* out;            // [M, ldo] fp32 or null
+  const float* bias;     // [N] or null
+  const float* res;      // [M/res_div, ldr] or null
+  __half* planes;        // optional fp16 hi/lo planes of the result: [2][M][ld_planes]
+  long long plane_stride;
+  int ld_planes;
+  float planes_scale;    // result * planes_scale is what gets split
+  int planes_relu;
+  int ldo, ldr, res_mode, res_div, act;
+  float scale;           // 2^-(sa+sw): undo the operand pre-scaling
+  int M, N;
+  int a_rows_per_clip;   // conv mode (4-D A map): T; 0 = plain 2-D GEMM
+  int taps, dil, kb_per_tap;
+};
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+  switch (act) {
+    case ACT_GELU: return v * 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+    case ACT_RELU: return fmaxf(v, 0.0f);
+    case ACT_LRELU: return v > 0.0f ? v : v * 0.01f;
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+  v = fminf(fmaxf(v, -65000.0f), 65000.0f);
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcEpi ep, const int num_kb) {
+  constexpr int W_PLANE = BN * TC_BK * 2;
+  constexpr int STAGE_BYTES = 2 * TC_A_PLANE + 2 * W_PLANE;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        if (ep.a_rows_per_clip == 0) {
+          tma_load_3d(st, &tmA, &full_bar[s], kb * TC_BK, m0, 0);
+        } else {
+          // implicit conv: K block kb = (tap j, channel block); rows (clip, t) read from t + (j - taps/2)*dil,
+          // out-of-range t is zero-filled by TMA = the conv's zero padding
+          const int j = kb / ep.kb_per_tap, cb = kb - j * ep.kb_per_tap;
+          tma_load_4d(st, &tmA, &full_bar[s], cb * TC_BK, (j - ep.taps / 2) * ep.dil, m0 / ep.a_rows_per_clip, 0);
+        }
+        tma_load_3d(st + 2 * TC_A_PLANE, &tmW, &full_bar[s], kb * TC_BK, n0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_f16(TC_BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t a_lo = a_hi + TC_A_PLANE;
+        const uint32_t w_hi = a_hi + 2 * TC_A_PLANE;
+        const uint32_t w_lo = w_hi + W_PLANE;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t dah = umma_desc_sw128(a_hi) + 2 * k, dal = umma_desc_sw128(a_lo) + 2 * k;
+          const uint64_t dwh = umma_desc_sw128(w_hi) + 2 * k, dwl = umma_desc_sw128(w_lo) + 2 * k;
+          umma_f16(tmem_base, dah, dwh, idesc, (kb | k) != 0);
+          umma_f16(tmem_base, dah, dwl, idesc, 1);
+          umma_f16(tmem_base, dal, dwh, idesc, 1);
+        }
+        umma_commit(&empty_bar[s]);     // slot reusable once these MMAs have read it
+      }
+      umma_commit(acc_bar);             // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
+    const int lg = warp & 3;
+    const int row = m0 + lg * 32 + lane;
+    const bool row_ok = row < ep.M;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const float* rrow = (ep.res && row_ok) ? ep.res + (long long)(row / ep.res_div) * ep.ldr : nullptr;
+    float* orow = (ep.out && row_ok) ? ep.out + (long long)row * ep.ldo : nullptr;
+    __half* prow = (ep.planes && row_ok) ? ep.planes + (long long)row * ep.ld_planes : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      const int nb = n0 + c * 32;
+      if (!row_ok || nb >= ep.N) continue;
+      float x[32];
+      const bool full = nb + 32 <= ep.N;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(v[j]) * ep.scale;
+        if (full || nb + j < ep.N) {
+          if (ep.bias) t += __ldg(ep.bias + nb + j);
+          const float r = rrow ? rrow[nb + j] : 0.f;
+          if (ep.res_mode == RES_PRE) t += r;
+          t = tc_act(t, ep.act);
+          if (ep.res_mode == RES_POST) t += r;
+        }
+        x[j] = t;
+      }
+      if (orow) {
+        if (full && (ep.ldo & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + nb + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < ep.N) orow[nb + j] = x[j];
+        }
+      }
+      if (prow) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          if (nb + j + 1 < ep.N + 1 && nb + j < ep.N) {
+            float a = x[j] * ep.planes_scale, b = x[j + 1] * ep.planes_scale;
+            if (ep.planes_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            __half ah, al, bh, bl;
+            split_f16(a, ah, al);
+            split_f16(b, bh, bl);
+            *reinterpret_cast<__half2*>(prow + nb + j) = __halves2half2(ah, bh);
+            *reinterpret_cast<__half2*>(prow + ep.plane_stride + nb + j) = __halves2half2(al, bl);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// fp32 [M,K] (row stride lda) -> fp16 planes [2][M][Kp], value * scale split into hi + lo
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ a, int lda, int M, int K, int Kp, float scale, int relu,
+                                                           __half* __restrict__ planes) {
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;     // one thread per 4 elements
+  const int kq = Kp >> 2;
+  if (gid >= (long long)M * kq) return;
+  const int m = (int)(gid / kq), k = (int)(gid - (long long)m * kq) * 4;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k + 3 < K && (lda & 3) == 0) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(a + (long long)m * lda + k));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    for (int q = 0; q < 4; ++q)
+      if (k + q < K) v[q] = a[(long long)m * lda + k + q];
+  }
+  __half h[4], l[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float t = v[q] * scale;
+    if (relu) t = fmaxf(t, 0.f);
+    split_f16(t, h[q], l[q]);
+  }
+  __half* ph = planes + (long long)m * Kp + k;
+  __half* pl = ph + (long long)M * Kp;
+  *reinterpret_cast<__half2*>(ph) = __halves2half2(h[0], h[1]);
+  *reinterpret_cast<__half2*>(ph + 2) = __halves2half2(h[2], h[3]);
+  *reinterpret_cast<__half2*>(pl) = __halves2half2(l[0], l[1]);
+  *reinterpret_cast<__half2*>(pl + 2) = __halves2half2(l[2], l[3]);
+}
+
+__global__ void absmax_kernel(const float* __restrict__ a, long long n, float* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(a[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));   // non-negative floats order like ints
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// planes [2][rows][Kp] fp16 -> 3-D map {Kp, rows, 2}, box {64, box_rows, 2}, 128B swizzle, zero OOB fill
+static int make_map_3d(CUtensorMap* m, const __half* base, int rows, int Kp, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ST_ECUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, 2};
+  cuuint64_t gstr[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)rows * Kp * 2};
+  cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_rows, 2};
+  cuuint32_t est[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d rows=%d Kp=%d box=%d) failed: %d", rows, Kp, box_rows, (int)r); return ST_ECUDA; }
+  return ST_OK;
+}
+// planes [2][clips][T][C] fp16 -> 4-D map {C, T, clips, 2}, box {64, T, 128/T, 2}
+static int make_map_4d(CUtensorMap* m, const __half* base, int clips, int T, int C) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ST_ECUDA; }
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)clips, 2};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2, (cuuint64_t)clips * T * C * 2};
+  cuuint32_t box[4] = {TC_BK, (cuuint32_t)T, (cuuint32_t)(TC_BM / T), 2};
+  cuuint32_t est[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(4d clips=%d T=%d C=%d) failed: %d", clips, T, C, (int)r); return ST_ECUDA; }
+  return ST_OK;
+}
+
+struct WPlanes {
+  __half* planes = nullptr;
+  int N = 0, Kp = 0;
+  float inv_scale = 1.f;   // 2^-sw
+  CUtensorMap map64, map128;
+};
+static std::unordered_map<const float*, WPlanes> g_wplanes;
+static std::mutex g_tc_mu;
+static Arena g_scratch;          // activation planes of the GEMM in flight (stream order serialises reuse)
+static const float kActScale = 16.0f;
+
+static int split_launch(const float* a, int lda, int M, int K, int Kp, float scale, int relu, __half* planes, cudaStream_t s) {
+  const long long n = (long long)M * (Kp >> 2);
+  split_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, lda, M, K, Kp, scale, relu, planes);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+// Weight planes are made once per weight matrix (first use): per-tensor power-of-two scale so that max|w| lands in
+// [2^12, 2^13), then the fp16 hi/lo split.  This synchronises; it happens during warm-up, never in steady state.
+static int get_wplanes(const GemmP& p, cudaStream_t s, WPlanes** out) {
+  std::lock_guard<std::mutex> lk(g_tc_mu);
+  auto it = g_wplanes.find(p.W);
+  if (it != g_wplanes.end() && it->second.N == p.N) { *out = &it->second; return ST_OK; }
+  WPlanes w;
+  w.N = p.N;
+  w.Kp = (p.K + TC_BK - 1) / TC_BK * TC_BK;
+  float* d_max = nullptr;
+  ST_CHECK_CUDA(cudaMalloc(&d_max, sizeof(float)));
+  ST_CHECK_CUDA(cudaMemsetAsync(d_max, 0, sizeof(float), s));
+  absmax_kernel<<<148, 256, 0, s>>>(p.W, (long long)p.N * p.ldw, d_max);
+  ST_CHECK_LAUNCH();
+  float h_max = 0.f;
+  ST_CHECK_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
+  ST_CHECK_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_max);
+  int e = 0;
+  if (h_max > 0.f) {
+    frexpf(h_max, &e);            // h_max = f * 2^e, f in [0.5, 1)
+    e = 13 - e;                   // h_max * 2^e in [2^12, 2^13)
+  }
+  const float scale = ldexpf(1.0f, e);
+  w.inv_scale = ldexpf(1.0f, -e);
+  const size_t bytes = (size_t)2 * p.N * w.Kp * sizeof(__half);
+  if (cudaMalloc(&w.planes, bytes) != cudaSuccess) { set_error("cudaMalloc(weight planes %zu B) failed", bytes); return ST_ENOMEM; }
+  ST_TRY(split_launch(p.W, p.ldw, p.N, p.K, w.Kp, scale, 0, w.planes, s));
+  ST_TRY(make_map_3d(&w.map64, w.planes, p.N, w.Kp, 64));
+  ST_TRY(make_map_3d(&w.map128, w.planes, p.N, w.Kp, 128));
+  ST_CHECK_CUDA(cudaStreamSynchronize(s));
+  g_wplanes[p.W] = w;
+  *out = &g_wplanes[p.W];
+  return ST_OK;
+}
+
+void tc_forget_weights(const float* W) {
+  std::lock_guard<std::mutex> lk(g_tc_mu);
+  auto it = g_wplanes.find(W);
+  if (it != g_wplanes.end()) { cudaFree(it->second.planes); g_wplanes.erase(it); }
+}
+
+bool tc_supported(const GemmP& p) {
+  if (!p.out || p.out_scale != 1.0f || p.M < 128 || p.N < 16) return false;
+  if (p.stride != 1 || p.ups) return false;
+  const bool plain = (p.Lout == p.M && p.Lin == p.M && p.C == p.K && p.pad == 0);
+  if (plain) return (p.K % TC_BK) == 0;
+  // channels-last k-tap conv with "same" padding over clips of Lout == Lin rows, 128 % T == 0
+  const int taps = p.K / p.C;
+  return p.Lout == p.Lin && (TC_BM % p.Lout) == 0 && (p.M % p.Lout) == 0 && (p.C % TC_BK) == 0 && taps * p.C == p.K && (taps & 1) &&
+         p.pad == (taps / 2) * p.dil && p.lda == p.C && p.a_batch == (long long)p.Lin * p.C;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcEpi& ep, int num_kb, cudaStream_t s) {
+  constexpr int smem = STAGES * (2 * TC_A_PLANE + 2 * BN * TC_BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  dim3 grid((ep.M + TC_BM - 1) / TC_BM, (ep.N + BN - 1) / BN);
+  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, ep, num_kb);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+int gemm_tc(const GemmP& p, cudaStream_t s) {
+  if (!tc_supported(p)) { set_error("gemm_tc: unsupported problem"); return ST_EUNSUPPORTED; }
+  WPlanes* w = nullptr;
+  ST_TRY(get_wplanes(p, s, &w));
+  const bool plain = (p.Lout == p.M && p.C == p.K);
+  const int Ka = plain ? p.K : p.C;                       // columns of the activation planes
+  const int rows = plain ? p.M : p.M;                     // conv: clips * T rows, same count
+  // activation planes (scratch, reused in stream order)
+  {
+    std::lock_guard<std::mutex> lk(g_tc_mu);
+    const size_t need = (size_t)2 * rows * Ka * sizeof(__half) + 1024;
+    if (need > g_scratch.cap) ST_TRY(g_scratch.reserve(need * 2));
+  }
+  __half* planes = reinterpret_cast<__half*>(g_scratch.base);
+  ST_TRY(split_launch(p.A, p.lda, rows, Ka, Ka, kActScale, p.a_relu, planes, s));
+  CUtensorMap tmA;
+  TcEpi ep;
+  ep.a_rows_per_clip = 0; ep.taps = 1; ep.dil = 1; ep.kb_per_tap = 0;
+  if (plain) {
+    ST_TRY(make_map_3d(&tmA, planes, rows, Ka, TC_BM));
+  } else {
+    ST_TRY(make_map_4d(&tmA, planes, p.M / p.Lout, p.Lout, p.C));
+    ep.a_rows_per_clip = p.Lout; ep.taps = p.K / p.C; ep.dil = p.dil; ep.kb_per_tap = p.C / TC_BK;
+  }
+  ep.out = p.out; ep.bias = p.bias; ep.res = p.res; ep.planes = nullptr; ep.plane_stride = 0; ep.ld_planes = 0; ep.planes_scale = 1.f;
+  ep.planes_relu = 0; ep.ldo = p.ldo; ep.ldr = p.ldr; ep.res_mode = p.res ? p.res_mode : RES_NONE; ep.res_div = p.res_div; ep.act = p.act;
+  ep.scale = w->inv_scale / kActScale;
+  ep.M = p.M; ep.N = p.N;
+  const int num_kb = w->Kp / TC_BK;
+  if (p.N <= 512) return launch_tc<64, 4>(tmA, w->map64, ep, num_kb, s);
+  return launch_tc<128, 3>(tmA, w->map128, ep, num_kb, s);
+}
+
 }  // namespace st

@@ -71,6 +71,36 @@ class Window330:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    def run_device(self, audio, word, seed, x_init, y=None, styles=None, jaw_aa=None, noise_tape=None, out=None):
+        """Same pipeline with every input already resident in HBM (CUDA tensors); no host sync.
+        Returns (rec_pose, rec_trans, sample) CUDA tensors (st_generate_330)."""
+        B, dev = self.B, self.base.device
+        y = dict(y or {})
+        if styles is None and self.base.variant != "beatx":
+            sf = y.get("style_feature")
+            styles = [sf.get("upper_mask"), sf.get("hands_mask"), sf.get("lower_mask")] if isinstance(sf, dict) else [sf, None, None]
+        styles = styles or [None, None, None]
+        c = _lib.StCond()
+        c.audio, c.word, c.seed = audio.data_ptr(), word.data_ptr(), seed.data_ptr()
+        assert audio.is_cuda and audio.dtype == torch.float32 and word.dtype == torch.int32 and seed.is_contiguous()
+        for k in range(3):
+            c.style[k] = styles[k].data_ptr() if (styles[k] is not None and self.base.variant != "beatx") else None
+        if not hasattr(self, "_ms_dev"):
+            m = self.ms
+            self._ms_dev = torch.cat([m["mean"], m["std"], m["trans_mean"], m["trans_std"]]).float().to(dev).contiguous()
+        if out is None:
+            out = (torch.empty((B, 128, 330), device=dev), torch.empty((B, 128, 3), device=dev), torch.empty((B, 1536, 1, 32), device=dev))
+        g = self.wrapper.guidance(y) if self.wrapper is not None else Guidance(_lib.ST_CFG_NONE)
+        sched, _ = self.diffusion._native(self.mode, self.eta)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().st_generate_330(
+                self.base.handle, sched, C.byref(g.struct(B)), self.vqs[0].handle, self.vqs[1].handle, self.vqs[2].handle,
+                C.byref(c), x_init.data_ptr(), noise_tape.data_ptr() if noise_tape is not None else None,
+                jaw_aa.data_ptr() if jaw_aa is not None else None, self._ms_dev.data_ptr(), B, self.latent_scale,
+                out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), _lib.stream_ptr()))
+        self.base._cond_key.key = None
+        return out
+
     def run(self, audio, word, seed, x_init, y=None, styles=None, jaw_aa=None, noise_tape=None, want_sample=False):
         """All inputs are CPU tensors. Returns (rec_pose [B,128,330], rec_trans [B,128,3]) pinned CPU tensors."""
         B, h = self.B, self.h
