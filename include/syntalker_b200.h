@@ -73,6 +73,8 @@ int st_abi_version(void);
 int64_t st_launch_count(void);
 int st_set_engine(int engine);
 int st_get_engine(void);
+/* The sampling loop replays one captured CUDA graph per diffusion step (default on); 0 = launch every kernel eagerly. */
+int st_set_graphs(int on);
 
 /* ---- weights -------------------------------------------------------------------------------------
  * Replaces: MDM(args) construction + load_checkpoints (train.py:85-94, utils/other_tools.py:771-790).

@@ -60,7 +60,7 @@ const float* Weights::get(const std::string& name, int64_t expect, int* err) con
   return it->second;
 }
 void Weights::release() {
-  for (auto& kv : dev) cudaFree(kv.second);
+  for (auto& kv : dev) { tc_forget_weights(kv.second); cudaFree(kv.second); }
   dev.clear(); numel.clear();
 }
 
@@ -82,6 +82,8 @@ int gemm(const GemmP& p, cudaStream_t s) {
   }
   return r;
 }
+
+bool profiling() { return g_prof; }
 
 int profile_begin() {
   for (auto e : g_prof_ev) cudaEventDestroy(e);
@@ -140,7 +142,18 @@ struct st_model {
   float *wavbuf[4] = {nullptr, nullptr, nullptr, nullptr}, *atcat = nullptr, *pooled = nullptr;
   float *scale_dev = nullptr, *scale2_dev = nullptr;
   int64_t* t_tmp = nullptr;
+  // fp16 hi/lo operand planes for the tcgen05 engine
+  __half *H_p = nullptr, *ATT_p = nullptr, *G_p = nullptr, *X_p = nullptr;
+  // sampling-loop state on the device + one captured step graph per (plan, mode, engine)
+  LoopState* loop = nullptr;
+  int32_t* t_model_dev = nullptr;
+  float* coef_dev = nullptr;
+  std::map<std::string, cudaGraphExec_t> graphs;
+  std::map<std::string, int64_t> graph_nodes;
+  std::map<std::string, int> warmed;
 };
+
+static bool g_use_graphs = true;
 
 struct st_schedule {
   int S = 0, mode = 0;
@@ -166,6 +179,7 @@ extern "C" int st_set_engine(int engine) {
   return ST_OK;
 }
 extern "C" int st_get_engine(void) { return g_engine; }
+extern "C" int st_set_graphs(int on) { g_use_graphs = on != 0; return ST_OK; }
 extern "C" int st_profile_begin(void) { return st::profile_begin(); }
 extern "C" int st_profile_end(double* ms_total, double* flops_total, int64_t* launches) { return st::profile_end(ms_total, flops_total, launches); }
 
@@ -229,6 +243,7 @@ extern "C" int st_model_create(const st_tensor* packed, int n, int variant, st_m
 extern "C" void st_model_destroy(st_model* m) {
   if (!m) return;
   cudaDeviceSynchronize();
+  for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
   m->w.release(); m->ws.release(); m->io.release(); m->stage.release();
   if (m->cst_null) cudaFree(m->cst_null);
   delete m;
@@ -244,7 +259,11 @@ static int model_workspace(st_model* m, int B) {
   f += nE * rows * (512 * 3 + 1536 * 2 + 1024);                // X,H,ATT,QKV,O,G
   f += 4 * (size_t)cb * kWavLen[1] * 64 + (size_t)cb * 128 * 512 + (size_t)cb * 32 * 512;
   f += 2 * (size_t)B + 64;
+  f += nE * rows * (512 * 3 + 1024);                           // fp16 hi+lo planes H_p, ATT_p, X_p, G_p (2 halves = 1 float each)
+  f += 1000 * (1 + ST_COEF_STRIDE) + 64;
   size_t bytes = f * sizeof(float) + (size_t)B * sizeof(int64_t) + 64 * 256;
+  for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);  // captured pointers die with the old block
+  m->graphs.clear(); m->warmed.clear(); m->graph_nodes.clear();
   ST_TRY(m->ws.reserve(bytes));
   Arena& a = m->ws;
   m->cst_real = a.take<float>(rows * 512);
@@ -265,6 +284,13 @@ static int model_workspace(st_model* m, int B) {
   m->scale_dev = a.take<float>(B);
   m->scale2_dev = a.take<float>(B);
   m->t_tmp = a.take<int64_t>(B);
+  m->H_p = a.take<__half>(2 * nE * rows * 512);
+  m->ATT_p = a.take<__half>(2 * nE * rows * 512);
+  m->X_p = a.take<__half>(2 * nE * rows * 512);
+  m->G_p = a.take<__half>(2 * nE * rows * 1024);
+  m->loop = a.take<LoopState>(1);
+  m->t_model_dev = a.take<int32_t>(1000);
+  m->coef_dev = a.take<float>(1000 * ST_COEF_STRIDE);
   m->ws_B = B;
   m->cond_B = 0;   // the cache lived in the old block
   return ST_OK;
@@ -413,12 +439,17 @@ static int make_plan(const st_model* m, const st_guidance* g, Plan* pl) {
 }
 
 // ---- one trunk pass over the state m->xs for all planned evaluations -> m->O ---------------------------
-static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, int t_scalar, cudaStream_t s) {
+// SIMT engine: every activation stays fp32.  tcgen05 engine: LayerNorm, attention and the GELU epilogue emit the
+// fp16 hi/lo planes the next GEMM streams with TMA; only the residual stream, QKV and the outputs stay fp32.
+static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, int t_scalar, bool loop, cudaStream_t s) {
   const int rows = B * 32, R = pl.nE * rows;
+  const bool tc = (st_get_engine() == ST_ENGINE_TC) && R >= 128;
+  const long long ps512 = (long long)R * 512, ps1024 = (long long)R * 1024;
   GemmP pz = linear(m->xs, rows, 1536, m->w_x, nullptr, m->z, 512);
   ST_TRY(gemm(pz, s));
   TokensInP tp;
   tp.z = m->z; tp.vt_table = m->vt_table; tp.t_dev = t_dev; tp.t_scalar = t_scalar; tp.g2 = m->g2;
+  tp.ls = loop ? m->loop : nullptr; tp.t_model_dev = m->t_model_dev;
   tp.rope_cos = m->rope_cos; tp.rope_sin = m->rope_sin; tp.x = m->X; tp.B = B; tp.nE = pl.nE;
   for (int e = 0; e < ST_MAX_EVALS; ++e) { tp.cst[e] = m->cst_real; tp.cst_bcast[e] = 0; tp.sv[e] = nullptr; tp.sv_bcast[e] = 0; }
   for (int e = 0; e < pl.nE; ++e) {
@@ -430,22 +461,30 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   ST_TRY(tokens_in(tp, s));
   for (int i = 0; i < 8; ++i) {
     const BlkW& b = m->blk[i];
-    ST_TRY(layernorm512(m->X, b.ln1g, b.ln1b, m->H, R, s));
+    ST_TRY(layernorm512(m->X, b.ln1g, b.ln1b, tc ? nullptr : m->H, tc ? m->H_p : nullptr, R, s));
     GemmP pq = linear(m->H, R, 512, b.qkv, nullptr, m->QKV, 1536);
+    if (tc) { pq.a_planes = m->H_p; pq.a_plane_stride = ps512; }
     ST_TRY(gemm(pq, s));
-    ST_TRY(attention32(m->QKV, m->ATT, pl.nE * B, s));
+    ST_TRY(attention32(m->QKV, tc ? nullptr : m->ATT, tc ? m->ATT_p : nullptr, pl.nE * B, s));
     GemmP pp = linear(m->ATT, R, 512, b.projw, b.projb, m->X, 512);
     pp.res = m->X; pp.res_mode = RES_POST; pp.ldr = 512;
+    if (tc) { pp.a_planes = m->ATT_p; pp.a_plane_stride = ps512; }
     ST_TRY(gemm(pp, s));
-    ST_TRY(layernorm512(m->X, b.ln2g, b.ln2b, m->H, R, s));
+    ST_TRY(layernorm512(m->X, b.ln2g, b.ln2b, tc ? nullptr : m->H, tc ? m->H_p : nullptr, R, s));
     GemmP p1 = linear(m->H, R, 512, b.fc1w, b.fc1b, m->G, 1024);
     p1.act = ACT_GELU;
+    if (tc) { p1.a_planes = m->H_p; p1.a_plane_stride = ps512; p1.out = nullptr; p1.o_planes = m->G_p; p1.o_plane_stride = ps1024; p1.o_planes_ld = 1024; }
     ST_TRY(gemm(p1, s));
     GemmP p2 = linear(m->G, R, 1024, b.fc2w, b.fc2b, m->X, 512);
     p2.res = m->X; p2.res_mode = RES_POST; p2.ldr = 512;
+    if (tc) {
+      p2.a_planes = m->G_p; p2.a_plane_stride = ps1024;
+      if (i == 7) { p2.o_planes = m->X_p; p2.o_plane_stride = ps512; p2.o_planes_ld = 512; }   // operand of the output projection
+    }
     ST_TRY(gemm(p2, s));
   }
   GemmP po = linear(m->X, R, 512, m->out_w, m->out_b, m->O, 1536);
+  if (tc) { po.a_planes = m->X_p; po.a_plane_stride = ps512; }
   ST_TRY(gemm(po, s));
   return ST_OK;
 }
@@ -475,7 +514,7 @@ extern "C" int st_denoise(st_model* m, const float* x, const int64_t* t, const s
   Plan pl;
   ST_TRY(make_plan(m, g, &pl));
   ST_TRY(transpose_to_tokens(x, m->xs, B, 1536, 32, 1.0f, s));
-  ST_TRY(run_trunk(m, pl, B, t, 0, s));
+  ST_TRY(run_trunk(m, pl, B, t, 0, false, s));
   StepP sp;
   ST_TRY(upload_scales(m, pl, g, B, &sp, s));
   sp.xs = m->comb; sp.eps = nullptr; sp.mode = -1;
@@ -497,6 +536,25 @@ extern "C" int st_schedule_create(int S, int mode, const int32_t* t_model, const
 }
 extern "C" void st_schedule_destroy(st_schedule* s) { delete s; }
 
+static std::string plan_key(const Plan& pl, int B, int mode) {
+  char buf[256];
+  int n = snprintf(buf, sizeof buf, "B%d m%d e%d c%d n%d", B, mode, st_get_engine(), pl.cfg_mode, pl.nE);
+  for (int e = 0; e < pl.nE; ++e) n += snprintf(buf + n, sizeof buf - n, " %d:%d", pl.ev[e].cst_null, pl.ev[e].sv_src);
+  for (int k = 0; k < 3; ++k) n += snprintf(buf + n, sizeof buf - n, " p%g/%g/%d", pl.part_sa[k], pl.part_sp[k], pl.part_ua[k]);
+  return buf;
+}
+
+// one diffusion step: trunk for every planned evaluation, CFG mix + sampler update, k -= 1  (all step-dependent
+// values are read from device memory, so the same launch sequence -- or its captured graph -- serves every step)
+static int one_step(st_model* m, const Plan& pl, const StepP& sp0, int B, cudaStream_t s) {
+  ST_TRY(run_trunk(m, pl, B, nullptr, 0, true, s));
+  StepP sp = sp0;
+  sp.xs = m->xs; sp.eps = nullptr; sp.ls = m->loop; sp.coef_dev = m->coef_dev;
+  ST_TRY(step_update(sp, s));
+  ST_TRY(advance_loop(m->loop, s));
+  return ST_OK;
+}
+
 extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* g, const float* x_init, const float* noise_tape,
                          int B, float* x_out, void* stream) {
   ST_REQUIRE(m && sc && x_init && x_out && B > 0, "st_sample: null argument or B <= 0");
@@ -509,15 +567,39 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
   ST_REQUIRE(!any_sigma || noise_tape, "st_sample: schedule has sigma != 0 but noise_tape is NULL");
   StepP sp;
   ST_TRY(upload_scales(m, pl, g, B, &sp, s));
+  sp.mode = sc->mode;
+  ST_CHECK_CUDA(cudaMemcpyAsync(m->t_model_dev, sc->t_model.data(), sc->S * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  ST_CHECK_CUDA(cudaMemcpyAsync(m->coef_dev, sc->coef.data(), (size_t)sc->S * ST_COEF_STRIDE * sizeof(float), cudaMemcpyHostToDevice, s));
+  ST_TRY(init_loop(m->loop, sc->S, noise_tape, s));
   ST_TRY(transpose_to_tokens(x_init, m->xs, B, 1536, 32, 1.0f, s));
-  const size_t per = (size_t)B * ST_LATENT * ST_TOKENS;
-  for (int k = sc->S - 1; k >= 0; --k) {
-    ST_TRY(run_trunk(m, pl, B, nullptr, sc->t_model[k], s));
-    sp.xs = m->xs; sp.mode = sc->mode;
-    sp.eps = noise_tape ? noise_tape + (size_t)(sc->S - 1 - k) * per : nullptr;
-    for (int q = 0; q < ST_COEF_STRIDE; ++q) sp.c[q] = sc->coef[(size_t)k * ST_COEF_STRIDE + q];
-    ST_TRY(step_update(sp, s));
+  // The first call with a given plan runs eagerly (it creates weight planes, tensor maps, scratch); the second
+  // captures one step into a CUDA graph; from then on every step is one graph launch.
+  const std::string key = plan_key(pl, B, sc->mode);
+  cudaGraphExec_t exec = nullptr;
+  const bool graphs_ok = g_use_graphs && !st::profiling();
+  if (graphs_ok) {
+    auto it = m->graphs.find(key);
+    if (it != m->graphs.end()) exec = it->second;
+    else if (m->warmed[key] >= 1) {
+      cudaGraph_t graph = nullptr;
+      const int64_t l0 = g_launches;
+      ST_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+      const int r = one_step(m, pl, sp, B, s);
+      m->graph_nodes[key] = g_launches - l0;     // kernels per replay; capturing itself executed nothing
+      g_launches = l0;
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (r != ST_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+      ST_CHECK_CUDA(ce);
+      ST_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      m->graphs[key] = exec;
+    }
   }
+  for (int k = sc->S - 1; k >= 0; --k) {
+    if (exec) { ST_CHECK_CUDA(cudaGraphLaunch(exec, s)); g_launches += m->graph_nodes[key]; }
+    else ST_TRY(one_step(m, pl, sp, B, s));
+  }
+  m->warmed[key] += 1;
   ST_TRY(transpose_from_tokens(m->xs, x_out, B, 1536, 32, s));
   return ST_OK;
 }
@@ -745,7 +827,11 @@ extern "C" int st_selftest_gemm(int M, int N, int K, int engine, const float* A,
   GemmP p = linear(A, M, K, W, bias, out, N);
   if (engine == ST_ENGINE_TC) {
     if (!tc_supported(p)) { set_error("st_selftest_gemm: shape M=%d N=%d K=%d not supported by the tcgen05 engine", M, N, K); return ST_EUNSUPPORTED; }
-    return gemm_tc(p, (cudaStream_t)stream);
+    tc_forget_weights(W);                 // the caller may reuse the address with new contents
+    const int r = gemm_tc(p, (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    tc_forget_weights(W);
+    return r;
   }
   return gemm_simt(p, (cudaStream_t)stream);
 }

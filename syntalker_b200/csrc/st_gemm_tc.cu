@@ -15,7 +15,9 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <unordered_map>
 
 namespace st {
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcEpi ep, const int num_kb) {
   constexpr int W_PLANE = BN * TC_BK * 2;
   constexpr int STAGE_BYTES = 2 * TC_A_PLANE + 2 * W_PLANE;
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // main + correction accumulators
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -221,9 +223,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int k = 0; k < TC_BK / 16; ++k) {
           const uint64_t dah = umma_desc_sw128(a_hi) + 2 * k, dal = umma_desc_sw128(a_lo) + 2 * k;
           const uint64_t dwh = umma_desc_sw128(w_hi) + 2 * k, dwl = umma_desc_sw128(w_lo) + 2 * k;
+          // hi.hi goes to the main accumulator; the two 2^-11-sized cross terms go to their own accumulator so that
+          // the tensor core's truncating fp32 adds see a 3x shorter chain on the large sum (measured: error / 3)
           umma_f16(tmem_base, dah, dwh, idesc, (kb | k) != 0);
-          umma_f16(tmem_base, dah, dwl, idesc, 1);
-          umma_f16(tmem_base, dal, dwh, idesc, 1);
+          umma_f16(tmem_base + BN, dah, dwl, idesc, (kb | k) != 0);
+          umma_f16(tmem_base + BN, dal, dwh, idesc, 1);
         }
         umma_commit(&empty_bar[s]);     // slot reusable once these MMAs have read it
       }
@@ -241,8 +245,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __half* prow = (ep.planes && row_ok) ? ep.planes + (long long)row * ep.ld_planes : nullptr;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
+      uint32_t v[32], vc[32];
       tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + c * 32, v);
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + BN + c * 32, vc);
       tmem_ld_wait();
       const int nb = n0 + c * 32;
       if (!row_ok || nb >= ep.N) continue;
@@ -250,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool full = nb + 32 <= ep.N;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(v[j]) * ep.scale;
+        float t = (__uint_as_float(v[j]) + __uint_as_float(vc[j])) * ep.scale;
         if (full || nb + j < ep.N) {
           if (ep.bias) t += __ldg(ep.bias + nb + j);
           const float r = rrow ? rrow[nb + j] : 0.f;
@@ -272,7 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (prow) {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          if (nb + j + 1 < ep.N + 1 && nb + j < ep.N) {
+          if (nb + j < ep.N) {
             float a = x[j] * ep.planes_scale, b = x[j + 1] * ep.planes_scale;
             if (ep.planes_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
             __half ah, al, bh, bl;
@@ -350,30 +355,52 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// planes [2][rows][Kp] fp16 -> 3-D map {Kp, rows, 2}, box {64, box_rows, 2}, 128B swizzle, zero OOB fill
-static int make_map_3d(CUtensorMap* m, const __half* base, int rows, int Kp, int box_rows) {
+struct MapKey {
+  const void* base; long long plane_stride; int d0, d1, d2, box;
+  bool operator<(const MapKey& o) const {
+    return std::tie(base, plane_stride, d0, d1, d2, box) < std::tie(o.base, o.plane_stride, o.d0, o.d1, o.d2, o.box);
+  }
+};
+static std::map<MapKey, CUtensorMap> g_maps;    // a tensor map encodes address and geometry only, never data: safe to reuse
+static std::mutex g_tc_mu;
+
+// planes [2][rows][Kp] fp16 (planes `plane_stride` elements apart) -> 3-D map {Kp, rows, 2}, box {64, box_rows, 2},
+// 128B swizzle, zero fill outside the tensor
+static int get_map_3d(const CUtensorMap** out, const __half* base, long long plane_stride, int rows, int Kp, int box_rows) {
+  MapKey key{base, plane_stride, Kp, rows, 0, box_rows};
+  std::lock_guard<std::mutex> lk(g_tc_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = &it->second; return ST_OK; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ST_ECUDA; }
   cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, 2};
-  cuuint64_t gstr[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)rows * Kp * 2};
+  cuuint64_t gstr[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)plane_stride * 2};
   cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_rows, 2};
   cuuint32_t est[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d rows=%d Kp=%d box=%d) failed: %d", rows, Kp, box_rows, (int)r); return ST_ECUDA; }
+  *out = &(g_maps[key] = m);
   return ST_OK;
 }
 // planes [2][clips][T][C] fp16 -> 4-D map {C, T, clips, 2}, box {64, T, 128/T, 2}
-static int make_map_4d(CUtensorMap* m, const __half* base, int clips, int T, int C) {
+static int get_map_4d(const CUtensorMap** out, const __half* base, long long plane_stride, int clips, int T, int C) {
+  MapKey key{base, plane_stride, C, T, clips, -1};
+  std::lock_guard<std::mutex> lk(g_tc_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = &it->second; return ST_OK; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ST_ECUDA; }
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)clips, 2};
-  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2, (cuuint64_t)clips * T * C * 2};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2, (cuuint64_t)plane_stride * 2};
   cuuint32_t box[4] = {TC_BK, (cuuint32_t)T, (cuuint32_t)(TC_BM / T), 2};
   cuuint32_t est[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(4d clips=%d T=%d C=%d) failed: %d", clips, T, C, (int)r); return ST_ECUDA; }
+  *out = &(g_maps[key] = m);
   return ST_OK;
 }
 
@@ -381,12 +408,10 @@ struct WPlanes {
   __half* planes = nullptr;
   int N = 0, Kp = 0;
   float inv_scale = 1.f;   // 2^-sw
-  CUtensorMap map64, map128;
 };
 static std::unordered_map<const float*, WPlanes> g_wplanes;
-static std::mutex g_tc_mu;
+static std::mutex g_w_mu;
 static Arena g_scratch;          // activation planes of the GEMM in flight (stream order serialises reuse)
-static const float kActScale = 16.0f;
 
 static int split_launch(const float* a, int lda, int M, int K, int Kp, float scale, int relu, __half* planes, cudaStream_t s) {
   const long long n = (long long)M * (Kp >> 2);
@@ -398,9 +423,12 @@ static int split_launch(const float* a, int lda, int M, int K, int Kp, float sca
 // Weight planes are made once per weight matrix (first use): per-tensor power-of-two scale so that max|w| lands in
 // [2^12, 2^13), then the fp16 hi/lo split.  This synchronises; it happens during warm-up, never in steady state.
 static int get_wplanes(const GemmP& p, cudaStream_t s, WPlanes** out) {
-  std::lock_guard<std::mutex> lk(g_tc_mu);
+  std::lock_guard<std::mutex> lk(g_w_mu);
   auto it = g_wplanes.find(p.W);
   if (it != g_wplanes.end() && it->second.N == p.N) { *out = &it->second; return ST_OK; }
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  if (cap != cudaStreamCaptureStatusNone) { set_error("weight planes must exist before graph capture"); return ST_ESTATE; }
   WPlanes w;
   w.N = p.N;
   w.Kp = (p.K + TC_BK - 1) / TC_BK * TC_BK;
@@ -423,8 +451,6 @@ static int get_wplanes(const GemmP& p, cudaStream_t s, WPlanes** out) {
   const size_t bytes = (size_t)2 * p.N * w.Kp * sizeof(__half);
   if (cudaMalloc(&w.planes, bytes) != cudaSuccess) { set_error("cudaMalloc(weight planes %zu B) failed", bytes); return ST_ENOMEM; }
   ST_TRY(split_launch(p.W, p.ldw, p.N, p.K, w.Kp, scale, 0, w.planes, s));
-  ST_TRY(make_map_3d(&w.map64, w.planes, p.N, w.Kp, 64));
-  ST_TRY(make_map_3d(&w.map128, w.planes, p.N, w.Kp, 128));
   ST_CHECK_CUDA(cudaStreamSynchronize(s));
   g_wplanes[p.W] = w;
   *out = &g_wplanes[p.W];
@@ -432,13 +458,19 @@ static int get_wplanes(const GemmP& p, cudaStream_t s, WPlanes** out) {
 }
 
 void tc_forget_weights(const float* W) {
-  std::lock_guard<std::mutex> lk(g_tc_mu);
+  std::lock_guard<std::mutex> lk(g_w_mu);
   auto it = g_wplanes.find(W);
-  if (it != g_wplanes.end()) { cudaFree(it->second.planes); g_wplanes.erase(it); }
+  if (it == g_wplanes.end()) return;
+  {
+    std::lock_guard<std::mutex> lk2(g_tc_mu);
+    for (auto m = g_maps.begin(); m != g_maps.end();) m = (m->first.base == it->second.planes) ? g_maps.erase(m) : std::next(m);
+  }
+  cudaFree(it->second.planes);
+  g_wplanes.erase(it);
 }
 
 bool tc_supported(const GemmP& p) {
-  if (!p.out || p.out_scale != 1.0f || p.M < 128 || p.N < 16) return false;
+  if ((!p.out && !p.o_planes) || p.out_scale != 1.0f || p.M < 128 || p.N < 16) return false;
   if (p.stride != 1 || p.ups) return false;
   const bool plain = (p.Lout == p.M && p.Lin == p.M && p.C == p.K && p.pad == 0);
   if (plain) return (p.K % TC_BK) == 0;
@@ -468,31 +500,43 @@ int gemm_tc(const GemmP& p, cudaStream_t s) {
   ST_TRY(get_wplanes(p, s, &w));
   const bool plain = (p.Lout == p.M && p.C == p.K);
   const int Ka = plain ? p.K : p.C;                       // columns of the activation planes
-  const int rows = plain ? p.M : p.M;                     // conv: clips * T rows, same count
-  // activation planes (scratch, reused in stream order)
-  {
-    std::lock_guard<std::mutex> lk(g_tc_mu);
+  const int rows = p.M;                                   // conv: clips * T rows
+  const __half* planes = p.a_planes;
+  long long pstride = p.a_plane_stride;
+  if (!planes) {
+    // operand still fp32: split it into the scratch planes first (stream order serialises reuse of the scratch)
     const size_t need = (size_t)2 * rows * Ka * sizeof(__half) + 1024;
-    if (need > g_scratch.cap) ST_TRY(g_scratch.reserve(need * 2));
+    if (need > g_scratch.cap) {
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(s, &cap);
+      if (cap != cudaStreamCaptureStatusNone) { set_error("split scratch must be sized before graph capture"); return ST_ESTATE; }
+      ST_TRY(g_scratch.reserve(need * 2));
+    }
+    __half* sp = reinterpret_cast<__half*>(g_scratch.base);
+    ST_TRY(split_launch(p.A, p.lda, rows, Ka, Ka, kActScale, p.a_relu, sp, s));
+    planes = sp;
+    pstride = (long long)rows * Ka;
   }
-  __half* planes = reinterpret_cast<__half*>(g_scratch.base);
-  ST_TRY(split_launch(p.A, p.lda, rows, Ka, Ka, kActScale, p.a_relu, planes, s));
-  CUtensorMap tmA;
+  const CUtensorMap* tmA = nullptr;
+  const CUtensorMap* tmW = nullptr;
   TcEpi ep;
   ep.a_rows_per_clip = 0; ep.taps = 1; ep.dil = 1; ep.kb_per_tap = 0;
   if (plain) {
-    ST_TRY(make_map_3d(&tmA, planes, rows, Ka, TC_BM));
+    ST_TRY(get_map_3d(&tmA, planes, pstride, rows, Ka, TC_BM));
   } else {
-    ST_TRY(make_map_4d(&tmA, planes, p.M / p.Lout, p.Lout, p.C));
+    ST_TRY(get_map_4d(&tmA, planes, pstride, p.M / p.Lout, p.Lout, p.C));
     ep.a_rows_per_clip = p.Lout; ep.taps = p.K / p.C; ep.dil = p.dil; ep.kb_per_tap = p.C / TC_BK;
   }
-  ep.out = p.out; ep.bias = p.bias; ep.res = p.res; ep.planes = nullptr; ep.plane_stride = 0; ep.ld_planes = 0; ep.planes_scale = 1.f;
-  ep.planes_relu = 0; ep.ldo = p.ldo; ep.ldr = p.ldr; ep.res_mode = p.res ? p.res_mode : RES_NONE; ep.res_div = p.res_div; ep.act = p.act;
+  const int BN = p.N <= 512 ? 64 : 128;
+  ST_TRY(get_map_3d(&tmW, w->planes, (long long)p.N * w->Kp, p.N, w->Kp, BN));
+  ep.out = p.out; ep.bias = p.bias; ep.res = p.res;
+  ep.planes = p.o_planes; ep.plane_stride = p.o_plane_stride; ep.ld_planes = p.o_planes_ld; ep.planes_scale = kActScale;
+  ep.planes_relu = p.o_planes_relu; ep.ldo = p.ldo; ep.ldr = p.ldr; ep.res_mode = p.res ? p.res_mode : RES_NONE; ep.res_div = p.res_div; ep.act = p.act;
   ep.scale = w->inv_scale / kActScale;
   ep.M = p.M; ep.N = p.N;
   const int num_kb = w->Kp / TC_BK;
-  if (p.N <= 512) return launch_tc<64, 4>(tmA, w->map64, ep, num_kb, s);
-  return launch_tc<128, 3>(tmA, w->map128, ep, num_kb, s);
+  if (BN == 64) return launch_tc<64, 4>(*tmA, *tmW, ep, num_kb, s);
+  return launch_tc<128, 3>(*tmA, *tmW, ep, num_kb, s);
 }
 
 }  // namespace st

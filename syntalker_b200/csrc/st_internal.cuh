@@ -1,6 +1,7 @@
 // Internal declarations shared by the translation units of libsyntalker_b200.so (not installed).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -69,6 +70,22 @@ struct GemmP {
   int lda = 0;
   int a_relu = 0, act = ACT_NONE, res_mode = RES_NONE, ldr = 0, res_div = 1, ldo = 0;
   float out_scale = 1.0f;        // applied to the accumulator before bias (used by nothing exact-critical)
+  // tcgen05 engine only: operand already split into fp16 hi/lo planes [2][rows][K] (value * kActScale), and / or
+  // the result wanted as such planes for the next GEMM.  `out` may then be null.
+  const __half* a_planes = nullptr;
+  long long a_plane_stride = 0;   // elements between the hi and the lo plane
+  __half* o_planes = nullptr;
+  long long o_plane_stride = 0;
+  int o_planes_ld = 0, o_planes_relu = 0;
+};
+
+constexpr float kActScale = 16.0f;   // activations are stored in fp16 planes as (v * 16): |v| < 4e3 representable, lo normal for |v| > 2^-6
+
+// state of the sampling loop that lives on the device so that ONE captured step graph serves every step
+struct LoopState {
+  int k;                 // current step index, S-1 .. 0
+  int S;
+  const float* tape;     // [S,B,1536,1,32] or null
 };
 
 GemmP linear(const float* A, int M, int K, const float* W, const float* bias, float* out, int N);
@@ -77,17 +94,24 @@ int gemm_simt(const GemmP& p, cudaStream_t s);
 int gemm(const GemmP& p, cudaStream_t s);   // dispatches on the engine (TC falls back to SIMT for shapes it does not take)
 bool tc_supported(const GemmP& p);
 int gemm_tc(const GemmP& p, cudaStream_t s);
+bool profiling();
 int profile_begin();
 int profile_end(double* ms, double* flops, int64_t* n);
 
 // ---- other kernels --------------------------------------------------------------------------------------
-int layernorm512(const float* x, const float* gamma, const float* beta, float* y, int rows, cudaStream_t s);
-int attention32(const float* qkv, float* out, int nseq, cudaStream_t s);   // qkv [nseq*32,1536] -> out [nseq*32,512]
+// y (fp32) and / or planes (fp16 hi/lo of y * kActScale, [2][rows][512]) may be null
+int layernorm512(const float* x, const float* gamma, const float* beta, float* y, __half* planes, int rows, cudaStream_t s);
+int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStream_t s);   // qkv [nseq*32,1536] -> out [nseq*32,512]
+void tc_forget_weights(const float* W);
+int advance_loop(LoopState* ls, cudaStream_t s);
+int init_loop(LoopState* ls, int S, const float* tape, cudaStream_t s);
 struct TokensInP {
   const float* z;            // [B*32,512] = x_t . Wx^T
   const float* vt_table;     // [1000,512]
   const int64_t* t_dev;      // [B] or null
-  int t_scalar;              // used when t_dev == null
+  int t_scalar;              // used when t_dev == null and ls == null
+  const LoopState* ls;       // sampling loop: t = t_model_dev[ls->k]
+  const int32_t* t_model_dev;
   const float* cst[ST_MAX_EVALS];   // per eval: [B*32,512] or [32,512] (cst_bcast) conditioning constant
   int cst_bcast[ST_MAX_EVALS];
   const float* g2;           // [B,512] seed term (always added)
@@ -112,6 +136,8 @@ struct StepP {
   int part_ua[3];                // eval index of the part's prompt evaluation or -1
   int mode;                  // ST_MODE_DDPM / ST_MODE_DDIM / -1 = write combined model output only
   float c[ST_COEF_STRIDE];
+  const LoopState* ls;       // when set: coefficients = coef_dev[ls->k], eps = ls->tape + (S-1-k) * B*1536*32
+  const float* coef_dev;
 };
 int step_update(const StepP& p, cudaStream_t s);
 

@@ -206,8 +206,27 @@ int gemm_simt(const GemmP& p, cudaStream_t s) {
 // =========================================================================================================
 // 2. LayerNorm over 512 channels, eps 1e-5, affine (transformer.py:172,185).  One warp per row.
 // =========================================================================================================
+__device__ __forceinline__ void split16(float v, __half& hi, __half& lo) {
+  v = fminf(fmaxf(v * kActScale, -65000.0f), 65000.0f);
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+// store 4 consecutive values as fp16 hi/lo planes (8-byte stores)
+__device__ __forceinline__ void store_planes4(__half* hi_ptr, long long plane_stride, float a, float b, float c, float d) {
+  __half h[4], l[4];
+  split16(a, h[0], l[0]); split16(b, h[1], l[1]); split16(c, h[2], l[2]); split16(d, h[3], l[3]);
+  __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+  __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+  uint2 hv, lv;
+  hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+  lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+  *reinterpret_cast<uint2*>(hi_ptr) = hv;
+  *reinterpret_cast<uint2*>(hi_ptr + plane_stride) = lv;
+}
+
 __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restrict__ x, const float* __restrict__ g,
-                                                           const float* __restrict__ b, float* __restrict__ y, int rows) {
+                                                           const float* __restrict__ b, float* __restrict__ y,
+                                                           __half* __restrict__ planes, int rows) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -231,7 +250,7 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = 1.0f / sqrtf(q * (1.0f / 512.0f) + 1e-5f);
-  float4* yr = reinterpret_cast<float4*>(y + (long long)row * 512);
+  float4* yr = y ? reinterpret_cast<float4*>(y + (long long)row * 512) : nullptr;
   const float4* g4 = reinterpret_cast<const float4*>(g);
   const float4* b4 = reinterpret_cast<const float4*>(b);
 #pragma unroll
@@ -242,12 +261,13 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
     o.y = (v[i].y - mean) * rstd * gg.y + bb.y;
     o.z = (v[i].z - mean) * rstd * gg.z + bb.z;
     o.w = (v[i].w - mean) * rstd * gg.w + bb.w;
-    yr[lane + 32 * i] = o;
+    if (yr) yr[lane + 32 * i] = o;
+    if (planes) store_planes4(planes + (long long)row * 512 + (lane + 32 * i) * 4, (long long)rows * 512, o.x, o.y, o.z, o.w);
   }
 }
 
-int layernorm512(const float* x, const float* gamma, const float* beta, float* y, int rows, cudaStream_t s) {
-  layernorm512_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, gamma, beta, y, rows);
+int layernorm512(const float* x, const float* gamma, const float* beta, float* y, __half* planes, int rows, cudaStream_t s) {
+  layernorm512_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, gamma, beta, y, planes, rows);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -258,7 +278,8 @@ int layernorm512(const float* x, const float* gamma, const float* beta, float* y
 // =========================================================================================================
 constexpr int ATT_LD = 132;   // padded row stride (floats) -> conflict-free float4 reads
 
-__global__ void __launch_bounds__(256) attention32_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) attention32_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                          __half* __restrict__ planes, long long plane_stride) {
   extern __shared__ __align__(16) float att_smem[];
   float (*q)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem);
   float (*k)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 32 * ATT_LD);
@@ -318,19 +339,22 @@ __global__ void __launch_bounds__(256) attention32_kernel(const float* __restric
       o4[dd].w = fmaf(pj, vv.w, o4[dd].w);
     }
   }
-  float* orow = out + ((long long)seq * 32 + i) * 512 + head * 128;
+  const long long off = ((long long)seq * 32 + i) * 512 + head * 128;
 #pragma unroll
-  for (int dd = 0; dd < 4; ++dd) *reinterpret_cast<float4*>(orow + u * 4 + 32 * dd) = o4[dd];
+  for (int dd = 0; dd < 4; ++dd) {
+    if (out) *reinterpret_cast<float4*>(out + off + u * 4 + 32 * dd) = o4[dd];
+    if (planes) store_planes4(planes + off + u * 4 + 32 * dd, plane_stride, o4[dd].x, o4[dd].y, o4[dd].z, o4[dd].w);
+  }
 }
 
-int attention32(const float* qkv, float* out, int nseq, cudaStream_t s) {
+int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStream_t s) {
   constexpr int smem = (96 * ATT_LD + 32 * 33) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     ST_CHECK_CUDA(cudaFuncSetAttribute(attention32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  attention32_kernel<<<dim3(nseq, 4), 256, smem, s>>>(qkv, out);
+  attention32_kernel<<<dim3(nseq, 4), 256, smem, s>>>(qkv, out, planes, (long long)nseq * 32 * 512);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -352,7 +376,7 @@ __global__ void __launch_bounds__(256) tokens_in_kernel(TokensInP p) {
   const int grp = pj >> 5, j = pj & 31;
   const int c1 = grp * 64 + j, c2 = c1 + 32;
   const int b = row >> 5, tau = row & 31;
-  const int t = p.t_dev ? (int)p.t_dev[b] : p.t_scalar;
+  const int t = p.ls ? p.t_model_dev[p.ls->k] : (p.t_dev ? (int)p.t_dev[b] : p.t_scalar);
   const float* vt = p.vt_table + (long long)t * 512;
   const float* cst = p.cst[e] + (long long)(p.cst_bcast[e] ? tau : row) * 512;
   const float* g2 = p.g2 + (long long)b * 512;
@@ -422,30 +446,54 @@ __global__ void __launch_bounds__(256) step_update_kernel(StepP p) {
   }
   float4* xs4 = reinterpret_cast<float4*>(p.xs + e0);
   if (p.mode < 0) { *xs4 = make_float4(x0[0], x0[1], x0[2], x0[3]); return; }
+  float cf[ST_COEF_STRIDE];
+  const float* eps_ptr = p.eps;
+  if (p.ls) {
+    const int k = p.ls->k;
+#pragma unroll
+    for (int q = 0; q < ST_COEF_STRIDE; ++q) cf[q] = p.coef_dev[k * ST_COEF_STRIDE + q];
+    eps_ptr = p.ls->tape ? p.ls->tape + (long long)(p.ls->S - 1 - k) * p.B * 1536 * 32 : nullptr;
+  } else {
+#pragma unroll
+    for (int q = 0; q < ST_COEF_STRIDE; ++q) cf[q] = p.c[q];
+  }
   const float4 xv4 = *xs4;
   const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
   float nz[4] = {0.f, 0.f, 0.f, 0.f};
-  const float sigma = p.mode == ST_MODE_DDPM ? p.c[2] : p.c[4];
-  if (p.eps && sigma != 0.f) {
+  const float sigma = p.mode == ST_MODE_DDPM ? cf[2] : cf[4];
+  if (eps_ptr && sigma != 0.f) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) nz[q] = p.eps[((long long)b * 1536 + col + q) * 32 + tau];   // caller layout [B,1536,1,32]
+    for (int q = 0; q < 4; ++q) nz[q] = eps_ptr[((long long)b * 1536 + col + q) * 32 + tau];   // caller layout [B,1536,1,32]
   }
   float o[4];
   if (p.mode == ST_MODE_DDPM) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float mean = __fadd_rn(__fmul_rn(p.c[0], x0[q]), __fmul_rn(p.c[1], xv[q]));
+      const float mean = __fadd_rn(__fmul_rn(cf[0], x0[q]), __fmul_rn(cf[1], xv[q]));
       o[q] = sigma != 0.f ? __fadd_rn(mean, __fmul_rn(sigma, nz[q])) : mean;
     }
   } else {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(p.c[0], xv[q]), x0[q]), p.c[1]);
-      const float mean = __fadd_rn(__fmul_rn(x0[q], p.c[2]), __fmul_rn(p.c[3], eps));
+      const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(cf[0], xv[q]), x0[q]), cf[1]);
+      const float mean = __fadd_rn(__fmul_rn(x0[q], cf[2]), __fmul_rn(cf[3], eps));
       o[q] = sigma != 0.f ? __fadd_rn(mean, __fmul_rn(sigma, nz[q])) : mean;
     }
   }
   *xs4 = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void advance_loop_kernel(LoopState* ls) { ls->k -= 1; }
+__global__ void init_loop_kernel(LoopState* ls, int S, const float* tape) { ls->k = S - 1; ls->S = S; ls->tape = tape; }
+int advance_loop(LoopState* ls, cudaStream_t s) {
+  advance_loop_kernel<<<1, 1, 0, s>>>(ls);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+int init_loop(LoopState* ls, int S, const float* tape, cudaStream_t s) {
+  init_loop_kernel<<<1, 1, 0, s>>>(ls, S, tape);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
 }
 
 int step_update(const StepP& p, cudaStream_t s) {

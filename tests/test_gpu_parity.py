@@ -81,7 +81,9 @@ def test_gemm_engine_vs_fp64(M, N, K, engine):
     Ad, Wd, bd = A.cuda(), Wt.cuda(), b.cuda()
     _lib.check(_lib.lib().st_selftest_gemm(M, N, K, 1 if engine == "tc" else 0, Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), out.data_ptr(), _lib.stream_ptr()))
     ref = A.double() @ Wt.double().t() + b.double()
-    assert maxabs(out, ref) < 2e-5
+    err = maxabs(out, ref)
+    print(f"gemm {engine} M={M} N={N} K={K}: max-abs err vs fp64 {err:.2e}")
+    assert err < (3e-5 if engine == "tc" else 2e-5)
 
 
 # ---- 1. single denoiser evaluation ------------------------------------------------------------------------
