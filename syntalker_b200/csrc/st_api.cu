@@ -148,6 +148,8 @@ struct st_model {
   LoopState* loop = nullptr;
   int32_t* t_model_dev = nullptr;
   float* coef_dev = nullptr;
+  cudaStream_t loop_stream = nullptr;       // graphs cannot be captured on the legacy default stream
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   std::map<std::string, cudaGraphExec_t> graphs;
   std::map<std::string, int64_t> graph_nodes;
   std::map<std::string, int> warmed;
@@ -244,6 +246,9 @@ extern "C" void st_model_destroy(st_model* m) {
   if (!m) return;
   cudaDeviceSynchronize();
   for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+  if (m->loop_stream) cudaStreamDestroy(m->loop_stream);
+  if (m->ev_in) cudaEventDestroy(m->ev_in);
+  if (m->ev_out) cudaEventDestroy(m->ev_out);
   m->w.release(); m->ws.release(); m->io.release(); m->stage.release();
   if (m->cst_null) cudaFree(m->cst_null);
   delete m;
@@ -573,22 +578,33 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
   ST_TRY(init_loop(m->loop, sc->S, noise_tape, s));
   ST_TRY(transpose_to_tokens(x_init, m->xs, B, 1536, 32, 1.0f, s));
   // The first call with a given plan runs eagerly (it creates weight planes, tensor maps, scratch); the second
-  // captures one step into a CUDA graph; from then on every step is one graph launch.
+  // captures one step into a CUDA graph; from then on every step is one graph launch.  Capture and replay run
+  // on the model's own stream (the caller's may be the legacy default stream, which cannot capture), fenced
+  // against the caller's stream with events on both sides.
   const std::string key = plan_key(pl, B, sc->mode);
   cudaGraphExec_t exec = nullptr;
   const bool graphs_ok = g_use_graphs && !st::profiling();
-  if (graphs_ok) {
+  cudaStream_t ls = s;
+  if (graphs_ok && m->warmed[key] >= 1) {
+    if (!m->loop_stream) {
+      ST_CHECK_CUDA(cudaStreamCreateWithFlags(&m->loop_stream, cudaStreamNonBlocking));
+      ST_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_in, cudaEventDisableTiming));
+      ST_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_out, cudaEventDisableTiming));
+    }
+    ls = m->loop_stream;
+    ST_CHECK_CUDA(cudaEventRecord(m->ev_in, s));
+    ST_CHECK_CUDA(cudaStreamWaitEvent(ls, m->ev_in, 0));
     auto it = m->graphs.find(key);
     if (it != m->graphs.end()) exec = it->second;
-    else if (m->warmed[key] >= 1) {
+    else {
       cudaGraph_t graph = nullptr;
       const int64_t l0 = g_launches;
-      ST_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-      const int r = one_step(m, pl, sp, B, s);
+      ST_CHECK_CUDA(cudaStreamBeginCapture(ls, cudaStreamCaptureModeRelaxed));
+      const int r = one_step(m, pl, sp, B, ls);
       m->graph_nodes[key] = g_launches - l0;     // kernels per replay; capturing itself executed nothing
       g_launches = l0;
-      cudaError_t ce = cudaStreamEndCapture(s, &graph);
-      if (r != ST_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+      cudaError_t ce = cudaStreamEndCapture(ls, &graph);
+      if (r != ST_OK) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return r; }
       ST_CHECK_CUDA(ce);
       ST_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
       cudaGraphDestroy(graph);
@@ -596,8 +612,12 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
     }
   }
   for (int k = sc->S - 1; k >= 0; --k) {
-    if (exec) { ST_CHECK_CUDA(cudaGraphLaunch(exec, s)); g_launches += m->graph_nodes[key]; }
-    else ST_TRY(one_step(m, pl, sp, B, s));
+    if (exec) { ST_CHECK_CUDA(cudaGraphLaunch(exec, ls)); g_launches += m->graph_nodes[key]; }
+    else ST_TRY(one_step(m, pl, sp, B, ls));
+  }
+  if (ls != s) {
+    ST_CHECK_CUDA(cudaEventRecord(m->ev_out, ls));
+    ST_CHECK_CUDA(cudaStreamWaitEvent(s, m->ev_out, 0));
   }
   m->warmed[key] += 1;
   ST_TRY(transpose_from_tokens(m->xs, x_out, B, 1536, 32, s));
@@ -825,6 +845,10 @@ extern "C" int st_selftest_gemm(int M, int N, int K, int engine, const float* A,
                                 void* stream) {
   ST_REQUIRE(A && W && out && M > 0 && N > 0 && K > 0, "st_selftest_gemm: null argument");
   GemmP p = linear(A, M, K, W, bias, out, N);
+  if (engine == 2) {                       // tcgen05, weight planes kept from the previous call (caller keeps W unchanged)
+    if (!tc_supported(p)) { set_error("st_selftest_gemm: shape not supported by the tcgen05 engine"); return ST_EUNSUPPORTED; }
+    return gemm_tc(p, (cudaStream_t)stream);
+  }
   if (engine == ST_ENGINE_TC) {
     if (!tc_supported(p)) { set_error("st_selftest_gemm: shape M=%d N=%d K=%d not supported by the tcgen05 engine", M, N, K); return ST_EUNSUPPORTED; }
     tc_forget_weights(W);                 // the caller may reuse the address with new contents

@@ -20,6 +20,7 @@ extern thread_local int64_t g_launches;
   do {                                                                                           \
     cudaError_t _e = (expr);                                                                     \
     if (_e != cudaSuccess) {                                                                     \
+      (void)cudaGetLastError();                                                                  \
       st::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));       \
       return ST_ECUDA;                                                                           \
     }                                                                                            \
@@ -28,7 +29,7 @@ extern thread_local int64_t g_launches;
 #define ST_CHECK_LAUNCH()                                                                        \
   do {                                                                                           \
     st::g_launches++;                                                                            \
-    cudaError_t _e = cudaPeekAtLastError();                                                      \
+    cudaError_t _e = cudaGetLastError();                                                         \
     if (_e != cudaSuccess) {                                                                     \
       st::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e));   \
       return ST_ECUDA;                                                                           \
