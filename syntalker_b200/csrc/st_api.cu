@@ -181,6 +181,8 @@ extern "C" int st_set_engine(int engine) {
   return ST_OK;
 }
 extern "C" int st_get_engine(void) { return g_engine; }
+namespace st { extern long long* g_tc_dbg; }
+extern "C" int st_debug_timeline(long long* dev_buf) { st::g_tc_dbg = dev_buf; return ST_OK; }
 extern "C" int st_set_graphs(int on) { g_use_graphs = on != 0; return ST_OK; }
 extern "C" int st_profile_begin(void) { return st::profile_begin(); }
 extern "C" int st_profile_end(double* ms_total, double* flops_total, int64_t* launches) { return st::profile_end(ms_total, flops_total, launches); }

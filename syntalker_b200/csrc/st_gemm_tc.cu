@@ -135,6 +135,7 @@ struct TcEpi {
   int M, N;
   int a_rows_per_clip;   // conv mode (4-D A map): T; 0 = plain 2-D GEMM
   int taps, dil, kb_per_tap;
+  long long* dbg;        // optional timeline of CTA (0,0): clock64 stamps (debug / profiling only)
 };
 
 __device__ __forceinline__ float tc_act(float v, int act) {
@@ -166,7 +167,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;     // n fastest: CTAs that share an A tile run together
+  long long* dbg = (ep.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? ep.dbg : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -185,6 +188,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -204,6 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_4d(st, &tmA, &full_bar[s], cb * TC_BK, (j - ep.taps / 2) * ep.dil, m0 / ep.a_rows_per_clip, 0);
         }
         tma_load_3d(st + 2 * TC_A_PLANE, &tmW, &full_bar[s], kb * TC_BK, n0, 0);
+        if (dbg && kb < 16) dbg[8 + kb] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -215,6 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (dbg && kb < 16) dbg[24 + kb] = clock64();
         const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t a_lo = a_hi + TC_A_PLANE;
         const uint32_t w_hi = a_hi + 2 * TC_A_PLANE;
@@ -232,70 +238,101 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(&empty_bar[s]);     // slot reusable once these MMAs have read it
       }
       umma_commit(acc_bar);             // accumulator complete
+      if (dbg) dbg[2] = clock64();
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
+    // Phase 1: accumulators (main + correction) -> registers -> this warp's 32 rows of a padded fp32 tile in the
+    // now idle stage memory (lane = row, so direct global stores would hit 32 different lines per instruction:
+    // measured 7000 cycles per 32 columns).  Phase 2: the same warp walks its rows with lanes along the columns,
+    // so bias / residual loads and fp32 / fp16-plane stores are full-line coalesced.
     const int lg = warp & 3;
-    const int row = m0 + lg * 32 + lane;
-    const bool row_ok = row < ep.M;
     mbar_wait(acc_bar, 0);
     tc_fence_after();
-    const float* rrow = (ep.res && row_ok) ? ep.res + (long long)(row / ep.res_div) * ep.ldr : nullptr;
-    float* orow = (ep.out && row_ok) ? ep.out + (long long)row * ep.ldo : nullptr;
-    __half* prow = (ep.planes && row_ok) ? ep.planes + (long long)row * ep.ld_planes : nullptr;
+    if (dbg && threadIdx.x == 64) dbg[3] = clock64();
+    constexpr int LDT = BN + 4;
+    float* tile = reinterpret_cast<float*>(smem) + (size_t)(lg * 32) * LDT;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32], vc[32];
       tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + c * 32, v);
       tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + BN + c * 32, vc);
       tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (!row_ok || nb >= ep.N) continue;
-      float x[32];
-      const bool full = nb + 32 <= ep.N;
+      float* trow = tile + lane * LDT + c * 32;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float t = (__uint_as_float(v[j]) + __uint_as_float(vc[j])) * ep.scale;
-        if (full || nb + j < ep.N) {
-          if (ep.bias) t += __ldg(ep.bias + nb + j);
-          const float r = rrow ? rrow[nb + j] : 0.f;
-          if (ep.res_mode == RES_PRE) t += r;
-          t = tc_act(t, ep.act);
-          if (ep.res_mode == RES_POST) t += r;
-        }
-        x[j] = t;
+      for (int j = 0; j < 32; j += 4) {
+        float4 t;
+        t.x = (__uint_as_float(v[j]) + __uint_as_float(vc[j])) * ep.scale;
+        t.y = (__uint_as_float(v[j + 1]) + __uint_as_float(vc[j + 1])) * ep.scale;
+        t.z = (__uint_as_float(v[j + 2]) + __uint_as_float(vc[j + 2])) * ep.scale;
+        t.w = (__uint_as_float(v[j + 3]) + __uint_as_float(vc[j + 3])) * ep.scale;
+        *reinterpret_cast<float4*>(trow + j) = t;
       }
-      if (orow) {
-        if (full && (ep.ldo & 3) == 0) {
+    }
+    __syncwarp();
+    constexpr int LPR = BN / 4;            // lanes per row
+    constexpr int RPI = 32 / LPR;          // rows per warp instruction
+    const int cl = (lane % LPR) * 4;
+    const int n = n0 + cl;
+    const bool vec = (n + 3 < ep.N) && ((ep.ldo & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
+    float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ep.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + nb + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+      for (int q = 0; q < 4; ++q)
+        if (n + q < ep.N) bias4[q] = __ldg(ep.bias + n + q);
+    }
+#pragma unroll 4
+    for (int r0 = 0; r0 < 32; r0 += RPI) {
+      const int r = r0 + lane / LPR;
+      const int row = m0 + lg * 32 + r;
+      if (row >= ep.M || n >= ep.N) continue;
+      const float4 t4 = *reinterpret_cast<const float4*>(tile + r * LDT + cl);
+      float x[4] = {t4.x + bias4[0], t4.y + bias4[1], t4.z + bias4[2], t4.w + bias4[3]};
+      float rs[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ep.res) {
+        const float* rrow = ep.res + (long long)(row / ep.res_div) * ep.ldr + n;
+        if (vec) { const float4 r4 = *reinterpret_cast<const float4*>(rrow); rs[0] = r4.x; rs[1] = r4.y; rs[2] = r4.z; rs[3] = r4.w; }
+        else { for (int q = 0; q < 4; ++q) if (n + q < ep.N) rs[q] = rrow[q]; }
+      }
+      if (ep.res_mode == RES_PRE) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
+      if (ep.act != ACT_NONE) { x[0] = tc_act(x[0], ep.act); x[1] = tc_act(x[1], ep.act); x[2] = tc_act(x[2], ep.act); x[3] = tc_act(x[3], ep.act); }
+      if (ep.res_mode == RES_POST) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
+      if (ep.out) {
+        float* orow = ep.out + (long long)row * ep.ldo + n;
+        if (vec) *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
+        else { for (int q = 0; q < 4; ++q) if (n + q < ep.N) orow[q] = x[q]; }
+      }
+      if (ep.planes) {
+        __half h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float a = x[q] * ep.planes_scale;
+          if (ep.planes_relu) a = fmaxf(a, 0.f);
+          split_f16(a, h[q], l[q]);
+        }
+        __half* prow = ep.planes + (long long)row * ep.ld_planes + n;
+        if (n + 3 < ep.N && (ep.ld_planes & 3) == 0) {
+          __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+          __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+          uint2 hv, lv;
+          hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+          lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+          *reinterpret_cast<uint2*>(prow) = hv;
+          *reinterpret_cast<uint2*>(prow + ep.plane_stride) = lv;
         } else {
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < ep.N) orow[nb + j] = x[j];
-        }
-      }
-      if (prow) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          if (nb + j < ep.N) {
-            float a = x[j] * ep.planes_scale, b = x[j + 1] * ep.planes_scale;
-            if (ep.planes_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            __half ah, al, bh, bl;
-            split_f16(a, ah, al);
-            split_f16(b, bh, bl);
-            *reinterpret_cast<__half2*>(prow + nb + j) = __halves2half2(ah, bh);
-            *reinterpret_cast<__half2*>(prow + ep.plane_stride + nb + j) = __halves2half2(al, bl);
-          }
+          for (int q = 0; q < 4; ++q) if (n + q < ep.N) { prow[q] = h[q]; prow[ep.plane_stride + q] = l[q]; }
         }
       }
     }
     tc_fence_before();
+    if (dbg && threadIdx.x == 64) dbg[4] = clock64();
   }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (dbg && threadIdx.x == 0) dbg[5] = clock64();
 }
 
 // fp32 [M,K] (row stride lda) -> fp16 planes [2][M][Kp], value * scale split into hi + lo
@@ -411,6 +448,7 @@ struct WPlanes {
 };
 static std::unordered_map<const float*, WPlanes> g_wplanes;
 static std::mutex g_w_mu;
+long long* g_tc_dbg = nullptr;  // set by st_debug_timeline
 static Arena g_scratch;          // activation planes of the GEMM in flight (stream order serialises reuse)
 
 static int split_launch(const float* a, int lda, int M, int K, int Kp, float scale, int relu, __half* planes, cudaStream_t s) {
@@ -488,7 +526,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcEpi
     ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  dim3 grid((ep.M + TC_BM - 1) / TC_BM, (ep.N + BN - 1) / BN);
+  dim3 grid((ep.N + BN - 1) / BN, (ep.M + TC_BM - 1) / TC_BM);
   gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, ep, num_kb);
   ST_CHECK_LAUNCH();
   return ST_OK;
@@ -534,6 +572,7 @@ int gemm_tc(const GemmP& p, cudaStream_t s) {
   ep.planes_relu = p.o_planes_relu; ep.ldo = p.ldo; ep.ldr = p.ldr; ep.res_mode = p.res ? p.res_mode : RES_NONE; ep.res_div = p.res_div; ep.act = p.act;
   ep.scale = w->inv_scale / kActScale;
   ep.M = p.M; ep.N = p.N;
+  ep.dbg = g_tc_dbg;
   const int num_kb = w->Kp / TC_BK;
   if (BN == 64) return launch_tc<64, 4>(*tmA, *tmW, ep, num_kb, s);
   return launch_tc<128, 3>(*tmA, *tmW, ep, num_kb, s);
