@@ -201,10 +201,10 @@ int st_generate_330_host(st_model* m, const st_schedule* s, const st_guidance* g
                          float* rec_trans_host, float* sample_host /* nullable [B,1536,1,32] */, void* stream);
 
 /* ---- GEMM-engine profiling (bench.py roofline leg) -------------------------------------------------
- * Between begin and end every GEMM-engine launch is bracketed by CUDA events on its stream.  end()
- * synchronises and returns the summed device time (ms), the summed algorithmic FLOPs (2*M*N*K per
- * launch, K counting every tap of a conv) and the launch count.  Slows the run slightly; never on
- * during timed throughput runs. */
+ * Between begin and end every GEMM-engine launch is recorded.  end() replays exactly that launch sequence as
+ * one captured CUDA graph bracketed by two CUDA events on its stream and returns the device time of the GEMM
+ * kernels alone (ms), their summed algorithmic FLOPs (2*M*N*K per launch, K counting every tap of a conv) and
+ * the launch count.  The sampler runs without its step graph while recording; never on in timed runs. */
 int st_profile_begin(void);
 int st_profile_end(double* ms_total, double* flops_total, int64_t* launches);
 

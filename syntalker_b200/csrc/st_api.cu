@@ -64,30 +64,31 @@ void Weights::release() {
   dev.clear(); numel.clear();
 }
 
+// ---- GEMM-engine profiling -----------------------------------------------------------------------------
+// Between begin and end every GEMM-engine launch is recorded (its full descriptor; all buffers it names are
+// workspace that outlives the step).  end() replays exactly that launch sequence as ONE captured CUDA graph
+// between two events, so the measured time is device time of the GEMM kernels alone, not host launch latency
+// (events around individual eager launches of 5 us kernels mostly measure the host).
 static bool g_prof = false;
-static std::vector<cudaEvent_t> g_prof_ev;
+static std::vector<GemmP> g_prof_list;
 static double g_prof_flops = 0.0;
 
+static int gemm_dispatch(const GemmP& p, cudaStream_t s) {
+  return (g_engine == ST_ENGINE_TC && tc_supported(p)) ? gemm_tc(p, s) : gemm_simt(p, s);
+}
+
 int gemm(const GemmP& p, cudaStream_t s) {
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof) {
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, s);
-  }
-  const int r = (g_engine == ST_ENGINE_TC && tc_supported(p)) ? gemm_tc(p, s) : gemm_simt(p, s);
-  if (g_prof) {
-    cudaEventRecord(e1, s);
-    g_prof_ev.push_back(e0); g_prof_ev.push_back(e1);
+    g_prof_list.push_back(p);
     g_prof_flops += 2.0 * (double)p.M * (double)p.N * (double)p.K;
   }
-  return r;
+  return gemm_dispatch(p, s);
 }
 
 bool profiling() { return g_prof; }
 
 int profile_begin() {
-  for (auto e : g_prof_ev) cudaEventDestroy(e);
-  g_prof_ev.clear();
+  g_prof_list.clear();
   g_prof_flops = 0.0;
   g_prof = true;
   return ST_OK;
@@ -95,17 +96,37 @@ int profile_begin() {
 int profile_end(double* ms, double* flops, int64_t* n) {
   g_prof = false;
   ST_CHECK_CUDA(cudaDeviceSynchronize());
-  double tot = 0.0;
-  for (size_t i = 0; i + 1 < g_prof_ev.size(); i += 2) {
-    float t = 0.f;
-    ST_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof_ev[i], g_prof_ev[i + 1]));
-    tot += t;
-  }
-  if (ms) *ms = tot;
   if (flops) *flops = g_prof_flops;
-  if (n) *n = (int64_t)(g_prof_ev.size() / 2);
-  for (auto e : g_prof_ev) cudaEventDestroy(e);
-  g_prof_ev.clear();
+  if (n) *n = (int64_t)g_prof_list.size();
+  if (ms) *ms = 0.0;
+  if (g_prof_list.empty()) return ST_OK;
+  cudaStream_t s = nullptr;
+  ST_CHECK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  const int64_t l0 = g_launches;
+  ST_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+  int r = ST_OK;
+  for (const GemmP& p : g_prof_list) { r = gemm_dispatch(p, s); if (r != ST_OK) break; }
+  cudaError_t ce = cudaStreamEndCapture(s, &graph);
+  g_launches = l0;
+  if (r != ST_OK) { if (graph) cudaGraphDestroy(graph); cudaStreamDestroy(s); (void)cudaGetLastError(); return r; }
+  ST_CHECK_CUDA(ce);
+  ST_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  cudaEvent_t e0, e1;
+  ST_CHECK_CUDA(cudaEventCreate(&e0));
+  ST_CHECK_CUDA(cudaEventCreate(&e1));
+  ST_CHECK_CUDA(cudaGraphLaunch(exec, s));            // warm
+  ST_CHECK_CUDA(cudaEventRecord(e0, s));
+  ST_CHECK_CUDA(cudaGraphLaunch(exec, s));
+  ST_CHECK_CUDA(cudaEventRecord(e1, s));
+  ST_CHECK_CUDA(cudaStreamSynchronize(s));
+  float t = 0.f;
+  ST_CHECK_CUDA(cudaEventElapsedTime(&t, e0, e1));
+  if (ms) *ms = t;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); cudaStreamDestroy(s);
+  g_prof_list.clear();
   return ST_OK;
 }
 

@@ -118,7 +118,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) { return (1u
 // ---------------------------------------------------------------------------------------------------------
 // Kernel
 // ---------------------------------------------------------------------------------------------------------
-constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane group)
 constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;   // bytes of one A plane tile (128 rows x 128 B)
 
 struct TcEpi {
@@ -241,19 +241,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (dbg) dbg[2] = clock64();
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
-    // Phase 1: accumulators (main + correction) -> registers -> this warp's 32 rows of a padded fp32 tile in the
-    // now idle stage memory (lane = row, so direct global stores would hit 32 different lines per instruction:
-    // measured 7000 cycles per 32 columns).  Phase 2: the same warp walks its rows with lanes along the columns,
-    // so bias / residual loads and fp32 / fp16-plane stores are full-line coalesced.
+    // ===== epilogue: warps 2..9; TMEM lane group = warp % 4, two warps per group (column halves, then row halves) =====
+    // Phase 1: accumulators (main + correction) -> registers -> a padded fp32 tile in the now idle stage memory
+    // (lane = row, so direct global stores would hit 32 different lines per instruction: measured 7000 cycles per
+    // 32 columns).  Phase 2: lanes run along the columns, so bias / residual loads and fp32 / fp16-plane stores are
+    // full-line coalesced; four rows are in flight per iteration to hide latency with one warp per scheduler.
     const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;             // 0: warps 2..5, 1: warps 6..9
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     if (dbg && threadIdx.x == 64) dbg[3] = clock64();
     constexpr int LDT = BN + 4;
     float* tile = reinterpret_cast<float*>(smem) + (size_t)(lg * 32) * LDT;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    constexpr int CH = BN / 32;                   // 32-column chunks; each warp of the pair takes CH/2 of them
+#pragma unroll
+    for (int cc = 0; cc < CH / 2; ++cc) {
+      const int c = half * (CH / 2) + cc;
       uint32_t v[32], vc[32];
       tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + c * 32, v);
       tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + BN + c * 32, vc);
@@ -269,58 +272,75 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         *reinterpret_cast<float4*>(trow + j) = t;
       }
     }
-    __syncwarp();
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");     // the two warps of this lane group
     constexpr int LPR = BN / 4;            // lanes per row
     constexpr int RPI = 32 / LPR;          // rows per warp instruction
     const int cl = (lane % LPR) * 4;
     const int n = n0 + cl;
     const bool vec = (n + 3 < ep.N) && ((ep.ldo & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
+    const bool pvec = (n + 3 < ep.N) && ((ep.ld_planes & 3) == 0);
     float bias4[4] = {0.f, 0.f, 0.f, 0.f};
     if (ep.bias) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         if (n + q < ep.N) bias4[q] = __ldg(ep.bias + n + q);
     }
-#pragma unroll 4
-    for (int r0 = 0; r0 < 32; r0 += RPI) {
-      const int r = r0 + lane / LPR;
-      const int row = m0 + lg * 32 + r;
-      if (row >= ep.M || n >= ep.N) continue;
-      const float4 t4 = *reinterpret_cast<const float4*>(tile + r * LDT + cl);
-      float x[4] = {t4.x + bias4[0], t4.y + bias4[1], t4.z + bias4[2], t4.w + bias4[3]};
-      float rs[4] = {0.f, 0.f, 0.f, 0.f};
-      if (ep.res) {
-        const float* rrow = ep.res + (long long)(row / ep.res_div) * ep.ldr + n;
-        if (vec) { const float4 r4 = *reinterpret_cast<const float4*>(rrow); rs[0] = r4.x; rs[1] = r4.y; rs[2] = r4.z; rs[3] = r4.w; }
-        else { for (int q = 0; q < 4; ++q) if (n + q < ep.N) rs[q] = rrow[q]; }
-      }
-      if (ep.res_mode == RES_PRE) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
-      if (ep.act != ACT_NONE) { x[0] = tc_act(x[0], ep.act); x[1] = tc_act(x[1], ep.act); x[2] = tc_act(x[2], ep.act); x[3] = tc_act(x[3], ep.act); }
-      if (ep.res_mode == RES_POST) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
-      if (ep.out) {
-        float* orow = ep.out + (long long)row * ep.ldo + n;
-        if (vec) *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
-        else { for (int q = 0; q < 4; ++q) if (n + q < ep.N) orow[q] = x[q]; }
-      }
-      if (ep.planes) {
-        __half h[4], l[4];
+    constexpr int UN = 4;                  // row-instructions in flight
+#pragma unroll 1
+    for (int r0 = half * 16; r0 < half * 16 + 16; r0 += RPI * UN) {
+      float4 t4[UN], r4[UN];
+      int rowv[UN];
+      bool ok[UN];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float a = x[q] * ep.planes_scale;
-          if (ep.planes_relu) a = fmaxf(a, 0.f);
-          split_f16(a, h[q], l[q]);
+      for (int u = 0; u < UN; ++u) {
+        const int r = r0 + u * RPI + lane / LPR;
+        rowv[u] = m0 + lg * 32 + r;
+        ok[u] = rowv[u] < ep.M && n < ep.N;
+        t4[u] = *reinterpret_cast<const float4*>(tile + r * LDT + cl);
+        r4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.res && ok[u]) {
+          const float* rrow = ep.res + (long long)(rowv[u] / ep.res_div) * ep.ldr + n;
+          if (vec) r4[u] = *reinterpret_cast<const float4*>(rrow);
+          else {
+            float rs[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int q = 0; q < 4; ++q) if (n + q < ep.N) rs[q] = rrow[q];
+            r4[u] = make_float4(rs[0], rs[1], rs[2], rs[3]);
+          }
         }
-        __half* prow = ep.planes + (long long)row * ep.ld_planes + n;
-        if (n + 3 < ep.N && (ep.ld_planes & 3) == 0) {
-          __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
-          __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
-          uint2 hv, lv;
-          hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
-          lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
-          *reinterpret_cast<uint2*>(prow) = hv;
-          *reinterpret_cast<uint2*>(prow + ep.plane_stride) = lv;
-        } else {
-          for (int q = 0; q < 4; ++q) if (n + q < ep.N) { prow[q] = h[q]; prow[ep.plane_stride + q] = l[q]; }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (!ok[u]) continue;
+        float x[4] = {t4[u].x + bias4[0], t4[u].y + bias4[1], t4[u].z + bias4[2], t4[u].w + bias4[3]};
+        const float rs[4] = {r4[u].x, r4[u].y, r4[u].z, r4[u].w};
+        if (ep.res_mode == RES_PRE) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
+        if (ep.act != ACT_NONE) { x[0] = tc_act(x[0], ep.act); x[1] = tc_act(x[1], ep.act); x[2] = tc_act(x[2], ep.act); x[3] = tc_act(x[3], ep.act); }
+        if (ep.res_mode == RES_POST) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
+        if (ep.out) {
+          float* orow = ep.out + (long long)rowv[u] * ep.ldo + n;
+          if (vec) *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
+          else { for (int q = 0; q < 4; ++q) if (n + q < ep.N) orow[q] = x[q]; }
+        }
+        if (ep.planes) {
+          __half h[4], l[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float a = x[q] * ep.planes_scale;
+            if (ep.planes_relu) a = fmaxf(a, 0.f);
+            split_f16(a, h[q], l[q]);
+          }
+          __half* prow = ep.planes + (long long)rowv[u] * ep.ld_planes + n;
+          if (pvec) {
+            __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+            __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+            uint2 hv, lv;
+            hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+            lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+            *reinterpret_cast<uint2*>(prow) = hv;
+            *reinterpret_cast<uint2*>(prow + ep.plane_stride) = lv;
+          } else {
+            for (int q = 0; q < 4; ++q) if (n + q < ep.N) { prow[q] = h[q]; prow[ep.plane_stride + q] = l[q]; }
+          }
         }
       }
     }
