@@ -208,6 +208,10 @@ int st_generate_330_host(st_model* m, const st_schedule* s, const st_guidance* g
 int st_profile_begin(void);
 int st_profile_end(double* ms_total, double* flops_total, int64_t* launches);
 
+/* Steady-state device time (ms) of one GEMM launch: `reps` launches in one CUDA graph between two events. */
+int st_bench_gemm(int M, int N, int K, int engine, int reps, const float* A, const float* W, const float* bias, float* out,
+                  double* ms_per_launch);
+
 /* ---- self test (no oracle involved): split-fp16 tcgen05 GEMM vs the SIMT fp32 GEMM on device ----- */
 int st_selftest_gemm(int M, int N, int K, int engine, const float* A, const float* W, const float* bias, float* out,
                      void* stream);

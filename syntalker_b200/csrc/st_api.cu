@@ -864,6 +864,50 @@ extern "C" int st_generate_330_host(st_model* m, const st_schedule* sc, const st
   return ST_OK;
 }
 
+// Device time per launch of one GEMM in steady state: `reps` launches captured into one CUDA graph, timed by two
+// events (no host launch latency in the number).  engine 0 = SIMT, 1 = tcgen05.
+extern "C" int st_bench_gemm(int M, int N, int K, int engine, int reps, const float* A, const float* W, const float* bias, float* out,
+                             double* ms_per_launch) {
+  ST_REQUIRE(A && W && out && ms_per_launch && M > 0 && N > 0 && K > 0 && reps > 0, "st_bench_gemm: null argument");
+  GemmP p = linear(A, M, K, W, bias, out, N);
+  cudaStream_t s = nullptr;
+  ST_CHECK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  const bool tc = engine == ST_ENGINE_TC;
+  if (tc && !tc_supported(p)) { cudaStreamDestroy(s); set_error("st_bench_gemm: shape not supported by the tcgen05 engine"); return ST_EUNSUPPORTED; }
+  __half* planes = nullptr;
+  if (tc) {
+    tc_forget_weights(W);
+    ST_TRY(gemm_tc(p, s));                              // builds weight planes, sizes the scratch, splits A once
+    ST_CHECK_CUDA(cudaStreamSynchronize(s));
+    ST_CHECK_CUDA(cudaMalloc(&planes, (size_t)2 * M * K * sizeof(__half)));
+    ST_TRY(tc_split(A, K, M, K, planes, s));            // steady state of the product: the operand arrives as planes
+    p.a_planes = planes; p.a_plane_stride = (long long)M * K;
+  }
+  cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+  const int64_t l0 = g_launches;
+  ST_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+  int r = ST_OK;
+  for (int i = 0; i < reps && r == ST_OK; ++i) r = tc ? gemm_tc(p, s) : gemm_simt(p, s);
+  cudaError_t ce = cudaStreamEndCapture(s, &graph);
+  g_launches = l0;
+  if (r != ST_OK) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return r; }
+  ST_CHECK_CUDA(ce);
+  ST_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  ST_CHECK_CUDA(cudaGraphLaunch(exec, s));
+  ST_CHECK_CUDA(cudaEventRecord(e0, s));
+  ST_CHECK_CUDA(cudaGraphLaunch(exec, s));
+  ST_CHECK_CUDA(cudaEventRecord(e1, s));
+  ST_CHECK_CUDA(cudaStreamSynchronize(s));
+  float t = 0.f;
+  cudaEventElapsedTime(&t, e0, e1);
+  *ms_per_launch = (double)t / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); cudaStreamDestroy(s);
+  if (tc) { tc_forget_weights(W); cudaFree(planes); }
+  return ST_OK;
+}
+
 extern "C" int st_selftest_gemm(int M, int N, int K, int engine, const float* A, const float* W, const float* bias, float* out,
                                 void* stream) {
   ST_REQUIRE(A && W && out && M > 0 && N > 0 && K > 0, "st_selftest_gemm: null argument");

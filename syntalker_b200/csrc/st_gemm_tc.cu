@@ -515,6 +515,8 @@ static int get_wplanes(const GemmP& p, cudaStream_t s, WPlanes** out) {
   return ST_OK;
 }
 
+int tc_split(const float* a, int lda, int M, int K, __half* planes, cudaStream_t s) { return split_launch(a, lda, M, K, K, kActScale, 0, planes, s); }
+
 void tc_forget_weights(const float* W) {
   std::lock_guard<std::mutex> lk(g_w_mu);
   auto it = g_wplanes.find(W);

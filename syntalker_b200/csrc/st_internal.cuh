@@ -104,6 +104,7 @@ int profile_end(double* ms, double* flops, int64_t* n);
 int layernorm512(const float* x, const float* gamma, const float* beta, float* y, __half* planes, int rows, cudaStream_t s);
 int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStream_t s);   // qkv [nseq*32,1536] -> out [nseq*32,512]
 void tc_forget_weights(const float* W);
+int tc_split(const float* a, int lda, int M, int K, __half* planes, cudaStream_t s);   // fp32 -> hi/lo planes of a*kActScale
 int advance_loop(LoopState* ls, cudaStream_t s);
 int init_loop(LoopState* ls, int S, const float* tape, cudaStream_t s);
 struct TokensInP {

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) attention32_kernel(const float* __restric
   float (*q)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem);
   float (*k)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 32 * ATT_LD);
   float (*v)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 64 * ATT_LD);
-  float (*pr)[33] = reinterpret_cast<float (*)[33]>(att_smem + 96 * ATT_LD);
+  float (*pt)[36] = reinterpret_cast<float (*)[36]>(att_smem + 96 * ATT_LD);      // softmax, transposed: pt[j][i]
   const int seq = blockIdx.x, head = blockIdx.y, tid = threadIdx.x;
   const float* base = qkv + (long long)seq * 32 * 1536 + head * 128;
   for (int i = tid; i < 32 * 32; i += 256) {           // 32 rows x 32 float4 per matrix
@@ -295,60 +295,89 @@ __global__ void __launch_bounds__(256) attention32_kernel(const float* __restric
     *reinterpret_cast<float4*>(&v[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(src + 1024));
   }
   __syncthreads();
-  const int i = tid >> 3, u = tid & 7;                 // row i, 8 threads per row
-  float sc[4] = {0.f, 0.f, 0.f, 0.f};                  // scores for j = u + 8*jj
-#pragma unroll 8
-  for (int d = 0; d < 128; d += 4) {
-    const float4 qa = *reinterpret_cast<const float4*>(&q[i][d]);
+  // ---- scores: each thread owns a 4x4 block of S over one interleaved quarter of the 128 dims (8 LDS.128 per
+  //      64 FMA instead of 5 per 16), quarters are summed with two xor-shuffles ----
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane & 3, bj = lane >> 2, bi = warp;   // rows 4*bi.., cols 4*bj..; a warp holds 4 full rows of S
+  float acc[4][4];
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const float4 kb = *reinterpret_cast<const float4*>(&k[u + 8 * jj][d]);
-      sc[jj] = fmaf(qa.x, kb.x, sc[jj]);
-      sc[jj] = fmaf(qa.y, kb.y, sc[jj]);
-      sc[jj] = fmaf(qa.z, kb.z, sc[jj]);
-      sc[jj] = fmaf(qa.w, kb.w, sc[jj]);
-    }
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll
+  for (int d4 = 0; d4 < 8; ++d4) {
+    const int col = (4 * d4 + g) * 4;
+    float4 qa[4], kb[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) qa[r] = *reinterpret_cast<const float4*>(&q[4 * bi + r][col]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) kb[c] = *reinterpret_cast<const float4*>(&k[4 * bj + c][col]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc[r][c] = fmaf(qa[r].x, kb[c].x, acc[r][c]);
+        acc[r][c] = fmaf(qa[r].y, kb[c].y, acc[r][c]);
+        acc[r][c] = fmaf(qa[r].z, kb[c].z, acc[r][c]);
+        acc[r][c] = fmaf(qa[r].w, kb[c].w, acc[r][c]);
+      }
   }
   const float scale = 0.08838834764831845f;            // 128^-0.5
-  float mx = -INFINITY;
 #pragma unroll
-  for (int jj = 0; jj < 4; ++jj) { sc[jj] *= scale; mx = fmaxf(mx, sc[jj]); }
+  for (int r = 0; r < 4; ++r) {
+    float mx = -INFINITY;
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float sum = 0.f;
+    for (int c = 0; c < 4; ++c) {
+      float a = acc[r][c];
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      acc[r][c] = a * scale;
+      mx = fmaxf(mx, acc[r][c]);
+    }
 #pragma unroll
-  for (int jj = 0; jj < 4; ++jj) { sc[jj] = expf(sc[jj] - mx); sum += sc[jj]; }
+    for (int o = 4; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float inv = 1.0f / sum;
+    for (int c = 0; c < 4; ++c) { acc[r][c] = expf(acc[r][c] - mx); sum += acc[r][c]; }
 #pragma unroll
-  for (int jj = 0; jj < 4; ++jj) pr[i][u + 8 * jj] = sc[jj] * inv;
+    for (int o = 4; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] *= inv;
+  }
+  if (g == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<float4*>(&pt[4 * bj + c][4 * bi]) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+  }
   __syncthreads();
-  // out[i][d]: thread owns d = u*4 + 32*dd, dd = 0..3 (float4 each)
+  // ---- out = P V: warp = 4 rows, lane = 4 columns; P^T row is a broadcast float4, V row a conflict-free one ----
   float4 o4[4];
 #pragma unroll
-  for (int dd = 0; dd < 4; ++dd) o4[dd] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < 4; ++r) o4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
   for (int j = 0; j < 32; ++j) {
-    const float pj = pr[i][j];
+    const float4 p4 = *reinterpret_cast<const float4*>(&pt[j][4 * warp]);
+    const float4 vv = *reinterpret_cast<const float4*>(&v[j][lane * 4]);
+    const float pr[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
-    for (int dd = 0; dd < 4; ++dd) {
-      const float4 vv = *reinterpret_cast<const float4*>(&v[j][u * 4 + 32 * dd]);
-      o4[dd].x = fmaf(pj, vv.x, o4[dd].x);
-      o4[dd].y = fmaf(pj, vv.y, o4[dd].y);
-      o4[dd].z = fmaf(pj, vv.z, o4[dd].z);
-      o4[dd].w = fmaf(pj, vv.w, o4[dd].w);
+    for (int r = 0; r < 4; ++r) {
+      o4[r].x = fmaf(pr[r], vv.x, o4[r].x);
+      o4[r].y = fmaf(pr[r], vv.y, o4[r].y);
+      o4[r].z = fmaf(pr[r], vv.z, o4[r].z);
+      o4[r].w = fmaf(pr[r], vv.w, o4[r].w);
     }
   }
-  const long long off = ((long long)seq * 32 + i) * 512 + head * 128;
 #pragma unroll
-  for (int dd = 0; dd < 4; ++dd) {
-    if (out) *reinterpret_cast<float4*>(out + off + u * 4 + 32 * dd) = o4[dd];
-    if (planes) store_planes4(planes + off + u * 4 + 32 * dd, plane_stride, o4[dd].x, o4[dd].y, o4[dd].z, o4[dd].w);
+  for (int r = 0; r < 4; ++r) {
+    const long long off = ((long long)seq * 32 + 4 * warp + r) * 512 + head * 128 + lane * 4;
+    if (out) *reinterpret_cast<float4*>(out + off) = o4[r];
+    if (planes) store_planes4(planes + off, plane_stride, o4[r].x, o4[r].y, o4[r].z, o4[r].w);
   }
 }
 
 int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStream_t s) {
-  constexpr int smem = (96 * ATT_LD + 32 * 33) * sizeof(float);
+  constexpr int smem = (96 * ATT_LD + 32 * 36) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     ST_CHECK_CUDA(cudaFuncSetAttribute(attention32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -1,6 +1,7 @@
 """GPU probe (not a pytest file): accuracy and speed of the two GEMM engines on the path's shapes.
     python tests/tc_probe.py [out.json]
 Accuracy is against an fp64 product of the same fp32 inputs; speed is CUDA-event time over 20 launches."""
+import ctypes as C
 import json
 import sys
 import os
@@ -29,7 +30,9 @@ def run(engine, M, N, K, A, W, b, out, reps=20):
     torch.cuda.synchronize()
     if engine == 1:
         call(1)                                    # drop the cached planes again: the address will be reused
-    return e0.elapsed_time(e1) / reps
+    ms = C.c_double()
+    _lib.check(L.st_bench_gemm(M, N, K, engine, 50, A.data_ptr(), W.data_ptr(), b.data_ptr(), out.data_ptr(), C.byref(ms)))
+    return ms.value                                # device time per launch inside a CUDA graph
 
 
 def main():
