@@ -139,7 +139,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("ST_ENGINE", "simt"), choices=["simt", "tc"])
+    ap.add_argument("--engine", default=os.environ.get("ST_ENGINE", "tc"), choices=["simt", "tc"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

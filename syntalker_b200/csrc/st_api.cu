@@ -9,7 +9,7 @@ namespace st {
 
 thread_local char g_err[1024] = "";
 thread_local int64_t g_launches = 0;
-static int g_engine = ST_ENGINE_SIMT;
+static int g_engine = ST_ENGINE_TC;   // the product engine; SIMT is the exact-fp32 anchor (st_set_engine)
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -31,9 +31,11 @@ def test_library_exports_every_header_symbol():
 
 def test_engine_switch_and_error_text():
     L = _lib.lib()
+    assert _lib.get_engine() == "tc"                     # the product engine is the default
     assert L.st_set_engine(0) == 0 and _lib.get_engine() == "simt"
     assert L.st_set_engine(7) == -1
     assert b"unknown engine" in L.st_last_error()
+    assert L.st_set_engine(1) == 0
 
 
 def test_schedule_host_tables_match_golden(golden):

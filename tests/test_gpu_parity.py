@@ -30,7 +30,7 @@ def engine(request):
     """Run the test once per GEMM engine: exact-fp32 SIMT and tcgen05 split-fp16."""
     _lib.set_engine(request.param)
     yield request.param
-    _lib.set_engine("simt")
+    _lib.set_engine("tc")
 
 
 def maxabs(a, b):
