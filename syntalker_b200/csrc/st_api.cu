@@ -74,7 +74,10 @@ static std::vector<GemmP> g_prof_list;
 static double g_prof_flops = 0.0;
 
 static int gemm_dispatch(const GemmP& p, cudaStream_t s) {
-  return (g_engine == ST_ENGINE_TC && tc_supported(p)) ? gemm_tc(p, s) : gemm_simt(p, s);
+  if (g_engine == ST_ENGINE_TC && tc_supported(p)) return gemm_tc(p, s);
+  const bool plain = p.Lout == p.M && p.Lin == p.M && p.C == p.K && p.pad == 0 && p.stride == 1 && !p.ups;
+  if (plain && p.M <= 64 && p.K >= 256 && !p.res && p.act == ACT_NONE && !p.a_relu && p.out_scale == 1.0f) return gemm_skinny(p, s);
+  return gemm_simt(p, s);
 }
 
 int gemm(const GemmP& p, cudaStream_t s) {
@@ -188,7 +191,7 @@ struct st_vq {
   int out_dim = 0, ldw_last = 0;
   Weights w;
   const float *cb[6], *cnorm[6];
-  ConvW c0, res1[2][3], res2[2][3], up[2], c4, c6;
+  ConvW c0, res1[2][3], res2[2][3], up[2], up_eo[2][2], c4, c6;
   Arena ws;
 };
 
@@ -678,6 +681,10 @@ static int vq_resolve(st_vq* v) {
     char n3[32];
     snprintf(n3, sizeof n3, "%d.2", i + 2);
     v->up[i] = conv(n3, 512, 1536);
+    snprintf(n3, sizeof n3, "%d.2.even", i + 2);
+    v->up_eo[i][0] = conv(n3, 512, 1024);
+    snprintf(n3, sizeof n3, "%d.2.odd", i + 2);
+    v->up_eo[i][1] = conv(n3, 512, 1024);
   }
   v->c4 = conv("4", 512, 1536);
   v->c6 = conv("6", v->out_dim, 1536);
@@ -749,8 +756,21 @@ extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, flo
       p2.a_relu = 1; p2.res = h; p2.res_mode = RES_POST; p2.ldr = 512;
       ST_TRY(gemm(p2, s));
     }
-    GemmP pu = conv3(h, v->up[i], nxt, B, T, 2 * T, 512, 1, 1);
-    ST_TRY(gemm(pu, s));
+    if (st_get_engine() == ST_ENGINE_TC && B * T >= 128) {
+      // nearest x2 upsample + k3 conv = two 2-tap convs on the low-resolution rows (even / odd outputs), weights
+      // pre-summed by the packer:  out[2u] = W0 in[u-1] + (W1+W2) in[u];  out[2u+1] = (W0+W1) in[u] + W2 in[u+1]
+      for (int par = 0; par < 2; ++par) {
+        GemmP pu;
+        pu.A = h; pu.W = v->up_eo[i][par].w; pu.bias = v->up_eo[i][par].b; pu.out = nxt + par * 512;
+        pu.M = B * T; pu.N = 512; pu.K = 1024; pu.ldw = 1024;
+        pu.Lout = T; pu.Lin = T; pu.C = 512; pu.stride = 1; pu.pad = par == 0 ? 1 : 0; pu.dil = 1;
+        pu.a_batch = (long long)T * 512; pu.lda = 512; pu.ldo = 1024;
+        ST_TRY(gemm(pu, s));
+      }
+    } else {
+      GemmP pu = conv3(h, v->up[i], nxt, B, T, 2 * T, 512, 1, 1);
+      ST_TRY(gemm(pu, s));
+    }
     T *= 2;
     float* o = h; h = nxt; nxt = o;
   }

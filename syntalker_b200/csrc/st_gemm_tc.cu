@@ -133,8 +133,12 @@ struct TcEpi {
   int ldo, ldr, res_mode, res_div, act;
   float scale;           // 2^-(sa+sw): undo the operand pre-scaling
   int M, N;
-  int a_rows_per_clip;   // conv mode (4-D A map): T; 0 = plain 2-D GEMM
-  int taps, dil, kb_per_tap;
+  // operand addressing of A:
+  //  mode 0  plain rows            3-D map {K, rows, 2}                coords (kb*64, m0, 0)
+  //  mode 1  conv, clips packed    4-D map {C, T, clips, 2}, T | 128   coords (cb*64, j*dil - pad, m0/T, 0)
+  //  mode 2  conv, long clips      4-D map {C, Lin, B, 2}              coords (cb*64, t0 + j*dil - pad, b, 0)      tile -> (b, t0)
+  //  mode 3  strided conv, pad 0   3-D map {s*C, ceil(B*Lin/s), 2}     coords ((G%s)*C + cb*64, G/s, 0), G = b*Lin + t0*s + j
+  int mode, T, kb_per_tap, dil, pad, stride, C, Lin, Lout, tpc;
   long long* dbg;        // optional timeline of CTA (0,0): clock64 stamps (debug / profiling only)
 };
 
@@ -167,7 +171,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;     // n fastest: CTAs that share an A tile run together
+  const int n0 = blockIdx.x * BN;                    // n fastest: CTAs that share an A tile run together
+  // output rows of this tile: [row_base, row_base + rows_valid)
+  int row_base, rows_valid, clip_b = 0, t0 = 0;
+  if (ep.mode >= 2) {
+    clip_b = blockIdx.y / ep.tpc;
+    t0 = (blockIdx.y - clip_b * ep.tpc) * TC_BM;
+    row_base = clip_b * ep.Lout + t0;
+    rows_valid = min(TC_BM, ep.Lout - t0);
+  } else {
+    row_base = blockIdx.y * TC_BM;
+    rows_valid = min(TC_BM, ep.M - row_base);
+  }
+  const int m0 = row_base;
   long long* dbg = (ep.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? ep.dbg : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
@@ -199,13 +215,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + s * STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        if (ep.a_rows_per_clip == 0) {
+        if (ep.mode == 0) {
           tma_load_3d(st, &tmA, &full_bar[s], kb * TC_BK, m0, 0);
         } else {
-          // implicit conv: K block kb = (tap j, channel block); rows (clip, t) read from t + (j - taps/2)*dil,
-          // out-of-range t is zero-filled by TMA = the conv's zero padding
+          // implicit conv: K block kb = (tap j, channel block cb); out-of-range positions are zero-filled by TMA,
+          // which is exactly the conv's zero padding
           const int j = kb / ep.kb_per_tap, cb = kb - j * ep.kb_per_tap;
-          tma_load_4d(st, &tmA, &full_bar[s], cb * TC_BK, (j - ep.taps / 2) * ep.dil, m0 / ep.a_rows_per_clip, 0);
+          if (ep.mode == 1) tma_load_4d(st, &tmA, &full_bar[s], cb * TC_BK, j * ep.dil - ep.pad, m0 / ep.T, 0);
+          else if (ep.mode == 2) tma_load_4d(st, &tmA, &full_bar[s], cb * TC_BK, t0 + j * ep.dil - ep.pad, clip_b, 0);
+          else {
+            const long long G = (long long)clip_b * ep.Lin + (long long)t0 * ep.stride + j;
+            const int gr = (int)(G / ep.stride), gp = (int)(G - (long long)gr * ep.stride);
+            tma_load_3d(st, &tmA, &full_bar[s], gp * ep.C + cb * TC_BK, gr, 0);
+          }
         }
         tma_load_3d(st + 2 * TC_A_PLANE, &tmW, &full_bar[s], kb * TC_BK, n0, 0);
         if (dbg && kb < 16) dbg[8 + kb] = clock64();
@@ -295,7 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int u = 0; u < UN; ++u) {
         const int r = r0 + u * RPI + lane / LPR;
         rowv[u] = m0 + lg * 32 + r;
-        ok[u] = rowv[u] < ep.M && n < ep.N;
+        ok[u] = (lg * 32 + r) < rows_valid && n < ep.N;
         t4[u] = *reinterpret_cast<const float4*>(tile + r * LDT + cl);
         r4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ep.res && ok[u]) {
@@ -357,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // fp32 [M,K] (row stride lda) -> fp16 planes [2][M][Kp], value * scale split into hi + lo
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ a, int lda, int M, int K, int Kp, float scale, int relu,
-                                                           __half* __restrict__ planes) {
+                                                           __half* __restrict__ planes, long long plane_stride) {
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;     // one thread per 4 elements
   const int kq = Kp >> 2;
   if (gid >= (long long)M * kq) return;
@@ -378,7 +400,7 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
     split_f16(t, h[q], l[q]);
   }
   __half* ph = planes + (long long)m * Kp + k;
-  __half* pl = ph + (long long)M * Kp;
+  __half* pl = ph + plane_stride;
   *reinterpret_cast<__half2*>(ph) = __halves2half2(h[0], h[1]);
   *reinterpret_cast<__half2*>(ph + 2) = __halves2half2(h[2], h[3]);
   *reinterpret_cast<__half2*>(pl) = __halves2half2(l[0], l[1]);
@@ -473,7 +495,7 @@ static Arena g_scratch;          // activation planes of the GEMM in flight (str
 
 static int split_launch(const float* a, int lda, int M, int K, int Kp, float scale, int relu, __half* planes, cudaStream_t s) {
   const long long n = (long long)M * (Kp >> 2);
-  split_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, lda, M, K, Kp, scale, relu, planes);
+  split_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, lda, M, K, Kp, scale, relu, planes, (long long)M * Kp);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -529,28 +551,81 @@ void tc_forget_weights(const float* W) {
   g_wplanes.erase(it);
 }
 
+static int conv_mode(const GemmP& p) {
+  // 0 plain, 1 packed clips, 2 long clips stride 1, 3 strided pad-0, -1 unsupported
+  if (p.ups) return -1;
+  if (p.Lout == p.M && p.Lin == p.M && p.C == p.K && p.pad == 0 && p.stride == 1) return 0;
+  const int taps = p.K / p.C;
+  if (taps * p.C != p.K || (p.C % TC_BK) != 0 || p.lda != p.C || p.a_batch != (long long)p.Lin * p.C || (p.M % p.Lout) != 0) return -1;
+  if (p.stride == 1) {
+    if (p.Lout == p.Lin && (TC_BM % p.Lout) == 0) return 1;
+    if (p.Lout == p.Lin + 2 * p.pad - p.dil * (taps - 1)) return 2;
+    return -1;
+  }
+  if (p.pad == 0 && p.dil == 1 && (long long)(p.Lout - 1) * p.stride + taps <= p.Lin) return 3;
+  return -1;
+}
+
 bool tc_supported(const GemmP& p) {
   if ((!p.out && !p.o_planes) || p.out_scale != 1.0f || p.M < 128 || p.N < 16) return false;
-  if (p.stride != 1 || p.ups) return false;
-  const bool plain = (p.Lout == p.M && p.Lin == p.M && p.C == p.K && p.pad == 0);
-  if (plain) return (p.K % TC_BK) == 0;
-  // channels-last k-tap conv with "same" padding over clips of Lout == Lin rows, 128 % T == 0
-  const int taps = p.K / p.C;
-  return p.Lout == p.Lin && (TC_BM % p.Lout) == 0 && (p.M % p.Lout) == 0 && (p.C % TC_BK) == 0 && taps * p.C == p.K && (taps & 1) &&
-         p.pad == (taps / 2) * p.dil && p.lda == p.C && p.a_batch == (long long)p.Lin * p.C;
+  const int mode = conv_mode(p);
+  if (mode < 0) return false;
+  if (mode == 0) return (p.K % TC_BK) == 0;
+  if (mode == 3 && p.a_planes) return false;      // the flat strided view is only built over the split scratch
+  return true;
 }
 
 template <int BN, int STAGES>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcEpi& ep, int num_kb, cudaStream_t s) {
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcEpi& ep, int num_kb, int mtiles, cudaStream_t s) {
   constexpr int smem = STAGES * (2 * TC_A_PLANE + 2 * BN * TC_BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
   static bool attr = false;
   if (!attr) {
     ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  dim3 grid((ep.N + BN - 1) / BN, (ep.M + TC_BM - 1) / TC_BM);
+  dim3 grid((ep.N + BN - 1) / BN, mtiles);
   gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, ep, num_kb);
   ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+// 3-D flat view for strided convs: planes [2][rows(+slack)][C] seen as {s*C, ceil(rows/s), 2}
+static int get_map_strided(const CUtensorMap** out, const __half* base, long long plane_stride, long long rows, int C, int stride) {
+  const int rows_v = (int)((rows + stride - 1) / stride);
+  MapKey key{base, plane_stride, stride * C, rows_v, -7, TC_BM};
+  std::lock_guard<std::mutex> lk(g_tc_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = &it->second; return ST_OK; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ST_ECUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)stride * C, (cuuint64_t)rows_v, 2};
+  cuuint64_t gstr[2] = {(cuuint64_t)stride * C * 2, (cuuint64_t)plane_stride * 2};
+  cuuint32_t box[3] = {TC_BK, TC_BM, 2};
+  cuuint32_t est[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(strided rows=%lld C=%d s=%d) failed: %d", rows, C, stride, (int)r); return ST_ECUDA; }
+  *out = &(g_maps[key] = m);
+  return ST_OK;
+}
+// 4-D long-clip view {C, Lin, B, 2}, box {64, 128, 1, 2}
+static int get_map_long(const CUtensorMap** out, const __half* base, long long plane_stride, int B, int Lin, int C) {
+  MapKey key{base, plane_stride, C, Lin, B, -2};
+  std::lock_guard<std::mutex> lk(g_tc_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = &it->second; return ST_OK; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ST_ECUDA; }
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Lin, (cuuint64_t)B, 2};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Lin * C * 2, (cuuint64_t)plane_stride * 2};
+  cuuint32_t box[4] = {TC_BK, TC_BM, 1, 2};
+  cuuint32_t est[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(long B=%d Lin=%d C=%d) failed: %d", B, Lin, C, (int)r); return ST_ECUDA; }
+  *out = &(g_maps[key] = m);
   return ST_OK;
 }
 
@@ -558,35 +633,38 @@ int gemm_tc(const GemmP& p, cudaStream_t s) {
   if (!tc_supported(p)) { set_error("gemm_tc: unsupported problem"); return ST_EUNSUPPORTED; }
   WPlanes* w = nullptr;
   ST_TRY(get_wplanes(p, s, &w));
-  const bool plain = (p.Lout == p.M && p.C == p.K);
-  const int Ka = plain ? p.K : p.C;                       // columns of the activation planes
-  const int rows = p.M;                                   // conv: clips * T rows
+  const int mode = conv_mode(p);
+  const int Ka = mode == 0 ? p.K : p.C;                   // columns of the activation planes
+  const int nclips = mode == 0 ? 1 : p.M / p.Lout;
+  const long long rows = mode == 0 ? p.M : (long long)nclips * p.Lin;   // rows of the activation tensor
   const __half* planes = p.a_planes;
   long long pstride = p.a_plane_stride;
   if (!planes) {
     // operand still fp32: split it into the scratch planes first (stream order serialises reuse of the scratch)
-    const size_t need = (size_t)2 * rows * Ka * sizeof(__half) + 1024;
+    pstride = (rows + 16) * Ka;                           // slack rows keep the strided flat view inside the buffer
+    const size_t need = (size_t)2 * pstride * sizeof(__half) + 1024;
     if (need > g_scratch.cap) {
       cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
       cudaStreamIsCapturing(s, &cap);
       if (cap != cudaStreamCaptureStatusNone) { set_error("split scratch must be sized before graph capture"); return ST_ESTATE; }
-      ST_TRY(g_scratch.reserve(need * 2));
+      ST_TRY(g_scratch.reserve(need + need / 2));
+      ST_CHECK_CUDA(cudaMemsetAsync(g_scratch.base, 0, g_scratch.cap, s));
     }
     __half* sp = reinterpret_cast<__half*>(g_scratch.base);
-    ST_TRY(split_launch(p.A, p.lda, rows, Ka, Ka, kActScale, p.a_relu, sp, s));
+    const long long n4 = rows * (Ka >> 2);
+    split_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(p.A, p.lda, (int)rows, Ka, Ka, kActScale, p.a_relu, sp, pstride);
+    ST_CHECK_LAUNCH();
     planes = sp;
-    pstride = (long long)rows * Ka;
   }
   const CUtensorMap* tmA = nullptr;
   const CUtensorMap* tmW = nullptr;
   TcEpi ep;
-  ep.a_rows_per_clip = 0; ep.taps = 1; ep.dil = 1; ep.kb_per_tap = 0;
-  if (plain) {
-    ST_TRY(get_map_3d(&tmA, planes, pstride, rows, Ka, TC_BM));
-  } else {
-    ST_TRY(get_map_4d(&tmA, planes, pstride, p.M / p.Lout, p.Lout, p.C));
-    ep.a_rows_per_clip = p.Lout; ep.taps = p.K / p.C; ep.dil = p.dil; ep.kb_per_tap = p.C / TC_BK;
-  }
+  ep.mode = mode; ep.T = p.Lout; ep.kb_per_tap = mode == 0 ? 1 : p.C / TC_BK; ep.dil = p.dil; ep.pad = p.pad; ep.stride = p.stride;
+  ep.C = p.C; ep.Lin = p.Lin; ep.Lout = p.Lout; ep.tpc = (p.Lout + TC_BM - 1) / TC_BM;
+  if (mode == 0) ST_TRY(get_map_3d(&tmA, planes, pstride, (int)rows, Ka, TC_BM));
+  else if (mode == 1) ST_TRY(get_map_4d(&tmA, planes, pstride, nclips, p.Lin, p.C));
+  else if (mode == 2) ST_TRY(get_map_long(&tmA, planes, pstride, nclips, p.Lin, p.C));
+  else ST_TRY(get_map_strided(&tmA, planes, pstride, rows, p.C, p.stride));
   const int BN = p.N <= 512 ? 64 : 128;
   ST_TRY(get_map_3d(&tmW, w->planes, (long long)p.N * w->Kp, p.N, w->Kp, BN));
   ep.out = p.out; ep.bias = p.bias; ep.res = p.res;
@@ -596,8 +674,9 @@ int gemm_tc(const GemmP& p, cudaStream_t s) {
   ep.M = p.M; ep.N = p.N;
   ep.dbg = g_tc_dbg;
   const int num_kb = w->Kp / TC_BK;
-  if (BN == 64) return launch_tc<64, 4>(*tmA, *tmW, ep, num_kb, s);
-  return launch_tc<128, 3>(*tmA, *tmW, ep, num_kb, s);
+  const int mtiles = mode >= 2 ? nclips * ep.tpc : (p.M + TC_BM - 1) / TC_BM;
+  if (BN == 64) return launch_tc<64, 4>(*tmA, *tmW, ep, num_kb, mtiles, s);
+  return launch_tc<128, 3>(*tmA, *tmW, ep, num_kb, mtiles, s);
 }
 
 }  // namespace st

@@ -133,4 +133,13 @@ def pack_rvq(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         key = "decoder.model." + src
         out[f"dec.{dst}.w"] = _t32(_conv_layout(_f64(sd[key + ".weight"])))
         out[f"dec.{dst}.b"] = sd[key + ".bias"].detach().cpu().float().contiguous()
+    # nearest x2 upsample followed by the k=3 conv (encdec.py:59-61) == two 2-tap convs on the low-res rows:
+    #   out[2u] = W0 in[u-1] + (W1+W2) in[u];   out[2u+1] = (W0+W1) in[u] + W2 in[u+1]       (tap-major [C_out, 2*C_in])
+    for i in (2, 3):
+        w = _f64(sd[f"decoder.model.{i}.2.weight"])                       # [C_out, C_in, 3]
+        b = sd[f"decoder.model.{i}.2.bias"].detach().cpu().float().contiguous()
+        even = np.concatenate([w[:, :, 0], w[:, :, 1] + w[:, :, 2]], axis=1)
+        odd = np.concatenate([w[:, :, 0] + w[:, :, 1], w[:, :, 2]], axis=1)
+        out[f"dec.{i}.2.even.w"], out[f"dec.{i}.2.even.b"] = _t32(even), b
+        out[f"dec.{i}.2.odd.w"], out[f"dec.{i}.2.odd.b"] = _t32(odd), b.clone()
     return out

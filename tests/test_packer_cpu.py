@@ -53,3 +53,19 @@ def test_packed_rvq_decoder(dim):
     xq = torch.randn(2, 512, 32, generator=torch.Generator().manual_seed(3))
     assert float((orvq.decoder(W, xq) - emu.rvq_decoder(P, xq, dim)).abs().max()) < 1e-5
     assert P[f"dec.6.w"].shape == (dim, 1536)
+
+
+def test_upsample_conv_even_odd_split():
+    """nearest x2 upsample + k3 conv (encdec.py:59-61) == the two 2-tap convs the packer builds for the TC engine."""
+    import torch.nn.functional as F
+    W = synth.rvq_state_dict(78, seed=0)
+    P = packer.pack_rvq(W)
+    h = torch.randn(2, 512, 32, generator=torch.Generator().manual_seed(9))
+    ref = F.conv1d(F.interpolate(h, scale_factor=2, mode="nearest"), W["decoder.model.2.2.weight"], W["decoder.model.2.2.bias"], padding=1)
+    hp = F.pad(h, (1, 1))
+    we, wo = P["dec.2.2.even.w"].reshape(512, 2, 512), P["dec.2.2.odd.w"].reshape(512, 2, 512)
+    mm = lambda w, x: torch.einsum("oc,bct->bot", w, x)
+    even = mm(we[:, 0], hp[:, :, 0:32]) + mm(we[:, 1], hp[:, :, 1:33]) + P["dec.2.2.even.b"][None, :, None]
+    odd = mm(wo[:, 0], hp[:, :, 1:33]) + mm(wo[:, 1], hp[:, :, 2:34]) + P["dec.2.2.odd.b"][None, :, None]
+    out = torch.stack([even, odd], dim=-1).reshape(2, 512, 64)
+    assert float((out - ref).abs().max()) < 1e-5
