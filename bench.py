@@ -166,6 +166,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _lib.set_engine(args.engine)
+    _lib.check(_lib.lib().st_set_pdl(int(os.environ.get("ST_PDL", "1"))))
+    _lib.check(_lib.lib().st_set_graphs(int(os.environ.get("ST_GRAPHS", "1"))))
     B = args.batch
     model = MDM(None).load_state_dict(synth.mdm_state_dict("beatx_motionclip", seed=0))
     wrapped = ClassifierFreeSampleModel(model)

@@ -75,6 +75,8 @@ int st_set_engine(int engine);
 int st_get_engine(void);
 /* The sampling loop replays one captured CUDA graph per diffusion step (default on); 0 = launch every kernel eagerly. */
 int st_set_graphs(int on);
+/* Programmatic dependent launch between consecutive kernels (default on); 0 = plain stream order. */
+int st_set_pdl(int on);
 /* Debug: device buffer of >= 64 int64 receiving clock64() stamps of CTA (0,0) of every tcgen05 GEMM launch; NULL = off. */
 int st_debug_timeline(long long* dev_buf);
 

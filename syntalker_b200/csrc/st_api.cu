@@ -9,6 +9,7 @@ namespace st {
 
 thread_local char g_err[1024] = "";
 thread_local int64_t g_launches = 0;
+bool g_pdl = true;
 static int g_engine = ST_ENGINE_TC;   // the product engine; SIMT is the exact-fp32 anchor (st_set_engine)
 
 void set_error(const char* fmt, ...) {
@@ -75,8 +76,6 @@ static double g_prof_flops = 0.0;
 
 static int gemm_dispatch(const GemmP& p, cudaStream_t s) {
   if (g_engine == ST_ENGINE_TC && tc_supported(p)) return gemm_tc(p, s);
-  const bool plain = p.Lout == p.M && p.Lin == p.M && p.C == p.K && p.pad == 0 && p.stride == 1 && !p.ups;
-  if (plain && p.M <= 64 && p.K >= 256 && !p.res && p.act == ACT_NONE && !p.a_relu && p.out_scale == 1.0f) return gemm_skinny(p, s);
   return gemm_simt(p, s);
 }
 
@@ -207,6 +206,7 @@ extern "C" int st_set_engine(int engine) {
 extern "C" int st_get_engine(void) { return g_engine; }
 namespace st { extern long long* g_tc_dbg; }
 extern "C" int st_debug_timeline(long long* dev_buf) { st::g_tc_dbg = dev_buf; return ST_OK; }
+extern "C" int st_set_pdl(int on) { st::g_pdl = on != 0; return ST_OK; }
 extern "C" int st_set_graphs(int on) { g_use_graphs = on != 0; return ST_OK; }
 extern "C" int st_profile_begin(void) { return st::profile_begin(); }
 extern "C" int st_profile_end(double* ms_total, double* flops_total, int64_t* launches) { return st::profile_end(ms_total, flops_total, launches); }
@@ -474,7 +474,7 @@ static int make_plan(const st_model* m, const st_guidance* g, Plan* pl) {
 // fp16 hi/lo planes the next GEMM streams with TMA; only the residual stream, QKV and the outputs stay fp32.
 static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, int t_scalar, bool loop, cudaStream_t s) {
   const int rows = B * 32, R = pl.nE * rows;
-  const bool tc = (st_get_engine() == ST_ENGINE_TC) && R >= 128;
+  const bool tc = (st_get_engine() == ST_ENGINE_TC);
   const long long ps512 = (long long)R * 512, ps1024 = (long long)R * 1024;
   GemmP pz = linear(m->xs, rows, 1536, m->w_x, nullptr, m->z, 512);
   ST_TRY(gemm(pz, s));
@@ -756,7 +756,7 @@ extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, flo
       p2.a_relu = 1; p2.res = h; p2.res_mode = RES_POST; p2.ldr = 512;
       ST_TRY(gemm(p2, s));
     }
-    if (st_get_engine() == ST_ENGINE_TC && B * T >= 128) {
+    if (st_get_engine() == ST_ENGINE_TC) {
       // nearest x2 upsample + k3 conv = two 2-tap convs on the low-resolution rows (even / odd outputs), weights
       // pre-summed by the packer:  out[2u] = W0 in[u-1] + (W1+W2) in[u];  out[2u+1] = (W0+W1) in[u] + W2 in[u+1]
       for (int par = 0; par < 2; ++par) {

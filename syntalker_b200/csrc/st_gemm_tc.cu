@@ -204,6 +204,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, TMEM and descriptor prefetch above overlap the predecessor's tail; nothing before this line touches
+  // global memory
+  pdl_wait();
+  pdl_launch();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
@@ -380,6 +384,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // fp32 [M,K] (row stride lda) -> fp16 planes [2][M][Kp], value * scale split into hi + lo
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ a, int lda, int M, int K, int Kp, float scale, int relu,
                                                            __half* __restrict__ planes, long long plane_stride) {
+  pdl_wait();
+  pdl_launch();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;     // one thread per 4 elements
   const int kq = Kp >> 2;
   if (gid >= (long long)M * kq) return;
@@ -408,6 +414,8 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 }
 
 __global__ void absmax_kernel(const float* __restrict__ a, long long n, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   float m = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(a[i]));
 #pragma unroll
@@ -495,7 +503,7 @@ static Arena g_scratch;          // activation planes of the GEMM in flight (str
 
 static int split_launch(const float* a, int lda, int M, int K, int Kp, float scale, int relu, __half* planes, cudaStream_t s) {
   const long long n = (long long)M * (Kp >> 2);
-  split_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, lda, M, K, Kp, scale, relu, planes, (long long)M * Kp);
+launch_k(split_planes_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, a, lda, M, K, Kp, scale, relu, planes, (long long)M * Kp);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -515,7 +523,7 @@ static int get_wplanes(const GemmP& p, cudaStream_t s, WPlanes** out) {
   float* d_max = nullptr;
   ST_CHECK_CUDA(cudaMalloc(&d_max, sizeof(float)));
   ST_CHECK_CUDA(cudaMemsetAsync(d_max, 0, sizeof(float), s));
-  absmax_kernel<<<148, 256, 0, s>>>(p.W, (long long)p.N * p.ldw, d_max);
+launch_k(absmax_kernel, dim3(148), dim3(256), 0, s, p.W, (long long)p.N * p.ldw, d_max);
   ST_CHECK_LAUNCH();
   float h_max = 0.f;
   ST_CHECK_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -567,7 +575,7 @@ static int conv_mode(const GemmP& p) {
 }
 
 bool tc_supported(const GemmP& p) {
-  if ((!p.out && !p.o_planes) || p.out_scale != 1.0f || p.M < 128 || p.N < 16) return false;
+  if ((!p.out && !p.o_planes) || p.out_scale != 1.0f || p.M < 1 || p.N < 16) return false;   // rows beyond M: TMA zero fill + masked stores
   const int mode = conv_mode(p);
   if (mode < 0) return false;
   if (mode == 0) return (p.K % TC_BK) == 0;
@@ -584,7 +592,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcEpi
     attr = true;
   }
   dim3 grid((ep.N + BN - 1) / BN, mtiles);
-  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, s>>>(tmA, tmW, ep, num_kb);
+launch_k(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(TC_THREADS), smem, s, tmA, tmW, ep, num_kb);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -652,7 +660,7 @@ int gemm_tc(const GemmP& p, cudaStream_t s) {
     }
     __half* sp = reinterpret_cast<__half*>(g_scratch.base);
     const long long n4 = rows * (Ka >> 2);
-    split_planes_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(p.A, p.lda, (int)rows, Ka, Ka, kActScale, p.a_relu, sp, pstride);
+launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, s, p.A, p.lda, (int)rows, Ka, Ka, kActScale, p.a_relu, sp, pstride);
     ST_CHECK_LAUNCH();
     planes = sp;
   }

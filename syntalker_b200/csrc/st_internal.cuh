@@ -7,6 +7,7 @@
 #include <string>
 #include <map>
 #include <vector>
+#include <utility>
 
 #include "../../include/syntalker_b200.h"
 
@@ -49,6 +50,26 @@ extern thread_local int64_t g_launches;
       return ST_EINVAL;            \
     }                              \
   } while (0)
+
+// ---- launches: every kernel of the path goes through launch_k.  With PDL on (default) the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs may be scheduled while its predecessor
+// drains; every kernel therefore executes pdl_wait() before it touches global memory (reads AND writes) and
+// pdl_launch() right after, which keeps the chain transitively ordered (N+2 cannot pass N+1's wait).
+extern bool g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ---- generic implicit-GEMM descriptor ------------------------------------------------------------------
 // out[m, n] = act( sum_k A(m,k) * W[n,k] + bias[n] + res_pre[m/res_div, n] ) + res_post[m/res_div, n]

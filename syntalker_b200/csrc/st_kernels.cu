@@ -28,6 +28,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 template <bool VEC_A>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_simt_kernel(GemmP p) {
+  pdl_wait();
+  pdl_launch();
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
 
@@ -197,8 +199,8 @@ int gemm_simt(const GemmP& p, cudaStream_t s) {
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
   const bool vec = ((p.C & 3) == 0) && ((p.lda & 3) == 0) && ((p.a_batch & 3) == 0) &&
                    ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
-  if (vec) gemm_simt_kernel<true><<<grid, GEMM_THREADS, 0, s>>>(p);
-  else gemm_simt_kernel<false><<<grid, GEMM_THREADS, 0, s>>>(p);
+  if (vec) launch_k(gemm_simt_kernel<true>, dim3(grid), dim3(GEMM_THREADS), 0, s, p);
+  else launch_k(gemm_simt_kernel<false>, dim3(grid), dim3(GEMM_THREADS), 0, s, p);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -210,6 +212,8 @@ int gemm_simt(const GemmP& p, cudaStream_t s) {
 __global__ void __launch_bounds__(256) gemm_skinny_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
                                                           const float* __restrict__ bias, float* __restrict__ out, int ldo, int M, int N,
                                                           int K) {
+  pdl_wait();
+  pdl_launch();
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const float* __restric
 }
 
 int gemm_skinny(const GemmP& p, cudaStream_t s) {
-  gemm_skinny_kernel<<<(p.N + 7) / 8, 256, 0, s>>>(p.A, p.lda, p.W, p.ldw, p.bias, p.out, p.ldo, p.M, p.N, p.K);
+  launch_k(gemm_skinny_kernel, dim3((p.N + 7) / 8), dim3(256), 0, s, p.A, p.lda, p.W, p.ldw, p.bias, p.out, p.ldo, p.M, p.N, p.K);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -265,6 +269,8 @@ __device__ __forceinline__ void store_planes4(__half* hi_ptr, long long plane_st
 __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                            const float* __restrict__ b, float* __restrict__ y,
                                                            __half* __restrict__ planes, int rows) {
+  pdl_wait();
+  pdl_launch();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
 }
 
 int layernorm512(const float* x, const float* gamma, const float* beta, float* y, __half* planes, int rows, cudaStream_t s) {
-  layernorm512_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, gamma, beta, y, planes, rows);
+  launch_k(layernorm512_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, gamma, beta, y, planes, rows);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -318,6 +324,8 @@ constexpr int ATT_LD = 132;   // padded row stride (floats) -> conflict-free flo
 
 __global__ void __launch_bounds__(256) attention32_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                           __half* __restrict__ planes, long long plane_stride) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ __align__(16) float att_smem[];
   float (*q)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem);
   float (*k)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 32 * ATT_LD);
@@ -421,7 +429,7 @@ int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStre
     ST_CHECK_CUDA(cudaFuncSetAttribute(attention32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  attention32_kernel<<<dim3(nseq, 4), 256, smem, s>>>(qkv, out, planes, (long long)nseq * 32 * 512);
+  launch_k(attention32_kernel, dim3(dim3(nseq, 4)), dim3(256), smem, s, qkv, out, planes, (long long)nseq * 32 * 512);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -433,6 +441,8 @@ int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStre
 //    One thread per (eval, row, pair j<256): columns g*64 + j' and g*64 + j' + 32.
 // =========================================================================================================
 __global__ void __launch_bounds__(256) tokens_in_kernel(TokensInP p) {
+  pdl_wait();
+  pdl_launch();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long per_eval = (long long)p.B * 32 * 256;
   if (gid >= per_eval * p.nE) return;
@@ -463,7 +473,7 @@ __global__ void __launch_bounds__(256) tokens_in_kernel(TokensInP p) {
 
 int tokens_in(const TokensInP& p, cudaStream_t s) {
   const long long n = (long long)p.nE * p.B * 32 * 256;
-  tokens_in_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
+  launch_k(tokens_in_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, p);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -475,6 +485,8 @@ int tokens_in(const TokensInP& p, cudaStream_t s) {
 //    separate fp32 roundings (no FMA contraction), so given equal inputs the update is bit-identical.
 // =========================================================================================================
 __global__ void __launch_bounds__(256) step_update_kernel(StepP p) {
+  pdl_wait();
+  pdl_launch();
   const long long n4 = (long long)p.B * 32 * 1536 / 4;
   const long long i4 = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i4 >= n4) return;
@@ -550,22 +562,30 @@ __global__ void __launch_bounds__(256) step_update_kernel(StepP p) {
   *xs4 = make_float4(o[0], o[1], o[2], o[3]);
 }
 
-__global__ void advance_loop_kernel(LoopState* ls) { ls->k -= 1; }
-__global__ void init_loop_kernel(LoopState* ls, int S, const float* tape) { ls->k = S - 1; ls->S = S; ls->tape = tape; }
+__global__ void advance_loop_kernel(LoopState* ls) {
+  pdl_wait();
+  pdl_launch();
+  ls->k -= 1;
+}
+__global__ void init_loop_kernel(LoopState* ls, int S, const float* tape) {
+  pdl_wait();
+  pdl_launch();
+  ls->k = S - 1; ls->S = S; ls->tape = tape;
+}
 int advance_loop(LoopState* ls, cudaStream_t s) {
-  advance_loop_kernel<<<1, 1, 0, s>>>(ls);
+  launch_k(advance_loop_kernel, dim3(1), dim3(1), 0, s, ls);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
 int init_loop(LoopState* ls, int S, const float* tape, cudaStream_t s) {
-  init_loop_kernel<<<1, 1, 0, s>>>(ls, S, tape);
+  launch_k(init_loop_kernel, dim3(1), dim3(1), 0, s, ls, S, tape);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
 
 int step_update(const StepP& p, cudaStream_t s) {
   const long long n4 = (long long)p.B * 32 * 1536 / 4;
-  step_update_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(p);
+  launch_k(step_update_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, s, p);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -575,6 +595,8 @@ int step_update(const StepP& p, cudaStream_t s) {
 // =========================================================================================================
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc,
                                                         float scale) {
+  pdl_wait();
+  pdl_launch();
   // in: [B, R, Cc] -> out: [B, Cc, R]
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -594,12 +616,12 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 }
 
 int transpose_to_tokens(const float* x, float* tok, int B, int C, int T, float scale, cudaStream_t s) {
-  transpose_kernel<<<dim3((T + 31) / 32, (C + 31) / 32, B), 256, 0, s>>>(x, tok, C, T, scale);
+  launch_k(transpose_kernel, dim3(dim3((T + 31) / 32, (C + 31) / 32, B)), dim3(256), 0, s, x, tok, C, T, scale);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
 int transpose_from_tokens(const float* tok, float* x, int B, int C, int T, cudaStream_t s) {
-  transpose_kernel<<<dim3((C + 31) / 32, (T + 31) / 32, B), 256, 0, s>>>(tok, x, T, C, 1.0f);
+  launch_k(transpose_kernel, dim3(dim3((C + 31) / 32, (T + 31) / 32, B)), dim3(256), 0, s, tok, x, T, C, 1.0f);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -610,6 +632,8 @@ int transpose_from_tokens(const float* tok, float* x, int B, int C, int T, cudaS
 // =========================================================================================================
 __global__ void __launch_bounds__(256) gather_words_kernel(const int32_t* __restrict__ word, const float* __restrict__ table,
                                                            float* __restrict__ out, int ldo, int rows, int force_zero) {
+  pdl_wait();
+  pdl_launch();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;    // rows x 64 float4
   if (gid >= (long long)rows * 64) return;
   const int r = (int)(gid >> 6), c4 = (int)(gid & 63);
@@ -619,13 +643,15 @@ __global__ void __launch_bounds__(256) gather_words_kernel(const int32_t* __rest
 }
 int gather_words(const int32_t* word, const float* table, float* out, int ldo, int rows, int force_zero, cudaStream_t s) {
   const long long n = (long long)rows * 64;
-  gather_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(word, table, out, ldo, rows, force_zero);
+  launch_k(gather_words_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, word, table, out, ldo, rows, force_zero);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
 
 __global__ void __launch_bounds__(256) avgpool4_kernel(const float* __restrict__ in, float* __restrict__ out, long long n4,
                                                        int cols4) {
+  pdl_wait();
+  pdl_launch();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
   if (gid >= n4) return;
   const long long r = gid / cols4;
@@ -641,13 +667,15 @@ __global__ void __launch_bounds__(256) avgpool4_kernel(const float* __restrict__
 }
 int avgpool4(const float* in, float* out, int rows_out, int cols, cudaStream_t s) {
   const long long n4 = (long long)rows_out * cols / 4;
-  avgpool4_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(in, out, n4, cols / 4);
+  launch_k(avgpool4_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, s, in, out, n4, cols / 4);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
 
 __global__ void __launch_bounds__(256) copy_strided_scale_kernel(const float* __restrict__ in, long long in_stride, float scale,
                                                                  float* __restrict__ out, long long n4, int cols4) {
+  pdl_wait();
+  pdl_launch();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
   if (gid >= n4) return;
   const long long r = gid / cols4;
@@ -658,7 +686,7 @@ __global__ void __launch_bounds__(256) copy_strided_scale_kernel(const float* __
 }
 int copy_strided_scale(const float* in, long long in_stride, float scale, float* out, int rows, int cols, cudaStream_t s) {
   const long long n4 = (long long)rows * cols / 4;
-  copy_strided_scale_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(in, in_stride, scale, out, n4, cols / 4);
+  launch_k(copy_strided_scale_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, s, in, in_stride, scale, out, n4, cols / 4);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -673,6 +701,8 @@ __global__ void __launch_bounds__(256) vq_select_kernel(const float* __restrict_
                                                         const float* __restrict__ codebook, float* __restrict__ residual,
                                                         float* __restrict__ qsum, int64_t* __restrict__ idx, int idx_stride,
                                                         int rows, int first) {
+  pdl_wait();
+  pdl_launch();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -726,7 +756,7 @@ __global__ void __launch_bounds__(256) vq_select_kernel(const float* __restrict_
 
 int vq_select(const float* dot, const float* cnorm, const float* codebook, float* residual, float* qsum, int64_t* idx,
               int idx_stride, int rows, int first, cudaStream_t s) {
-  vq_select_kernel<<<(rows + 7) / 8, 256, 0, s>>>(dot, cnorm, codebook, residual, qsum, idx, idx_stride, rows, first);
+  launch_k(vq_select_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, dot, cnorm, codebook, residual, qsum, idx, idx_stride, rows, first);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -792,6 +822,8 @@ __global__ void __launch_bounds__(256) pose330_kernel(const float* __restrict__ 
                                                       const float* __restrict__ lo, const float* __restrict__ mean,
                                                       const float* __restrict__ std, const float* __restrict__ jaw, int BN_,
                                                       float* __restrict__ pose) {
+  pdl_wait();
+  pdl_launch();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
   if (gid >= (long long)BN_ * 55) return;
   const int f = (int)(gid / 55), j = (int)(gid - (long long)f * 55);
@@ -822,6 +854,8 @@ __global__ void __launch_bounds__(256) pose330_kernel(const float* __restrict__ 
 
 __global__ void trans_kernel(const float* __restrict__ lo, const float* __restrict__ tmean, const float* __restrict__ tstd,
                              int B, int n, float* __restrict__ trans) {
+  pdl_wait();
+  pdl_launch();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= B * 3) return;
   const int b = gid / 3, c = gid - b * 3;
@@ -836,10 +870,10 @@ __global__ void trans_kernel(const float* __restrict__ lo, const float* __restri
 int pose330(const float* up, const float* ha, const float* lo, const float* mean, const float* std, const float* tmean,
             const float* tstd, const float* jaw, int B, int n, float* pose, float* trans, cudaStream_t s) {
   const long long tot = (long long)B * n * 55;
-  pose330_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(up, ha, lo, mean, std, jaw, B * n, pose);
+  launch_k(pose330_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, s, up, ha, lo, mean, std, jaw, B * n, pose);
   ST_CHECK_LAUNCH();
   if (trans) {
-    trans_kernel<<<(B * 3 + 127) / 128, 128, 0, s>>>(lo, tmean, tstd, B, n, trans);
+    launch_k(trans_kernel, dim3((B * 3 + 127) / 128), dim3(128), 0, s, lo, tmean, tstd, B, n, trans);
     ST_CHECK_LAUNCH();
   }
   return ST_OK;
@@ -880,6 +914,8 @@ __device__ int h3d_lookup(int c, int* part) {
 
 __global__ void __launch_bounds__(256) pose623_kernel(const float* __restrict__ up, const float* __restrict__ ha,
                                                       const float* __restrict__ lo, int frames, float* __restrict__ pose) {
+  pdl_wait();
+  pdl_launch();
   __shared__ int s_part[623], s_pos[623];
   for (int c = threadIdx.x; c < 623; c += 256) {
     int part = -1;
@@ -902,7 +938,7 @@ __global__ void __launch_bounds__(256) pose623_kernel(const float* __restrict__ 
 
 int pose623(const float* up, const float* ha, const float* lo, int B, int n, float* pose, cudaStream_t s) {
   const int frames = B * n;
-  pose623_kernel<<<frames < 1184 ? frames : 1184, 256, 0, s>>>(up, ha, lo, frames, pose);
+  launch_k(pose623_kernel, dim3(frames < 1184 ? frames : 1184), dim3(256), 0, s, up, ha, lo, frames, pose);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }

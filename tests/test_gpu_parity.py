@@ -73,7 +73,7 @@ def y_of(inp, dev=True):
 # ---- 0. the GEMM engine alone ---------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(128, 64, 16), (1024, 512, 512), (2048, 1536, 512), (300, 78, 1536), (33, 512, 6144), (64, 64, 32)])
 def test_gemm_engine_vs_fp64(M, N, K, engine):
-    if engine == "tc" and (M < 128 or K % 64):
+    if engine == "tc" and K % 64:
         pytest.skip("shape is served by the SIMT engine")
     g = torch.Generator().manual_seed(M + N + K)
     A, Wt, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
@@ -151,10 +151,10 @@ def test_cfg_text_limits(models):
     w = ClassifierFreeSampleModel(m)
     for s, ref in ((1.0, cond), (0.0, unc)):
         yy = dict(y); yy["scale"] = torch.ones(1) * s
-        assert maxabs(w(x, t, yy), ref) < 2e-6
+        assert maxabs(w(x, t, yy), ref) < 2e-5            # 1 vs 2 stacked evaluations: different tiles, fp32 round-off only
     yy = dict(y); yy["scale"] = torch.tensor([0.0, 1.0])           # per-clip scales
     out = w(x, t, yy)
-    assert maxabs(out[0], unc[0]) < 2e-6 and maxabs(out[1], cond[1]) < 2e-6
+    assert maxabs(out[0], unc[0]) < 2e-5 and maxabs(out[1], cond[1]) < 2e-5
 
 
 def test_cfg_is_identity_without_motionclip(models):
