@@ -299,73 +299,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");     // the two warps of this lane group
-    constexpr int LPR = BN / 4;            // lanes per row
-    constexpr int RPI = 32 / LPR;          // rows per warp instruction
-    const int cl = (lane % LPR) * 4;
-    const int n = n0 + cl;
-    const bool vec = (n + 3 < ep.N) && ((ep.ldo & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
-    const bool pvec = (n + 3 < ep.N) && ((ep.ld_planes & 3) == 0);
-    float bias4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (ep.bias) {
+    // pieces of the tile row handled with 32 lanes x float4 (128 columns) or 16 lanes x float4 (64 columns)
+    constexpr int NPIECE = BN == 192 ? 2 : 1;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (n + q < ep.N) bias4[q] = __ldg(ep.bias + n + q);
-    }
-    constexpr int UN = 4;                  // row-instructions in flight
-#pragma unroll 1
-    for (int r0 = half * 16; r0 < half * 16 + 16; r0 += RPI * UN) {
-      float4 t4[UN], r4[UN];
-      int rowv[UN];
-      bool ok[UN];
+    for (int piece = 0; piece < NPIECE; ++piece) {
+      const int pc0 = piece * 128;                                  // first column of the piece
+      const int pw = (BN - pc0) >= 128 ? 128 : 64;                  // its width
+      const int LPR = pw / 4;                                       // lanes per row
+      const int RPI = 32 / LPR;                                     // rows per warp instruction
+      const int cl = pc0 + (lane % LPR) * 4;
+      const int n = n0 + cl;
+      const bool vec = (n + 3 < ep.N) && ((ep.ldo & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
+      const bool pvec = (n + 3 < ep.N) && ((ep.ld_planes & 3) == 0);
+      float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ep.bias) {
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int r = r0 + u * RPI + lane / LPR;
-        rowv[u] = m0 + lg * 32 + r;
-        ok[u] = (lg * 32 + r) < rows_valid && n < ep.N;
-        t4[u] = *reinterpret_cast<const float4*>(tile + r * LDT + cl);
-        r4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ep.res && ok[u]) {
-          const float* rrow = ep.res + (long long)(rowv[u] / ep.res_div) * ep.ldr + n;
-          if (vec) r4[u] = *reinterpret_cast<const float4*>(rrow);
-          else {
-            float rs[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int q = 0; q < 4; ++q) if (n + q < ep.N) rs[q] = rrow[q];
-            r4[u] = make_float4(rs[0], rs[1], rs[2], rs[3]);
-          }
-        }
+        for (int q = 0; q < 4; ++q)
+          if (n + q < ep.N) bias4[q] = __ldg(ep.bias + n + q);
       }
+      constexpr int UN = 4;                  // row-instructions in flight
+#pragma unroll 1
+      for (int r0 = half * 16; r0 < half * 16 + 16; r0 += RPI * UN) {
+        float4 t4[UN], r4[UN];
+        int rowv[UN];
+        bool ok[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        if (!ok[u]) continue;
-        float x[4] = {t4[u].x + bias4[0], t4[u].y + bias4[1], t4[u].z + bias4[2], t4[u].w + bias4[3]};
-        const float rs[4] = {r4[u].x, r4[u].y, r4[u].z, r4[u].w};
-        if (ep.res_mode == RES_PRE) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
-        if (ep.act != ACT_NONE) { x[0] = tc_act(x[0], ep.act); x[1] = tc_act(x[1], ep.act); x[2] = tc_act(x[2], ep.act); x[3] = tc_act(x[3], ep.act); }
-        if (ep.res_mode == RES_POST) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
-        if (ep.out) {
-          float* orow = ep.out + (long long)rowv[u] * ep.ldo + n;
-          if (vec) *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
-          else { for (int q = 0; q < 4; ++q) if (n + q < ep.N) orow[q] = x[q]; }
-        }
-        if (ep.planes) {
-          __half h[4], l[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float a = x[q] * ep.planes_scale;
-            if (ep.planes_relu) a = fmaxf(a, 0.f);
-            split_f16(a, h[q], l[q]);
+        for (int u = 0; u < UN; ++u) {
+          const int r = r0 + u * RPI + lane / LPR;
+          rowv[u] = m0 + lg * 32 + r;
+          ok[u] = (lg * 32 + r) < rows_valid && n < ep.N;
+          t4[u] = *reinterpret_cast<const float4*>(tile + r * LDT + cl);
+          r4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.res && ok[u]) {
+            const float* rrow = ep.res + (long long)(rowv[u] / ep.res_div) * ep.ldr + n;
+            if (vec) r4[u] = *reinterpret_cast<const float4*>(rrow);
+            else {
+              float rs[4] = {0.f, 0.f, 0.f, 0.f};
+              for (int q = 0; q < 4; ++q) if (n + q < ep.N) rs[q] = rrow[q];
+              r4[u] = make_float4(rs[0], rs[1], rs[2], rs[3]);
+            }
           }
-          __half* prow = ep.planes + (long long)rowv[u] * ep.ld_planes + n;
-          if (pvec) {
-            __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
-            __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
-            uint2 hv, lv;
-            hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
-            lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
-            *reinterpret_cast<uint2*>(prow) = hv;
-            *reinterpret_cast<uint2*>(prow + ep.plane_stride) = lv;
-          } else {
-            for (int q = 0; q < 4; ++q) if (n + q < ep.N) { prow[q] = h[q]; prow[ep.plane_stride + q] = l[q]; }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          if (!ok[u]) continue;
+          float x[4] = {t4[u].x + bias4[0], t4[u].y + bias4[1], t4[u].z + bias4[2], t4[u].w + bias4[3]};
+          const float rs[4] = {r4[u].x, r4[u].y, r4[u].z, r4[u].w};
+          if (ep.res_mode == RES_PRE) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
+          if (ep.act != ACT_NONE) { x[0] = tc_act(x[0], ep.act); x[1] = tc_act(x[1], ep.act); x[2] = tc_act(x[2], ep.act); x[3] = tc_act(x[3], ep.act); }
+          if (ep.res_mode == RES_POST) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
+          if (ep.out) {
+            float* orow = ep.out + (long long)rowv[u] * ep.ldo + n;
+            if (vec) *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
+            else { for (int q = 0; q < 4; ++q) if (n + q < ep.N) orow[q] = x[q]; }
+          }
+          if (ep.planes) {
+            __half h[4], l[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float a = x[q] * ep.planes_scale;
+              if (ep.planes_relu) a = fmaxf(a, 0.f);
+              split_f16(a, h[q], l[q]);
+            }
+            __half* prow = ep.planes + (long long)rowv[u] * ep.ld_planes + n;
+            if (pvec) {
+              __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+              __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+              uint2 hv, lv;
+              hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+              lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+              *reinterpret_cast<uint2*>(prow) = hv;
+              *reinterpret_cast<uint2*>(prow + ep.plane_stride) = lv;
+            } else {
+              for (int q = 0; q < 4; ++q) if (n + q < ep.N) { prow[q] = h[q]; prow[ep.plane_stride + q] = l[q]; }
+            }
           }
         }
       }
@@ -673,7 +680,10 @@ launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 
   else if (mode == 1) ST_TRY(get_map_4d(&tmA, planes, pstride, nclips, p.Lin, p.C));
   else if (mode == 2) ST_TRY(get_map_long(&tmA, planes, pstride, nclips, p.Lin, p.C));
   else ST_TRY(get_map_strided(&tmA, planes, pstride, rows, p.C, p.stride));
-  const int BN = p.N <= 512 ? 64 : 128;
+  // tile width: keep the grid at one wave of <= 148 CTAs (1 CTA per SM) whenever the shape allows it
+  const int mt = mode >= 2 ? nclips * ((p.Lout + TC_BM - 1) / TC_BM) : (p.M + TC_BM - 1) / TC_BM;
+  int BN = p.N <= 512 ? 64 : 128;
+  if (p.N % 192 == 0 && mt * (p.N / 128) > 148 && mt * (p.N / 192) <= 148) BN = 192;
   ST_TRY(get_map_3d(&tmW, w->planes, (long long)p.N * w->Kp, p.N, w->Kp, BN));
   ep.out = p.out; ep.bias = p.bias; ep.res = p.res;
   ep.planes = p.o_planes; ep.plane_stride = p.o_plane_stride; ep.ld_planes = p.o_planes_ld; ep.planes_scale = kActScale;
@@ -684,6 +694,7 @@ launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 
   const int num_kb = w->Kp / TC_BK;
   const int mtiles = mode >= 2 ? nclips * ep.tpc : (p.M + TC_BM - 1) / TC_BM;
   if (BN == 64) return launch_tc<64, 4>(*tmA, *tmW, ep, num_kb, mtiles, s);
+  if (BN == 192) return launch_tc<192, 2>(*tmA, *tmW, ep, num_kb, mtiles, s);
   return launch_tc<128, 3>(*tmA, *tmW, ep, num_kb, mtiles, s);
 }
 
