@@ -274,6 +274,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // full-line coalesced; four rows are in flight per iteration to hide latency with one warp per scheduler.
     const int lg = warp & 3;
     const int half = (warp - 2) >> 2;             // 0: warps 2..5, 1: warps 6..9
+    // While the main loop runs these warps are idle: fetch everything phase 2 needs from global memory now (bias,
+    // the residual rows of this warp, kernel parameters), so that after the accumulator is ready only shared-memory
+    // reads, arithmetic and stores remain.
+    constexpr int NPIECE = BN == 192 ? 2 : 1;
+    constexpr int LPR0 = BN >= 128 ? 32 : 16, RPI0 = 32 / LPR0, NRI = 16 / RPI0;   // piece 0 geometry, row-instructions per warp
+    const int cl0 = (lane % LPR0) * 4, n_0 = n0 + cl0;
+    const bool vec0 = (n_0 + 3 < ep.N) && ((ep.ldo & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
+    float bias0[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ep.bias) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (n_0 + q < ep.N) bias0[q] = __ldg(ep.bias + n_0 + q);
+    }
+    float4 rpre[NPIECE == 1 ? NRI : 1];
+    if (NPIECE == 1) {
+#pragma unroll
+      for (int i = 0; i < NRI; ++i) {
+        rpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int r = half * 16 + i * RPI0 + lane / LPR0;
+        if (ep.res && (lg * 32 + r) < rows_valid && n_0 < ep.N) {
+          const float* rrow = ep.res + (long long)((m0 + lg * 32 + r) / ep.res_div) * ep.ldr + n_0;
+          if (vec0) rpre[i] = *reinterpret_cast<const float4*>(rrow);
+          else {
+            float rs[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int q = 0; q < 4; ++q) if (n_0 + q < ep.N) rs[q] = rrow[q];
+            rpre[i] = make_float4(rs[0], rs[1], rs[2], rs[3]);
+          }
+        }
+      }
+    }
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     if (dbg && threadIdx.x == 64) dbg[3] = clock64();
@@ -298,9 +328,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         *reinterpret_cast<float4*>(trow + j) = t;
       }
     }
+    if (dbg && threadIdx.x == 64) dbg[6] = clock64();
     asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");     // the two warps of this lane group
+    if (dbg && threadIdx.x == 64) dbg[7] = clock64();
     // pieces of the tile row handled with 32 lanes x float4 (128 columns) or 16 lanes x float4 (64 columns)
-    constexpr int NPIECE = BN == 192 ? 2 : 1;
 #pragma unroll
     for (int piece = 0; piece < NPIECE; ++piece) {
       const int pc0 = piece * 128;                                  // first column of the piece
@@ -311,14 +342,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n = n0 + cl;
       const bool vec = (n + 3 < ep.N) && ((ep.ldo & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
       const bool pvec = (n + 3 < ep.N) && ((ep.ld_planes & 3) == 0);
-      float bias4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (ep.bias) {
+      float bias4[4] = {bias0[0], bias0[1], bias0[2], bias0[3]};
+      if (piece > 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (n + q < ep.N) bias4[q] = __ldg(ep.bias + n + q);
+        for (int q = 0; q < 4; ++q) bias4[q] = (ep.bias && n + q < ep.N) ? __ldg(ep.bias + n + q) : 0.f;
       }
       constexpr int UN = 4;                  // row-instructions in flight
-#pragma unroll 1
+#pragma unroll
       for (int r0 = half * 16; r0 < half * 16 + 16; r0 += RPI * UN) {
         float4 t4[UN], r4[UN];
         int rowv[UN];
@@ -330,7 +360,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ok[u] = (lg * 32 + r) < rows_valid && n < ep.N;
           t4[u] = *reinterpret_cast<const float4*>(tile + r * LDT + cl);
           r4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ep.res && ok[u]) {
+          if (NPIECE == 1) r4[u] = rpre[(r0 - half * 16) / RPI + u];
+          else if (ep.res && ok[u]) {
             const float* rrow = ep.res + (long long)(rowv[u] / ep.res_div) * ep.ldr + n;
             if (vec) r4[u] = *reinterpret_cast<const float4*>(rrow);
             else {

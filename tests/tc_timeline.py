@@ -18,5 +18,5 @@ for (M, N, K) in [(2048, 512, 512), (2048, 1536, 512), (2048, 512, 1024), (16384
     d = dbg.cpu().tolist(); t0 = d[0]
     nkb = K // 64
     print(f"M={M} N={N} K={K}: setup {d[1]-t0}, tma issue {[x-t0 for x in d[8:8+nkb]]}, full ready {[x-t0 for x in d[24:24+nkb]]}, "
-          f"mma issued {d[2]-t0}, acc ready {d[3]-t0}, epilogue done {d[4]-t0}, end {d[5]-t0}")
+          f"mma issued {d[2]-t0}, acc ready {d[3]-t0}, phase1 done {d[6]-t0}, pair sync {d[7]-t0}, epilogue done {d[4]-t0}, end {d[5]-t0}")
     call(1)
