@@ -104,6 +104,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
@@ -277,15 +285,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // While the main loop runs these warps are idle: fetch everything phase 2 needs from global memory now (bias,
     // the residual rows of this warp, kernel parameters), so that after the accumulator is ready only shared-memory
     // reads, arithmetic and stores remain.
+    const float e_scale = ep.scale, e_pscale = ep.planes_scale;
+    const int e_N = ep.N, e_ldo = ep.ldo, e_ldr = ep.ldr, e_ldp = ep.ld_planes, e_act = ep.act, e_prelu = ep.planes_relu;
+    const int e_resmode = ep.res ? ep.res_mode : RES_NONE, e_resdiv = ep.res_div;
+    const long long e_pstride = ep.plane_stride;
+    float* const e_out = ep.out;
+    const float* const e_res = ep.res;
+    __half* const e_planes = ep.planes;
     constexpr int NPIECE = BN == 192 ? 2 : 1;
     constexpr int LPR0 = BN >= 128 ? 32 : 16, RPI0 = 32 / LPR0, NRI = 16 / RPI0;   // piece 0 geometry, row-instructions per warp
     const int cl0 = (lane % LPR0) * 4, n_0 = n0 + cl0;
-    const bool vec0 = (n_0 + 3 < ep.N) && ((ep.ldo & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
+    const bool vec0 = (n_0 + 3 < e_N) && ((e_ldo & 3) == 0) && (!e_res || (e_ldr & 3) == 0);
     float bias0[4] = {0.f, 0.f, 0.f, 0.f};
     if (ep.bias) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (n_0 + q < ep.N) bias0[q] = __ldg(ep.bias + n_0 + q);
+        if (n_0 + q < e_N) bias0[q] = __ldg(ep.bias + n_0 + q);
     }
     float4 rpre[NPIECE == 1 ? NRI : 1];
     if (NPIECE == 1) {
@@ -293,12 +308,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = 0; i < NRI; ++i) {
         rpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int r = half * 16 + i * RPI0 + lane / LPR0;
-        if (ep.res && (lg * 32 + r) < rows_valid && n_0 < ep.N) {
-          const float* rrow = ep.res + (long long)((m0 + lg * 32 + r) / ep.res_div) * ep.ldr + n_0;
+        if (e_res && (lg * 32 + r) < rows_valid && n_0 < e_N) {
+          const int grow = m0 + lg * 32 + r;
+          const float* rrow = e_res + (long long)(e_resdiv == 1 ? grow : grow / e_resdiv) * e_ldr + n_0;
           if (vec0) rpre[i] = *reinterpret_cast<const float4*>(rrow);
           else {
             float rs[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int q = 0; q < 4; ++q) if (n_0 + q < ep.N) rs[q] = rrow[q];
+            for (int q = 0; q < 4; ++q) if (n_0 + q < e_N) rs[q] = rrow[q];
             rpre[i] = make_float4(rs[0], rs[1], rs[2], rs[3]);
           }
         }
@@ -308,7 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     if (dbg && threadIdx.x == 64) dbg[3] = clock64();
     constexpr int LDT = BN + 4;
-    float* tile = reinterpret_cast<float*>(smem) + (size_t)(lg * 32) * LDT;
+    const uint32_t tile = smem_u32(smem) + (uint32_t)(lg * 32) * LDT * 4;      // shared-space byte address of this lane group's rows
     constexpr int CH = BN / 32;                   // 32-column chunks; each warp of the pair takes CH/2 of them
 #pragma unroll
     for (int cc = 0; cc < CH / 2; ++cc) {
@@ -317,15 +333,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + c * 32, v);
       tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + BN + c * 32, vc);
       tmem_ld_wait();
-      float* trow = tile + lane * LDT + c * 32;
+      const uint32_t trow = tile + (uint32_t)(lane * LDT + c * 32) * 4;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 t;
-        t.x = (__uint_as_float(v[j]) + __uint_as_float(vc[j])) * ep.scale;
-        t.y = (__uint_as_float(v[j + 1]) + __uint_as_float(vc[j + 1])) * ep.scale;
-        t.z = (__uint_as_float(v[j + 2]) + __uint_as_float(vc[j + 2])) * ep.scale;
-        t.w = (__uint_as_float(v[j + 3]) + __uint_as_float(vc[j + 3])) * ep.scale;
-        *reinterpret_cast<float4*>(trow + j) = t;
+        t.x = (__uint_as_float(v[j]) + __uint_as_float(vc[j])) * e_scale;
+        t.y = (__uint_as_float(v[j + 1]) + __uint_as_float(vc[j + 1])) * e_scale;
+        t.z = (__uint_as_float(v[j + 2]) + __uint_as_float(vc[j + 2])) * e_scale;
+        t.w = (__uint_as_float(v[j + 3]) + __uint_as_float(vc[j + 3])) * e_scale;
+        sts128(trow + j * 4, t);
       }
     }
     if (dbg && threadIdx.x == 64) dbg[6] = clock64();
@@ -340,12 +356,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int RPI = 32 / LPR;                                     // rows per warp instruction
       const int cl = pc0 + (lane % LPR) * 4;
       const int n = n0 + cl;
-      const bool vec = (n + 3 < ep.N) && ((ep.ldo & 3) == 0) && (!ep.res || (ep.ldr & 3) == 0);
-      const bool pvec = (n + 3 < ep.N) && ((ep.ld_planes & 3) == 0);
+      const bool vec = (n + 3 < e_N) && ((e_ldo & 3) == 0) && (!e_res || (e_ldr & 3) == 0);
+      const bool pvec = (n + 3 < e_N) && ((e_ldp & 3) == 0);
       float bias4[4] = {bias0[0], bias0[1], bias0[2], bias0[3]};
       if (piece > 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bias4[q] = (ep.bias && n + q < ep.N) ? __ldg(ep.bias + n + q) : 0.f;
+        for (int q = 0; q < 4; ++q) bias4[q] = (ep.bias && n + q < e_N) ? __ldg(ep.bias + n + q) : 0.f;
       }
       constexpr int UN = 4;                  // row-instructions in flight
 #pragma unroll
@@ -357,16 +373,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int u = 0; u < UN; ++u) {
           const int r = r0 + u * RPI + lane / LPR;
           rowv[u] = m0 + lg * 32 + r;
-          ok[u] = (lg * 32 + r) < rows_valid && n < ep.N;
-          t4[u] = *reinterpret_cast<const float4*>(tile + r * LDT + cl);
+          ok[u] = (lg * 32 + r) < rows_valid && n < e_N;
+          t4[u] = lds128(tile + (uint32_t)(r * LDT + cl) * 4);
           r4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (NPIECE == 1) r4[u] = rpre[(r0 - half * 16) / RPI + u];
-          else if (ep.res && ok[u]) {
-            const float* rrow = ep.res + (long long)(rowv[u] / ep.res_div) * ep.ldr + n;
+          else if (e_res && ok[u]) {
+            const float* rrow = e_res + (long long)(e_resdiv == 1 ? rowv[u] : rowv[u] / e_resdiv) * e_ldr + n;
             if (vec) r4[u] = *reinterpret_cast<const float4*>(rrow);
             else {
               float rs[4] = {0.f, 0.f, 0.f, 0.f};
-              for (int q = 0; q < 4; ++q) if (n + q < ep.N) rs[q] = rrow[q];
+              for (int q = 0; q < 4; ++q) if (n + q < e_N) rs[q] = rrow[q];
               r4[u] = make_float4(rs[0], rs[1], rs[2], rs[3]);
             }
           }
@@ -376,23 +392,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!ok[u]) continue;
           float x[4] = {t4[u].x + bias4[0], t4[u].y + bias4[1], t4[u].z + bias4[2], t4[u].w + bias4[3]};
           const float rs[4] = {r4[u].x, r4[u].y, r4[u].z, r4[u].w};
-          if (ep.res_mode == RES_PRE) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
-          if (ep.act != ACT_NONE) { x[0] = tc_act(x[0], ep.act); x[1] = tc_act(x[1], ep.act); x[2] = tc_act(x[2], ep.act); x[3] = tc_act(x[3], ep.act); }
-          if (ep.res_mode == RES_POST) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
-          if (ep.out) {
-            float* orow = ep.out + (long long)rowv[u] * ep.ldo + n;
-            if (vec) *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
-            else { for (int q = 0; q < 4; ++q) if (n + q < ep.N) orow[q] = x[q]; }
+          if (e_resmode == RES_PRE) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
+          if (e_act == ACT_GELU) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = x[q] * 0.5f * (1.0f + erff(x[q] * 0.70710678118654752440f));
+          } else if (e_act == ACT_RELU) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = fmaxf(x[q], 0.0f);
+          } else if (e_act == ACT_LRELU) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = x[q] > 0.0f ? x[q] : x[q] * 0.01f;
           }
-          if (ep.planes) {
+          if (e_resmode == RES_POST) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
+          if (e_out) {
+            float* orow = e_out + (long long)rowv[u] * e_ldo + n;
+            if (vec) *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
+            else { for (int q = 0; q < 4; ++q) if (n + q < e_N) orow[q] = x[q]; }
+          }
+          if (e_planes) {
             __half h[4], l[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              float a = x[q] * ep.planes_scale;
-              if (ep.planes_relu) a = fmaxf(a, 0.f);
+              float a = x[q] * e_pscale;
+              if (e_prelu) a = fmaxf(a, 0.f);
               split_f16(a, h[q], l[q]);
             }
-            __half* prow = ep.planes + (long long)rowv[u] * ep.ld_planes + n;
+            __half* prow = e_planes + (long long)rowv[u] * e_ldp + n;
             if (pvec) {
               __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
               __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
@@ -400,9 +425,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
               lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
               *reinterpret_cast<uint2*>(prow) = hv;
-              *reinterpret_cast<uint2*>(prow + ep.plane_stride) = lv;
+              *reinterpret_cast<uint2*>(prow + e_pstride) = lv;
             } else {
-              for (int q = 0; q < 4; ++q) if (n + q < ep.N) { prow[q] = h[q]; prow[ep.plane_stride + q] = l[q]; }
+              for (int q = 0; q < 4; ++q) if (n + q < e_N) { prow[q] = h[q]; prow[e_pstride + q] = l[q]; }
             }
           }
         }
