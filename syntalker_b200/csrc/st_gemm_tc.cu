@@ -302,24 +302,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int q = 0; q < 4; ++q)
         if (n_0 + q < e_N) bias0[q] = __ldg(ep.bias + n_0 + q);
     }
-    float4 rpre[NPIECE == 1 ? NRI : 1];
-    if (NPIECE == 1) {
-#pragma unroll
-      for (int i = 0; i < NRI; ++i) {
-        rpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int r = half * 16 + i * RPI0 + lane / LPR0;
-        if (e_res && (lg * 32 + r) < rows_valid && n_0 < e_N) {
-          const int grow = m0 + lg * 32 + r;
-          const float* rrow = e_res + (long long)(e_resdiv == 1 ? grow : grow / e_resdiv) * e_ldr + n_0;
-          if (vec0) rpre[i] = *reinterpret_cast<const float4*>(rrow);
-          else {
-            float rs[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int q = 0; q < 4; ++q) if (n_0 + q < e_N) rs[q] = rrow[q];
-            rpre[i] = make_float4(rs[0], rs[1], rs[2], rs[3]);
-          }
-        }
-      }
-    }
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     if (dbg && threadIdx.x == 64) dbg[3] = clock64();
@@ -347,15 +329,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (dbg && threadIdx.x == 64) dbg[6] = clock64();
     asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");     // the two warps of this lane group
     if (dbg && threadIdx.x == 64) dbg[7] = clock64();
-    // pieces of the tile row handled with 32 lanes x float4 (128 columns) or 16 lanes x float4 (64 columns)
+    // pieces of the tile row handled with 32 lanes x float4 (128 columns) or 16 lanes x float4 (64 columns).
+    // The row loop is deliberately NOT unrolled: this code runs once per CTA, and an unrolled epilogue (40 KB of
+    // SASS) spent ~2000 cycles per row-instruction in instruction-cache misses.  Loads run two rows ahead instead.
 #pragma unroll
     for (int piece = 0; piece < NPIECE; ++piece) {
       const int pc0 = piece * 128;                                  // first column of the piece
       const int pw = (BN - pc0) >= 128 ? 128 : 64;                  // its width
       const int LPR = pw / 4;                                       // lanes per row
       const int RPI = 32 / LPR;                                     // rows per warp instruction
+      const int iters = 16 / RPI;                                   // row-instructions for this warp's 16 rows
       const int cl = pc0 + (lane % LPR) * 4;
       const int n = n0 + cl;
+      const int rsub = lane / LPR;
+      const bool col_ok = n < e_N;
       const bool vec = (n + 3 < e_N) && ((e_ldo & 3) == 0) && (!e_res || (e_ldr & 3) == 0);
       const bool pvec = (n + 3 < e_N) && ((e_ldp & 3) == 0);
       float bias4[4] = {bias0[0], bias0[1], bias0[2], bias0[3]};
@@ -363,35 +350,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int q = 0; q < 4; ++q) bias4[q] = (ep.bias && n + q < e_N) ? __ldg(ep.bias + n + q) : 0.f;
       }
-      constexpr int UN = 4;                  // row-instructions in flight
-#pragma unroll
-      for (int r0 = half * 16; r0 < half * 16 + 16; r0 += RPI * UN) {
-        float4 t4[UN], r4[UN];
-        int rowv[UN];
-        bool ok[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          const int r = r0 + u * RPI + lane / LPR;
-          rowv[u] = m0 + lg * 32 + r;
-          ok[u] = (lg * 32 + r) < rows_valid && n < e_N;
-          t4[u] = lds128(tile + (uint32_t)(r * LDT + cl) * 4);
-          r4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (NPIECE == 1) r4[u] = rpre[(r0 - half * 16) / RPI + u];
-          else if (e_res && ok[u]) {
-            const float* rrow = e_res + (long long)(e_resdiv == 1 ? rowv[u] : rowv[u] / e_resdiv) * e_ldr + n;
-            if (vec) r4[u] = *reinterpret_cast<const float4*>(rrow);
-            else {
-              float rs[4] = {0.f, 0.f, 0.f, 0.f};
-              for (int q = 0; q < 4; ++q) if (n + q < e_N) rs[q] = rrow[q];
-              r4[u] = make_float4(rs[0], rs[1], rs[2], rs[3]);
-            }
+      auto load_row = [&](int it, float4& t4, float4& r4) {
+        const int r = half * 16 + it * RPI + rsub;
+        t4 = lds128(tile + (uint32_t)(r * LDT + cl) * 4);
+        r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e_res && col_ok && (lg * 32 + r) < rows_valid) {
+          const int grow = m0 + lg * 32 + r;
+          const float* rrow = e_res + (long long)(e_resdiv == 1 ? grow : grow / e_resdiv) * e_ldr + n;
+          if (vec) r4 = *reinterpret_cast<const float4*>(rrow);
+          else {
+            r4.x = rrow[0];
+            if (n + 1 < e_N) r4.y = rrow[1];
+            if (n + 2 < e_N) r4.z = rrow[2];
+            if (n + 3 < e_N) r4.w = rrow[3];
           }
         }
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          if (!ok[u]) continue;
-          float x[4] = {t4[u].x + bias4[0], t4[u].y + bias4[1], t4[u].z + bias4[2], t4[u].w + bias4[3]};
-          const float rs[4] = {r4[u].x, r4[u].y, r4[u].z, r4[u].w};
+      };
+      float4 tA, rA, tB, rB, tC, rC;
+      load_row(0, tA, rA);
+      load_row(iters > 1 ? 1 : 0, tB, rB);
+#pragma unroll 1
+      for (int it = 0; it < iters; ++it) {
+        if (it + 2 < iters) load_row(it + 2, tC, rC);
+        const int r = half * 16 + it * RPI + rsub;
+        if (col_ok && (lg * 32 + r) < rows_valid) {
+          const int grow = m0 + lg * 32 + r;
+          float x[4] = {tA.x + bias4[0], tA.y + bias4[1], tA.z + bias4[2], tA.w + bias4[3]};
+          const float rs[4] = {rA.x, rA.y, rA.z, rA.w};
           if (e_resmode == RES_PRE) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
           if (e_act == ACT_GELU) {
 #pragma unroll
@@ -405,7 +390,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (e_resmode == RES_POST) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
           if (e_out) {
-            float* orow = e_out + (long long)rowv[u] * e_ldo + n;
+            float* orow = e_out + (long long)grow * e_ldo + n;
             if (vec) *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
             else { for (int q = 0; q < 4; ++q) if (n + q < e_N) orow[q] = x[q]; }
           }
@@ -417,7 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (e_prelu) a = fmaxf(a, 0.f);
               split_f16(a, h[q], l[q]);
             }
-            __half* prow = e_planes + (long long)rowv[u] * e_ldp + n;
+            __half* prow = e_planes + (long long)grow * e_ldp + n;
             if (pvec) {
               __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
               __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
@@ -431,6 +416,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        tA = tB; rA = rB; tB = tC; rB = rC;
       }
     }
     tc_fence_before();
