@@ -139,3 +139,31 @@ class Window330:
         self.h2d_bytes = nb
         self.d2h_bytes = (h["pose"].numel() + h["trans"].numel() + (h["sample"].numel() if want_sample else 0)) * 4
         return h["pose"], h["trans"]
+
+
+class Window623:
+    """HumanML3D-623 window (h3d_diffusion_new_trainer.py:548-607): conditioning -> DDIM-50 with the body-part
+    CFG wrapper -> x latent_scale -> latent2origin x3 (156 / 360 / 107) -> 623-d scatter. Device tensors in and out;
+    every stage is a native call (st_cond_encode, st_sample, st_rvq_decode, st_pose_assemble_623)."""
+
+    def __init__(self, model, diffusion, vq_upper, vq_hands, vq_lower, latent_scale=5.0):
+        self.model, self.diffusion = model, diffusion
+        self.vqs = (vq_upper, vq_hands, vq_lower)
+        self.latent_scale = float(latent_scale)
+
+    def run(self, audio, word, seed, x_init, style_feature, use_ddim=True):
+        B = x_init.shape[0]
+        y = {"audio": audio, "word": word, "seed": seed, "style_feature": style_feature}
+        loop = self.diffusion.ddim_sample_loop if use_ddim else self.diffusion.p_sample_loop
+        sample = loop(self.model, (B, 1536, 1, 32), noise=x_init, clip_denoised=False, model_kwargs={"y": y})
+        dev = sample.device
+        tok = torch.empty((B, 32, 1536), device=dev)
+        recs = []
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().st_sample_to_tokens(sample.data_ptr(), B, 32, 1.0, tok.data_ptr(), _lib.stream_ptr()))
+            for k, vq in enumerate(self.vqs):
+                rec = torch.empty((B, 128, vq.input_width), device=dev)
+                _lib.check(_lib.lib().st_rvq_decode(vq.handle, tok.data_ptr() + 4 * 512 * k, 1536, self.latent_scale, B, 32,
+                                                   rec.data_ptr(), None, None, _lib.stream_ptr()))
+                recs.append(rec)
+        return pose_assemble_623(recs[0], recs[1], recs[2]), sample

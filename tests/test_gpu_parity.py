@@ -17,7 +17,7 @@ from syntalker_b200.cfg_sampler import ClassifierFreeSampleModel, TwoClassifierF
 from syntalker_b200.denoiser import MDM
 from syntalker_b200.denoiser_h3d import MDM as MDM_H3D
 from syntalker_b200.diffusion import create_gaussian_diffusion
-from syntalker_b200.pipeline import Window330, load_mean_std, pose_assemble_330, pose_assemble_623
+from syntalker_b200.pipeline import Window330, Window623, load_mean_std, pose_assemble_330, pose_assemble_623
 from syntalker_b200.vq import RVQVAE
 
 torch.set_grad_enabled(False)
@@ -371,3 +371,60 @@ def test_e2e_config2_shape_properties(W, vq_w, models, vqs, engine):
     bad = np.abs(pose[:2].numpy() - pose_ref.numpy()) > 1e-3
     print(f"config2 parity: latent max-abs {maxabs(sample[:2], s_ref):.2e}, pose elements over 1e-3: {bad.mean():.2e}")
     assert bad.mean() < 2e-2        # an index flip at an fp32 near-tie moves one 4-frame block of one body part
+
+
+# ---- 7. the other BASELINE configurations ------------------------------------------------------------------------
+def test_config4_h3d_bodypart_pipeline_vs_oracle(W, models, engine):
+    """BASELINE config 4 at reduced size: denoiser_h3d inside TwoClassifierFreeSampleModel_Bodypart (9 evaluations per
+    step in the reference, 4 here), upper + lower prompts, DDIM, 156/360/107 decoders, 623-d scatter."""
+    B = 2
+    inp = synth.make_inputs(B, seed=41, variant="h3d")
+    sf = {"upper_mask": inp["style_upper"], "hands_mask": None, "lower_mask": inp["style_lower"]}
+    vq_w = {d: synth.rvq_state_dict(d, seed=0) for d in synth.PART_DIMS_H3D}
+    vqs_h = [RVQVAE(None, d).load_state_dict(vq_w[d]) for d in synth.PART_DIMS_H3D]
+    d = create_gaussian_diffusion(timestep_respacing="ddim10")
+    win = Window623(TwoClassifierFreeSampleModel_Bodypart(models["h3d"]), d, *vqs_h)
+    sfd = {k: (v.cuda() if v is not None else None) for k, v in sf.items()}
+    pose, sample = win.run(inp["audio"].cuda(), inp["word"].cuda(), inp["seed"].cuda(), inp["noise"].cuda(), sfd)
+    assert pose.shape == (B, 128, 623)
+    y = {"audio": inp["audio"], "word": inp["word"], "seed": inp["seed"], "style_feature": sf}
+    fn = lambda x, t, yy: omdm.cfg_bodypart(lambda a, b, c: omdm.mdm_forward(W["h3d"], a, b, c, "h3d"), x, t, yy)
+    s_ref = odiff.ddim_sample_loop(odiff.make_schedule(respacing="ddim10"), fn, inp["noise"], y)
+    assert maxabs(sample, s_ref) < 1e-3
+    lats = opose.sample_to_parts(s_ref, 5.0)
+    outs = [orvq.latent2origin(vq_w[dd], l) for dd, l in zip(synth.PART_DIMS_H3D, lats)]
+    pose_ref = opose.assemble_623(outs[0][0], outs[1][0], outs[2][0])
+    bad = np.abs(pose.cpu().numpy() - pose_ref.numpy()) > 1e-3
+    assert bad.mean() < 2e-2          # zero unless a code index sits on an fp32 near-tie
+
+
+def test_config3_ddpm1000_properties(models):
+    """BASELINE config 3's loop (1000-step p_sample_loop) at B=2: finite, seed-deterministic, noise-dependent, and the
+    1000 graph replays use the same device loop state as the 20-step golden case."""
+    m = models["beatx"]
+    inp = synth.make_inputs(2, seed=51)
+    kw = {"y": y_of(inp)}
+    d = create_gaussian_diffusion()
+    assert d.num_timesteps == 1000
+    outs = []
+    for seed in (5, 5, 6):
+        torch.manual_seed(seed)
+        outs.append(d.p_sample_loop(m, (2, 1536, 1, 32), noise=inp["noise"].cuda(), clip_denoised=False, model_kwargs=kw))
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+
+
+def test_config5_decode_only_large_batch(vq_w, vqs):
+    """BASELINE config 5 (RVQ decode-only) at B=256 x 128 frames: row-block independence and agreement with the
+    oracle on a slice; the full B=1024 shape is exercised by profiles/ runs."""
+    g = torch.Generator().manual_seed(61)
+    lat = 5.0 * torch.randn(256, 32, 512, generator=g)
+    for d in synth.PART_DIMS_BEATX:
+        rec = vqs[d].latent2origin(lat.cuda().clone())[0]
+        assert rec.shape == (256, 128, d) and torch.isfinite(rec).all()
+        part = vqs[d].latent2origin(lat[100:104].cuda().clone())[0]
+        assert maxabs(part, rec[100:104]) < 2e-5
+    rec_ref, idx_ref = orvq.latent2origin(vq_w[78], lat[:8])
+    rec8, _, _, idx8 = vqs[78].latent2origin(lat[:8].cuda().clone(), return_indices=True)
+    clean = ~(idx8.cpu() != idx_ref).any(dim=-1).any(dim=-1)
+    assert clean.float().mean() > 0.8 and maxabs(rec8.cpu()[clean], rec_ref[clean]) < 3e-4
