@@ -166,7 +166,7 @@ struct st_model {
   float *scale_dev = nullptr, *scale2_dev = nullptr;
   int64_t* t_tmp = nullptr;
   // fp16 hi/lo operand planes for the tcgen05 engine
-  __half *H_p = nullptr, *ATT_p = nullptr, *G_p = nullptr, *X_p = nullptr;
+  __half *H_p = nullptr, *ATT_p = nullptr, *G_p = nullptr, *X_p = nullptr, *xs_p = nullptr;
   // sampling-loop state on the device + one captured step graph per (plan, mode, engine)
   LoopState* loop = nullptr;
   int32_t* t_model_dev = nullptr;
@@ -290,7 +290,7 @@ static int model_workspace(st_model* m, int B) {
   f += nE * rows * (512 * 3 + 1536 * 2 + 1024);                // X,H,ATT,QKV,O,G
   f += 4 * (size_t)cb * kWavLen[1] * 64 + (size_t)cb * 128 * 512 + (size_t)cb * 32 * 512;
   f += 2 * (size_t)B + 64;
-  f += nE * rows * (512 * 3 + 1024);                           // fp16 hi+lo planes H_p, ATT_p, X_p, G_p (2 halves = 1 float each)
+  f += nE * rows * (512 * 3 + 1024) + rows * 1536;             // fp16 hi+lo planes H_p, ATT_p, X_p, G_p, xs_p (2 halves = 1 float each)
   f += 1000 * (1 + ST_COEF_STRIDE) + 64;
   size_t bytes = f * sizeof(float) + (size_t)B * sizeof(int64_t) + 64 * 256;
   for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);  // captured pointers die with the old block
@@ -319,6 +319,7 @@ static int model_workspace(st_model* m, int B) {
   m->ATT_p = a.take<__half>(2 * nE * rows * 512);
   m->X_p = a.take<__half>(2 * nE * rows * 512);
   m->G_p = a.take<__half>(2 * nE * rows * 1024);
+  m->xs_p = a.take<__half>(2 * rows * 1536);
   m->loop = a.take<LoopState>(1);
   m->t_model_dev = a.take<int32_t>(1000);
   m->coef_dev = a.take<float>(1000 * ST_COEF_STRIDE);
@@ -477,6 +478,12 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   const bool tc = (st_get_engine() == ST_ENGINE_TC);
   const long long ps512 = (long long)R * 512, ps1024 = (long long)R * 1024;
   GemmP pz = linear(m->xs, rows, 1536, m->w_x, nullptr, m->z, 512);
+  if (tc) {
+    // the state is split into the model's own planes: a captured step graph must not point into the engine's
+    // global split scratch, which is reallocated when some other call needs a larger one
+    ST_TRY(tc_split(m->xs, 1536, rows, 1536, m->xs_p, s));
+    pz.a_planes = m->xs_p; pz.a_plane_stride = (long long)rows * 1536;
+  }
   ST_TRY(gemm(pz, s));
   TokensInP tp;
   tp.z = m->z; tp.vt_table = m->vt_table; tp.t_dev = t_dev; tp.t_scalar = t_scalar; tp.g2 = m->g2;
