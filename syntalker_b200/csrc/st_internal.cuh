@@ -113,7 +113,6 @@ struct LoopState {
 GemmP linear(const float* A, int M, int K, const float* W, const float* bias, float* out, int N);
 
 int gemm_simt(const GemmP& p, cudaStream_t s);
-int gemm_skinny(const GemmP& p, cudaStream_t s);   // plain Linear with M <= 64, bias only
 int gemm(const GemmP& p, cudaStream_t s);   // dispatches on the engine (TC falls back to SIMT for shapes it does not take)
 bool tc_supported(const GemmP& p);
 int gemm_tc(const GemmP& p, cudaStream_t s);

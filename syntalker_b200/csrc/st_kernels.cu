@@ -205,46 +205,6 @@ int gemm_simt(const GemmP& p, cudaStream_t s) {
   return ST_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// 1b. Skinny Linear (M <= 64 rows, e.g. the per-clip seed / style projections, denoiser.py:147-149): one warp per
-//     output column streams its weight row once (HBM-bound), 32 rows of A per pass are kept in registers.
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gemm_skinny_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-                                                          const float* __restrict__ bias, float* __restrict__ out, int ldo, int M, int N,
-                                                          int K) {
-  pdl_wait();
-  pdl_launch();
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (n >= N) return;
-  const float* wrow = W + (long long)n * ldw;
-  for (int m0 = 0; m0 < M; m0 += 32) {
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    const int mr = min(32, M - m0);
-    for (int k = lane; k < K; k += 32) {
-      const float w = __ldg(wrow + k);
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < mr) acc[i] = fmaf(__ldg(A + (long long)(m0 + i) * lda + k), w, acc[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float v = acc[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && i < mr) out[(long long)(m0 + i) * ldo + n] = v + (bias ? bias[n] : 0.f);
-    }
-  }
-}
-
-int gemm_skinny(const GemmP& p, cudaStream_t s) {
-  launch_k(gemm_skinny_kernel, dim3((p.N + 7) / 8), dim3(256), 0, s, p.A, p.lda, p.W, p.ldw, p.bias, p.out, p.ldo, p.M, p.N, p.K);
-  ST_CHECK_LAUNCH();
-  return ST_OK;
-}
-
 // =========================================================================================================
 // 2. LayerNorm over 512 channels, eps 1e-5, affine (transformer.py:172,185).  One warp per row.
 // =========================================================================================================

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from syntalker_b200 import _lib
 L = _lib.lib()
 dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
-for (M, N, K) in [(2048, 512, 512), (2048, 1536, 512), (2048, 512, 1024), (16384, 512, 512)]:
+for (M, N, K) in [(128, 512, 512), (512, 512, 512), (1024, 512, 512), (2048, 512, 512), (2048, 1536, 512), (2048, 1024, 512), (16384, 512, 512)]:
     A = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda") / K ** 0.5; b = torch.randn(N, device="cuda")
     out = torch.empty(M, N, device="cuda")
     call = lambda e: _lib.check(L.st_selftest_gemm(M, N, K, e, A.data_ptr(), W.data_ptr(), b.data_ptr(), out.data_ptr(), _lib.stream_ptr()))
