@@ -142,7 +142,10 @@ static const int kWavLen[7] = {68224, 14322, 2385, 2385, 396, 396, 128};
 static const int kCondChunk = 32;
 
 struct ConvW { const float* w; const float* b; int ldw; };
-struct BlkW { const float *ln1g, *ln1b, *qkv, *projw, *projb, *ln2g, *ln2b, *fc1w, *fc1b, *fc2w, *fc2b; };
+struct BlkW {
+  const float *ln1g, *ln1b, *qkv, *projw, *projb, *ln2g, *ln2b, *fc1w, *fc1b, *fc2w, *fc2b;
+  const float *qkv_wg, *qkv_s, *qkv_c, *fc1_wg, *fc1_s, *fc1_c;   // LayerNorm folded into the consuming Linear (tcgen05 engine)
+};
 struct EvalSpec { int cst_null; int sv_src; };   // sv_src: -1 none, 0..2 = style k, 3 = null embedding
 
 struct st_model {
@@ -167,6 +170,7 @@ struct st_model {
   int64_t* t_tmp = nullptr;
   // fp16 hi/lo operand planes for the tcgen05 engine
   __half *H_p = nullptr, *ATT_p = nullptr, *G_p = nullptr, *X_p = nullptr, *xs_p = nullptr;
+  float* ln_stats = nullptr;   // [nE*B*32][8][2] partial (mean, M2) of the residual rows
   // sampling-loop state on the device + one captured step graph per (plan, mode, engine)
   LoopState* loop = nullptr;
   int32_t* t_model_dev = nullptr;
@@ -251,6 +255,8 @@ static int model_resolve(st_model* m) {
     b.ln2g = g("ln2.g", 512); b.ln2b = g("ln2.b", 512);
     b.fc1w = g("fc1.w", 1024 * 512); b.fc1b = g("fc1.b", 1024);
     b.fc2w = g("fc2.w", 512 * 1024); b.fc2b = g("fc2.b", 512);
+    b.qkv_wg = g("qkv.wg", 1536 * 512); b.qkv_s = g("qkv.s", 1536); b.qkv_c = g("qkv.c", 1536);
+    b.fc1_wg = g("fc1.wg", 1024 * 512); b.fc1_s = g("fc1.s", 1024); b.fc1_c = g("fc1.c", 1024);
   }
   return err;
 }
@@ -291,7 +297,7 @@ static int model_workspace(st_model* m, int B) {
   f += 4 * (size_t)cb * kWavLen[1] * 64 + (size_t)cb * 128 * 512 + (size_t)cb * 32 * 512;
   f += 2 * (size_t)B + 64;
   f += nE * rows * (512 * 3 + 1024) + rows * 1536;             // fp16 hi+lo planes H_p, ATT_p, X_p, G_p, xs_p (2 halves = 1 float each)
-  f += 1000 * (1 + ST_COEF_STRIDE) + 64;
+  f += 1000 * (1 + ST_COEF_STRIDE) + 64 + nE * rows * 16;
   size_t bytes = f * sizeof(float) + (size_t)B * sizeof(int64_t) + 64 * 256;
   for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);  // captured pointers die with the old block
   m->graphs.clear(); m->warmed.clear(); m->graph_nodes.clear();
@@ -320,6 +326,7 @@ static int model_workspace(st_model* m, int B) {
   m->X_p = a.take<__half>(2 * nE * rows * 512);
   m->G_p = a.take<__half>(2 * nE * rows * 1024);
   m->xs_p = a.take<__half>(2 * rows * 1536);
+  m->ln_stats = a.take<float>(nE * rows * 16);
   m->loop = a.take<LoopState>(1);
   m->t_model_dev = a.take<int32_t>(1000);
   m->coef_dev = a.take<float>(1000 * ST_COEF_STRIDE);
@@ -489,6 +496,7 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   tp.z = m->z; tp.vt_table = m->vt_table; tp.t_dev = t_dev; tp.t_scalar = t_scalar; tp.g2 = m->g2;
   tp.ls = loop ? m->loop : nullptr; tp.t_model_dev = m->t_model_dev;
   tp.rope_cos = m->rope_cos; tp.rope_sin = m->rope_sin; tp.x = m->X; tp.B = B; tp.nE = pl.nE;
+  tp.x_planes = tc ? m->X_p : nullptr; tp.stats = tc ? m->ln_stats : nullptr;
   for (int e = 0; e < ST_MAX_EVALS; ++e) { tp.cst[e] = m->cst_real; tp.cst_bcast[e] = 0; tp.sv[e] = nullptr; tp.sv_bcast[e] = 0; }
   for (int e = 0; e < pl.nE; ++e) {
     if (pl.ev[e].cst_null) { tp.cst[e] = m->cst_null; tp.cst_bcast[e] = 1; }
@@ -499,26 +507,40 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   ST_TRY(tokens_in(tp, s));
   for (int i = 0; i < 8; ++i) {
     const BlkW& b = m->blk[i];
-    ST_TRY(layernorm512(m->X, b.ln1g, b.ln1b, tc ? nullptr : m->H, tc ? m->H_p : nullptr, R, s));
+    if (tc) {
+      // tcgen05 engine: 5 launches per block.  LayerNorm never runs as a kernel: the GEMM that consumes it reads the raw
+      // residual planes and applies (mean, 1/sigma) in its epilogue from the row statistics its producer left.
+      GemmP pq = linear(m->X, R, 512, b.qkv_wg, nullptr, m->QKV, 1536);
+      pq.a_planes = m->X_p; pq.a_plane_stride = ps512; pq.ln_stats = m->ln_stats; pq.ln_s = b.qkv_s; pq.ln_c = b.qkv_c;
+      ST_TRY(gemm(pq, s));
+      ST_TRY(attention32(m->QKV, nullptr, m->ATT_p, pl.nE * B, s));
+      GemmP pp = linear(m->ATT, R, 512, b.projw, b.projb, m->X, 512);
+      pp.res = m->X; pp.res_mode = RES_POST; pp.ldr = 512; pp.a_planes = m->ATT_p; pp.a_plane_stride = ps512;
+      pp.o_planes = m->X_p; pp.o_plane_stride = ps512; pp.o_planes_ld = 512; pp.stats_out = m->ln_stats;
+      ST_TRY(gemm(pp, s));
+      GemmP p1 = linear(m->X, R, 512, b.fc1_wg, nullptr, nullptr, 1024);
+      p1.act = ACT_GELU; p1.a_planes = m->X_p; p1.a_plane_stride = ps512; p1.ln_stats = m->ln_stats; p1.ln_s = b.fc1_s; p1.ln_c = b.fc1_c;
+      p1.o_planes = m->G_p; p1.o_plane_stride = ps1024; p1.o_planes_ld = 1024;
+      ST_TRY(gemm(p1, s));
+      GemmP p2 = linear(m->G, R, 1024, b.fc2w, b.fc2b, m->X, 512);
+      p2.res = m->X; p2.res_mode = RES_POST; p2.ldr = 512; p2.a_planes = m->G_p; p2.a_plane_stride = ps1024;
+      p2.o_planes = m->X_p; p2.o_plane_stride = ps512; p2.o_planes_ld = 512; p2.stats_out = m->ln_stats;
+      ST_TRY(gemm(p2, s));
+      continue;
+    }
+    ST_TRY(layernorm512(m->X, b.ln1g, b.ln1b, m->H, nullptr, R, s));
     GemmP pq = linear(m->H, R, 512, b.qkv, nullptr, m->QKV, 1536);
-    if (tc) { pq.a_planes = m->H_p; pq.a_plane_stride = ps512; }
     ST_TRY(gemm(pq, s));
-    ST_TRY(attention32(m->QKV, tc ? nullptr : m->ATT, tc ? m->ATT_p : nullptr, pl.nE * B, s));
+    ST_TRY(attention32(m->QKV, m->ATT, nullptr, pl.nE * B, s));
     GemmP pp = linear(m->ATT, R, 512, b.projw, b.projb, m->X, 512);
     pp.res = m->X; pp.res_mode = RES_POST; pp.ldr = 512;
-    if (tc) { pp.a_planes = m->ATT_p; pp.a_plane_stride = ps512; }
     ST_TRY(gemm(pp, s));
-    ST_TRY(layernorm512(m->X, b.ln2g, b.ln2b, tc ? nullptr : m->H, tc ? m->H_p : nullptr, R, s));
+    ST_TRY(layernorm512(m->X, b.ln2g, b.ln2b, m->H, nullptr, R, s));
     GemmP p1 = linear(m->H, R, 512, b.fc1w, b.fc1b, m->G, 1024);
     p1.act = ACT_GELU;
-    if (tc) { p1.a_planes = m->H_p; p1.a_plane_stride = ps512; p1.out = nullptr; p1.o_planes = m->G_p; p1.o_plane_stride = ps1024; p1.o_planes_ld = 1024; }
     ST_TRY(gemm(p1, s));
     GemmP p2 = linear(m->G, R, 1024, b.fc2w, b.fc2b, m->X, 512);
     p2.res = m->X; p2.res_mode = RES_POST; p2.ldr = 512;
-    if (tc) {
-      p2.a_planes = m->G_p; p2.a_plane_stride = ps1024;
-      if (i == 7) { p2.o_planes = m->X_p; p2.o_plane_stride = ps512; p2.o_planes_ld = 512; }   // operand of the output projection
-    }
     ST_TRY(gemm(p2, s));
   }
   GemmP po = linear(m->X, R, 512, m->out_w, m->out_b, m->O, 1536);

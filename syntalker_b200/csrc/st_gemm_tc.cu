@@ -112,6 +112,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
@@ -147,6 +153,10 @@ struct TcEpi {
   //  mode 2  conv, long clips      4-D map {C, Lin, B, 2}              coords (cb*64, t0 + j*dil - pad, b, 0)      tile -> (b, t0)
   //  mode 3  strided conv, pad 0   3-D map {s*C, ceil(B*Lin/s), 2}     coords ((G%s)*C + cb*64, G/s, 0), G = b*Lin + t0*s + j
   int mode, T, kb_per_tap, dil, pad, stride, C, Lin, Lout, tpc;
+  const float* ln_stats; // consumer: [rows][8][2] partial (mean, M2) of each 512-wide input row, or null
+  const float* ln_s;     //           [N] column sums of the gamma-scaled weight
+  const float* ln_c;     //           [N] W beta + bias
+  float* stats_out;      // producer (N = 512, BN = 64): [rows][8][2], this CTA writes slot blockIdx.x
   long long* dbg;        // optional timeline of CTA (0,0): clock64 stamps (debug / profiling only)
 };
 
@@ -296,11 +306,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int LPR0 = BN >= 128 ? 32 : 16, RPI0 = 32 / LPR0, NRI = 16 / RPI0;   // piece 0 geometry, row-instructions per warp
     const int cl0 = (lane % LPR0) * 4, n_0 = n0 + cl0;
     const bool vec0 = (n_0 + 3 < e_N) && ((e_ldo & 3) == 0) && (!e_res || (e_ldr & 3) == 0);
-    float bias0[4] = {0.f, 0.f, 0.f, 0.f};
-    if (ep.bias) {
+    const float* const e_bias = ep.ln_stats ? ep.ln_c : ep.bias;      // folded LayerNorm: c = W beta + b replaces the bias
+    const float* const e_lns = ep.ln_stats ? ep.ln_s : nullptr;
+    float* const e_stats_out = ep.stats_out;
+    float bias0[4] = {0.f, 0.f, 0.f, 0.f}, lns0[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (n_0 + q < e_N) bias0[q] = __ldg(ep.bias + n_0 + q);
+    for (int q = 0; q < 4; ++q)
+      if (n_0 + q < e_N) {
+        if (e_bias) bias0[q] = __ldg(e_bias + n_0 + q);
+        if (e_lns) lns0[q] = __ldg(e_lns + n_0 + q);
+      }
+    // folded LayerNorm, consumer side: this thread's phase-1 row needs (mean, 1/sigma) of its input row, combined
+    // from the 8 partials (mean_j, M2_j) its producer left (Chan et al.: M2 = sum M2_j + n_j sum (mean_j - mean)^2)
+    float ln_rstd = 1.0f, ln_mu = 0.0f;
+    if (ep.ln_stats && (lg * 32 + lane) < rows_valid) {
+      const float4* st4 = reinterpret_cast<const float4*>(ep.ln_stats + (long long)(m0 + lg * 32 + lane) * 16);
+      const float4 a = st4[0], b4 = st4[1], c4 = st4[2], d4 = st4[3];
+      const float mj[8] = {a.x, a.z, b4.x, b4.z, c4.x, c4.z, d4.x, d4.z};
+      const float qj[8] = {a.y, a.w, b4.y, b4.w, c4.y, c4.w, d4.y, d4.w};
+      float mu = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mu += mj[j];
+      mu *= 0.125f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float dm = mj[j] - mu; m2 += qj[j] + 64.0f * dm * dm; }
+      ln_mu = mu;
+      ln_rstd = 1.0f / sqrtf(m2 * (1.0f / 512.0f) + 1e-5f);
     }
     mbar_wait(acc_bar, 0);
     tc_fence_after();
@@ -316,16 +347,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + BN + c * 32, vc);
       tmem_ld_wait();
       const uint32_t trow = tile + (uint32_t)(lane * LDT + c * 32) * 4;
+      const float sc = e_scale * ln_rstd;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 t;
-        t.x = (__uint_as_float(v[j]) + __uint_as_float(vc[j])) * e_scale;
-        t.y = (__uint_as_float(v[j + 1]) + __uint_as_float(vc[j + 1])) * e_scale;
-        t.z = (__uint_as_float(v[j + 2]) + __uint_as_float(vc[j + 2])) * e_scale;
-        t.w = (__uint_as_float(v[j + 3]) + __uint_as_float(vc[j + 3])) * e_scale;
+        t.x = (__uint_as_float(v[j]) + __uint_as_float(vc[j])) * sc;
+        t.y = (__uint_as_float(v[j + 1]) + __uint_as_float(vc[j + 1])) * sc;
+        t.z = (__uint_as_float(v[j + 2]) + __uint_as_float(vc[j + 2])) * sc;
+        t.w = (__uint_as_float(v[j + 3]) + __uint_as_float(vc[j + 3])) * sc;
         sts128(trow + j * 4, t);
       }
     }
+    const uint32_t rowu = smem_u32(smem) + (uint32_t)(TC_BM * LDT) * 4;       // [128] rstd*mean per tile row, after the tile
+    if (e_lns && half == 0) sts32(rowu + (uint32_t)(lg * 32 + lane) * 4, ln_rstd * ln_mu);
     if (dbg && threadIdx.x == 64) dbg[6] = clock64();
     asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");     // the two warps of this lane group
     if (dbg && threadIdx.x == 64) dbg[7] = clock64();
@@ -346,9 +380,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool vec = (n + 3 < e_N) && ((e_ldo & 3) == 0) && (!e_res || (e_ldr & 3) == 0);
       const bool pvec = (n + 3 < e_N) && ((e_ldp & 3) == 0);
       float bias4[4] = {bias0[0], bias0[1], bias0[2], bias0[3]};
+      float lns4[4] = {lns0[0], lns0[1], lns0[2], lns0[3]};
       if (piece > 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bias4[q] = (ep.bias && n + q < e_N) ? __ldg(ep.bias + n + q) : 0.f;
+        for (int q = 0; q < 4; ++q) {
+          bias4[q] = (e_bias && n + q < e_N) ? __ldg(e_bias + n + q) : 0.f;
+          lns4[q] = (e_lns && n + q < e_N) ? __ldg(e_lns + n + q) : 0.f;
+        }
       }
       auto load_row = [&](int it, float4& t4, float4& r4) {
         const int r = half * 16 + it * RPI + rsub;
@@ -373,22 +411,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int it = 0; it < iters; ++it) {
         if (it + 2 < iters) load_row(it + 2, tC, rC);
         const int r = half * 16 + it * RPI + rsub;
-        if (col_ok && (lg * 32 + r) < rows_valid) {
-          const int grow = m0 + lg * 32 + r;
-          float x[4] = {tA.x + bias4[0], tA.y + bias4[1], tA.z + bias4[2], tA.w + bias4[3]};
-          const float rs[4] = {rA.x, rA.y, rA.z, rA.w};
-          if (e_resmode == RES_PRE) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
-          if (e_act == ACT_GELU) {
+        const bool valid = col_ok && (lg * 32 + r) < rows_valid;
+        const int grow = m0 + lg * 32 + r;
+        float x[4] = {tA.x + bias4[0], tA.y + bias4[1], tA.z + bias4[2], tA.w + bias4[3]};
+        if (e_lns) {                                   // folded LayerNorm: tile holds rstd*acc, rowu holds rstd*mean
+          const float u = lds32(rowu + (uint32_t)(lg * 32 + r) * 4);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) x[q] = x[q] * 0.5f * (1.0f + erff(x[q] * 0.70710678118654752440f));
-          } else if (e_act == ACT_RELU) {
+          for (int q = 0; q < 4; ++q) x[q] -= u * lns4[q];
+        }
+        const float rs[4] = {rA.x, rA.y, rA.z, rA.w};
+        if (e_resmode == RES_PRE) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
+        if (e_act == ACT_GELU) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) x[q] = fmaxf(x[q], 0.0f);
-          } else if (e_act == ACT_LRELU) {
+          for (int q = 0; q < 4; ++q) x[q] = x[q] * 0.5f * (1.0f + erff(x[q] * 0.70710678118654752440f));
+        } else if (e_act == ACT_RELU) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) x[q] = x[q] > 0.0f ? x[q] : x[q] * 0.01f;
+          for (int q = 0; q < 4; ++q) x[q] = fmaxf(x[q], 0.0f);
+        } else if (e_act == ACT_LRELU) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x[q] = x[q] > 0.0f ? x[q] : x[q] * 0.01f;
+        }
+        if (e_resmode == RES_POST) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
+        if (e_stats_out) {
+          // producer of a folded LayerNorm (BN = 64: the 16 lanes of a row hold this CTA's 64 columns): partial mean and
+          // M2 of the new residual row, slot blockIdx.x of 8.  All lanes take part in the shuffles.
+          float sm = (x[0] + x[1]) + (x[2] + x[3]);
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+          const float mj = sm * (1.0f / 64.0f);
+          float qd = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { const float dd = x[q] - mj; qd += dd * dd; }
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) qd += __shfl_xor_sync(0xffffffffu, qd, o);
+          if (valid && (lane % LPR) == 0) {
+            float* so = e_stats_out + ((long long)grow * 8 + blockIdx.x) * 2;
+            so[0] = mj; so[1] = qd;
           }
-          if (e_resmode == RES_POST) { x[0] += rs[0]; x[1] += rs[1]; x[2] += rs[2]; x[3] += rs[3]; }
+        }
+        if (valid) {
           if (e_out) {
             float* orow = e_out + (long long)grow * e_ldo + n;
             if (vec) *reinterpret_cast<float4*>(orow) = make_float4(x[0], x[1], x[2], x[3]);
@@ -732,6 +793,9 @@ launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 
   ep.planes_relu = p.o_planes_relu; ep.ldo = p.ldo; ep.ldr = p.ldr; ep.res_mode = p.res ? p.res_mode : RES_NONE; ep.res_div = p.res_div; ep.act = p.act;
   ep.scale = w->inv_scale / kActScale;
   ep.M = p.M; ep.N = p.N;
+  ep.ln_stats = p.ln_stats; ep.ln_s = p.ln_s; ep.ln_c = p.ln_c; ep.stats_out = p.stats_out;
+  if (p.stats_out && (p.N != 512 || BN != 64)) { set_error("gemm_tc: stats_out needs N = 512 (8 tiles of 64 columns)"); return ST_EINVAL; }
+  if (p.ln_stats && (!p.ln_s || !p.ln_c)) { set_error("gemm_tc: ln_stats needs ln_s and ln_c"); return ST_EINVAL; }
   ep.dbg = g_tc_dbg;
   const int num_kb = w->Kp / TC_BK;
   const int mtiles = mode >= 2 ? nclips * ep.tpc : (p.M + TC_BM - 1) / TC_BM;

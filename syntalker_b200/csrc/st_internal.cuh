@@ -99,6 +99,13 @@ struct GemmP {
   __half* o_planes = nullptr;
   long long o_plane_stride = 0;
   int o_planes_ld = 0, o_planes_relu = 0;
+  // LayerNorm folded around the GEMM (tcgen05 engine, N = 512 producers / any-N consumers):
+  //  consumer: out = rstd[m] * (acc - mean[m] * ln_s[n]) + ln_c[n]  with (mean, rstd) combined from ln_stats[m][8][2]
+  //  producer: stats_out[m][n_block][2] = (mean, M2) of the 64 result columns this CTA owns (Chan-combinable)
+  const float* ln_stats = nullptr;
+  const float* ln_s = nullptr;
+  const float* ln_c = nullptr;
+  float* stats_out = nullptr;
 };
 
 constexpr float kActScale = 16.0f;   // activations are stored in fp16 planes as (v * 16): |v| < 4e3 representable, lo normal for |v| > 2^-6
@@ -143,6 +150,8 @@ struct TokensInP {
   const float* rope_cos;     // [32,32]
   const float* rope_sin;
   float* x;                  // [nE*B*32,512]
+  __half* x_planes;          // optional: fp16 hi/lo planes of x (* kActScale), [2][nE*B*32][512]
+  float* stats;              // optional: LayerNorm row statistics of x as 8 combinable partials, [nE*B*32][8][2]
   int B, nE;
 };
 int tokens_in(const TokensInP& p, cudaStream_t s);

@@ -26,6 +26,24 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+__device__ __forceinline__ void split16(float v, __half& hi, __half& lo) {
+  v = fminf(fmaxf(v * kActScale, -65000.0f), 65000.0f);
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+// store 4 consecutive values as fp16 hi/lo planes (8-byte stores)
+__device__ __forceinline__ void store_planes4(__half* hi_ptr, long long plane_stride, float a, float b, float c, float d) {
+  __half h[4], l[4];
+  split16(a, h[0], l[0]); split16(b, h[1], l[1]); split16(c, h[2], l[2]); split16(d, h[3], l[3]);
+  __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+  __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+  uint2 hv, lv;
+  hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+  lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
+  *reinterpret_cast<uint2*>(hi_ptr) = hv;
+  *reinterpret_cast<uint2*>(hi_ptr + plane_stride) = lv;
+}
+
 template <bool VEC_A>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_simt_kernel(GemmP p) {
   pdl_wait();
@@ -196,6 +214,7 @@ GemmP linear(const float* A, int M, int K, const float* W, const float* bias, fl
 int gemm_simt(const GemmP& p, cudaStream_t s) {
   ST_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   ST_REQUIRE((p.ldw & 3) == 0 && p.ldw >= p.K, "gemm: ldw=%d must be a multiple of 4 and >= K=%d", p.ldw, p.K);
+  ST_REQUIRE(p.A && p.out && !p.ln_stats && !p.stats_out, "gemm_simt: fp32 operand and output required; LayerNorm folding is a tcgen05-engine feature");
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
   const bool vec = ((p.C & 3) == 0) && ((p.lda & 3) == 0) && ((p.a_batch & 3) == 0) &&
                    ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
@@ -208,24 +227,6 @@ int gemm_simt(const GemmP& p, cudaStream_t s) {
 // =========================================================================================================
 // 2. LayerNorm over 512 channels, eps 1e-5, affine (transformer.py:172,185).  One warp per row.
 // =========================================================================================================
-__device__ __forceinline__ void split16(float v, __half& hi, __half& lo) {
-  v = fminf(fmaxf(v * kActScale, -65000.0f), 65000.0f);
-  hi = __float2half_rn(v);
-  lo = __float2half_rn(v - __half2float(hi));
-}
-// store 4 consecutive values as fp16 hi/lo planes (8-byte stores)
-__device__ __forceinline__ void store_planes4(__half* hi_ptr, long long plane_stride, float a, float b, float c, float d) {
-  __half h[4], l[4];
-  split16(a, h[0], l[0]); split16(b, h[1], l[1]); split16(c, h[2], l[2]); split16(d, h[3], l[3]);
-  __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
-  __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
-  uint2 hv, lv;
-  hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
-  lv.x = *reinterpret_cast<uint32_t*>(&l01); lv.y = *reinterpret_cast<uint32_t*>(&l23);
-  *reinterpret_cast<uint2*>(hi_ptr) = hv;
-  *reinterpret_cast<uint2*>(hi_ptr + plane_stride) = lv;
-}
-
 __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                            const float* __restrict__ b, float* __restrict__ y,
                                                            __half* __restrict__ planes, int rows) {
@@ -403,37 +404,64 @@ int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStre
 __global__ void __launch_bounds__(256) tokens_in_kernel(TokensInP p) {
   pdl_wait();
   pdl_launch();
-  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long per_eval = (long long)p.B * 32 * 256;
-  if (gid >= per_eval * p.nE) return;
-  const int e = (int)(gid / per_eval);
-  const long long r = gid - e * per_eval;
-  const int row = (int)(r >> 8);              // b*32 + tau
-  const int pj = (int)(r & 255);
-  const int grp = pj >> 5, j = pj & 31;
-  const int c1 = grp * 64 + j, c2 = c1 + 32;
+  // one warp per (evaluation, row); lane l owns the rotary pairs (g*64 + l, g*64 + l + 32), g = 0..7
+  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const long long rows_e = (long long)p.B * 32;
+  if (wid >= rows_e * p.nE) return;
+  const int e = (int)(wid / rows_e);
+  const int row = (int)(wid - e * rows_e);          // b*32 + tau
   const int b = row >> 5, tau = row & 31;
   const int t = p.ls ? p.t_model_dev[p.ls->k] : (p.t_dev ? (int)p.t_dev[b] : p.t_scalar);
   const float* vt = p.vt_table + (long long)t * 512;
   const float* cst = p.cst[e] + (long long)(p.cst_bcast[e] ? tau : row) * 512;
   const float* g2 = p.g2 + (long long)b * 512;
   const float* zr = p.z + (long long)row * 512;
-  float x1 = zr[c1] + vt[c1] + cst[c1] + g2[c1];
-  float x2 = zr[c2] + vt[c2] + cst[c2] + g2[c2];
-  if (p.sv[e]) {
-    const float* sv = p.sv[e] + (p.sv_bcast[e] ? 0 : (long long)b * 512);
-    x1 += sv[c1];
-    x2 += sv[c2];
+  const float* sv = p.sv[e] ? p.sv[e] + (p.sv_bcast[e] ? 0 : (long long)b * 512) : nullptr;
+  const float cs = p.rope_cos[tau * 32 + lane], sn = p.rope_sin[tau * 32 + lane];
+  const long long orow = (long long)e * rows_e + row;
+  float v1[8], v2[8];
+  float sum = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int c1 = g * 64 + lane, c2 = c1 + 32;
+    float x1 = zr[c1] + vt[c1] + cst[c1] + g2[c1];
+    float x2 = zr[c2] + vt[c2] + cst[c2] + g2[c2];
+    if (sv) { x1 += sv[c1]; x2 += sv[c2]; }
+    v1[g] = __fadd_rn(__fmul_rn(x1, cs), __fmul_rn(-x2, sn));
+    v2[g] = __fadd_rn(__fmul_rn(x2, cs), __fmul_rn(x1, sn));
+    sum += v1[g] + v2[g];
   }
-  const float cs = p.rope_cos[tau * 32 + j], sn = p.rope_sin[tau * 32 + j];
-  float* xo = p.x + ((long long)e * p.B * 32 + row) * 512;
-  xo[c1] = __fadd_rn(__fmul_rn(x1, cs), __fmul_rn(-x2, sn));
-  xo[c2] = __fadd_rn(__fmul_rn(x2, cs), __fmul_rn(x1, sn));
+  float* xo = p.x + orow * 512;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) { xo[g * 64 + lane] = v1[g]; xo[g * 64 + lane + 32] = v2[g]; }
+  if (p.x_planes) {
+    const long long ps = rows_e * p.nE * 512;
+    __half* xp = p.x_planes + orow * 512;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      __half h, l;
+      split16(v1[g], h, l); xp[g * 64 + lane] = h; xp[ps + g * 64 + lane] = l;
+      split16(v2[g], h, l); xp[g * 64 + lane + 32] = h; xp[ps + g * 64 + lane + 32] = l;
+    }
+  }
+  if (p.stats) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / 512.0f);
+    float m2 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { const float d1 = v1[g] - mean, d2 = v2[g] - mean; m2 += d1 * d1 + d2 * d2; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    // eight identical partials (mean, M2/8) combine to exactly (mean, M2)
+    if (lane < 8) { p.stats[(orow * 8 + lane) * 2] = mean; p.stats[(orow * 8 + lane) * 2 + 1] = m2 * 0.125f; }
+  }
 }
 
 int tokens_in(const TokensInP& p, cudaStream_t s) {
-  const long long n = (long long)p.nE * p.B * 32 * 256;
-  launch_k(tokens_in_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, p);
+  const long long n = (long long)p.nE * p.B * 32;      // warps
+  launch_k(tokens_in_kernel, dim3((unsigned)((n + 7) / 8)), dim3(256), 0, s, p);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }

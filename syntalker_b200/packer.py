@@ -110,6 +110,18 @@ def pack_mdm(sd: Dict[str, torch.Tensor], variant: str | None = None) -> Dict[st
                          ("norm2.bias", "ln2.b"), ("mlp.fc1.weight", "fc1.w"), ("mlp.fc1.bias", "fc1.b"),
                          ("mlp.fc2.weight", "fc2.w"), ("mlp.fc2.bias", "fc2.b")):
             out[f"blk.{i}.{dst}"] = sd[p + src].detach().cpu().float().contiguous()
+    # LayerNorm folded into the Linear that consumes it (tcgen05 engine):
+    #   W (gamma*(x-mu)/sigma + beta) + b = (1/sigma) (W' x - mu s) + c,   W' = W*gamma,  s = W' 1,  c = W beta + b
+    # so the GEMM runs on the raw residual stream and the epilogue applies the per-row (mu, 1/sigma).
+    for i in range(8):
+        p = f"mytimmblocks.{i}."
+        for norm, lin, dst, has_b in (("norm1", "attn.qkv", "qkv", False), ("norm2", "mlp.fc1", "fc1", True)):
+            g, be = _f64(sd[p + norm + ".weight"]), _f64(sd[p + norm + ".bias"])
+            Wl = _f64(sd[p + lin + ".weight"])
+            Wg = Wl * g[None, :]
+            out[f"blk.{i}.{dst}.wg"] = _t32(Wg)
+            out[f"blk.{i}.{dst}.s"] = _t32(Wg.sum(axis=1))
+            out[f"blk.{i}.{dst}.c"] = _t32(Wl @ be + (_f64(sd[p + lin + ".bias"]) if has_b else 0.0))
     out["out.w"] = sd["output_process.poseFinal.weight"].detach().cpu().float().contiguous()
     out["out.b"] = sd["output_process.poseFinal.bias"].detach().cpu().float().contiguous()
     return out

@@ -69,3 +69,21 @@ def test_upsample_conv_even_odd_split():
     odd = mm(wo[:, 0], hp[:, :, 1:33]) + mm(wo[:, 1], hp[:, :, 2:34]) + P["dec.2.2.odd.b"][None, :, None]
     out = torch.stack([even, odd], dim=-1).reshape(2, 512, 64)
     assert float((out - ref).abs().max()) < 1e-5
+
+
+def test_layernorm_folded_into_linear():
+    """(1/sigma)(W' x - mu s) + c == Linear(LayerNorm(x)) for the qkv and fc1 layers (what the TC epilogue computes)."""
+    import torch.nn.functional as F
+    W = synth.mdm_state_dict("beatx", seed=0)
+    P = packer.pack_mdm(W)
+    x = 3.0 * torch.randn(64, 512, generator=torch.Generator().manual_seed(2)) + 0.7
+    mu = x.mean(-1, keepdim=True)
+    rstd = 1.0 / torch.sqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-5)
+    for i in (0, 7):
+        p = f"mytimmblocks.{i}."
+        ref = F.linear(F.layer_norm(x, (512,), W[p + "norm1.weight"], W[p + "norm1.bias"], 1e-5), W[p + "attn.qkv.weight"])
+        got = rstd * (x @ P[f"blk.{i}.qkv.wg"].t() - mu * P[f"blk.{i}.qkv.s"]) + P[f"blk.{i}.qkv.c"]
+        assert float((ref - got).abs().max()) < 2e-5
+        ref = F.linear(F.layer_norm(x, (512,), W[p + "norm2.weight"], W[p + "norm2.bias"], 1e-5), W[p + "mlp.fc1.weight"], W[p + "mlp.fc1.bias"])
+        got = rstd * (x @ P[f"blk.{i}.fc1.wg"].t() - mu * P[f"blk.{i}.fc1.s"]) + P[f"blk.{i}.fc1.c"]
+        assert float((ref - got).abs().max()) < 2e-5
