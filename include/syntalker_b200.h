@@ -79,6 +79,8 @@ int st_set_graphs(int on);
 int st_set_pdl(int on);
 /* Debug: device buffer of >= 64 int64 receiving clock64() stamps of CTA (0,0) of every tcgen05 GEMM launch; NULL = off. */
 int st_debug_timeline(long long* dev_buf);
+/* Debug: device buffer of 120000 uint64; every kernel's first thread appends (%globaltimer ns, kernel id); slot 0 = count. NULL = off. */
+int st_debug_trace(unsigned long long* dev_buf);
 
 /* ---- weights -------------------------------------------------------------------------------------
  * Replaces: MDM(args) construction + load_checkpoints (train.py:85-94, utils/other_tools.py:771-790).

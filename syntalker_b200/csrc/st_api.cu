@@ -210,6 +210,10 @@ extern "C" int st_set_engine(int engine) {
 extern "C" int st_get_engine(void) { return g_engine; }
 namespace st { extern long long* g_tc_dbg; }
 extern "C" int st_debug_timeline(long long* dev_buf) { st::g_tc_dbg = dev_buf; return ST_OK; }
+extern "C" int st_debug_trace(unsigned long long* dev_buf) {
+  ST_TRY(st::set_trace_kernels(dev_buf));
+  return st::set_trace_tc(dev_buf);
+}
 extern "C" int st_set_pdl(int on) { st::g_pdl = on != 0; return ST_OK; }
 extern "C" int st_set_graphs(int on) { g_use_graphs = on != 0; return ST_OK; }
 extern "C" int st_profile_begin(void) { return st::profile_begin(); }

@@ -226,6 +226,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // global memory
   pdl_wait();
   pdl_launch();
+  trace_stamp(1);
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
@@ -495,6 +496,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ a, int lda, int M, int K, int Kp, float scale, int relu,
                                                            __half* __restrict__ planes, long long plane_stride) {
   pdl_wait();
+  trace_stamp(6);
   pdl_launch();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;     // one thread per 4 elements
   const int kq = Kp >> 2;
@@ -802,6 +804,11 @@ launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 
   if (BN == 64) return launch_tc<64, 4>(*tmA, *tmW, ep, num_kb, mtiles, s);
   if (BN == 192) return launch_tc<192, 2>(*tmA, *tmW, ep, num_kb, mtiles, s);
   return launch_tc<128, 3>(*tmA, *tmW, ep, num_kb, mtiles, s);
+}
+
+int set_trace_tc(unsigned long long* p) {
+  ST_CHECK_CUDA(cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)));
+  return ST_OK;
 }
 
 }  // namespace st

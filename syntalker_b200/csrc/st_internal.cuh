@@ -67,6 +67,17 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 #ifdef __CUDACC__
+// Debug trace (st_debug_trace): CTA (0,0) thread 0 of every kernel stamps %globaltimer and a kernel id at entry.
+static __device__ unsigned long long* g_trace_buf = nullptr;   // per translation unit (no -rdc); [cap][2] = (ns, id); slot 0 = counter
+__device__ __forceinline__ void trace_stamp(int id) {
+  unsigned long long* t = g_trace_buf;
+  if (t && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    const unsigned long long slot = atomicAdd(t, 1ull) + 1;
+    if (slot < 60000) { t[slot * 2] = now; t[slot * 2 + 1] = (unsigned long long)id; }
+  }
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
@@ -124,6 +135,8 @@ int gemm(const GemmP& p, cudaStream_t s);   // dispatches on the engine (TC fall
 bool tc_supported(const GemmP& p);
 int gemm_tc(const GemmP& p, cudaStream_t s);
 bool profiling();
+int set_trace_kernels(unsigned long long* p);
+int set_trace_tc(unsigned long long* p);
 int profile_begin();
 int profile_end(double* ms, double* flops, int64_t* n);
 

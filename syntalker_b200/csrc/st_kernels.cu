@@ -47,6 +47,7 @@ __device__ __forceinline__ void store_planes4(__half* hi_ptr, long long plane_st
 template <bool VEC_A>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_simt_kernel(GemmP p) {
   pdl_wait();
+  trace_stamp(8);
   pdl_launch();
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
                                                            const float* __restrict__ b, float* __restrict__ y,
                                                            __half* __restrict__ planes, int rows) {
   pdl_wait();
+  trace_stamp(7);
   pdl_launch();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -286,6 +288,7 @@ constexpr int ATT_LD = 132;   // padded row stride (floats) -> conflict-free flo
 __global__ void __launch_bounds__(256) attention32_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                           __half* __restrict__ planes, long long plane_stride) {
   pdl_wait();
+  trace_stamp(2);
   pdl_launch();
   extern __shared__ __align__(16) float att_smem[];
   float (*q)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem);
@@ -403,6 +406,7 @@ int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStre
 // =========================================================================================================
 __global__ void __launch_bounds__(256) tokens_in_kernel(TokensInP p) {
   pdl_wait();
+  trace_stamp(3);
   pdl_launch();
   // one warp per (evaluation, row); lane l owns the rotary pairs (g*64 + l, g*64 + l + 32), g = 0..7
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -474,6 +478,7 @@ int tokens_in(const TokensInP& p, cudaStream_t s) {
 // =========================================================================================================
 __global__ void __launch_bounds__(256) step_update_kernel(StepP p) {
   pdl_wait();
+  trace_stamp(4);
   pdl_launch();
   const long long n4 = (long long)p.B * 32 * 1536 / 4;
   const long long i4 = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -552,6 +557,7 @@ __global__ void __launch_bounds__(256) step_update_kernel(StepP p) {
 
 __global__ void advance_loop_kernel(LoopState* ls) {
   pdl_wait();
+  trace_stamp(5);
   pdl_launch();
   ls->k -= 1;
 }
@@ -928,6 +934,11 @@ int pose623(const float* up, const float* ha, const float* lo, int B, int n, flo
   const int frames = B * n;
   launch_k(pose623_kernel, dim3(frames < 1184 ? frames : 1184), dim3(256), 0, s, up, ha, lo, frames, pose);
   ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+int set_trace_kernels(unsigned long long* p) {
+  ST_CHECK_CUDA(cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)));
   return ST_OK;
 }
 
