@@ -290,40 +290,41 @@ __global__ void __launch_bounds__(256) attention32_kernel(const float* __restric
   pdl_wait();
   trace_stamp(2);
   pdl_launch();
+  // One CTA per (sequence, head, half of the 32 query rows): 512 CTAs for a config-2 step keep ~28 warps per SM busy and
+  // halve each warp's instruction stream (the kernel is latency-bound: 1800 dependent instructions per warp before).
   extern __shared__ __align__(16) float att_smem[];
-  float (*q)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem);
-  float (*k)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 32 * ATT_LD);
-  float (*v)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 64 * ATT_LD);
-  float (*pt)[36] = reinterpret_cast<float (*)[36]>(att_smem + 96 * ATT_LD);      // softmax, transposed: pt[j][i]
-  const int seq = blockIdx.x, head = blockIdx.y, tid = threadIdx.x;
+  float (*q)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem);                    // 16 rows
+  float (*k)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 16 * ATT_LD);      // 32 rows
+  float (*v)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem + 48 * ATT_LD);      // 32 rows
+  float (*pt)[20] = reinterpret_cast<float (*)[20]>(att_smem + 80 * ATT_LD);             // softmax, transposed: pt[j][i_local]
+  const int seq = blockIdx.x, head = blockIdx.y, qh = blockIdx.z, tid = threadIdx.x;
   const float* base = qkv + (long long)seq * 32 * 1536 + head * 128;
-  for (int i = tid; i < 32 * 32; i += 256) {           // 32 rows x 32 float4 per matrix
+  for (int i = tid; i < 32 * 32; i += 256) {
     const int r = i >> 5, c4 = i & 31;
     const float* src = base + (long long)r * 1536 + c4 * 4;
-    *reinterpret_cast<float4*>(&q[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(src));
     *reinterpret_cast<float4*>(&k[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(src + 512));
     *reinterpret_cast<float4*>(&v[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(src + 1024));
+    if (r < 16) *reinterpret_cast<float4*>(&q[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(src + (long long)qh * 16 * 1536));
   }
   __syncthreads();
-  // ---- scores: each thread owns a 4x4 block of S over one interleaved quarter of the 128 dims (8 LDS.128 per
-  //      64 FMA instead of 5 per 16), quarters are summed with two xor-shuffles ----
+  // ---- scores: thread = 2 rows x 4 cols of S over one interleaved quarter of the 128 dims ----
   const int lane = tid & 31, warp = tid >> 5;
-  const int g = lane & 3, bj = lane >> 2, bi = warp;   // rows 4*bi.., cols 4*bj..; a warp holds 4 full rows of S
-  float acc[4][4];
+  const int g = lane & 3, bj = lane >> 2;              // a warp holds 2 full rows of S
+  float acc[2][4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < 2; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
 #pragma unroll
   for (int d4 = 0; d4 < 8; ++d4) {
     const int col = (4 * d4 + g) * 4;
-    float4 qa[4], kb[4];
+    float4 qa[2], kb[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) qa[r] = *reinterpret_cast<const float4*>(&q[4 * bi + r][col]);
+    for (int r = 0; r < 2; ++r) qa[r] = *reinterpret_cast<const float4*>(&q[2 * warp + r][col]);
 #pragma unroll
     for (int c = 0; c < 4; ++c) kb[c] = *reinterpret_cast<const float4*>(&k[4 * bj + c][col]);
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 2; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         acc[r][c] = fmaf(qa[r].x, kb[c].x, acc[r][c]);
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(256) attention32_kernel(const float* __restric
   }
   const float scale = 0.08838834764831845f;            // 128^-0.5
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < 2; ++r) {
     float mx = -INFINITY;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -357,43 +358,38 @@ __global__ void __launch_bounds__(256) attention32_kernel(const float* __restric
   }
   if (g == 0) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      *reinterpret_cast<float4*>(&pt[4 * bj + c][4 * bi]) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+    for (int c = 0; c < 4; ++c) *reinterpret_cast<float2*>(&pt[4 * bj + c][2 * warp]) = make_float2(acc[0][c], acc[1][c]);
   }
   __syncthreads();
-  // ---- out = P V: warp = 4 rows, lane = 4 columns; P^T row is a broadcast float4, V row a conflict-free one ----
-  float4 o4[4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) o4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // ---- out = P V: warp = 2 rows, lane = 4 columns ----
+  float4 o4[2];
+  o4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  o4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
   for (int j = 0; j < 32; ++j) {
-    const float4 p4 = *reinterpret_cast<const float4*>(&pt[j][4 * warp]);
+    const float2 p2 = *reinterpret_cast<const float2*>(&pt[j][2 * warp]);
     const float4 vv = *reinterpret_cast<const float4*>(&v[j][lane * 4]);
-    const float pr[4] = {p4.x, p4.y, p4.z, p4.w};
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      o4[r].x = fmaf(pr[r], vv.x, o4[r].x);
-      o4[r].y = fmaf(pr[r], vv.y, o4[r].y);
-      o4[r].z = fmaf(pr[r], vv.z, o4[r].z);
-      o4[r].w = fmaf(pr[r], vv.w, o4[r].w);
-    }
+    o4[0].x = fmaf(p2.x, vv.x, o4[0].x); o4[0].y = fmaf(p2.x, vv.y, o4[0].y);
+    o4[0].z = fmaf(p2.x, vv.z, o4[0].z); o4[0].w = fmaf(p2.x, vv.w, o4[0].w);
+    o4[1].x = fmaf(p2.y, vv.x, o4[1].x); o4[1].y = fmaf(p2.y, vv.y, o4[1].y);
+    o4[1].z = fmaf(p2.y, vv.z, o4[1].z); o4[1].w = fmaf(p2.y, vv.w, o4[1].w);
   }
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const long long off = ((long long)seq * 32 + 4 * warp + r) * 512 + head * 128 + lane * 4;
+  for (int r = 0; r < 2; ++r) {
+    const long long off = ((long long)seq * 32 + qh * 16 + 2 * warp + r) * 512 + head * 128 + lane * 4;
     if (out) *reinterpret_cast<float4*>(out + off) = o4[r];
     if (planes) store_planes4(planes + off, plane_stride, o4[r].x, o4[r].y, o4[r].z, o4[r].w);
   }
 }
 
 int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStream_t s) {
-  constexpr int smem = (96 * ATT_LD + 32 * 36) * sizeof(float);
+  constexpr int smem = (80 * ATT_LD + 32 * 20) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     ST_CHECK_CUDA(cudaFuncSetAttribute(attention32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  launch_k(attention32_kernel, dim3(dim3(nseq, 4)), dim3(256), smem, s, qkv, out, planes, (long long)nseq * 32 * 512);
+  launch_k(attention32_kernel, dim3(nseq, 4, 2), dim3(256), smem, s, qkv, out, planes, (long long)nseq * 32 * 512);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
