@@ -175,12 +175,15 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   lo = __float2half_rn(v - __half2float(hi));
 }
 
-template <int BN, int STAGES>
+// One binary for every tile width (BN = 64 / 128 / 192 and the ring depth are run-time values): the sampling loop
+// alternates GEMMs of different widths back to back, and separate template instantiations evicted each other from
+// the instruction cache at every launch (the in-chain cost of a GEMM was ~4 us above its same-kernel-chain cost).
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcEpi ep, const int num_kb) {
-  constexpr int W_PLANE = BN * TC_BK * 2;
-  constexpr int STAGE_BYTES = 2 * TC_A_PLANE + 2 * W_PLANE;
-  constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // main + correction accumulators
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcEpi ep, const int num_kb,
+               const int BN, const int STAGES) {
+  const int W_PLANE = BN * TC_BK * 2;
+  const int STAGE_BYTES = 2 * TC_A_PLANE + 2 * W_PLANE;
+  const int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // main + correction accumulators
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -259,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc_f16(TC_BM, BN);
+      const uint32_t idesc = umma_idesc_f16(TC_BM, BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -303,8 +306,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* const e_out = ep.out;
     const float* const e_res = ep.res;
     __half* const e_planes = ep.planes;
-    constexpr int NPIECE = BN == 192 ? 2 : 1;
-    constexpr int LPR0 = BN >= 128 ? 32 : 16, RPI0 = 32 / LPR0, NRI = 16 / RPI0;   // piece 0 geometry, row-instructions per warp
+    const int NPIECE = BN == 192 ? 2 : 1;
+    const int LPR0 = BN >= 128 ? 32 : 16;         // piece 0 geometry: lanes per row
     const int cl0 = (lane % LPR0) * 4, n_0 = n0 + cl0;
     const bool vec0 = (n_0 + 3 < e_N) && ((e_ldo & 3) == 0) && (!e_res || (e_ldr & 3) == 0);
     const float* const e_bias = ep.ln_stats ? ep.ln_c : ep.bias;      // folded LayerNorm: c = W beta + b replaces the bias
@@ -337,10 +340,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     if (dbg && threadIdx.x == 64) dbg[3] = clock64();
-    constexpr int LDT = BN + 4;
+    const int LDT = BN + 4;
     const uint32_t tile = smem_u32(smem) + (uint32_t)(lg * 32) * LDT * 4;      // shared-space byte address of this lane group's rows
-    constexpr int CH = BN / 32;                   // 32-column chunks; each warp of the pair takes CH/2 of them
-#pragma unroll
+    const int CH = BN / 32;                       // 32-column chunks; each warp of the pair takes CH/2 of them
+#pragma unroll 1
     for (int cc = 0; cc < CH / 2; ++cc) {
       const int c = half * (CH / 2) + cc;
       uint32_t v[32], vc[32];
@@ -367,7 +370,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // pieces of the tile row handled with 32 lanes x float4 (128 columns) or 16 lanes x float4 (64 columns).
     // The row loop is deliberately NOT unrolled: this code runs once per CTA, and an unrolled epilogue (40 KB of
     // SASS) spent ~2000 cycles per row-instruction in instruction-cache misses.  Loads run two rows ahead instead.
-#pragma unroll
+#pragma unroll 1
     for (int piece = 0; piece < NPIECE; ++piece) {
       const int pc0 = piece * 128;                                  // first column of the piece
       const int pw = (BN - pc0) >= 128 ? 128 : 64;                  // its width
@@ -695,16 +698,18 @@ bool tc_supported(const GemmP& p) {
   return true;
 }
 
-template <int BN, int STAGES>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcEpi& ep, int num_kb, int mtiles, cudaStream_t s) {
-  constexpr int smem = STAGES * (2 * TC_A_PLANE + 2 * BN * TC_BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcEpi& ep, int num_kb, int mtiles, int BN, cudaStream_t s) {
+  // ring depth: as many stages as fit beside the barriers in 227 KB (4 / 3 / 2 for BN = 64 / 128 / 192)
+  const int stage_bytes = 2 * TC_A_PLANE + 2 * BN * TC_BK * 2;
+  const int stages = BN == 64 ? 4 : BN == 128 ? 3 : 2;
+  const int smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
   static bool attr = false;
   if (!attr) {
-    ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * TC_A_PLANE + 2 * 64 * TC_BK * 2) + 9 * 8 + 16 + 1024));
     attr = true;
   }
   dim3 grid((ep.N + BN - 1) / BN, mtiles);
-launch_k(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(TC_THREADS), smem, s, tmA, tmW, ep, num_kb);
+  launch_k(gemm_tc_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, tmA, tmW, ep, num_kb, BN, stages);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -801,9 +806,7 @@ launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 
   ep.dbg = g_tc_dbg;
   const int num_kb = w->Kp / TC_BK;
   const int mtiles = mode >= 2 ? nclips * ep.tpc : (p.M + TC_BM - 1) / TC_BM;
-  if (BN == 64) return launch_tc<64, 4>(*tmA, *tmW, ep, num_kb, mtiles, s);
-  if (BN == 192) return launch_tc<192, 2>(*tmA, *tmW, ep, num_kb, mtiles, s);
-  return launch_tc<128, 3>(*tmA, *tmW, ep, num_kb, mtiles, s);
+  return launch_tc(*tmA, *tmW, ep, num_kb, mtiles, BN, s);
 }
 
 int set_trace_tc(unsigned long long* p) {
