@@ -81,6 +81,8 @@ int st_set_pdl(int on);
 int st_debug_timeline(long long* dev_buf);
 /* Debug: device buffer of 120000 uint64; every kernel's first thread appends (%globaltimer ns, kernel id); slot 0 = count. NULL = off. */
 int st_debug_trace(unsigned long long* dev_buf);
+/* debug: timing-only variants of the tcgen05 GEMM main loop (results are garbage when flags != 0) */
+int st_debug_probe(int flags);
 
 /* ---- weights -------------------------------------------------------------------------------------
  * Replaces: MDM(args) construction + load_checkpoints (train.py:85-94, utils/other_tools.py:771-790).

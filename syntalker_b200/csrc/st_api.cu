@@ -170,7 +170,7 @@ struct st_model {
   int64_t* t_tmp = nullptr;
   // fp16 hi/lo operand planes for the tcgen05 engine
   __half *H_p = nullptr, *ATT_p = nullptr, *G_p = nullptr, *X_p = nullptr, *xs_p = nullptr;
-  float* ln_stats = nullptr;   // [nE*B*32][8][2] partial (mean, M2) of the residual rows
+  float* ln_stats = nullptr;   // [nE*B*32][16][2] partial (mean, M2) over 32 columns each of the residual rows
   // sampling-loop state on the device + one captured step graph per (plan, mode, engine)
   LoopState* loop = nullptr;
   int32_t* t_model_dev = nullptr;
@@ -208,7 +208,8 @@ extern "C" int st_set_engine(int engine) {
   return ST_OK;
 }
 extern "C" int st_get_engine(void) { return g_engine; }
-namespace st { extern long long* g_tc_dbg; }
+namespace st { extern long long* g_tc_dbg; extern int g_tc_probe; extern bool g_tc_fast; }
+extern "C" int st_debug_probe(int flags) { st::g_tc_probe = flags & 15; st::g_tc_fast = !(flags & 16); return ST_OK; }
 extern "C" int st_debug_timeline(long long* dev_buf) { st::g_tc_dbg = dev_buf; return ST_OK; }
 extern "C" int st_debug_trace(unsigned long long* dev_buf) {
   ST_TRY(st::set_trace_kernels(dev_buf));
@@ -301,7 +302,7 @@ static int model_workspace(st_model* m, int B) {
   f += 4 * (size_t)cb * kWavLen[1] * 64 + (size_t)cb * 128 * 512 + (size_t)cb * 32 * 512;
   f += 2 * (size_t)B + 64;
   f += nE * rows * (512 * 3 + 1024) + rows * 1536;             // fp16 hi+lo planes H_p, ATT_p, X_p, G_p, xs_p (2 halves = 1 float each)
-  f += 1000 * (1 + ST_COEF_STRIDE) + 64 + nE * rows * 16;
+  f += 1000 * (1 + ST_COEF_STRIDE) + 64 + nE * rows * 32;
   size_t bytes = f * sizeof(float) + (size_t)B * sizeof(int64_t) + 64 * 256;
   for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);  // captured pointers die with the old block
   m->graphs.clear(); m->warmed.clear(); m->graph_nodes.clear();
@@ -330,7 +331,7 @@ static int model_workspace(st_model* m, int B) {
   m->X_p = a.take<__half>(2 * nE * rows * 512);
   m->G_p = a.take<__half>(2 * nE * rows * 1024);
   m->xs_p = a.take<__half>(2 * rows * 1536);
-  m->ln_stats = a.take<float>(nE * rows * 16);
+  m->ln_stats = a.take<float>(nE * rows * 32);
   m->loop = a.take<LoopState>(1);
   m->t_model_dev = a.take<int32_t>(1000);
   m->coef_dev = a.take<float>(1000 * ST_COEF_STRIDE);

@@ -27,6 +27,19 @@ namespace st {
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp.  ptxas recognises elect.sync and issues the uniform-datapath instructions of the elected
+// branch (UTCHMMA, UTMALDG, UTCBAR) straight; under a plain `lane == 0` test it wraps each of them in an
+// ELECT / BRA.U.ANY loop (measured: 99 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p mov.u32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -158,6 +171,7 @@ struct TcEpi {
   const float* ln_c;     //           [N] W beta + bias
   float* stats_out;      // producer (N = 512, BN = 64): [rows][8][2], this CTA writes slot blockIdx.x
   long long* dbg;        // optional timeline of CTA (0,0): clock64 stamps (debug / profiling only)
+  int probe;             // debug: 1 skip MMAs, 2 skip TMA, 4 MMAs grouped by accumulator, 8 single accumulator (timing only)
 };
 
 __device__ __forceinline__ float tc_act(float v, int act) {
@@ -224,7 +238,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // REDUX leaves its result in a uniform register: ptxas then issues the UTCHMMAs back to back instead of wrapping each
+  // one in an ELECT / R2UR / BRA.U.ANY waterfall (measured: 99 cycles per MMA, 3x the N = 64 tensor floor)
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
   // barriers, TMEM and descriptor prefetch above overlap the predecessor's tail; nothing before this line touches
   // global memory
   pdl_wait();
@@ -233,13 +249,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== TMA producer =====
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + s * STAGE_BYTES;
+        if (ep.probe & 2) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+          continue;
+        }
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         if (ep.mode == 0) {
           tma_load_3d(st, &tmA, &full_bar[s], kb * TC_BK, m0, 0);
@@ -260,7 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== MMA issuer =====
       const uint32_t idesc = umma_idesc_f16(TC_BM, BN);
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -273,6 +293,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a_lo = a_hi + TC_A_PLANE;
         const uint32_t w_hi = a_hi + 2 * TC_A_PLANE;
         const uint32_t w_lo = w_hi + W_PLANE;
+        if (ep.probe & 13) {
+          if (!(ep.probe & 1)) {
+            const uint32_t corr = (ep.probe & 8) ? tmem_base : tmem_base + BN;
+            if (ep.probe & 4) {
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                umma_f16(tmem_base, umma_desc_sw128(a_hi) + 2 * k, umma_desc_sw128(w_hi) + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                umma_f16(corr, umma_desc_sw128(a_hi) + 2 * k, umma_desc_sw128(w_lo) + 2 * k, idesc, (kb | k) != 0);
+                umma_f16(corr, umma_desc_sw128(a_lo) + 2 * k, umma_desc_sw128(w_hi) + 2 * k, idesc, 1);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                umma_f16(tmem_base, umma_desc_sw128(a_hi) + 2 * k, umma_desc_sw128(w_hi) + 2 * k, idesc, (kb | k) != 0);
+                umma_f16(corr, umma_desc_sw128(a_hi) + 2 * k, umma_desc_sw128(w_lo) + 2 * k, idesc, 1);
+                umma_f16(corr, umma_desc_sw128(a_lo) + 2 * k, umma_desc_sw128(w_hi) + 2 * k, idesc, 1);
+              }
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          continue;
+        }
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
           const uint64_t dah = umma_desc_sw128(a_hi) + 2 * k, dal = umma_desc_sw128(a_lo) + 2 * k;
@@ -495,6 +539,316 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (dbg && threadIdx.x == 0) dbg[5] = clock64();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Trunk kernel: the Linear layers of the sampling loop (plain row-major operands, N a multiple of 64).
+//
+// Same TMA / mbarrier / TMEM pipeline as gemm_tc_kernel, with the two parts the timeline showed to dominate rebuilt:
+//  * main loop: for tiles up to 128 columns the hi and lo weight planes sit back to back in a stage, so ONE MMA of
+//    width 2*BN computes a_hi.[w_hi ; w_lo] -- the main accumulator and the first cross term -- and a second one of
+//    width BN adds a_lo.w_hi.  Eight MMAs per K block instead of twelve, and the A tile is read from shared memory
+//    twice instead of three times (the SS-mode operand path, ~90 B/cycle, is what bounds 128 x 64 tiles).
+//  * epilogue: thread = accumulator row.  A thread reads 32 columns of both accumulators with tcgen05.ld and finishes
+//    them in registers (scale, folded LayerNorm, bias, residual from a TMA-prefetched swizzled tile, exact-erf GELU,
+//    row statistics, fp16 hi/lo split), writes the results into 128B-swizzled staging tiles (conflict-free for
+//    lane = row) and one elected thread hands them to TMA stores.  No per-row loop, no global address arithmetic.
+// ---------------------------------------------------------------------------------------------------------
+struct FastEpi {
+  const float* bias;       // [N] or null; folded LayerNorm: c = W beta + b
+  const float* ln_s;       // [N] column sums of the gamma-scaled weight, or null (no folded LayerNorm)
+  const float* ln_stats;   // consumer: [rows][16][2] partial (mean, M2) over 32 columns each of the 512-wide input row
+  float* stats_out;        // producer (N = 512): [rows][16][2]
+  float scale;             // undoes the operand pre-scaling
+  int act, has_res, has_out, has_planes;
+  int M, N;
+  long long* dbg;
+  int probe;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  __half2 h = __halves2half2(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int FAST_BOX_F32 = 128 * 32 * 4;       // one fp32 staging box: 128 rows x 32 columns, 128B rows
+constexpr int FAST_BOX_PL = 2 * TC_A_PLANE;      // one plane staging box: 2 planes x 128 rows x 64 halfs
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, const FastEpi ep,
+                    const int num_kb, const int BN, const int STAGES) {
+  const int W_PLANE = BN * TC_BK * 2;
+  const int STAGE_BYTES = 2 * TC_A_PLANE + 2 * W_PLANE;
+  const int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  const int NCH = BN >> 5;                            // 32-column chunks of the tile
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* res_tile = smem + STAGES * STAGE_BYTES;                              // NCH boxes (only when has_res)
+  float* bias_s = reinterpret_cast<float*>(res_tile + (ep.has_res ? NCH * FAST_BOX_F32 : 0));
+  float* lns_s = bias_s + 192;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(lns_s + 192);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_bar = empty_bar + STAGES;
+  uint64_t* res_bar = acc_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
+  long long* dbg = (ep.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? ep.dbg : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    if (ep.has_out || ep.has_res) tma_prefetch_desc(&tmO);
+    if (ep.has_planes) tma_prefetch_desc(&tmP);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(acc_bar, 1);
+    mbar_init(res_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    // bias and LayerNorm column sums are weights: safe to read before the predecessor has finished
+    const int et = threadIdx.x - 64;
+    if (et < BN) {
+      const bool ok = n0 + et < ep.N;
+      bias_s[et] = (ep.bias && ok) ? __ldg(ep.bias + n0 + et) : 0.f;
+      lns_s[et] = (ep.ln_s && ok) ? __ldg(ep.ln_s + n0 + et) : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);   // REDUX result lives in a uniform register
+  pdl_launch();     // dependents may be scheduled; they still wait for this grid's completion before touching memory
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ===== TMA producer =====
+      // the weight halves of the first ring pass do not depend on the predecessor kernel: issue them before the wait
+      const int pre = num_kb < STAGES ? num_kb : STAGES;
+      if (!(ep.probe & 2)) {
+        for (int kb = 0; kb < pre; ++kb) {
+          mbar_expect_tx(&full_bar[kb], STAGE_BYTES);
+          tma_load_3d(smem + kb * STAGE_BYTES + 2 * TC_A_PLANE, &tmW, &full_bar[kb], kb * TC_BK, n0, 0);
+        }
+      }
+      pdl_wait();
+      trace_stamp(1, true);
+      if (dbg) dbg[1] = clock64();
+      if (ep.has_res) {
+        mbar_expect_tx(res_bar, NCH * FAST_BOX_F32);
+        for (int c = 0; c < NCH; ++c) tma_load_2d(res_tile + c * FAST_BOX_F32, &tmO, res_bar, n0 + c * 32, m0);
+      }
+      int s = 0;
+      uint32_t ph = 0;                       // ring pass parity
+      for (int kb = 0; kb < num_kb; ++kb) {
+        uint8_t* st = smem + s * STAGE_BYTES;
+        if (ep.probe & 2) {
+          if (kb >= pre) mbar_wait(&empty_bar[s], ph ^ 1);
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+        } else {
+          if (kb >= pre) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            tma_load_3d(st + 2 * TC_A_PLANE, &tmW, &full_bar[s], kb * TC_BK, n0, 0);
+          }
+          tma_load_3d(st, &tmA, &full_bar[s], kb * TC_BK, m0, 0);
+          if (dbg && kb < 16) dbg[8 + kb] = clock64();
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ===== MMA issuer =====
+      const bool cat = BN <= 128;
+      const uint32_t idesc_w = umma_idesc_f16(TC_BM, cat ? 2 * BN : BN);
+      const uint32_t idesc_n = umma_idesc_f16(TC_BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (dbg && kb < 16) dbg[24 + kb] = clock64();
+        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t a_lo = a_hi + TC_A_PLANE;
+        const uint32_t w_hi = a_hi + 2 * TC_A_PLANE;
+        const uint32_t w_lo = w_hi + W_PLANE;
+        if (!(ep.probe & 1)) {
+          if (cat) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t dah = umma_desc_sw128(a_hi) + 2 * k, dal = umma_desc_sw128(a_lo) + 2 * k;
+              const uint64_t dwh = umma_desc_sw128(w_hi) + 2 * k;
+              // columns [0, BN) = a_hi.w_hi (main), [BN, 2BN) = a_hi.w_lo; then a_lo.w_hi joins the second half
+              umma_f16(tmem_base, dah, dwh, idesc_w, (kb | k) != 0);
+              umma_f16(tmem_base + BN, dal, dwh, idesc_n, 1);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t dah = umma_desc_sw128(a_hi) + 2 * k, dal = umma_desc_sw128(a_lo) + 2 * k;
+              const uint64_t dwh = umma_desc_sw128(w_hi) + 2 * k, dwl = umma_desc_sw128(w_lo) + 2 * k;
+              umma_f16(tmem_base, dah, dwh, idesc_n, (kb | k) != 0);
+              umma_f16(tmem_base + BN, dah, dwl, idesc_n, (kb | k) != 0);
+              umma_f16(tmem_base + BN, dal, dwh, idesc_n, 1);
+            }
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(acc_bar);
+      if (dbg) dbg[2] = clock64();
+    }
+  } else {
+    // ===== epilogue: warps 2..9; TMEM lane group = warp % 4 (rows), the two warps of a group alternate 32-column chunks =====
+    pdl_wait();
+    const int lg = warp & 3, cpart = (warp - 2) >> 2;
+    const int r = lg * 32 + lane, grow = m0 + r;
+    const bool row_ok = grow < ep.M;
+    const uint32_t sw = (uint32_t)(r & 7);
+    float rstd = 1.0f, u = 0.0f;
+    const bool ln = ep.ln_s != nullptr;
+    if (ln && row_ok) {
+      // folded LayerNorm, consumer side: (mean, 1/sigma) of this thread's input row from its 16 partials over 32
+      // columns each (Chan et al.: M2 = sum M2_j + n_j sum (mean_j - mean)^2)
+      const float4* st4 = reinterpret_cast<const float4*>(ep.ln_stats + (long long)grow * 32);
+      float mj[16], qj[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 t = st4[i];
+        mj[2 * i] = t.x; qj[2 * i] = t.y; mj[2 * i + 1] = t.z; qj[2 * i + 1] = t.w;
+      }
+      float mu = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mu += mj[j];
+      mu *= 0.0625f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { const float dm = mj[j] - mu; m2 += qj[j] + 32.0f * dm * dm; }
+      rstd = 1.0f / sqrtf(m2 * (1.0f / 512.0f) + 1e-5f);
+      u = rstd * mu;
+    }
+    const float sc = ep.scale * rstd;
+    if (ep.has_res) mbar_wait(res_bar, 0);
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    if (dbg && threadIdx.x == 64) dbg[3] = clock64();
+    const uint32_t stage0 = smem_u32(smem);
+    const uint32_t out_base = stage0;                                                  // NCH fp32 boxes
+    const uint32_t pl_base = stage0 + (ep.has_out ? NCH * FAST_BOX_F32 : 0);           // BN / 64 plane boxes
+    const uint32_t res_base = smem_u32(res_tile);
+#pragma unroll 1
+    for (int c = cpart; c < NCH; c += 2) {
+      uint32_t v[32], vc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + c * 32, v);
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + BN + c * 32, vc);
+      tmem_ld_wait();
+      float x[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + q * 4);
+        x[4 * q + 0] = (__uint_as_float(v[4 * q + 0]) + __uint_as_float(vc[4 * q + 0])) * sc + b4.x;
+        x[4 * q + 1] = (__uint_as_float(v[4 * q + 1]) + __uint_as_float(vc[4 * q + 1])) * sc + b4.y;
+        x[4 * q + 2] = (__uint_as_float(v[4 * q + 2]) + __uint_as_float(vc[4 * q + 2])) * sc + b4.z;
+        x[4 * q + 3] = (__uint_as_float(v[4 * q + 3]) + __uint_as_float(vc[4 * q + 3])) * sc + b4.w;
+      }
+      if (ln) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 s4 = *reinterpret_cast<const float4*>(lns_s + c * 32 + q * 4);
+          x[4 * q + 0] -= u * s4.x; x[4 * q + 1] -= u * s4.y; x[4 * q + 2] -= u * s4.z; x[4 * q + 3] -= u * s4.w;
+        }
+      }
+      if (ep.act == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = x[j] * 0.5f * (1.0f + erff(x[j] * 0.70710678118654752440f));
+      }
+      if (ep.has_res) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 r4 = lds128(res_base + (uint32_t)(c * FAST_BOX_F32 + r * 128) + (((uint32_t)q ^ sw) << 4));
+          x[4 * q + 0] += r4.x; x[4 * q + 1] += r4.y; x[4 * q + 2] += r4.z; x[4 * q + 3] += r4.w;
+        }
+      }
+      if (ep.stats_out) {
+        // producer of a folded LayerNorm: (mean, M2) of this thread's 32 columns of the new residual row
+        float sm = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sm += x[j];
+        const float mj = sm * (1.0f / 32.0f);
+        float qd = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float dd = x[j] - mj; qd += dd * dd; }
+        if (row_ok) *reinterpret_cast<float2*>(ep.stats_out + ((long long)grow * 16 + blockIdx.x * NCH + c) * 2) = make_float2(mj, qd);
+      }
+      if (ep.has_out) {
+        const uint32_t orow = out_base + (uint32_t)(c * FAST_BOX_F32 + r * 128);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sts128(orow + (((uint32_t)q ^ sw) << 4), make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
+      }
+      if (ep.has_planes) {
+        const uint32_t prow = pl_base + (uint32_t)((c >> 1) * FAST_BOX_PL + r * 128);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __half h[8], l[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_f16(x[8 * q + e] * kActScale, h[e], l[e]);
+          const uint32_t off = (((uint32_t)((c & 1) * 4 + q)) ^ sw) << 4;
+          sts128u(prow + off, make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
+          sts128u(prow + TC_A_PLANE + off, make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7])));
+        }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();                                            // staging writes -> visible to the TMA engine
+    asm volatile("bar.sync 1, 256;" ::: "memory");                  // the eight epilogue warps
+    if (dbg && threadIdx.x == 64) dbg[6] = clock64();
+    if (warp == 2 && elect_one()) {
+      if (ep.has_out)
+        for (int c = 0; c < NCH; ++c) tma_store_2d(&tmO, out_base + c * FAST_BOX_F32, n0 + c * 32, m0);
+      if (ep.has_planes)
+        for (int b = 0; b < (BN >> 6); ++b) tma_store_3d(&tmP, pl_base + b * FAST_BOX_PL, n0 + b * 64, m0, 0);
+      tma_store_commit_wait();
+    }
+    if (dbg && threadIdx.x == 64) dbg[4] = clock64();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+  if (dbg && threadIdx.x == 0) dbg[5] = clock64();
+}
+
 // fp32 [M,K] (row stride lda) -> fp16 planes [2][M][Kp], value * scale split into hi + lo
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ a, int lda, int M, int K, int Kp, float scale, int relu,
                                                            __half* __restrict__ planes, long long plane_stride) {
@@ -614,6 +968,8 @@ struct WPlanes {
 static std::unordered_map<const float*, WPlanes> g_wplanes;
 static std::mutex g_w_mu;
 long long* g_tc_dbg = nullptr;  // set by st_debug_timeline
+int g_tc_probe = 0;             // set by st_debug_probe
+bool g_tc_fast = true;          // trunk kernel for the shapes it takes (st_debug_probe bit 16 turns it off)
 static Arena g_scratch;          // activation planes of the GEMM in flight (stream order serialises reuse)
 
 static int split_launch(const float* a, int lda, int M, int K, int Kp, float scale, int relu, __half* planes, cudaStream_t s) {
@@ -754,6 +1110,84 @@ static int get_map_long(const CUtensorMap** out, const __half* base, long long p
   return ST_OK;
 }
 
+// fp32 [rows, ld] row-major -> 2-D map {cols, rows}, box {32, 128}, 128B swizzle (residual prefetch and result store of
+// the trunk kernel)
+static int get_map_2d_f32(const CUtensorMap** out, const float* base, int rows, int cols, int ld) {
+  MapKey key{base, (long long)ld, cols, rows, -9, 32};
+  std::lock_guard<std::mutex> lk(g_tc_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = &it->second; return ST_OK; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ST_ECUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, TC_BM};
+  cuuint32_t est[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d f32 rows=%d cols=%d ld=%d) failed: %d", rows, cols, ld, (int)r); return ST_ECUDA; }
+  *out = &(g_maps[key] = m);
+  return ST_OK;
+}
+
+static int fast_bn(const GemmP& p) {
+  const int mt = (p.M + TC_BM - 1) / TC_BM;
+  int BN = p.N <= 512 ? 64 : 128;
+  if (p.N % 192 == 0 && mt * (p.N / 128) > 148 && mt * (p.N / 192) <= 148) BN = 192;
+  return BN;
+}
+
+// The trunk kernel takes plain Linear layers whose operand / result layouts TMA can describe.
+static bool tc_fast_supported(const GemmP& p) {
+  if (conv_mode(p) != 0 || (p.K % TC_BK) != 0 || (p.N % 64) != 0 || p.out_scale != 1.0f || p.a_relu || p.o_planes_relu) return false;
+  if (!p.out && !p.o_planes) return false;
+  if (p.act != ACT_NONE && p.act != ACT_GELU) return false;
+  if (p.res && (p.res != p.out || p.res_div != 1 || p.ldr != p.ldo || (p.res_mode == RES_PRE && p.act != ACT_NONE))) return false;
+  if (p.out && ((p.ldo & 3) || (reinterpret_cast<uintptr_t>(p.out) & 15))) return false;
+  if (p.o_planes && ((p.o_planes_ld & 7) || p.o_planes_ld < p.N || (reinterpret_cast<uintptr_t>(p.o_planes) & 15))) return false;
+  if (p.stats_out && p.N != 512) return false;
+  if (p.ln_stats && (!p.ln_s || !p.ln_c)) return false;
+  const int BN = fast_bn(p);
+  const int stage = 2 * TC_A_PLANE + 2 * BN * TC_BK * 2;
+  const int staging = (p.out ? (BN / 32) * FAST_BOX_F32 : 0) + (p.o_planes ? ((BN + 63) / 64) * FAST_BOX_PL : 0);
+  const int res = p.res ? (BN / 32) * FAST_BOX_F32 : 0;
+  int stages = (232448 - 4096 - res) / stage;
+  if (stages > 4) stages = 4;
+  return stages >= 2 && staging <= stages * stage && (BN % 64 == 0 || !p.o_planes);
+}
+
+static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long long pstride, cudaStream_t s) {
+  const int BN = fast_bn(p);
+  const int stage = 2 * TC_A_PLANE + 2 * BN * TC_BK * 2;
+  const int res = p.res ? (BN / 32) * FAST_BOX_F32 : 0;
+  int stages = (232448 - 4096 - res) / stage;
+  if (stages > 4) stages = 4;
+  const int smem = stages * stage + res + 2 * 192 * 4 + (2 * stages + 2) * 8 + 16 + 1024;
+  const CUtensorMap *tmA = nullptr, *tmW = nullptr, *tmO = nullptr, *tmP = nullptr;
+  ST_TRY(get_map_3d(&tmA, planes, pstride, p.M, p.K, TC_BM));
+  ST_TRY(get_map_3d(&tmW, w->planes, (long long)p.N * w->Kp, p.N, w->Kp, BN));
+  tmO = tmA; tmP = tmA;
+  if (p.out) ST_TRY(get_map_2d_f32(&tmO, p.out, p.M, p.N, p.ldo));
+  if (p.o_planes) ST_TRY(get_map_3d(&tmP, p.o_planes, p.o_plane_stride, p.M, p.o_planes_ld, TC_BM));
+  FastEpi ep;
+  ep.bias = p.ln_stats ? p.ln_c : p.bias;
+  ep.ln_s = p.ln_stats ? p.ln_s : nullptr;
+  ep.ln_stats = p.ln_stats; ep.stats_out = p.stats_out;
+  ep.scale = w->inv_scale / kActScale;
+  ep.act = p.act; ep.has_res = p.res ? 1 : 0; ep.has_out = p.out ? 1 : 0; ep.has_planes = p.o_planes ? 1 : 0;
+  ep.M = p.M; ep.N = p.N; ep.dbg = g_tc_dbg; ep.probe = g_tc_probe;
+  static bool attr = false;
+  if (!attr) {
+    ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM);
+  launch_k(gemm_tc_fast_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, *tmA, *tmW, *tmO, *tmP, ep, w->Kp / TC_BK, BN, stages);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
 int gemm_tc(const GemmP& p, cudaStream_t s) {
   if (!tc_supported(p)) { set_error("gemm_tc: unsupported problem"); return ST_EUNSUPPORTED; }
   WPlanes* w = nullptr;
@@ -781,6 +1215,8 @@ launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 
     ST_CHECK_LAUNCH();
     planes = sp;
   }
+  if (g_tc_fast && tc_fast_supported(p)) return gemm_tc_fast(p, w, planes, pstride, s);
+  if (p.ln_stats || p.stats_out) { set_error("gemm_tc: folded LayerNorm is served by the trunk kernel only"); return ST_EUNSUPPORTED; }
   const CUtensorMap* tmA = nullptr;
   const CUtensorMap* tmW = nullptr;
   TcEpi ep;
@@ -804,6 +1240,7 @@ launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 
   if (p.stats_out && (p.N != 512 || BN != 64)) { set_error("gemm_tc: stats_out needs N = 512 (8 tiles of 64 columns)"); return ST_EINVAL; }
   if (p.ln_stats && (!p.ln_s || !p.ln_c)) { set_error("gemm_tc: ln_stats needs ln_s and ln_c"); return ST_EINVAL; }
   ep.dbg = g_tc_dbg;
+  ep.probe = g_tc_probe;
   const int num_kb = w->Kp / TC_BK;
   const int mtiles = mode >= 2 ? nclips * ep.tpc : (p.M + TC_BM - 1) / TC_BM;
   return launch_tc(*tmA, *tmW, ep, num_kb, mtiles, BN, s);

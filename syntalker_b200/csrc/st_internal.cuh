@@ -69,9 +69,9 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 #ifdef __CUDACC__
 // Debug trace (st_debug_trace): CTA (0,0) thread 0 of every kernel stamps %globaltimer and a kernel id at entry.
 static __device__ unsigned long long* g_trace_buf = nullptr;   // per translation unit (no -rdc); [cap][2] = (ns, id); slot 0 = counter
-__device__ __forceinline__ void trace_stamp(int id) {
+__device__ __forceinline__ void trace_stamp(int id, bool any_thread = false) {
   unsigned long long* t = g_trace_buf;
-  if (t && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+  if (t && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (any_thread || threadIdx.x == 0)) {
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
     const unsigned long long slot = atomicAdd(t, 1ull) + 1;
@@ -111,8 +111,8 @@ struct GemmP {
   long long o_plane_stride = 0;
   int o_planes_ld = 0, o_planes_relu = 0;
   // LayerNorm folded around the GEMM (tcgen05 engine, N = 512 producers / any-N consumers):
-  //  consumer: out = rstd[m] * (acc - mean[m] * ln_s[n]) + ln_c[n]  with (mean, rstd) combined from ln_stats[m][8][2]
-  //  producer: stats_out[m][n_block][2] = (mean, M2) of the 64 result columns this CTA owns (Chan-combinable)
+  //  consumer: out = rstd[m] * (acc - mean[m] * ln_s[n]) + ln_c[n]  with (mean, rstd) combined from ln_stats[m][16][2]
+  //  producer: stats_out[m][n / 32][2] = (mean, M2) of each 32-column run of the result row (Chan-combinable)
   const float* ln_stats = nullptr;
   const float* ln_s = nullptr;
   const float* ln_c = nullptr;
@@ -164,7 +164,7 @@ struct TokensInP {
   const float* rope_sin;
   float* x;                  // [nE*B*32,512]
   __half* x_planes;          // optional: fp16 hi/lo planes of x (* kActScale), [2][nE*B*32][512]
-  float* stats;              // optional: LayerNorm row statistics of x as 8 combinable partials, [nE*B*32][8][2]
+  float* stats;              // optional: LayerNorm row statistics of x as 16 combinable partials, [nE*B*32][16][2]
   int B, nE;
 };
 int tokens_in(const TokensInP& p, cudaStream_t s);

@@ -454,8 +454,8 @@ __global__ void __launch_bounds__(256) tokens_in_kernel(TokensInP p) {
     for (int g = 0; g < 8; ++g) { const float d1 = v1[g] - mean, d2 = v2[g] - mean; m2 += d1 * d1 + d2 * d2; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
-    // eight identical partials (mean, M2/8) combine to exactly (mean, M2)
-    if (lane < 8) { p.stats[(orow * 8 + lane) * 2] = mean; p.stats[(orow * 8 + lane) * 2 + 1] = m2 * 0.125f; }
+    // sixteen identical partials (mean, M2/16) combine to exactly (mean, M2)
+    if (lane < 16) *reinterpret_cast<float2*>(p.stats + (orow * 16 + lane) * 2) = make_float2(mean, m2 * 0.0625f);
   }
 }
 
