@@ -145,6 +145,7 @@ struct ConvW { const float* w; const float* b; int ldw; };
 struct BlkW {
   const float *ln1g, *ln1b, *qkv, *projw, *projb, *ln2g, *ln2b, *fc1w, *fc1b, *fc2w, *fc2b;
   const float *qkv_wg, *qkv_s, *qkv_c, *fc1_wg, *fc1_s, *fc1_c;   // LayerNorm folded into the consuming Linear (tcgen05 engine)
+  const float *qkv_wgp, *qkv_sp, *qkv_cp;                         // the same with rows permuted for the fused attention epilogue
 };
 struct EvalSpec { int cst_null; int sv_src; };   // sv_src: -1 none, 0..2 = style k, 3 = null embedding
 
@@ -183,6 +184,15 @@ struct st_model {
 };
 
 static bool g_use_graphs = true;
+static bool g_fused_attn = true;   // st_debug_probe bit 32 turns the fused qkv + attention kernel off
+
+namespace st { extern int g_tc_probe; extern bool g_tc_fast; }
+extern "C" int st_debug_probe(int flags) {
+  st::g_tc_probe = flags & 15;
+  st::g_tc_fast = !(flags & 16);
+  g_fused_attn = !(flags & 32);
+  return ST_OK;
+}
 
 struct st_schedule {
   int S = 0, mode = 0;
@@ -209,7 +219,7 @@ extern "C" int st_set_engine(int engine) {
 }
 extern "C" int st_get_engine(void) { return g_engine; }
 namespace st { extern long long* g_tc_dbg; extern int g_tc_probe; extern bool g_tc_fast; }
-extern "C" int st_debug_probe(int flags) { st::g_tc_probe = flags & 15; st::g_tc_fast = !(flags & 16); return ST_OK; }
+extern "C" int st_debug_probe(int flags);
 extern "C" int st_debug_timeline(long long* dev_buf) { st::g_tc_dbg = dev_buf; return ST_OK; }
 extern "C" int st_debug_trace(unsigned long long* dev_buf) {
   ST_TRY(st::set_trace_kernels(dev_buf));
@@ -261,6 +271,7 @@ static int model_resolve(st_model* m) {
     b.fc1w = g("fc1.w", 1024 * 512); b.fc1b = g("fc1.b", 1024);
     b.fc2w = g("fc2.w", 512 * 1024); b.fc2b = g("fc2.b", 512);
     b.qkv_wg = g("qkv.wg", 1536 * 512); b.qkv_s = g("qkv.s", 1536); b.qkv_c = g("qkv.c", 1536);
+    b.qkv_wgp = g("qkv.wgp", 1536 * 512); b.qkv_sp = g("qkv.sp", 1536); b.qkv_cp = g("qkv.cp", 1536);
     b.fc1_wg = g("fc1.wg", 1024 * 512); b.fc1_s = g("fc1.s", 1024); b.fc1_c = g("fc1.c", 1024);
   }
   return err;
@@ -515,10 +526,18 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
     if (tc) {
       // tcgen05 engine: 5 launches per block.  LayerNorm never runs as a kernel: the GEMM that consumes it reads the raw
       // residual planes and applies (mean, 1/sigma) in its epilogue from the row statistics its producer left.
-      GemmP pq = linear(m->X, R, 512, b.qkv_wg, nullptr, m->QKV, 1536);
-      pq.a_planes = m->X_p; pq.a_plane_stride = ps512; pq.ln_stats = m->ln_stats; pq.ln_s = b.qkv_s; pq.ln_c = b.qkv_c;
-      ST_TRY(gemm(pq, s));
-      ST_TRY(attention32(m->QKV, nullptr, m->ATT_p, pl.nE * B, s));
+      if (g_fused_attn) {
+        // qkv GEMM + 32-token attention in one kernel (cluster of 2 CTAs per (4 sequences, head))
+        GemmP pq = linear(m->X, R, 512, b.qkv_wgp, nullptr, nullptr, 1536);
+        pq.a_planes = m->X_p; pq.a_plane_stride = ps512; pq.ln_stats = m->ln_stats; pq.ln_s = b.qkv_sp; pq.ln_c = b.qkv_cp;
+        pq.attn = 1; pq.o_planes = m->ATT_p; pq.o_plane_stride = ps512; pq.o_planes_ld = 512;
+        ST_TRY(gemm(pq, s));
+      } else {
+        GemmP pq = linear(m->X, R, 512, b.qkv_wg, nullptr, m->QKV, 1536);
+        pq.a_planes = m->X_p; pq.a_plane_stride = ps512; pq.ln_stats = m->ln_stats; pq.ln_s = b.qkv_s; pq.ln_c = b.qkv_c;
+        ST_TRY(gemm(pq, s));
+        ST_TRY(attention32(m->QKV, nullptr, m->ATT_p, pl.nE * B, s));
+      }
       GemmP pp = linear(m->ATT, R, 512, b.projw, b.projb, m->X, 512);
       pp.res = m->X; pp.res_mode = RES_POST; pp.ldr = 512; pp.a_planes = m->ATT_p; pp.a_plane_stride = ps512;
       pp.o_planes = m->X_p; pp.o_plane_stride = ps512; pp.o_planes_ld = 512; pp.stats_out = m->ln_stats;

@@ -561,6 +561,7 @@ struct FastEpi {
   float scale;             // undoes the operand pre-scaling
   int act, has_res, has_out, has_planes;
   int M, N;
+  int attn;                // 1: the tile is [q 64 | k 64 | v 64] of one head half; the epilogue runs the 32-token attention
   long long* dbg;
   int probe;
 };
@@ -591,6 +592,11 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+constexpr int ATT_LDK = 68;                      // K / V staging row stride (floats): conflict-free float4 stores for lane = row
+constexpr int ATT_LDS = 36;                      // score row stride (floats)
+constexpr int ATT_SX_BYTES = 128 * ATT_LDS * 4;  // partial scores written by the peer CTA of the cluster
+constexpr int ATT_KV_BYTES = 128 * ATT_LDK * 4;
+constexpr int ATT_PL_OFF = 90112;                // plane staging box behind K, V and the own partial scores (1024-aligned)
 constexpr int FAST_BOX_F32 = 128 * 32 * 4;       // one fp32 staging box: 128 rows x 32 columns, 128B rows
 constexpr int FAST_BOX_PL = 2 * TC_A_PLANE;      // one plane staging box: 2 planes x 128 rows x 64 halfs
 
@@ -605,7 +611,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res_tile = smem + STAGES * STAGE_BYTES;                              // NCH boxes (only when has_res)
-  float* bias_s = reinterpret_cast<float*>(res_tile + (ep.has_res ? NCH * FAST_BOX_F32 : 0));
+  float* bias_s = reinterpret_cast<float*>(res_tile + (ep.attn ? ATT_SX_BYTES : ep.has_res ? NCH * FAST_BOX_F32 : 0));
   float* lns_s = bias_s + 192;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(lns_s + 192);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -766,6 +772,106 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t out_base = stage0;                                                  // NCH fp32 boxes
     const uint32_t pl_base = stage0 + (ep.has_out ? NCH * FAST_BOX_F32 : 0);           // BN / 64 plane boxes
     const uint32_t res_base = smem_u32(res_tile);
+    if (ep.attn) {
+      // ---- fused attention (transformer.py:83-104).  This CTA holds, for 4 sequences x 32 tokens (warp lane group = one
+      // sequence, lane = token), 64 of the 128 dims of q, k and v of one head; its cluster peer holds the other 64.
+      // Scores are summed over both halves through distributed shared memory, the softmax is per thread (one row),
+      // and each CTA forms its own 64 dims of P V.  fp32 SIMT like the stand-alone kernel it replaces.
+      const uint32_t ks = stage0, vs = stage0 + ATT_KV_BYTES, so = stage0 + 2 * ATT_KV_BYTES;
+      const uint32_t sx = smem_u32(res_tile);
+      uint32_t sx_peer;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(sx_peer) : "r"(sx), "r"((uint32_t)((blockIdx.x & 1) ^ 1)));
+      auto load_chunk = [&](int c, float* x) {
+        uint32_t v[32], vc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + c * 32, v);
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + BN + c * 32, vc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          x[j] = (__uint_as_float(v[j]) + __uint_as_float(vc[j])) * sc + bias_s[c * 32 + j] - u * lns_s[c * 32 + j];
+      };
+      float q[64];
+      load_chunk(0, q);
+      load_chunk(1, q + 32);
+      {
+        const uint32_t dst = (cpart == 0 ? ks : vs) + (uint32_t)(r * ATT_LDK) * 4;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          float x[32];
+          load_chunk(2 + 2 * cpart + cc, x);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) sts128(dst + (uint32_t)(cc * 32 + t * 4) * 4, make_float4(x[4 * t], x[4 * t + 1], x[4 * t + 2], x[4 * t + 3]));
+        }
+      }
+      tc_fence_before();
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory");     // k and v of this sequence are in place
+      // partial scores over this CTA's 64 dims: this warp takes 16 of the 32 keys
+#pragma unroll 1
+      for (int jj = 0; jj < 16; ++jj) {
+        const int j = cpart * 16 + jj;
+        const uint32_t krow = ks + (uint32_t)((lg * 32 + j) * ATT_LDK) * 4;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int d4 = 0; d4 < 16; ++d4) {
+          const float4 kk = lds128(krow + d4 * 16);
+          a0 = fmaf(q[4 * d4 + 0], kk.x, a0); a1 = fmaf(q[4 * d4 + 1], kk.y, a1);
+          a2 = fmaf(q[4 * d4 + 2], kk.z, a2); a3 = fmaf(q[4 * d4 + 3], kk.w, a3);
+        }
+        const float sp = (a0 + a1) + (a2 + a3);
+        const uint32_t off = (uint32_t)(r * ATT_LDS + j) * 4;
+        sts32(so + off, sp);
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(sx_peer + off), "f"(sp) : "memory");
+      }
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      // full score row -> softmax (scale 128^-0.5), in registers
+      float pr[32];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float4 a = lds128(so + (uint32_t)(r * ATT_LDS + 4 * t) * 4), b = lds128(sx + (uint32_t)(r * ATT_LDS + 4 * t) * 4);
+        pr[4 * t + 0] = (a.x + b.x) * 0.08838834764831845f; pr[4 * t + 1] = (a.y + b.y) * 0.08838834764831845f;
+        pr[4 * t + 2] = (a.z + b.z) * 0.08838834764831845f; pr[4 * t + 3] = (a.w + b.w) * 0.08838834764831845f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, pr[j]);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { pr[j] = expf(pr[j] - mx); sum += pr[j]; }
+      const float inv = 1.0f / sum;
+      // P V over this warp's 32 of the CTA's 64 dims
+      float o[32];
+#pragma unroll
+      for (int d = 0; d < 32; ++d) o[d] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float pj = pr[j] * inv;
+        const uint32_t vrow = vs + (uint32_t)((lg * 32 + j) * ATT_LDK + cpart * 32) * 4;
+#pragma unroll
+        for (int d4 = 0; d4 < 8; ++d4) {
+          const float4 vv = lds128(vrow + d4 * 16);
+          o[4 * d4 + 0] = fmaf(pj, vv.x, o[4 * d4 + 0]); o[4 * d4 + 1] = fmaf(pj, vv.y, o[4 * d4 + 1]);
+          o[4 * d4 + 2] = fmaf(pj, vv.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(pj, vv.w, o[4 * d4 + 3]);
+        }
+      }
+      const uint32_t prow = stage0 + ATT_PL_OFF + (uint32_t)(r * 128);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        __half h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_f16(o[8 * t + e] * kActScale, h[e], l[e]);
+        const uint32_t off = (((uint32_t)(cpart * 4 + t)) ^ sw) << 4;
+        sts128u(prow + off, make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
+        sts128u(prow + TC_A_PLANE + off, make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7])));
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && elect_one()) {
+        tma_store_3d(&tmP, stage0 + ATT_PL_OFF, blockIdx.x * 64, m0, 0);
+        tma_store_commit_wait();
+      }
+      if (dbg && threadIdx.x == 64) dbg[4] = clock64();
+    } else {
 #pragma unroll 1
     for (int c = cpart; c < NCH; c += 2) {
       uint32_t v[32], vc[32];
@@ -840,6 +946,13 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tma_store_commit_wait();
     }
     if (dbg && threadIdx.x == 64) dbg[4] = clock64();
+    }
+  }
+  if (ep.attn && warp < 2) {
+    // the producer and MMA warps take part in the cluster barrier of the attention epilogue
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
   __syncthreads();
   if (warp == 2) {
@@ -1045,7 +1158,9 @@ static int conv_mode(const GemmP& p) {
   return -1;
 }
 
+static bool tc_fast_supported(const GemmP& p);
 bool tc_supported(const GemmP& p) {
+  if (p.attn) return tc_fast_supported(p);
   if ((!p.out && !p.o_planes) || p.out_scale != 1.0f || p.M < 1 || p.N < 16) return false;   // rows beyond M: TMA zero fill + masked stores
   const int mode = conv_mode(p);
   if (mode < 0) return false;
@@ -1132,6 +1247,7 @@ static int get_map_2d_f32(const CUtensorMap** out, const float* base, int rows, 
 }
 
 static int fast_bn(const GemmP& p) {
+  if (p.attn) return 192;
   const int mt = (p.M + TC_BM - 1) / TC_BM;
   int BN = p.N <= 512 ? 64 : 128;
   if (p.N % 192 == 0 && mt * (p.N / 128) > 148 && mt * (p.N / 192) <= 148) BN = 192;
@@ -1140,6 +1256,9 @@ static int fast_bn(const GemmP& p) {
 
 // The trunk kernel takes plain Linear layers whose operand / result layouts TMA can describe.
 static bool tc_fast_supported(const GemmP& p) {
+  if (p.attn)
+    return conv_mode(p) == 0 && p.K == 512 && p.N == 1536 && (p.M % 32) == 0 && !p.out && p.o_planes && p.o_planes_ld == 512 && p.ln_stats &&
+           p.ln_s && p.ln_c && !p.res && p.act == ACT_NONE && !p.stats_out;
   if (conv_mode(p) != 0 || (p.K % TC_BK) != 0 || (p.N % 64) != 0 || p.out_scale != 1.0f || p.a_relu || p.o_planes_relu) return false;
   if (!p.out && !p.o_planes) return false;
   if (p.act != ACT_NONE && p.act != ACT_GELU) return false;
@@ -1163,7 +1282,8 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   const int res = p.res ? (BN / 32) * FAST_BOX_F32 : 0;
   int stages = (232448 - 4096 - res) / stage;
   if (stages > 4) stages = 4;
-  const int smem = stages * stage + res + 2 * 192 * 4 + (2 * stages + 2) * 8 + 16 + 1024;
+  if (p.attn) { stages = 2; }
+  const int smem = stages * stage + (p.attn ? ATT_SX_BYTES : res) + 2 * 192 * 4 + (2 * stages + 2) * 8 + 16 + 1024;
   const CUtensorMap *tmA = nullptr, *tmW = nullptr, *tmO = nullptr, *tmP = nullptr;
   ST_TRY(get_map_3d(&tmA, planes, pstride, p.M, p.K, TC_BM));
   ST_TRY(get_map_3d(&tmW, w->planes, (long long)p.N * w->Kp, p.N, w->Kp, BN));
@@ -1176,14 +1296,15 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   ep.ln_stats = p.ln_stats; ep.stats_out = p.stats_out;
   ep.scale = w->inv_scale / kActScale;
   ep.act = p.act; ep.has_res = p.res ? 1 : 0; ep.has_out = p.out ? 1 : 0; ep.has_planes = p.o_planes ? 1 : 0;
-  ep.M = p.M; ep.N = p.N; ep.dbg = g_tc_dbg; ep.probe = g_tc_probe;
+  ep.M = p.M; ep.N = p.N; ep.dbg = g_tc_dbg; ep.probe = g_tc_probe; ep.attn = p.attn;
   static bool attr = false;
   if (!attr) {
     ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM);
-  launch_k(gemm_tc_fast_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, *tmA, *tmW, *tmO, *tmP, ep, w->Kp / TC_BK, BN, stages);
+  if (p.attn) launch_k_cluster(gemm_tc_fast_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, 2, *tmA, *tmW, *tmO, *tmP, ep, w->Kp / TC_BK, BN, stages);
+  else launch_k(gemm_tc_fast_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, *tmA, *tmW, *tmO, *tmP, ep, w->Kp / TC_BK, BN, stages);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -1215,7 +1336,8 @@ launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 
     ST_CHECK_LAUNCH();
     planes = sp;
   }
-  if (g_tc_fast && tc_fast_supported(p)) return gemm_tc_fast(p, w, planes, pstride, s);
+  if ((g_tc_fast || p.attn) && tc_fast_supported(p)) return gemm_tc_fast(p, w, planes, pstride, s);
+  if (p.attn) { set_error("gemm_tc: fused attention needs the 1536 x 512 qkv layout"); return ST_EUNSUPPORTED; }
   if (p.ln_stats || p.stats_out) { set_error("gemm_tc: folded LayerNorm is served by the trunk kernel only"); return ST_EUNSUPPORTED; }
   const CUtensorMap* tmA = nullptr;
   const CUtensorMap* tmW = nullptr;

@@ -66,6 +66,19 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
+// same, for kernels that run as thread-block clusters of `cluster_x` CTAs along x
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 #ifdef __CUDACC__
 // Debug trace (st_debug_trace): CTA (0,0) thread 0 of every kernel stamps %globaltimer and a kernel id at entry.
 static __device__ unsigned long long* g_trace_buf = nullptr;   // per translation unit (no -rdc); [cap][2] = (ns, id); slot 0 = counter
@@ -117,6 +130,9 @@ struct GemmP {
   const float* ln_s = nullptr;
   const float* ln_c = nullptr;
   float* stats_out = nullptr;
+  // Fused attention (tcgen05 engine): W is the qkv weight with rows permuted to [head][half][q 64 | k 64 | v 64], so that
+  // CTA n owns 64 dims of q, k, v of one head; the epilogue runs the 32-token attention and writes o_planes [M, 512].
+  int attn = 0;
 };
 
 constexpr float kActScale = 16.0f;   // activations are stored in fp16 planes as (v * 16): |v| < 4e3 representable, lo normal for |v| > 2^-6

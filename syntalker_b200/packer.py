@@ -122,6 +122,11 @@ def pack_mdm(sd: Dict[str, torch.Tensor], variant: str | None = None) -> Dict[st
             out[f"blk.{i}.{dst}.wg"] = _t32(Wg)
             out[f"blk.{i}.{dst}.s"] = _t32(Wg.sum(axis=1))
             out[f"blk.{i}.{dst}.c"] = _t32(Wl @ be + (_f64(sd[p + lin + ".bias"]) if has_b else 0.0))
+        # rows of the qkv layer regrouped as [head h][half j][q 64 | k 64 | v 64] (row = which*512 + h*128 + j*64 + d,
+        # transformer.py:85-86): GEMM tile n = 2h + j of the fused qkv + attention kernel is then 192 consecutive rows
+        perm = np.concatenate([w * 512 + h * 128 + j * 64 + np.arange(64) for h in range(4) for j in range(2) for w in range(3)])
+        for suf in ("wg", "s", "c"):
+            out[f"blk.{i}.qkv.{suf}p"] = out[f"blk.{i}.qkv.{suf}"][torch.from_numpy(perm)].contiguous()
     out["out.w"] = sd["output_process.poseFinal.weight"].detach().cpu().float().contiguous()
     out["out.b"] = sd["output_process.poseFinal.bias"].detach().cpu().float().contiguous()
     return out
