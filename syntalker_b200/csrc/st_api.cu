@@ -184,6 +184,7 @@ struct st_model {
 };
 
 static bool g_use_graphs = true;
+static bool g_rank_simt = false;
 static bool g_fused_attn = true;   // st_debug_probe bit 32 turns the fused qkv + attention kernel off
 
 namespace st { extern int g_tc_probe; extern bool g_tc_fast; }
@@ -191,6 +192,7 @@ extern "C" int st_debug_probe(int flags) {
   st::g_tc_probe = flags & 15;
   st::g_tc_fast = !(flags & 16);
   g_fused_attn = !(flags & 32);
+  g_rank_simt = (flags & 64) != 0;
   return ST_OK;
 }
 
@@ -502,9 +504,9 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   const long long ps512 = (long long)R * 512, ps1024 = (long long)R * 1024;
   GemmP pz = linear(m->xs, rows, 1536, m->w_x, nullptr, m->z, 512);
   if (tc) {
-    // the state is split into the model's own planes: a captured step graph must not point into the engine's
-    // global split scratch, which is reallocated when some other call needs a larger one
-    ST_TRY(tc_split(m->xs, 1536, rows, 1536, m->xs_p, s));
+    // the state lives in the model's own planes (a captured step graph must not point into the engine's global split
+    // scratch); inside the sampling loop step_update keeps them current, a single evaluation splits here
+    if (!loop) ST_TRY(tc_split(m->xs, 1536, rows, 1536, m->xs_p, s));
     pz.a_planes = m->xs_p; pz.a_plane_stride = (long long)rows * 1536;
   }
   ST_TRY(gemm(pz, s));
@@ -634,8 +636,9 @@ static int one_step(st_model* m, const Plan& pl, const StepP& sp0, int B, cudaSt
   ST_TRY(run_trunk(m, pl, B, nullptr, 0, true, s));
   StepP sp = sp0;
   sp.xs = m->xs; sp.eps = nullptr; sp.ls = m->loop; sp.coef_dev = m->coef_dev;
+  sp.xs_planes = st_get_engine() == ST_ENGINE_TC ? m->xs_p : nullptr;
+  sp.ls_advance = m->loop;          // the update's last CTA also moves the loop to the next step
   ST_TRY(step_update(sp, s));
-  ST_TRY(advance_loop(m->loop, s));
   return ST_OK;
 }
 
@@ -656,6 +659,7 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
   ST_CHECK_CUDA(cudaMemcpyAsync(m->coef_dev, sc->coef.data(), (size_t)sc->S * ST_COEF_STRIDE * sizeof(float), cudaMemcpyHostToDevice, s));
   ST_TRY(init_loop(m->loop, sc->S, noise_tape, s));
   ST_TRY(transpose_to_tokens(x_init, m->xs, B, 1536, 32, 1.0f, s));
+  if (st_get_engine() == ST_ENGINE_TC) ST_TRY(tc_split(m->xs, 1536, B * 32, 1536, m->xs_p, s));
   // The first call with a given plan runs eagerly (it creates weight planes, tensor maps, scratch); the second
   // captures one step into a CUDA graph; from then on every step is one graph launch.  Capture and replay run
   // on the model's own stream (the caller's may be the legacy default stream, which cannot capture), fenced
@@ -789,7 +793,7 @@ extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, flo
   // residual quantisation, 6 layers (residual_vq.py:132-152)
   for (int q = 0; q < 6; ++q) {
     GemmP p = linear(r, (int)rows, 512, v->cb[q], nullptr, dot, 512);
-    ST_TRY(gemm_simt(p, s));   // code ranking always on the exact-fp32 engine
+    ST_TRY(g_rank_simt ? gemm_simt(p, s) : gemm(p, s));   // split-fp16 products carry fp32-class error; bit 64 of st_debug_probe forces SIMT
     ST_TRY(vq_select(dot, v->cnorm[q], v->cb[q], r, qsum, idx_out ? idx_out + q : nullptr, 6, (int)rows, q == 0, s));
   }
   if (residual_out) ST_CHECK_CUDA(cudaMemcpyAsync(residual_out, r, rows * 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -592,11 +592,20 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// packed fp32 pair FMA (sm_100): (d0, d1) += (a0, a1) * (b0, b1)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  unsigned long long a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(d0), "f"(d1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
+}
 constexpr int ATT_LDK = 68;                      // K / V staging row stride (floats): conflict-free float4 stores for lane = row
 constexpr int ATT_LDS = 36;                      // score row stride (floats)
 constexpr int ATT_SX_BYTES = 128 * ATT_LDS * 4;  // partial scores written by the peer CTA of the cluster
 constexpr int ATT_KV_BYTES = 128 * ATT_LDK * 4;
-constexpr int ATT_PL_OFF = 90112;                // plane staging box behind K, V and the own partial scores (1024-aligned)
+constexpr int ATT_PL_OFF = 124928;               // plane staging box behind Q, K, V and P (3 x 34816 + 18432 = 122880 -> 1024-aligned)
 constexpr int FAST_BOX_F32 = 128 * 32 * 4;       // one fp32 staging box: 128 rows x 32 columns, 128B rows
 constexpr int FAST_BOX_PL = 2 * TC_A_PLANE;      // one plane staging box: 2 planes x 128 rows x 64 halfs
 
@@ -773,103 +782,148 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t pl_base = stage0 + (ep.has_out ? NCH * FAST_BOX_F32 : 0);           // BN / 64 plane boxes
     const uint32_t res_base = smem_u32(res_tile);
     if (ep.attn) {
-      // ---- fused attention (transformer.py:83-104).  This CTA holds, for 4 sequences x 32 tokens (warp lane group = one
+      // ---- fused attention (transformer.py:83-104).  This CTA holds, for 4 sequences x 32 tokens (TMEM lane group = one
       // sequence, lane = token), 64 of the 128 dims of q, k and v of one head; its cluster peer holds the other 64.
-      // Scores are summed over both halves through distributed shared memory, the softmax is per thread (one row),
-      // and each CTA forms its own 64 dims of P V.  fp32 SIMT like the stand-alone kernel it replaces.
-      const uint32_t ks = stage0, vs = stage0 + ATT_KV_BYTES, so = stage0 + 2 * ATT_KV_BYTES;
+      // q, k, v go to shared memory (fp32); the two warps of a lane group then take 16 query rows each and work in
+      // 4 x 4 register tiles (packed fp32x2 FMAs): partial scores over the 64 local dims, exchanged with the peer
+      // through distributed shared memory, softmax across the 8 lanes of a row, and this CTA's 64 dims of P V.
+      const uint32_t qs = stage0, ks = stage0 + ATT_KV_BYTES, vs = stage0 + 2 * ATT_KV_BYTES, pp = stage0 + 3 * ATT_KV_BYTES;
       const uint32_t sx = smem_u32(res_tile);
       uint32_t sx_peer;
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(sx_peer) : "r"(sx), "r"((uint32_t)((blockIdx.x & 1) ^ 1)));
-      auto load_chunk = [&](int c, float* x) {
+      // phase A: the 6 chunks [q0 q1 k0 k1 v0 v1] of this lane group's rows -> shared memory, 3 chunks per warp
+#pragma unroll 1
+      for (int cc = 0; cc < 3; ++cc) {
+        const int c = cpart * 3 + cc;
         uint32_t v[32], vc[32];
         tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + c * 32, v);
         tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + BN + c * 32, vc);
         tmem_ld_wait();
+        const uint32_t dst = stage0 + (uint32_t)((c >> 1) * ATT_KV_BYTES + (r * ATT_LDK + (c & 1) * 32) * 4);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          x[j] = (__uint_as_float(v[j]) + __uint_as_float(vc[j])) * sc + bias_s[c * 32 + j] - u * lns_s[c * 32 + j];
-      };
-      float q[64];
-      load_chunk(0, q);
-      load_chunk(1, q + 32);
-      {
-        const uint32_t dst = (cpart == 0 ? ks : vs) + (uint32_t)(r * ATT_LDK) * 4;
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          float x[32];
-          load_chunk(2 + 2 * cpart + cc, x);
-#pragma unroll
-          for (int t = 0; t < 8; ++t) sts128(dst + (uint32_t)(cc * 32 + t * 4) * 4, make_float4(x[4 * t], x[4 * t + 1], x[4 * t + 2], x[4 * t + 3]));
+        for (int t = 0; t < 8; ++t) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + t * 4);
+          const float4 s4 = *reinterpret_cast<const float4*>(lns_s + c * 32 + t * 4);
+          float4 x;
+          x.x = (__uint_as_float(v[4 * t + 0]) + __uint_as_float(vc[4 * t + 0])) * sc + b4.x - u * s4.x;
+          x.y = (__uint_as_float(v[4 * t + 1]) + __uint_as_float(vc[4 * t + 1])) * sc + b4.y - u * s4.y;
+          x.z = (__uint_as_float(v[4 * t + 2]) + __uint_as_float(vc[4 * t + 2])) * sc + b4.z - u * s4.z;
+          x.w = (__uint_as_float(v[4 * t + 3]) + __uint_as_float(vc[4 * t + 3])) * sc + b4.w - u * s4.w;
+          sts128(dst + t * 16, x);
         }
       }
       tc_fence_before();
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory");     // k and v of this sequence are in place
-      // partial scores over this CTA's 64 dims: this warp takes 16 of the 32 keys
-#pragma unroll 1
-      for (int jj = 0; jj < 16; ++jj) {
-        const int j = cpart * 16 + jj;
-        const uint32_t krow = ks + (uint32_t)((lg * 32 + j) * ATT_LDK) * 4;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory");     // q, k, v of this sequence are in place
+      if (dbg && threadIdx.x == 64) { dbg[40] = dbg[0]; dbg[41] = dbg[3]; dbg[42] = clock64(); }
+      // phase B: thread (rq, kq) of warp (lg, cpart): query rows 16*cpart + rq + 4a, keys kq + 8b  (a, b = 0..3)
+      const int rq = lane >> 3, kq = lane & 7;
+      const int row0 = lg * 32 + cpart * 16 + rq;                     // tile row of a = 0
+      float acc[4][4][2];
 #pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.f;
+      {
+        const uint32_t qrow = qs + (uint32_t)(row0 * ATT_LDK) * 4, krow = ks + (uint32_t)((lg * 32 + kq) * ATT_LDK) * 4;
+#pragma unroll 2
         for (int d4 = 0; d4 < 16; ++d4) {
-          const float4 kk = lds128(krow + d4 * 16);
-          a0 = fmaf(q[4 * d4 + 0], kk.x, a0); a1 = fmaf(q[4 * d4 + 1], kk.y, a1);
-          a2 = fmaf(q[4 * d4 + 2], kk.z, a2); a3 = fmaf(q[4 * d4 + 3], kk.w, a3);
+          float4 qa[4], kb[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) qa[a] = lds128(qrow + (uint32_t)(4 * a * ATT_LDK + 4 * d4) * 4);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) kb[b] = lds128(krow + (uint32_t)(8 * b * ATT_LDK + 4 * d4) * 4);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              ffma2(acc[a][b][0], acc[a][b][1], qa[a].x, qa[a].y, kb[b].x, kb[b].y);
+              ffma2(acc[a][b][0], acc[a][b][1], qa[a].z, qa[a].w, kb[b].z, kb[b].w);
+            }
         }
-        const float sp = (a0 + a1) + (a2 + a3);
-        const uint32_t off = (uint32_t)(r * ATT_LDS + j) * 4;
-        sts32(so + off, sp);
-        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(sx_peer + off), "f"(sp) : "memory");
       }
+      float sv[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          sv[a][b] = acc[a][b][0] + acc[a][b][1];
+          asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(sx_peer + (uint32_t)((row0 + 4 * a) * ATT_LDS + kq + 8 * b) * 4), "f"(sv[a][b]) : "memory");
+        }
+      if (dbg && threadIdx.x == 64) dbg[43] = clock64();
       asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
       asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-      // full score row -> softmax (scale 128^-0.5), in registers
-      float pr[32];
-      float mx = -INFINITY;
+      if (dbg && threadIdx.x == 64) dbg[44] = clock64();
+      // phase C: add the peer's half, scale by 128^-0.5, softmax over the 32 keys of each row (8 lanes x 4 keys)
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float4 a = lds128(so + (uint32_t)(r * ATT_LDS + 4 * t) * 4), b = lds128(sx + (uint32_t)(r * ATT_LDS + 4 * t) * 4);
-        pr[4 * t + 0] = (a.x + b.x) * 0.08838834764831845f; pr[4 * t + 1] = (a.y + b.y) * 0.08838834764831845f;
-        pr[4 * t + 2] = (a.z + b.z) * 0.08838834764831845f; pr[4 * t + 3] = (a.w + b.w) * 0.08838834764831845f;
+      for (int a = 0; a < 4; ++a) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          sv[a][b] = (sv[a][b] + lds32(sx + (uint32_t)((row0 + 4 * a) * ATT_LDS + kq + 8 * b) * 4)) * 0.08838834764831845f;
+          mx = fmaxf(mx, sv[a][b]);
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { sv[a][b] = expf(sv[a][b] - mx); sum += sv[a][b]; }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) sts32(pp + (uint32_t)((row0 + 4 * a) * ATT_LDS + kq + 8 * b) * 4, sv[a][b] * inv);
       }
+      __syncwarp();                                                  // a warp consumes only the P rows it produced
+      if (dbg && threadIdx.x == 64) dbg[45] = clock64();
+      // phase D: thread (rq, dq): rows as above, dims 4*dq..+3 and 32 + 4*dq..+3 of this CTA's 64
+      float o[4][8];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, pr[j]);
-      float sum = 0.f;
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { pr[j] = expf(pr[j] - mx); sum += pr[j]; }
-      const float inv = 1.0f / sum;
-      // P V over this warp's 32 of the CTA's 64 dims
-      float o[32];
+        for (int d = 0; d < 8; ++d) o[a][d] = 0.f;
+      {
+        const uint32_t prow = pp + (uint32_t)(row0 * ATT_LDS) * 4, vrow = vs + (uint32_t)(lg * 32 * ATT_LDK + 4 * kq) * 4;
+#pragma unroll 2
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 pa[4];
 #pragma unroll
-      for (int d = 0; d < 32; ++d) o[d] = 0.f;
+          for (int a = 0; a < 4; ++a) pa[a] = lds128(prow + (uint32_t)(4 * a * ATT_LDS + 4 * j4) * 4);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float pj = pr[j] * inv;
-        const uint32_t vrow = vs + (uint32_t)((lg * 32 + j) * ATT_LDK + cpart * 32) * 4;
+          for (int jj = 0; jj < 4; ++jj) {
+            const float4 v0 = lds128(vrow + (uint32_t)((4 * j4 + jj) * ATT_LDK) * 4);
+            const float4 v1 = lds128(vrow + (uint32_t)((4 * j4 + jj) * ATT_LDK + 32) * 4);
 #pragma unroll
-        for (int d4 = 0; d4 < 8; ++d4) {
-          const float4 vv = lds128(vrow + d4 * 16);
-          o[4 * d4 + 0] = fmaf(pj, vv.x, o[4 * d4 + 0]); o[4 * d4 + 1] = fmaf(pj, vv.y, o[4 * d4 + 1]);
-          o[4 * d4 + 2] = fmaf(pj, vv.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(pj, vv.w, o[4 * d4 + 3]);
+            for (int a = 0; a < 4; ++a) {
+              const float pj = jj == 0 ? pa[a].x : jj == 1 ? pa[a].y : jj == 2 ? pa[a].z : pa[a].w;
+              ffma2(o[a][0], o[a][1], pj, pj, v0.x, v0.y); ffma2(o[a][2], o[a][3], pj, pj, v0.z, v0.w);
+              ffma2(o[a][4], o[a][5], pj, pj, v1.x, v1.y); ffma2(o[a][6], o[a][7], pj, pj, v1.z, v1.w);
+            }
+          }
         }
       }
-      const uint32_t prow = stage0 + ATT_PL_OFF + (uint32_t)(r * 128);
+      // fp16 hi/lo planes of the result into the swizzled staging box: row, 16-byte chunk (dq >> 1) and (dq >> 1) + 4
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        __half h[8], l[8];
+      for (int a = 0; a < 4; ++a) {
+        const int rr = row0 + 4 * a;
+        const uint32_t base = stage0 + ATT_PL_OFF + (uint32_t)(rr * 128) + (uint32_t)((kq & 1) * 8);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) split_f16(o[8 * t + e] * kActScale, h[e], l[e]);
-        const uint32_t off = (((uint32_t)(cpart * 4 + t)) ^ sw) << 4;
-        sts128u(prow + off, make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
-        sts128u(prow + TC_A_PLANE + off, make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7])));
+        for (int g = 0; g < 2; ++g) {
+          __half h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_f16(o[a][4 * g + e] * kActScale, h[e], l[e]);
+          const uint32_t off = (((uint32_t)((kq >> 1) + 4 * g)) ^ (uint32_t)(rr & 7)) << 4;
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + off), "r"(pack_h2(h[0], h[1])), "r"(pack_h2(h[2], h[3])) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + TC_A_PLANE + off), "r"(pack_h2(l[0], l[1])), "r"(pack_h2(l[2], l[3])) : "memory");
+        }
       }
+      if (dbg && threadIdx.x == 64) dbg[46] = clock64();
       fence_proxy_async();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (warp == 2 && elect_one()) {
         tma_store_3d(&tmP, stage0 + ATT_PL_OFF, blockIdx.x * 64, m0, 0);
         tma_store_commit_wait();
       }
+      if (dbg && threadIdx.x == 64) dbg[47] = clock64();
       if (dbg && threadIdx.x == 64) dbg[4] = clock64();
     } else {
 #pragma unroll 1

@@ -142,6 +142,7 @@ struct LoopState {
   int k;                 // current step index, S-1 .. 0
   int S;
   const float* tape;     // [S,B,1536,1,32] or null
+  unsigned done;         // CTAs of the current step_update that have finished (the last one advances k)
 };
 
 GemmP linear(const float* A, int M, int K, const float* W, const float* bias, float* out, int N);
@@ -199,6 +200,8 @@ struct StepP {
   float c[ST_COEF_STRIDE];
   const LoopState* ls;       // when set: coefficients = coef_dev[ls->k], eps = ls->tape + (S-1-k) * B*1536*32
   const float* coef_dev;
+  __half* xs_planes = nullptr;     // optional: fp16 hi/lo planes of the updated state, [2][B*32][1536]
+  LoopState* ls_advance = nullptr; // optional: the last CTA decrements ls->k (replaces a separate advance launch)
 };
 int step_update(const StepP& p, cudaStream_t s);
 

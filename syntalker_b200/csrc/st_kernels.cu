@@ -549,6 +549,17 @@ __global__ void __launch_bounds__(256) step_update_kernel(StepP p) {
     }
   }
   *xs4 = make_float4(o[0], o[1], o[2], o[3]);
+  // the next step's first GEMM streams the state as fp16 hi/lo planes: emit them here instead of a split pass
+  if (p.xs_planes) store_planes4(p.xs_planes + e0, per_eval, o[0], o[1], o[2], o[3]);
+  if (p.ls_advance) {
+    // last CTA to finish moves the loop to the next step (every thread of every CTA has read ls->k by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned t = atomicAdd(&p.ls_advance->done, 1u);
+      if (t == gridDim.x - 1) { p.ls_advance->done = 0; p.ls_advance->k -= 1; }
+    }
+  }
 }
 
 __global__ void advance_loop_kernel(LoopState* ls) {
@@ -559,8 +570,9 @@ __global__ void advance_loop_kernel(LoopState* ls) {
 }
 __global__ void init_loop_kernel(LoopState* ls, int S, const float* tape) {
   pdl_wait();
+  trace_stamp(10);
   pdl_launch();
-  ls->k = S - 1; ls->S = S; ls->tape = tape;
+  ls->k = S - 1; ls->S = S; ls->tape = tape; ls->done = 0;
 }
 int advance_loop(LoopState* ls, cudaStream_t s) {
   launch_k(advance_loop_kernel, dim3(1), dim3(1), 0, s, ls);
@@ -586,6 +598,7 @@ int step_update(const StepP& p, cudaStream_t s) {
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc,
                                                         float scale) {
   pdl_wait();
+  trace_stamp(10);
   pdl_launch();
   // in: [B, R, Cc] -> out: [B, Cc, R]
   __shared__ float tile[32][33];
@@ -623,6 +636,7 @@ int transpose_from_tokens(const float* tok, float* x, int B, int C, int T, cudaS
 __global__ void __launch_bounds__(256) gather_words_kernel(const int32_t* __restrict__ word, const float* __restrict__ table,
                                                            float* __restrict__ out, int ldo, int rows, int force_zero) {
   pdl_wait();
+  trace_stamp(10);
   pdl_launch();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;    // rows x 64 float4
   if (gid >= (long long)rows * 64) return;
@@ -641,6 +655,7 @@ int gather_words(const int32_t* word, const float* table, float* out, int ldo, i
 __global__ void __launch_bounds__(256) avgpool4_kernel(const float* __restrict__ in, float* __restrict__ out, long long n4,
                                                        int cols4) {
   pdl_wait();
+  trace_stamp(10);
   pdl_launch();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
   if (gid >= n4) return;
@@ -665,6 +680,7 @@ int avgpool4(const float* in, float* out, int rows_out, int cols, cudaStream_t s
 __global__ void __launch_bounds__(256) copy_strided_scale_kernel(const float* __restrict__ in, long long in_stride, float scale,
                                                                  float* __restrict__ out, long long n4, int cols4) {
   pdl_wait();
+  trace_stamp(10);
   pdl_launch();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
   if (gid >= n4) return;
@@ -692,6 +708,7 @@ __global__ void __launch_bounds__(256) vq_select_kernel(const float* __restrict_
                                                         float* __restrict__ qsum, int64_t* __restrict__ idx, int idx_stride,
                                                         int rows, int first) {
   pdl_wait();
+  trace_stamp(9);
   pdl_launch();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -813,6 +830,7 @@ __global__ void __launch_bounds__(256) pose330_kernel(const float* __restrict__ 
                                                       const float* __restrict__ std, const float* __restrict__ jaw, int BN_,
                                                       float* __restrict__ pose) {
   pdl_wait();
+  trace_stamp(10);
   pdl_launch();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
   if (gid >= (long long)BN_ * 55) return;
@@ -845,6 +863,7 @@ __global__ void __launch_bounds__(256) pose330_kernel(const float* __restrict__ 
 __global__ void trans_kernel(const float* __restrict__ lo, const float* __restrict__ tmean, const float* __restrict__ tstd,
                              int B, int n, float* __restrict__ trans) {
   pdl_wait();
+  trace_stamp(10);
   pdl_launch();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= B * 3) return;
@@ -905,6 +924,7 @@ __device__ int h3d_lookup(int c, int* part) {
 __global__ void __launch_bounds__(256) pose623_kernel(const float* __restrict__ up, const float* __restrict__ ha,
                                                       const float* __restrict__ lo, int frames, float* __restrict__ pose) {
   pdl_wait();
+  trace_stamp(10);
   pdl_launch();
   __shared__ int s_part[623], s_pos[623];
   for (int c = threadIdx.x; c < 623; c += 256) {
