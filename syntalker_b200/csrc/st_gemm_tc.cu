@@ -580,9 +580,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// the CTA only has to keep its staging memory alive until the TMA engine has read it; the writes themselves are
+// performed before the grid counts as complete, which is what the dependent kernel's griddepcontrol.wait observes
 __device__ __forceinline__ void tma_store_commit_wait() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -632,6 +634,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
   long long* dbg = (ep.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? ep.dbg : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  trace_stamp(20);                                   // CTA entry
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -649,14 +652,13 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
-  if (warp >= 2) {
-    // bias and LayerNorm column sums are weights: safe to read before the predecessor has finished
-    const int et = threadIdx.x - 64;
-    if (et < BN) {
-      const bool ok = n0 + et < ep.N;
-      bias_s[et] = (ep.bias && ok) ? __ldg(ep.bias + n0 + et) : 0.f;
-      lns_s[et] = (ep.ln_s && ok) ? __ldg(ep.ln_s + n0 + et) : 0.f;
-    }
+  // bias and LayerNorm column sums are weights: safe to read before the predecessor has finished.  The loads are issued
+  // here and land in shared memory after the CTA barrier, off the set-up critical path (an L2 round trip).
+  float bias_r = 0.f, lns_r = 0.f;
+  const int et = threadIdx.x - 64;
+  if (warp >= 2 && et < BN && n0 + et < ep.N) {
+    if (ep.bias) bias_r = __ldg(ep.bias + n0 + et);
+    if (ep.ln_s) lns_r = __ldg(ep.ln_s + n0 + et);
   }
   tc_fence_before();
   __syncthreads();
@@ -712,6 +714,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (kb == 0) trace_stamp(21, true);          // first operands landed
         if (dbg && kb < 16) dbg[24 + kb] = clock64();
         const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t a_lo = a_hi + TC_A_PLANE;
@@ -773,9 +776,12 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       u = rstd * mu;
     }
     const float sc = ep.scale * rstd;
+    if (et < BN) { bias_s[et] = bias_r; lns_s[et] = lns_r; }
+    asm volatile("bar.sync 1, 256;" ::: "memory");                  // bias_s / lns_s visible to the eight epilogue warps
     if (ep.has_res) mbar_wait(res_bar, 0);
     mbar_wait(acc_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) trace_stamp(22, true);    // accumulator complete
     if (dbg && threadIdx.x == 64) dbg[3] = clock64();
     const uint32_t stage0 = smem_u32(smem);
     const uint32_t out_base = stage0;                                                  // NCH fp32 boxes
@@ -1009,6 +1015,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
   __syncthreads();
+  trace_stamp(23);                                   // epilogue and stores done
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
