@@ -34,9 +34,9 @@ E_COND, E_TRUNK, E_DEC = 4.677e9, 1.2342e9 + 0.0336e9, 3.899e9
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, averaged over the launches of the
-    committed `ncu --set full` capture (profiles/r1_ncu_gemm_tc_full.csv; cold-cache replays). None if absent."""
+    committed `ncu --set full` capture (profiles/r1b_ncu_gemm_tc_fast_full.csv; cold-cache replays). None if absent."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r1_ncu_gemm_tc_full.csv")
+    p = os.path.join(ROOT, "profiles", "r1b_ncu_gemm_tc_fast_full.csv")
     if not os.path.exists(p):
         return None
     rows = list(csv.reader(open(p)))
@@ -260,7 +260,7 @@ def main():
     alg = B * (E_COND + S_STEPS * 2 * E_TRUNK + E_DEC)
     step_ms = tot_ms / args.steps
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": ncu_traffic(),
-            "kernel": "gemm_tc_kernel (tcgen05 split-fp16)" if args.engine == "tc" else "gemm_simt_kernel (exact fp32 FMA)",
+            "kernel": "gemm_tc_fast_kernel / gemm_tc_kernel (tcgen05 split-fp16; the qkv launches carry the fused attention)" if args.engine == "tc" else "gemm_simt_kernel (exact fp32 FMA)",
             "launches_profiled": g_n, "kernel_ms_per_step": g_ms, "kernel_share_of_step": g_ms / step_ms if step_ms else None,
             "executed_flops_per_step": g_flops, "algorithmic_flops_per_step": alg,
             "whole_step_tflops": alg / (step_ms / 1000) / 1e12, "peak_source": pk["src"]}
