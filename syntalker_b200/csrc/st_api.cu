@@ -775,6 +775,62 @@ static GemmP conv3(const float* in, const ConvW& w, float* out, int B, int Lin, 
   return p;
 }
 
+// Decoder conv stack on the tcgen05 engine: every conv streams its input as fp16 hi/lo planes written by the epilogue of its
+// producer (ReLU applied there when the consumer is `ReLU -> Conv`, resnet.py:48-69), so the only split pass is the one over
+// the quantised latent.  The fp32 copy of an activation is kept where it is a residual or the result.
+//   c0: relu(conv(x)) = h                       res block: h += conv1x1(relu(conv_k3_dil(relu(h))))
+//   x2 upsample + k3 conv = two 2-tap convs on the low-resolution rows (even / odd output rows, weights pre-summed by the
+//   packer): out[2u] = W0 in[u-1] + (W1+W2) in[u];  out[2u+1] = (W0+W1) in[u] + W2 in[u+1]
+static int decode_convs_tc(st_vq* v, const float* qsum, int B, int T4, float* rec, float* hA, float* hB, float* hC, cudaStream_t s) {
+  const size_t big = (size_t)B * T4 * 4 * 512;                 // elements of the largest activation [B, 4*T4, 512]
+  __half* P[3];
+  for (int k = 0; k < 3; ++k) P[k] = v->ws.take<__half>(2 * big);
+  int T = T4;
+  long long ps = (long long)B * T * 512;                        // plane stride of the current resolution
+  float* h = hA; float* nxt = hC;
+  __half* Ph = P[0]; __half* Pt = P[1]; __half* Pn = P[2];
+  GemmP p0 = conv3(qsum, v->c0, h, B, T, T, 512, 1, 0);
+  p0.act = ACT_RELU; p0.o_planes = Ph; p0.o_plane_stride = ps; p0.o_planes_ld = 512;
+  ST_TRY(gemm(p0, s));
+  const int dils[3] = {9, 3, 1};
+  for (int i = 0; i < 2; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      GemmP p1 = conv3(nullptr, v->res1[i][j], nullptr, B, T, T, 512, dils[j], 0);
+      p1.a_planes = Ph; p1.a_plane_stride = ps;                                   // relu(h)
+      p1.o_planes = Pt; p1.o_plane_stride = ps; p1.o_planes_ld = 512; p1.o_planes_relu = 1;
+      ST_TRY(gemm(p1, s));
+      GemmP p2 = linear(nullptr, B * T, 512, v->res2[i][j].w, v->res2[i][j].b, h, 512);
+      p2.a_planes = Pt; p2.a_plane_stride = ps;
+      p2.res = h; p2.res_mode = RES_POST; p2.ldr = 512;
+      p2.o_planes = Ph; p2.o_plane_stride = ps; p2.o_planes_ld = 512; p2.o_planes_relu = j < 2;   // the upsampling conv takes h itself
+      ST_TRY(gemm(p2, s));
+    }
+    const long long ps2 = (long long)B * 2 * T * 512;
+    for (int par = 0; par < 2; ++par) {
+      GemmP pu;
+      pu.W = v->up_eo[i][par].w; pu.bias = v->up_eo[i][par].b; pu.out = nxt + par * 512;
+      pu.M = B * T; pu.N = 512; pu.K = 1024; pu.ldw = 1024;
+      pu.Lout = T; pu.Lin = T; pu.C = 512; pu.stride = 1; pu.pad = par == 0 ? 1 : 0; pu.dil = 1;
+      pu.a_batch = (long long)T * 512; pu.lda = 512; pu.ldo = 1024;
+      pu.a_planes = Ph; pu.a_plane_stride = ps;
+      pu.o_planes = Pn + par * 512; pu.o_plane_stride = ps2; pu.o_planes_ld = 1024; pu.o_planes_relu = i == 0;   // next: res block / conv 4
+      ST_TRY(gemm(pu, s));
+    }
+    T *= 2; ps = ps2;
+    { float* o = h; h = nxt; nxt = o; }
+    { __half* o = Ph; Ph = Pn; Pn = o; }
+  }
+  GemmP p4 = conv3(nullptr, v->c4, nullptr, B, T, T, 512, 1, 0);
+  p4.act = ACT_RELU; p4.a_planes = Ph; p4.a_plane_stride = ps;
+  p4.o_planes = Pt; p4.o_plane_stride = ps; p4.o_planes_ld = 512;
+  ST_TRY(gemm(p4, s));
+  GemmP p6 = conv3(nullptr, v->c6, rec, B, T, T, v->out_dim, 1, 0);
+  p6.a_planes = Pt; p6.a_plane_stride = ps;
+  ST_TRY(gemm(p6, s));
+  (void)hB;
+  return ST_OK;
+}
+
 extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, float lat_scale, int B, int T4, float* rec,
                              int64_t* idx_out, float* residual_out, void* stream) {
   ST_REQUIRE(v && lat && rec && B > 0 && T4 > 0, "st_rvq_decode: null argument or empty batch");
@@ -782,7 +838,7 @@ extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, flo
   cudaStream_t s = (cudaStream_t)stream;
   const size_t rows = (size_t)B * T4;
   const size_t big = rows * 4 * 512;
-  ST_TRY(v->ws.reserve((rows * 512 * 3 + big * 3) * sizeof(float) + 16 * 256));
+  ST_TRY(v->ws.reserve((rows * 512 * 3 + big * 3) * sizeof(float) + 3 * 2 * big * sizeof(__half) + 32 * 256));
   float* r = v->ws.take<float>(rows * 512);
   float* dot = v->ws.take<float>(rows * 512);
   float* qsum = v->ws.take<float>(rows * 512);
@@ -798,6 +854,7 @@ extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, flo
   }
   if (residual_out) ST_CHECK_CUDA(cudaMemcpyAsync(residual_out, r, rows * 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   // decoder (encdec.py:51-68)
+  if (st_get_engine() == ST_ENGINE_TC) return decode_convs_tc(v, qsum, B, T4, rec, hA, hB, hC, s);
   int T = T4;
   GemmP p0 = conv3(qsum, v->c0, hA, B, T, T, 512, 1, 0);
   p0.act = ACT_RELU;
@@ -813,21 +870,8 @@ extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, flo
       p2.a_relu = 1; p2.res = h; p2.res_mode = RES_POST; p2.ldr = 512;
       ST_TRY(gemm(p2, s));
     }
-    if (st_get_engine() == ST_ENGINE_TC) {
-      // nearest x2 upsample + k3 conv = two 2-tap convs on the low-resolution rows (even / odd outputs), weights
-      // pre-summed by the packer:  out[2u] = W0 in[u-1] + (W1+W2) in[u];  out[2u+1] = (W0+W1) in[u] + W2 in[u+1]
-      for (int par = 0; par < 2; ++par) {
-        GemmP pu;
-        pu.A = h; pu.W = v->up_eo[i][par].w; pu.bias = v->up_eo[i][par].b; pu.out = nxt + par * 512;
-        pu.M = B * T; pu.N = 512; pu.K = 1024; pu.ldw = 1024;
-        pu.Lout = T; pu.Lin = T; pu.C = 512; pu.stride = 1; pu.pad = par == 0 ? 1 : 0; pu.dil = 1;
-        pu.a_batch = (long long)T * 512; pu.lda = 512; pu.ldo = 1024;
-        ST_TRY(gemm(pu, s));
-      }
-    } else {
-      GemmP pu = conv3(h, v->up[i], nxt, B, T, 2 * T, 512, 1, 1);
-      ST_TRY(gemm(pu, s));
-    }
+    GemmP pu = conv3(h, v->up[i], nxt, B, T, 2 * T, 512, 1, 1);
+    ST_TRY(gemm(pu, s));
     T *= 2;
     float* o = h; h = nxt; nxt = o;
   }

@@ -562,6 +562,10 @@ struct FastEpi {
   int act, has_res, has_out, has_planes;
   int M, N;
   int attn;                // 1: the tile is [q 64 | k 64 | v 64] of one head half; the epilogue runs the 32-token attention
+  // operand addressing: mode 0 plain rows (3-D map); mode 1 stride-1 "same" Conv1d over clips packed into the 128-row tile
+  // (4-D map {C, T, clips, 2}, T | 128): K block kb = (tap j, channel block cb), TMA zero-fills the padding
+  int mode, T, kb_per_tap, dil, pad;
+  int planes_relu;         // the planes carry max(result, 0)
   long long* dbg;
   int probe;
 };
@@ -697,7 +701,12 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_expect_tx(&full_bar[s], STAGE_BYTES);
             tma_load_3d(st + 2 * TC_A_PLANE, &tmW, &full_bar[s], kb * TC_BK, n0, 0);
           }
-          tma_load_3d(st, &tmA, &full_bar[s], kb * TC_BK, m0, 0);
+          if (ep.mode == 0) {
+            tma_load_3d(st, &tmA, &full_bar[s], kb * TC_BK, m0, 0);
+          } else {
+            const int j = kb / ep.kb_per_tap, cb = kb - j * ep.kb_per_tap;
+            tma_load_4d(st, &tmA, &full_bar[s], cb * TC_BK, j * ep.dil - ep.pad, m0 / ep.T, 0);
+          }
           if (dbg && kb < 16) dbg[8 + kb] = clock64();
         }
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -957,6 +966,9 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (ep.act == ACT_GELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = x[j] * 0.5f * (1.0f + erff(x[j] * 0.70710678118654752440f));
+      } else if (ep.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
       }
       if (ep.has_res) {
 #pragma unroll
@@ -987,7 +999,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int q = 0; q < 4; ++q) {
           __half h[8], l[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) split_f16(x[8 * q + e] * kActScale, h[e], l[e]);
+          for (int e = 0; e < 8; ++e) split_f16((ep.planes_relu ? fmaxf(x[8 * q + e], 0.f) : x[8 * q + e]) * kActScale, h[e], l[e]);
           const uint32_t off = (((uint32_t)((c & 1) * 4 + q)) ^ sw) << 4;
           sts128u(prow + off, make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
           sts128u(prow + TC_A_PLANE + off, make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7])));
@@ -1096,15 +1108,16 @@ static std::mutex g_tc_mu;
 
 // planes [2][rows][Kp] fp16 (planes `plane_stride` elements apart) -> 3-D map {Kp, rows, 2}, box {64, box_rows, 2},
 // 128B swizzle, zero fill outside the tensor
-static int get_map_3d(const CUtensorMap** out, const __half* base, long long plane_stride, int rows, int Kp, int box_rows) {
-  MapKey key{base, plane_stride, Kp, rows, 0, box_rows};
+static int get_map_3d(const CUtensorMap** out, const __half* base, long long plane_stride, int rows, int Kp, int box_rows, int ld = 0) {
+  if (ld == 0) ld = Kp;                 // row stride in elements (a column window of a wider tensor has ld > Kp)
+  MapKey key{base, plane_stride, Kp, rows, ld == Kp ? 0 : ld, box_rows};
   std::lock_guard<std::mutex> lk(g_tc_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = &it->second; return ST_OK; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ST_ECUDA; }
   cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, 2};
-  cuuint64_t gstr[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)plane_stride * 2};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
   cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_rows, 2};
   cuuint32_t est[3] = {1, 1, 1};
   CUtensorMap m;
@@ -1312,6 +1325,7 @@ static int fast_bn(const GemmP& p) {
   const int mt = (p.M + TC_BM - 1) / TC_BM;
   int BN = p.N <= 512 ? 64 : 128;
   if (p.N % 192 == 0 && mt * (p.N / 128) > 148 && mt * (p.N / 192) <= 148) BN = 192;
+  if (BN == 64 && (p.N % 128) == 0 && mt * (p.N / 64) > 148) BN = 128;   // more than a wave: 128-wide tiles run at the MMA floor
   return BN;
 }
 
@@ -1320,12 +1334,14 @@ static bool tc_fast_supported(const GemmP& p) {
   if (p.attn)
     return conv_mode(p) == 0 && p.K == 512 && p.N == 1536 && (p.M % 32) == 0 && !p.out && p.o_planes && p.o_planes_ld == 512 && p.ln_stats &&
            p.ln_s && p.ln_c && !p.res && p.act == ACT_NONE && !p.stats_out;
-  if (conv_mode(p) != 0 || (p.K % TC_BK) != 0 || (p.N % 64) != 0 || p.out_scale != 1.0f || p.a_relu || p.o_planes_relu) return false;
+  const int cmode = conv_mode(p);
+  if ((cmode != 0 && cmode != 1) || (p.K % TC_BK) != 0 || (p.N % 64) != 0 || p.out_scale != 1.0f) return false;
+  if (p.a_relu && p.a_planes) return false;          // a ReLU on the input is applied when the operand is split, or by the producer
   if (!p.out && !p.o_planes) return false;
-  if (p.act != ACT_NONE && p.act != ACT_GELU) return false;
+  if (p.act != ACT_NONE && p.act != ACT_GELU && p.act != ACT_RELU) return false;
   if (p.res && (p.res != p.out || p.res_div != 1 || p.ldr != p.ldo || (p.res_mode == RES_PRE && p.act != ACT_NONE))) return false;
   if (p.out && ((p.ldo & 3) || (reinterpret_cast<uintptr_t>(p.out) & 15))) return false;
-  if (p.o_planes && ((p.o_planes_ld & 7) || p.o_planes_ld < p.N || (reinterpret_cast<uintptr_t>(p.o_planes) & 15))) return false;
+  if (p.o_planes && ((p.o_planes_ld & 7) || p.o_planes_ld < p.N || (reinterpret_cast<uintptr_t>(p.o_planes) & 15) || (p.o_plane_stride & 7))) return false;
   if (p.stats_out && p.N != 512) return false;
   if (p.ln_stats && (!p.ln_s || !p.ln_c)) return false;
   const int BN = fast_bn(p);
@@ -1346,11 +1362,13 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   if (p.attn) { stages = 2; }
   const int smem = stages * stage + (p.attn ? ATT_SX_BYTES : res) + 2 * 192 * 4 + (2 * stages + 2) * 8 + 16 + 1024;
   const CUtensorMap *tmA = nullptr, *tmW = nullptr, *tmO = nullptr, *tmP = nullptr;
-  ST_TRY(get_map_3d(&tmA, planes, pstride, p.M, p.K, TC_BM));
+  const int cmode = conv_mode(p);
+  if (cmode == 0) ST_TRY(get_map_3d(&tmA, planes, pstride, p.M, p.K, TC_BM));
+  else ST_TRY(get_map_4d(&tmA, planes, pstride, p.M / p.Lout, p.Lin, p.C));
   ST_TRY(get_map_3d(&tmW, w->planes, (long long)p.N * w->Kp, p.N, w->Kp, BN));
   tmO = tmA; tmP = tmA;
   if (p.out) ST_TRY(get_map_2d_f32(&tmO, p.out, p.M, p.N, p.ldo));
-  if (p.o_planes) ST_TRY(get_map_3d(&tmP, p.o_planes, p.o_plane_stride, p.M, p.o_planes_ld, TC_BM));
+  if (p.o_planes) ST_TRY(get_map_3d(&tmP, p.o_planes, p.o_plane_stride, p.M, p.attn ? 512 : p.N, TC_BM, p.o_planes_ld));
   FastEpi ep;
   ep.bias = p.ln_stats ? p.ln_c : p.bias;
   ep.ln_s = p.ln_stats ? p.ln_s : nullptr;
@@ -1358,6 +1376,8 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   ep.scale = w->inv_scale / kActScale;
   ep.act = p.act; ep.has_res = p.res ? 1 : 0; ep.has_out = p.out ? 1 : 0; ep.has_planes = p.o_planes ? 1 : 0;
   ep.M = p.M; ep.N = p.N; ep.dbg = g_tc_dbg; ep.probe = g_tc_probe; ep.attn = p.attn;
+  ep.mode = cmode; ep.T = p.Lout; ep.kb_per_tap = cmode == 0 ? 1 : p.C / TC_BK; ep.dil = p.dil; ep.pad = p.pad;
+  ep.planes_relu = p.o_planes_relu;
   static bool attr = false;
   if (!attr) {
     ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));

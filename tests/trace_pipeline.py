@@ -30,7 +30,7 @@ torch.cuda.synchronize()
 _lib.check(L.st_debug_trace(None))
 t = buf.cpu().tolist()
 n = t[0]
-ev = sorted((t[2 * i], t[2 * i + 1]) for i in range(1, n + 1))
+ev = sorted((t[2 * i], t[2 * i + 1]) for i in range(1, n + 1) if t[2 * i + 1] < 20)   # ids >= 20 are in-kernel phase stamps
 names = {1: "gemm_tc", 2: "attention", 3: "tokens_in", 4: "step_update", 5: "advance", 6: "split", 7: "layernorm", 8: "gemm_simt", 9: "vq_select", 10: "misc"}
 print("kernels stamped:", n, "span us:", (ev[-1][0] - ev[0][0]) / 1e3)
 # phases: loop = from first tokens_in-preceding split ... last advance
@@ -45,7 +45,7 @@ def show(tag, seg):
     for (t0, k0), (t1, _) in zip(seg[:-1], seg[1:]):
         agg[k0].append((t1 - t0) / 1e3)
     for k, v in sorted(agg.items()):
-        print(f"   {names.get(k, k):12s} n={len(v):4d} total {sum(v):8.1f} us  mean {sum(v) / len(v):7.2f}  max {max(v):7.2f}")
+        print(f"   {str(names.get(k, k)):12s} n={len(v):4d} total {sum(v):8.1f} us  mean {sum(v) / len(v):7.2f}  max {max(v):7.2f}")
 show("cond encode", ev[:lo + 1])
 show("sampling loop", ev[lo:hi + 2])
 show("decode + pose", ev[hi + 1:])
