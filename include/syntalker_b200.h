@@ -168,6 +168,13 @@ int st_sample(st_model* m, const st_schedule* s, const st_guidance* g, const flo
 int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, float lat_scale, int B, int T4, float* rec,
                   int64_t* idx_out, float* residual_out, void* stream);
 
+/* ---- RVQ-VAE encode ---------------------------------------------------------
+ * Replaces: vq.map2latent(x) (models/vq/model.py:95-100, encdec.py:5-34; callers diffusion_rvqvae_trainer.py:290-294).
+ * pose: device [B,T,D] normalised pose features of one body part, T a multiple of 4; lat: device [B,T/4,512], the
+ * encoder output BEFORE quantisation (the trainer divides it by vqvae_latent_scale to form latent_in / the seed).
+ * Needs a handle created from a checkpoint that holds the encoder weights. */
+int st_rvq_encode(st_vq* v, const float* pose, int B, int T, float* lat, void* stream);
+
 /* ---- 330-d assembly ------------------------------------------------------------------------------
  * Replaces: diffusion_rvqvae_trainer.py:484-531.  rec_*: device decoder outputs [B,n,78|180|57];
  * mean/std: device [330]; trans_mean/std: device [3]; jaw_aa: device [B,n,3] or NULL (zeros).

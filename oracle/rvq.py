@@ -1,4 +1,4 @@
-"""Oracle: RVQVAE.latent2origin = 6-stage residual nearest-code search + conv decoder.
+"""Oracle: RVQVAE.latent2origin = 6-stage residual nearest-code search + conv decoder; RVQVAE.map2latent = conv encoder.
 
 Follows models/vq/model.py:102-109, residual_vq.py:99-169 (eval: no dropout), quantizer.py:67-84,132-158
 (distance, argmax(-d) first-index ties, straight-through x + (x_d - x)), encdec.py:37-68, resnet.py:12-84.
@@ -44,6 +44,26 @@ def decoder(W, h):
     h = F.relu(c("decoder.model.4", h))
     h = c("decoder.model.6", h)
     return h.permute(0, 2, 1)
+
+
+def encoder(W, x):
+    """encdec.py:5-34: [B,D,T] -> [B,512,T/4]. Conv k3 + ReLU; 2 x (Conv k4 stride 2 pad 1, 3 pre-activation res blocks with
+    dilations 9,3,1 -- Resnet1D's reverse_dilation defaults to True, resnet.py:72-80); Conv k3."""
+    c = lambda name, h, dil=1, pad=1, stride=1: F.conv1d(h, W[name + ".weight"], W[name + ".bias"], stride=stride, padding=pad, dilation=dil)
+    h = F.relu(c("encoder.model.0", x))
+    for i in (2, 3):
+        h = c(f"encoder.model.{i}.0", h, 1, 1, 2)
+        for j, dil in enumerate((9, 3, 1)):
+            p = f"encoder.model.{i}.1.model.{j}"
+            r = c(p + ".conv1", F.relu(h), dil, dil)
+            r = c(p + ".conv2", F.relu(r), 1, 0)
+            h = r + h
+    return c("encoder.model.4", h)
+
+
+def map2latent(W, pose):
+    """models/vq/model.py:95-100. pose [B,T,D] (normalised features) -> latent [B,T/4,512] (before quantisation)."""
+    return encoder(W, pose.permute(0, 2, 1)).permute(0, 2, 1)
 
 
 def latent2origin(W, lat):

@@ -207,6 +207,8 @@ struct st_vq {
   Weights w;
   const float *cb[6], *cnorm[6];
   ConvW c0, res1[2][3], res2[2][3], up[2], up_eo[2][2], c4, c6;
+  bool has_enc = false;
+  ConvW e0, edown[2], eres1[2][3], eres2[2][3], e4;    // encoder side (encdec.py:5-34)
   Arena ws;
 };
 
@@ -745,6 +747,31 @@ static int vq_resolve(st_vq* v) {
   }
   v->c4 = conv("4", 512, 1536);
   v->c6 = conv("6", v->out_dim, 1536);
+  v->has_enc = v->w.dev.count("enc.0.w") != 0;
+  if (v->has_enc) {
+    auto econv = [&](const char* name, int cout, int K) {
+      ConvW c;
+      c.ldw = (K + 3) & ~3;
+      snprintf(nm, sizeof nm, "enc.%s.w", name);
+      c.w = v->w.get(nm, (int64_t)cout * c.ldw, &err);
+      snprintf(nm, sizeof nm, "enc.%s.b", name);
+      c.b = v->w.get(nm, cout, &err);
+      return c;
+    };
+    v->e0 = econv("0", 512, 3 * v->out_dim);
+    for (int i = 0; i < 2; ++i) {
+      char n2[32];
+      snprintf(n2, sizeof n2, "%d.0", i + 2);
+      v->edown[i] = econv(n2, 512, 2048);
+      for (int j = 0; j < 3; ++j) {
+        snprintf(n2, sizeof n2, "%d.1.%d.conv1", i + 2, j);
+        v->eres1[i][j] = econv(n2, 512, 1536);
+        snprintf(n2, sizeof n2, "%d.1.%d.conv2", i + 2, j);
+        v->eres2[i][j] = econv(n2, 512, 512);
+      }
+    }
+    v->e4 = econv("4", 512, 1536);
+  }
   return err;
 }
 
@@ -880,6 +907,52 @@ extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, flo
   ST_TRY(gemm(p4, s));
   GemmP p6 = conv3(tmp, v->c6, rec, B, T, T, v->out_dim, 1, 0);
   ST_TRY(gemm(p6, s));
+  return ST_OK;
+}
+
+
+// ---- RVQ-VAE encode: pose features -> latent before quantisation (models/vq/model.py:95-100, encdec.py:5-34) ----
+// Conv k3 + ReLU; 2 x (Conv k4 stride 2 pad 1; 3 res blocks h += conv1x1(relu(conv_k3_dil(relu(h)))), dilations 9,3,1); Conv k3.
+// Channels-last implicit GEMMs through the engine dispatch: the D-channel input conv and the two strided convs run on the
+// exact-fp32 engine (C_in not a multiple of 64 / padded stride), the res blocks and the last conv on tcgen05.
+extern "C" int st_rvq_encode(st_vq* v, const float* pose, int B, int T, float* lat, void* stream) {
+  ST_REQUIRE(v && pose && lat && B > 0 && T > 0 && (T % 4) == 0, "st_rvq_encode: null argument or T not a multiple of 4");
+  ST_REQUIRE(v->has_enc, "st_rvq_encode: the checkpoint this handle was created from has no encoder weights");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t big = (size_t)B * T * 512;
+  ST_TRY(v->ws.reserve(big * 3 * sizeof(float) + 16 * 256));
+  float* h = v->ws.take<float>(big);
+  float* tmp = v->ws.take<float>(big);
+  float* nxt = v->ws.take<float>(big);
+  const int D = v->out_dim;
+  GemmP p0;
+  p0.A = pose; p0.W = v->e0.w; p0.bias = v->e0.b; p0.out = h;
+  p0.M = B * T; p0.N = 512; p0.K = 3 * D; p0.ldw = v->e0.ldw;
+  p0.Lout = T; p0.Lin = T; p0.C = D; p0.stride = 1; p0.pad = 1; p0.dil = 1;
+  p0.a_batch = (long long)T * D; p0.lda = D; p0.ldo = 512; p0.act = ACT_RELU;
+  ST_TRY(gemm(p0, s));
+  int L = T;
+  const int dils[3] = {9, 3, 1};
+  for (int i = 0; i < 2; ++i) {
+    GemmP pd;
+    pd.A = h; pd.W = v->edown[i].w; pd.bias = v->edown[i].b; pd.out = nxt;
+    pd.M = B * (L / 2); pd.N = 512; pd.K = 2048; pd.ldw = v->edown[i].ldw;
+    pd.Lout = L / 2; pd.Lin = L; pd.C = 512; pd.stride = 2; pd.pad = 1; pd.dil = 1;
+    pd.a_batch = (long long)L * 512; pd.lda = 512; pd.ldo = 512;
+    ST_TRY(gemm(pd, s));
+    L /= 2;
+    { float* o = h; h = nxt; nxt = o; }
+    for (int j = 0; j < 3; ++j) {
+      GemmP p1 = conv3(h, v->eres1[i][j], tmp, B, L, L, 512, dils[j], 0);
+      p1.a_relu = 1;
+      ST_TRY(gemm(p1, s));
+      GemmP p2 = linear(tmp, B * L, 512, v->eres2[i][j].w, v->eres2[i][j].b, h, 512);
+      p2.a_relu = 1; p2.res = h; p2.res_mode = RES_POST; p2.ldr = 512;
+      ST_TRY(gemm(p2, s));
+    }
+  }
+  GemmP p4 = conv3(h, v->e4, lat, B, L, L, 512, 1, 0);
+  ST_TRY(gemm(p4, s));
   return ST_OK;
 }
 

@@ -133,9 +133,20 @@ def pack_mdm(sd: Dict[str, torch.Tensor], variant: str | None = None) -> Dict[st
 
 
 def pack_rvq(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """'net' state dict of RVQVAE -> decoder-side tensors. The encoder keys are ignored."""
+    """'net' state dict of RVQVAE -> quantiser, decoder and (when the checkpoint has them) encoder tensors."""
     sd = strip_module_prefix(sd)
     out: Dict[str, torch.Tensor] = {}
+    if "encoder.model.0.weight" in sd:                       # encdec.py:5-34, channels-last tap-major like the decoder
+        enc = [("0", "0"), ("4", "4")]
+        for i in (2, 3):
+            enc.append((f"{i}.0", f"{i}.0"))
+            for j in range(3):
+                for c in ("conv1", "conv2"):
+                    enc.append((f"{i}.1.{j}.{c}", f"{i}.1.model.{j}.{c}"))
+        for dst, src in enc:
+            key = "encoder.model." + src
+            out[f"enc.{dst}.w"] = _t32(_conv_layout(_f64(sd[key + ".weight"])))
+            out[f"enc.{dst}.b"] = sd[key + ".bias"].detach().cpu().float().contiguous()
     for q in range(6):
         cb = sd[f"quantizer.layers.{q}.codebook"].detach().cpu().float().contiguous()
         out[f"cb.{q}"] = cb

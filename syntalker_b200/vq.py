@@ -1,4 +1,4 @@
-"""Drop-in for models/vq/model.py `RVQVAE` on the decode side: `vq.latent2origin(x)`.
+"""Drop-in for models/vq/model.py `RVQVAE`: `vq.latent2origin(x)` (decode side) and `vq.map2latent(x)` (encoder side).
 
 `RVQVAE(args, input_width, nb_code, code_dim, output_emb_width, down_t, stride_t, width, depth,
 dilation_growth_rate, activation, norm)` keeps the reference's constructor (diffusion_rvqvae_trainer.py:106-140);
@@ -89,4 +89,13 @@ class RVQVAE:
         return rec, None, None
 
     def map2latent(self, x):
-        raise NotImplementedError("the encoder side is the next row of SURVEY.md §8(f), not built yet")
+        """x [B,T,D] normalised pose features (T a multiple of 4) -> [B,T/4,512] encoder output before quantisation
+        (models/vq/model.py:95-100; diffusion_rvqvae_trainer.py:290-294 divides it by vqvae_latent_scale)."""
+        if x.dim() != 3 or x.shape[-1] != self.input_width or x.shape[1] % 4:
+            raise ValueError(f"pose must be [B,T,{self.input_width}] with T a multiple of 4, got {tuple(x.shape)}")
+        B, T, _ = x.shape
+        xs = x.to(self.device).float().contiguous()
+        lat = torch.empty((B, T // 4, 512), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().st_rvq_encode(self.handle, xs.data_ptr(), B, T, lat.data_ptr(), _lib.stream_ptr()))
+        return lat

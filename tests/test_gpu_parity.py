@@ -300,6 +300,39 @@ def test_rvq_decode_large_batch_properties(vq_w, vqs, engine):
     assert maxabs(one, rec[7:8]) < 1e-5
 
 
+def test_rvq_encode_vs_golden_and_oracle(golden, vq_w, vqs, engine):
+    """vq.map2latent against the real reference's output and the oracle (ragged batch / length too)."""
+    g = golden("rvq_enc")
+    for d in synth.PART_DIMS_BEATX:
+        pose = torch.from_numpy(g[f"pose{d}"])
+        lat = vqs[d].map2latent(pose.cuda())
+        assert lat.shape == (2, 32, 512) and lat.is_cuda
+        assert maxabs(lat, g[f"lat{d}"]) < 1e-4
+    gen = torch.Generator().manual_seed(23)
+    pose = torch.randn(5, 64, 78, generator=gen)                    # 5 clips of 64 frames
+    assert maxabs(vqs[78].map2latent(pose.cuda()), orvq.map2latent(vq_w[78], pose)) < 1e-4
+    one = vqs[78].map2latent(pose[3:4].cuda())
+    assert maxabs(one, vqs[78].map2latent(pose.cuda())[3:4]) < 1e-5   # clips are independent
+    with pytest.raises(ValueError):
+        vqs[78].map2latent(torch.zeros(1, 30, 78).cuda())           # T not a multiple of 4
+    with pytest.raises(ValueError):
+        vqs[78].map2latent(torch.zeros(1, 32, 57).cuda())           # wrong feature width
+
+
+def test_rvq_encode_quantise_decode_chain(vq_w, vqs, engine):
+    """encode -> x scale -> latent2origin: the CUDA chain picks the oracle chain's codes (except fp32 near-ties) and decodes alike."""
+    gen = torch.Generator().manual_seed(29)
+    pose = torch.randn(6, 128, 180, generator=gen)
+    lat_ref = orvq.map2latent(vq_w[180], pose) * 5.0
+    rec_ref, idx_ref = orvq.latent2origin(vq_w[180], lat_ref)
+    lat = vqs[180].map2latent(pose.cuda()) * 5.0
+    rec, _, _, idx = vqs[180].latent2origin(lat.clone(), return_indices=True)
+    mism = idx.cpu() != idx_ref
+    assert not bool((mism & ~near_tie_mask(vq_w[180], lat_ref, idx_ref)).any())
+    clean = ~mism.any(dim=-1).any(dim=-1)
+    assert clean.float().mean() > 0.8 and maxabs(rec.cpu()[clean], rec_ref[clean]) < 2e-4
+
+
 def test_rvq_rejects_bad_shapes(vqs):
     with pytest.raises(ValueError):
         vqs[78].latent2origin(torch.zeros(2, 32, 256).cuda())

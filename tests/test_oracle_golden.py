@@ -141,3 +141,13 @@ def test_e2e_config1(golden, weights):
     g = golden("e2e_config1")
     assert maxabs(trans, g["rec_trans"]) < 1e-4
     assert maxabs(pose, g["rec_pose"]) < 1e-3
+
+
+def test_rvq_encoder_oracle_vs_reference(golden):
+    """oracle.rvq.map2latent against RVQVAE.map2latent of the real reference (tests/golden/make_golden_enc.py)."""
+    g = golden("rvq_enc")
+    for d in synth.PART_DIMS_BEATX:
+        W = synth.rvq_state_dict(d, seed=0)
+        lat = orvq.map2latent(W, torch.from_numpy(g[f"pose{d}"]))
+        assert lat.shape == (2, 32, 512)
+        assert float((lat - torch.from_numpy(g[f"lat{d}"])).abs().max()) <= 2e-6
