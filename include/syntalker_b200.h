@@ -213,6 +213,21 @@ int st_generate_330_host(st_model* m, const st_schedule* s, const st_guidance* g
                          st_vq* vq_lower, const st_host_inputs* in, int B, float latent_scale, float* rec_pose_host,
                          float* rec_trans_host, float* sample_host /* nullable [B,1536,1,32] */, void* stream);
 
+/* ---- long clip: the window loop ----------------------------------------------
+ * Replaces: the `for i in range(0, roundt)` loop of _g_test with its seed hand-off and latent stitching, plus the single
+ * latent2origin x3 and 330-d assembly over the whole clip (diffusion_rvqvae_trainer.py:413-531).
+ * audio_long: device [B, audio_len, 2]; word_long: device int32 [B, n_words]; R windows need n_words >= 112 R + 16 and
+ * audio_len >= 533 (112 R + 16).  seed0: device [B,4,1536] (window 0; later windows take the previous sample's last 4
+ * tokens).  style: NULL or 3 device pointers like st_cond.  x_init: device [R,B,1536,1,32] start noise per window.
+ * noise_tape: NULL or device [R,S,B,1536,1,32].  jaw_aa: NULL or device [B,n,3].  ms: device [666] = mean 330, std 330,
+ * trans_mean 3, trans_std 3.  Output n = 4 (32 + 28 (R-1)) frames: rec_pose device [B,n,330], rec_trans device [B,n,3]
+ * or NULL, latents_out device [B, n/4, 1536] or NULL (the stitched sample, before x latent_scale). */
+int st_generate_long_330(st_model* m, const st_schedule* s, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands, st_vq* vq_lower,
+                         const float* audio_long, int64_t audio_len, const int32_t* word_long, int64_t n_words, const float* seed0,
+                         const float* const* style, const float* x_init, const float* noise_tape, const float* jaw_aa,
+                         const float* ms, int B, int R, float latent_scale, float* rec_pose, float* rec_trans, float* latents_out,
+                         void* stream);
+
 /* ---- GEMM-engine profiling (bench.py roofline leg) -------------------------------------------------
  * Between begin and end every GEMM-engine launch is recorded.  end() replays exactly that launch sequence as
  * one captured CUDA graph bracketed by two CUDA events on its stream and returns the device time of the GEMM

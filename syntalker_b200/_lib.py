@@ -24,7 +24,7 @@ SYMBOLS = [
     "st_model_create", "st_model_destroy", "st_vq_create", "st_vq_destroy", "st_vq_out_dim",
     "st_schedule_create", "st_schedule_destroy", "st_cond_encode", "st_denoise", "st_sample",
     "st_rvq_decode", "st_pose_assemble_330", "st_pose_assemble_623", "st_sample_to_tokens",
-    "st_rvq_encode", "st_generate_330", "st_generate_330_host", "st_selftest_gemm", "st_bench_gemm", "st_profile_begin", "st_profile_end",
+    "st_rvq_encode", "st_generate_330", "st_generate_330_host", "st_generate_long_330", "st_selftest_gemm", "st_bench_gemm", "st_profile_begin", "st_profile_end",
 ]
 
 
@@ -88,6 +88,7 @@ def lib():
     L.st_sample.argtypes = [vp, vp, C.POINTER(StGuidance), vp, vp, i32, vp, vp]
     L.st_rvq_decode.argtypes = [vp, vp, i64, f32, i32, i32, vp, vp, vp, vp]
     L.st_rvq_encode.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.st_generate_long_330.argtypes = [vp, vp, C.POINTER(StGuidance), vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp]
     L.st_pose_assemble_330.argtypes = [vp] * 8 + [i32, i32, vp, vp, vp]
     L.st_pose_assemble_623.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.st_sample_to_tokens.argtypes = [vp, i32, i32, f32, vp, vp]

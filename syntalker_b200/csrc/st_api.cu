@@ -160,7 +160,7 @@ struct st_model {
   float* cst_null = nullptr;   // [32,512]
   bool null_ready = false;
   // workspace
-  Arena ws, io, stage;
+  Arena ws, io, stage, longws;
   int ws_B = 0;
   float *cst_real = nullptr, *g2 = nullptr, *sv[3] = {nullptr, nullptr, nullptr};
   bool have_style[3] = {false, false, false};
@@ -301,7 +301,7 @@ extern "C" void st_model_destroy(st_model* m) {
   if (m->loop_stream) cudaStreamDestroy(m->loop_stream);
   if (m->ev_in) cudaEventDestroy(m->ev_in);
   if (m->ev_out) cudaEventDestroy(m->ev_out);
-  m->w.release(); m->ws.release(); m->io.release(); m->stage.release();
+  m->w.release(); m->ws.release(); m->io.release(); m->stage.release(); m->longws.release();
   if (m->cst_null) cudaFree(m->cst_null);
   delete m;
 }
@@ -1055,6 +1055,66 @@ extern "C" int st_generate_330_host(st_model* m, const st_schedule* sc, const st
   ST_CHECK_CUDA(cudaMemcpyAsync(rec_pose_host, d_pose, (size_t)B * 128 * 330 * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (want_trans) ST_CHECK_CUDA(cudaMemcpyAsync(rec_trans_host, d_trans, (size_t)B * 128 * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
   ST_CHECK_CUDA(cudaStreamSynchronize(s));
+  return ST_OK;
+}
+
+
+// ---- long clip: the trainer's window loop on the device (diffusion_rvqvae_trainer.py:413-531) ------------------------
+// R windows of 128 frames, consecutive windows share pre_frames * 4 = 16 frames: window i reads words
+// [112 i, 112 i + 128) and audio samples [533 * 112 i, + 68224); its seed is the GT-derived seed0 for i = 0 and the last 4
+// latent tokens of window i - 1's sample afterwards (trainer:431); window 0 contributes all 32 tokens, later windows
+// their last 28 (trainer:462-469).  The concatenated latents are decoded ONCE per body part over all 32 + 28 (R - 1)
+// tokens and assembled into 330-d features.  Stream-ordered, no host synchronisation, no return to the caller between
+// windows.  B long clips run side by side (the reference's glue is bs = 1; rows are independent).
+extern "C" int st_generate_long_330(st_model* m, const st_schedule* sc, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
+                                    st_vq* vq_lower, const float* audio_long, int64_t audio_len, const int32_t* word_long,
+                                    int64_t n_words, const float* seed0, const float* const* style, const float* x_init,
+                                    const float* noise_tape, const float* jaw_aa, const float* ms, int B, int R,
+                                    float latent_scale, float* rec_pose, float* rec_trans, float* latents_out, void* stream) {
+  ST_REQUIRE(m && sc && vq_upper && vq_hands && vq_lower && audio_long && word_long && seed0 && x_init && ms && rec_pose && B > 0 && R > 0,
+             "st_generate_long_330: null argument");
+  ST_REQUIRE(vq_upper->out_dim == 78 && vq_hands->out_dim == 180 && vq_lower->out_dim == 57, "st_generate_long_330: decoders must be 78/180/57 wide");
+  const int round_l = 128 - 16;                                    // pose_length - pre_frames * vqvae_squeeze_scale
+  const int64_t hop_a = (int64_t)(16000 / 30) * round_l;           // audio samples between windows (trainer:422)
+  ST_REQUIRE(n_words >= (int64_t)round_l * R + 16 && audio_len >= hop_a * R + (16000 / 30) * 16,
+             "st_generate_long_330: %d windows need %lld words and %lld audio samples", R, (long long)round_l * R + 16,
+             (long long)(hop_a * R + (16000 / 30) * 16));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Ttot = 32 + 28 * (R - 1), n = 4 * Ttot;
+  const size_t nx = (size_t)B * ST_LATENT * ST_TOKENS;
+  ST_TRY(m->longws.reserve(((size_t)B * ST_AUDIO_LEN * 2 + (size_t)B * 128 + (size_t)B * 6144 + nx + (size_t)B * Ttot * 1536 +
+                            (size_t)B * n * (78 + 180 + 57)) * sizeof(float) + 16 * 256));
+  Arena& a = m->longws;
+  float* d_audio = a.take<float>((size_t)B * ST_AUDIO_LEN * 2);
+  int32_t* d_word = a.take<int32_t>((size_t)B * 128);
+  float* d_seed = a.take<float>((size_t)B * 6144);
+  float* d_x = a.take<float>(nx);
+  float* d_lat = latents_out ? latents_out : a.take<float>((size_t)B * Ttot * 1536);
+  float* d_up = a.take<float>((size_t)B * n * 78);
+  float* d_ha = a.take<float>((size_t)B * n * 180);
+  float* d_lo = a.take<float>((size_t)B * n * 57);
+  const size_t tok_pitch = (size_t)32 * 1536 * sizeof(float), lat_pitch = (size_t)Ttot * 1536 * sizeof(float);
+  for (int i = 0; i < R; ++i) {
+    ST_CHECK_CUDA(cudaMemcpy2DAsync(d_audio, (size_t)ST_AUDIO_LEN * 2 * sizeof(float), audio_long + (size_t)i * hop_a * 2,
+                                    (size_t)audio_len * 2 * sizeof(float), (size_t)ST_AUDIO_LEN * 2 * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+    ST_CHECK_CUDA(cudaMemcpy2DAsync(d_word, 128 * sizeof(int32_t), word_long + (size_t)i * round_l, (size_t)n_words * sizeof(int32_t),
+                                    128 * sizeof(int32_t), B, cudaMemcpyDeviceToDevice, s));
+    st_cond c;
+    c.audio = d_audio; c.word = d_word; c.seed = i == 0 ? seed0 : d_seed;
+    for (int k = 0; k < 3; ++k) c.style[k] = style ? style[k] : nullptr;
+    ST_TRY(st_cond_encode(m, &c, B, stream));
+    const float* tape = noise_tape ? noise_tape + (size_t)i * sc->S * nx : nullptr;
+    ST_TRY(st_sample(m, sc, g, x_init + (size_t)i * nx, tape, B, d_x, stream));
+    // m->xs holds the sample token-major [B, 32, 1536]: hand the last 4 tokens over as the next seed, keep 32 / 28 tokens
+    ST_CHECK_CUDA(cudaMemcpy2DAsync(d_seed, 6144 * sizeof(float), m->xs + 28 * 1536, tok_pitch, 6144 * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+    const int first = i == 0 ? 0 : 4, ntok = 32 - first, at = i == 0 ? 0 : 32 + 28 * (i - 1);
+    ST_CHECK_CUDA(cudaMemcpy2DAsync(d_lat + (size_t)at * 1536, lat_pitch, m->xs + (size_t)first * 1536, tok_pitch,
+                                    (size_t)ntok * 1536 * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+  }
+  ST_TRY(st_rvq_decode(vq_upper, d_lat, 1536, latent_scale, B, Ttot, d_up, nullptr, nullptr, stream));
+  ST_TRY(st_rvq_decode(vq_hands, d_lat + 512, 1536, latent_scale, B, Ttot, d_ha, nullptr, nullptr, stream));
+  ST_TRY(st_rvq_decode(vq_lower, d_lat + 1024, 1536, latent_scale, B, Ttot, d_lo, nullptr, nullptr, stream));
+  ST_TRY(pose330(d_up, d_ha, d_lo, ms, ms + 330, ms + 660, ms + 663, jaw_aa, B, n, rec_pose, rec_trans, s));
   return ST_OK;
 }
 

@@ -1225,7 +1225,9 @@ static int conv_mode(const GemmP& p) {
   if (taps * p.C != p.K || (p.C % TC_BK) != 0 || p.lda != p.C || p.a_batch != (long long)p.Lin * p.C || (p.M % p.Lout) != 0) return -1;
   if (p.stride == 1) {
     if (p.Lout == p.Lin && (TC_BM % p.Lout) == 0) return 1;
-    if (p.Lout == p.Lin + 2 * p.pad - p.dil * (taps - 1)) return 2;
+    // long clips: one tile = 128 consecutive positions of one clip; TMA zero-fills positions outside [0, Lin), so any
+    // left pad works (the 2-tap even / odd upsampling convs pad on one side only)
+    if (p.Lout == p.Lin + 2 * p.pad - p.dil * (taps - 1) || p.Lout == p.Lin) return 2;
     return -1;
   }
   if (p.pad == 0 && p.dil == 1 && (long long)(p.Lout - 1) * p.stride + taps <= p.Lin) return 3;

@@ -141,6 +141,65 @@ class Window330:
         return h["pose"], h["trans"]
 
 
+class LongClip330:
+    """The trainer's window loop over a long clip (diffusion_rvqvae_trainer.py:413-531) as ONE native call
+    (st_generate_long_330): R overlapping 128-frame windows, seed hand-off from window to window on the device, the
+    latents stitched (32 + 28 per further window), decoded once per body part and assembled into 330-d features.
+    All tensors are CUDA tensors; B long clips run side by side."""
+
+    ROUND_L, PRE = 112, 16                 # pose_length - pre_frames * 4, pre_frames * 4
+    HOP_AUDIO = (16000 // 30) * 112
+
+    def __init__(self, model, diffusion, vq_upper, vq_hands, vq_lower, use_ddim=True, eta=0.0, latent_scale=5.0, ms=None):
+        self.base = model.base if isinstance(model, _Wrapper) else model
+        self.wrapper = model if isinstance(model, _Wrapper) else None
+        self.diffusion = diffusion
+        self.vqs = (vq_upper, vq_hands, vq_lower)
+        self.mode = _lib.ST_MODE_DDIM if use_ddim else _lib.ST_MODE_DDPM
+        self.eta, self.latent_scale = eta, float(latent_scale)
+        self.ms = ms or load_mean_std()
+
+    @classmethod
+    def windows(cls, n_frames):
+        """roundt of the trainer (trainer:413-415)."""
+        return (n_frames - cls.PRE) // cls.ROUND_L
+
+    def run(self, audio_long, word_long, seed0, x_init, y=None, styles=None, jaw_aa=None, noise_tape=None, want_latents=False):
+        """audio_long [B,La,2] fp32, word_long [B,Nw] int32, seed0 [B,4,1536], x_init [R,B,1536,1,32] (one start noise per
+        window). Returns (rec_pose [B,n,330], rec_trans [B,n,3][, latents [B,n/4,1536]]), n = 4 (32 + 28 (R-1))."""
+        dev = self.base.device
+        R, B = x_init.shape[0], x_init.shape[1]
+        for t in (audio_long, word_long, seed0, x_init):
+            if not (t.is_cuda and t.is_contiguous()):
+                raise ValueError("LongClip330.run takes contiguous CUDA tensors")
+        if audio_long.dtype != torch.float32 or word_long.dtype != torch.int32 or audio_long.shape[0] != B or word_long.shape[0] != B:
+            raise ValueError("audio_long must be fp32 [B,La,2] and word_long int32 [B,Nw]")
+        y = dict(y or {})
+        if styles is None and self.base.variant != "beatx":
+            sf = y.get("style_feature")
+            styles = [sf.get("upper_mask"), sf.get("hands_mask"), sf.get("lower_mask")] if isinstance(sf, dict) else [sf, None, None]
+        styles = styles or [None, None, None]
+        sarr = (C.c_void_p * 3)(*[(s.data_ptr() if (s is not None and self.base.variant != "beatx") else None) for s in styles])
+        if not hasattr(self, "_ms_dev"):
+            m = self.ms
+            self._ms_dev = torch.cat([m["mean"], m["std"], m["trans_mean"], m["trans_std"]]).float().to(dev).contiguous()
+        Ttot = 32 + 28 * (R - 1)
+        pose = torch.empty((B, 4 * Ttot, 330), device=dev)
+        trans = torch.empty((B, 4 * Ttot, 3), device=dev)
+        lat = torch.empty((B, Ttot, 1536), device=dev) if want_latents else None
+        g = self.wrapper.guidance(y) if self.wrapper is not None else Guidance(_lib.ST_CFG_NONE)
+        sched, _ = self.diffusion._native(self.mode, self.eta)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().st_generate_long_330(
+                self.base.handle, sched, C.byref(g.struct(B)), self.vqs[0].handle, self.vqs[1].handle, self.vqs[2].handle,
+                audio_long.data_ptr(), audio_long.shape[1], word_long.data_ptr(), word_long.shape[1], seed0.data_ptr(), sarr,
+                x_init.data_ptr(), noise_tape.data_ptr() if noise_tape is not None else None,
+                jaw_aa.data_ptr() if jaw_aa is not None else None, self._ms_dev.data_ptr(), B, R, self.latent_scale,
+                pose.data_ptr(), trans.data_ptr(), lat.data_ptr() if lat is not None else None, _lib.stream_ptr()))
+        self.base._cond_key.key = None
+        return (pose, trans, lat) if want_latents else (pose, trans)
+
+
 class Window623:
     """HumanML3D-623 window (h3d_diffusion_new_trainer.py:548-607): conditioning -> DDIM-50 with the body-part
     CFG wrapper -> x latent_scale -> latent2origin x3 (156 / 360 / 107) -> 623-d scatter. Device tensors in and out;

@@ -358,6 +358,48 @@ def test_pose_623_scatter():
     assert torch.equal(out.cpu(), ref)
 
 
+# ---- 5b. long clip: the window loop on the device ---------------------------------------------------
+def test_long_clip_window_loop_vs_oracle(W, models, vq_w, vqs, engine):
+    from oracle import longclip as olong
+    from syntalker_b200.pipeline import LongClip330
+    R, B = 3, 2
+    n_frames = olong.ROUND_L * R + 16
+    assert olong.n_windows(n_frames) == R and LongClip330.windows(n_frames) == R
+    g = torch.Generator().manual_seed(31)
+    La = olong.AUDIO_PER_FRAME * n_frames
+    audio = torch.stack([torch.rand(B, La, generator=g), (torch.rand(B, La, generator=g) < 2e-4).float()], dim=-1).contiguous()
+    word = torch.randint(0, synth.VOCAB_SIZE, (B, n_frames), generator=g).to(torch.int32)
+    seed0 = torch.randn(B, 4, 1536, generator=g)
+    x_init = torch.randn(R, B, 1536, 1, 32, generator=g)
+    diff10 = create_gaussian_diffusion(timestep_respacing="ddim10")
+    ms = load_mean_std()
+    lc = LongClip330(models["beatx"], diff10, vqs[78], vqs[180], vqs[57], use_ddim=True, ms=ms)
+    pose, trans, lat = lc.run(audio.cuda(), word.cuda(), seed0.cuda(), x_init.cuda(), want_latents=True)
+    Ttot = 32 + 28 * (R - 1)
+    assert pose.shape == (B, 4 * Ttot, 330) and trans.shape == (B, 4 * Ttot, 3) and lat.shape == (B, Ttot, 1536)
+    fn = lambda x, t, yy: omdm.mdm_forward(W["beatx"], x, t, yy, "beatx")
+    sched = odiff.make_schedule(respacing="ddim10")
+    vw = [vq_w[d] for d in synth.PART_DIMS_BEATX]
+    pose_ref, trans_ref, lat_ref, idx_ref = olong.long_clip_330(sched, fn, vw, audio, word, seed0, x_init, ms)
+    assert maxabs(lat, lat_ref) < 3e-4                      # three chained 10-step windows (seed hand-off included)
+    # decoded features: compare where the CUDA chain picked the oracle's codes (fp32 near-ties flip a 4-frame block)
+    recs = [v.latent2origin((lat[..., 512 * k:512 * (k + 1)] * 5.0).contiguous(), return_indices=True)[3] for k, v in enumerate((vqs[78], vqs[180], vqs[57]))]
+    same = torch.stack([(r.cpu() == i).all(dim=-1) for r, i in zip(recs, idx_ref)]).all(dim=0)      # [B, Ttot]
+    assert same.float().mean() > 0.97
+    frames = same.repeat_interleave(4, dim=1)
+    halo = frames.clone()                                    # the decoder's receptive field smears a flipped code over its neighbours
+    for sft in range(1, 40):
+        halo[:, sft:] &= frames[:, :-sft]; halo[:, :-sft] &= frames[:, sft:]
+    d = (pose.cpu() - pose_ref).abs()
+    assert float(d[halo].max()) < 1e-3 and float((d[halo] > 1e-5).float().mean()) < 1e-2
+    # the window slicing itself: a one-window run equals the plain window pipeline
+    p1, t1 = lc.run(audio[:, :olong.AUDIO_PER_FRAME * 128].contiguous().cuda(), word[:, :128].contiguous().cuda(), seed0.cuda(), x_init[:1].contiguous().cuda())
+    assert p1.shape == (B, 128, 330)
+    assert maxabs(p1[:, :64], pose[:, :64]) < 1e-3          # first frames of window 0 do not depend on later windows (receptive field)
+    with pytest.raises(_lib.StError):
+        lc.run(audio[:, :1000].contiguous().cuda(), word.cuda(), seed0.cuda(), x_init.cuda())       # audio too short for 3 windows
+
+
 # ---- 6. end to end through the host-buffer C-ABI call ----------------------------------------------------------------
 def test_e2e_config1_vs_golden(golden, models, vqs, engine):
     g = golden("e2e_config1")

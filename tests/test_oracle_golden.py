@@ -151,3 +151,33 @@ def test_rvq_encoder_oracle_vs_reference(golden):
         lat = orvq.map2latent(W, torch.from_numpy(g[f"pose{d}"]))
         assert lat.shape == (2, 32, 512)
         assert float((lat - torch.from_numpy(g[f"lat{d}"])).abs().max()) <= 2e-6
+
+
+def test_long_clip_window_slicing_and_seed_handoff():
+    """oracle.longclip restates trainer:413-474; checked here with a stub denoiser (x0 = 0.5 x + mean(seed))."""
+    from oracle import longclip as olong
+    from oracle import diffusion as odiff
+    R, B = 3, 2
+    n = olong.ROUND_L * R + 16
+    assert olong.n_windows(n) == R and olong.n_windows(n + 111) == R and olong.n_windows(n + 112) == R + 1
+    g = torch.Generator().manual_seed(3)
+    audio = torch.rand(B, olong.AUDIO_PER_FRAME * n, 2, generator=g)
+    word = torch.arange(B * n).reshape(B, n)
+    a1, w1 = olong.window_inputs(audio, word, 1)
+    assert a1.shape == (B, 68224, 2) and w1.shape == (B, 128) and int(w1[0, 0]) == 112 and int(w1[0, -1]) == 239
+    seeds = []
+
+    def fn(x, t, y):
+        seeds.append(y["seed"].clone())
+        return 0.5 * x + y["seed"].mean(dim=(1, 2)).view(-1, 1, 1, 1)
+
+    sched = odiff.make_schedule(respacing="ddim10")
+    seed0 = torch.randn(B, 4, 1536, generator=g)
+    x_init = torch.randn(R, B, 1536, 1, 32, generator=g)
+    lat = olong.long_clip_latents(sched, fn, audio, word, seed0, x_init)
+    assert lat.shape == (B, 32 + 28 * (R - 1), 1536)
+    assert torch.equal(seeds[0], seed0)
+    # window 1's seed = last 4 tokens of window 0's sample = tokens 28..31 of the stitched latents (window 0 is kept whole)
+    assert torch.equal(seeds[10], lat[:, 28:32])
+    # window 2's seed = last 4 tokens of window 1's sample = stitched tokens 56..59
+    assert torch.equal(seeds[20], lat[:, 56:60])
