@@ -205,8 +205,10 @@ def main():
         if world > 1:
             dist.all_gather_into_tensor(gathered, pose)
 
+    pinned = {k: inp[k].contiguous().pin_memory() for k in ("audio", "word", "seed", "noise")}   # the step's inputs live in pinned host memory
+
     def step_host():
-        win.run(inp["audio"], inp["word"], inp["seed"], inp["noise"], y=y_host)
+        win.run(pinned["audio"], pinned["word"], pinned["seed"], pinned["noise"], y=y_host)
 
     def timed(fn, n):
         evs = []

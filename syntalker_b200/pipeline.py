@@ -104,14 +104,24 @@ class Window330:
     def run(self, audio, word, seed, x_init, y=None, styles=None, jaw_aa=None, noise_tape=None, want_sample=False):
         """All inputs are CPU tensors. Returns (rec_pose [B,128,330], rec_trans [B,128,3]) pinned CPU tensors."""
         B, h = self.B, self.h
-        h["audio"].copy_(audio); h["word"].copy_(word.to(torch.int32)); h["seed"].copy_(seed.reshape(B, 4, 1536)); h["x_init"].copy_(x_init)
+
+        def stage(name, t, dtype=torch.float32):
+            """A caller's pinned, contiguous tensor of the right dtype is handed to the native call as it is; anything else is
+            copied into this object's pinned staging buffer first."""
+            if t.dtype == dtype and t.is_pinned() and t.is_contiguous() and t.numel() == h[name].numel():
+                return t
+            h[name].copy_(t.to(dtype).reshape(h[name].shape))
+            return h[name]
+
+        t_audio, t_word = stage("audio", audio), stage("word", word, torch.int32)
+        t_seed, t_x = stage("seed", seed), stage("x_init", x_init)
         y = dict(y or {})
         if styles is None and self.base.variant != "beatx":
             sf = y.get("style_feature")
             styles = [sf.get("upper_mask"), sf.get("hands_mask"), sf.get("lower_mask")] if isinstance(sf, dict) else [sf, None, None]
         styles = styles or [None, None, None]
         inp = _lib.StHostInputs()
-        inp.audio, inp.word, inp.seed, inp.x_init = h["audio"].data_ptr(), h["word"].data_ptr(), h["seed"].data_ptr(), h["x_init"].data_ptr()
+        inp.audio, inp.word, inp.seed, inp.x_init = t_audio.data_ptr(), t_word.data_ptr(), t_seed.data_ptr(), t_x.data_ptr()
         nb = h["audio"].numel() * 4 + h["word"].numel() * 4 + h["seed"].numel() * 4 + h["x_init"].numel() * 4 + 666 * 4
         for k in range(3):
             if styles[k] is not None and self.base.variant != "beatx":
