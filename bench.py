@@ -59,32 +59,43 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock, power and throttle reasons DURING the timed region: one `nvidia-smi -lms 20` process streams samples
+    (spawning nvidia-smi per sample costs 100+ ms, longer than a timed step)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.rows, self.proc = gpu, [], None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                c = [x.strip() for x in line.split(",")]
+                if len(c) >= 8:
+                    self.rows.append(c)
+        except Exception:
+            pass
 
     def summary(self):
-        self.stop_flag = True
-        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
-        mx = max([float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()] or [0])
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        rows = list(self.rows)
+        isnum = lambda v: v.replace(".", "", 1).isdigit()
+        sm = sorted(float(r[1]) for r in rows if isnum(r[1]))
+        mx = max([float(r[2]) for r in rows if isnum(r[2])] or [0])
+        pw = [float(r[3]) for r in rows if isnum(r[3])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in self.rows if len(r) > 4 + i)]
-        # under load = upper half of the samples (the sampler also sees the idle gaps between steps)
-        load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
+        # under load = upper half of the power-ranked samples (the sampler also sees the idle gaps between steps)
+        by_power = sorted((float(r[3]), float(r[1])) for r in rows if isnum(r[1]) and isnum(r[3]))
+        load = sorted(c for _, c in by_power[len(by_power) // 2:]) if by_power else sm
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm),
+                "power_w_max": max(pw) if pw else None}
 
 
 def cpu_reference_sample(B_s, S_s, threads, reps=1):

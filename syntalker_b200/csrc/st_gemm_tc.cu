@@ -840,19 +840,27 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.f;
       {
         const uint32_t qrow = qs + (uint32_t)(row0 * ATT_LDK) * 4, krow = ks + (uint32_t)((lg * 32 + kq) * ATT_LDK) * 4;
-#pragma unroll 2
+        // software pipeline: the operands of step d4 + 1 are fetched while step d4's FMAs issue
+        float4 qa[2][4], kb[2][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) qa[0][a] = lds128(qrow + (uint32_t)(4 * a * ATT_LDK) * 4);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) kb[0][b] = lds128(krow + (uint32_t)(8 * b * ATT_LDK) * 4);
+#pragma unroll
         for (int d4 = 0; d4 < 16; ++d4) {
-          float4 qa[4], kb[4];
+          const int cur = d4 & 1, nxt = cur ^ 1;
+          if (d4 + 1 < 16) {
 #pragma unroll
-          for (int a = 0; a < 4; ++a) qa[a] = lds128(qrow + (uint32_t)(4 * a * ATT_LDK + 4 * d4) * 4);
+            for (int a = 0; a < 4; ++a) qa[nxt][a] = lds128(qrow + (uint32_t)(4 * a * ATT_LDK + 4 * (d4 + 1)) * 4);
 #pragma unroll
-          for (int b = 0; b < 4; ++b) kb[b] = lds128(krow + (uint32_t)(8 * b * ATT_LDK + 4 * d4) * 4);
+            for (int b = 0; b < 4; ++b) kb[nxt][b] = lds128(krow + (uint32_t)(8 * b * ATT_LDK + 4 * (d4 + 1)) * 4);
+          }
 #pragma unroll
           for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-              ffma2(acc[a][b][0], acc[a][b][1], qa[a].x, qa[a].y, kb[b].x, kb[b].y);
-              ffma2(acc[a][b][0], acc[a][b][1], qa[a].z, qa[a].w, kb[b].z, kb[b].w);
+              ffma2(acc[a][b][0], acc[a][b][1], qa[cur][a].x, qa[cur][a].y, kb[cur][b].x, kb[cur][b].y);
+              ffma2(acc[a][b][0], acc[a][b][1], qa[cur][a].z, qa[cur][a].w, kb[cur][b].z, kb[cur][b].w);
             }
         }
       }
@@ -868,23 +876,35 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
       asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
       if (dbg && threadIdx.x == 64) dbg[44] = clock64();
-      // phase C: add the peer's half, scale by 128^-0.5, softmax over the 32 keys of each row (8 lanes x 4 keys)
+      // phase C: add the peer's half, scale by 128^-0.5, softmax over the 32 keys of each row (8 lanes x 4 keys).  The four
+      // rows of a thread advance in lock step so that their shuffle / exp chains overlap.
+      float mx[4], sum[4];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        float mx = -INFINITY;
+        mx[a] = -INFINITY;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           sv[a][b] = (sv[a][b] + lds32(sx + (uint32_t)((row0 + 4 * a) * ATT_LDS + kq + 8 * b) * 4)) * 0.08838834764831845f;
-          mx = fmaxf(mx, sv[a][b]);
+          mx[a] = fmaxf(mx[a], sv[a][b]);
         }
+      }
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float sum = 0.f;
+      for (int o = 1; o < 8; o <<= 1)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) { sv[a][b] = expf(sv[a][b] - mx); sum += sv[a][b]; }
+        for (int a = 0; a < 4; ++a) mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float inv = 1.0f / sum;
+      for (int a = 0; a < 4; ++a) {
+        sum[a] = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { sv[a][b] = expf(sv[a][b] - mx[a]); sum[a] += sv[a][b]; }
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) sum[a] += __shfl_xor_sync(0xffffffffu, sum[a], o);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float inv = 1.0f / sum[a];
 #pragma unroll
         for (int b = 0; b < 4; ++b) sts32(pp + (uint32_t)((row0 + 4 * a) * ATT_LDS + kq + 8 * b) * 4, sv[a][b] * inv);
       }
@@ -898,20 +918,27 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int d = 0; d < 8; ++d) o[a][d] = 0.f;
       {
         const uint32_t prow = pp + (uint32_t)(row0 * ATT_LDS) * 4, vrow = vs + (uint32_t)(lg * 32 * ATT_LDK + 4 * kq) * 4;
-#pragma unroll 2
+        // per key j: p[a][j] (4 rows) times v[j][8 dims]; the v rows of key j + 1 are fetched while key j's FMAs issue
+        float4 v0[2], v1[2];
+        v0[0] = lds128(vrow);
+        v1[0] = lds128(vrow + 32 * 4);
+#pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           float4 pa[4];
 #pragma unroll
           for (int a = 0; a < 4; ++a) pa[a] = lds128(prow + (uint32_t)(4 * a * ATT_LDS + 4 * j4) * 4);
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            const float4 v0 = lds128(vrow + (uint32_t)((4 * j4 + jj) * ATT_LDK) * 4);
-            const float4 v1 = lds128(vrow + (uint32_t)((4 * j4 + jj) * ATT_LDK + 32) * 4);
+            const int j = 4 * j4 + jj, cur = j & 1, nxt = cur ^ 1;
+            if (j + 1 < 32) {
+              v0[nxt] = lds128(vrow + (uint32_t)((j + 1) * ATT_LDK) * 4);
+              v1[nxt] = lds128(vrow + (uint32_t)((j + 1) * ATT_LDK + 32) * 4);
+            }
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
               const float pj = jj == 0 ? pa[a].x : jj == 1 ? pa[a].y : jj == 2 ? pa[a].z : pa[a].w;
-              ffma2(o[a][0], o[a][1], pj, pj, v0.x, v0.y); ffma2(o[a][2], o[a][3], pj, pj, v0.z, v0.w);
-              ffma2(o[a][4], o[a][5], pj, pj, v1.x, v1.y); ffma2(o[a][6], o[a][7], pj, pj, v1.z, v1.w);
+              ffma2(o[a][0], o[a][1], pj, pj, v0[cur].x, v0[cur].y); ffma2(o[a][2], o[a][3], pj, pj, v0[cur].z, v0[cur].w);
+              ffma2(o[a][4], o[a][5], pj, pj, v1[cur].x, v1[cur].y); ffma2(o[a][6], o[a][7], pj, pj, v1[cur].z, v1[cur].w);
             }
           }
         }
@@ -1322,13 +1349,26 @@ static int get_map_2d_f32(const CUtensorMap** out, const float* base, int rows, 
   return ST_OK;
 }
 
+// Tile width of the trunk kernel: the candidate with the smallest modelled time  waves * (K blocks * cadence + epilogue),
+// cadence and epilogue in cycles as measured per width (tests/probe_mainloop.py).  At M = 2048 this gives 64 / 128 / 192
+// for N = 512 / 1024 / 1536 (one wave of 128 CTAs each); at M = 1024 it gives 64 for N = 1024 (128 CTAs instead of 64).
 static int fast_bn(const GemmP& p) {
   if (p.attn) return 192;
   const int mt = (p.M + TC_BM - 1) / TC_BM;
-  int BN = p.N <= 512 ? 64 : 128;
-  if (p.N % 192 == 0 && mt * (p.N / 128) > 148 && mt * (p.N / 192) <= 148) BN = 192;
-  if (BN == 64 && (p.N % 128) == 0 && mt * (p.N / 64) > 148) BN = 128;   // more than a wave: 128-wide tiles run at the MMA floor
-  return BN;
+  const int nkb = (p.K + TC_BK - 1) / TC_BK;
+  const int cand[3] = {64, 128, 192};
+  const double cadence[3] = {638.0, 776.0, 1150.0}, epi[3] = {2600.0, 4300.0, 6000.0};
+  int best = 64;
+  double best_t = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    if (p.N % bn != 0 && !(bn == 64)) continue;                 // 64 is always admissible (N is a multiple of 64)
+    const long long ctas = (long long)mt * ((p.N + bn - 1) / bn);
+    const double waves = (double)((ctas + 147) / 148);
+    const double t = waves * (nkb * cadence[i] + epi[i] * (p.act == ACT_GELU ? 2.0 : 1.0) + 4000.0);
+    if (t < best_t) { best_t = t; best = bn; }
+  }
+  return best;
 }
 
 // The trunk kernel takes plain Linear layers whose operand / result layouts TMA can describe.
