@@ -167,6 +167,7 @@ struct st_model {
   int cond_B = 0;
   float *xs = nullptr, *comb = nullptr, *z = nullptr, *X = nullptr, *H = nullptr, *ATT = nullptr, *QKV = nullptr, *G = nullptr, *O = nullptr;
   float *wavbuf[4] = {nullptr, nullptr, nullptr, nullptr}, *atcat = nullptr, *pooled = nullptr;
+  __half* wavp[3] = {nullptr, nullptr, nullptr};   // WavEncoder activations as fp16 hi/lo planes (tcgen05 engine), 16 slack rows each
   float *scale_dev = nullptr, *scale2_dev = nullptr;
   int64_t* t_tmp = nullptr;
   // fp16 hi/lo operand planes for the tcgen05 engine
@@ -185,6 +186,7 @@ struct st_model {
 
 static bool g_use_graphs = true;
 static bool g_rank_simt = false;
+static bool g_wav_planes = true;   // st_debug_probe bit 128: WavEncoder with fp32 activations and a split pass per conv
 static bool g_fused_attn = true;   // st_debug_probe bit 32 turns the fused qkv + attention kernel off
 
 namespace st { extern int g_tc_probe; extern bool g_tc_fast; }
@@ -193,6 +195,7 @@ extern "C" int st_debug_probe(int flags) {
   st::g_tc_fast = !(flags & 16);
   g_fused_attn = !(flags & 32);
   g_rank_simt = (flags & 64) != 0;
+  g_wav_planes = !(flags & 128);
   return ST_OK;
 }
 
@@ -315,6 +318,7 @@ static int model_workspace(st_model* m, int B) {
   f += rows * 1536 * 2 + rows * 512;                           // xs, comb, z
   f += nE * rows * (512 * 3 + 1536 * 2 + 1024);                // X,H,ATT,QKV,O,G
   f += 4 * (size_t)cb * kWavLen[1] * 64 + (size_t)cb * 128 * 512 + (size_t)cb * 32 * 512;
+  f += 3 * ((size_t)cb * kWavLen[1] + 16) * 64 + 3 * 64;      // wavp: 2 halves = 1 float per element
   f += 2 * (size_t)B + 64;
   f += nE * rows * (512 * 3 + 1024) + rows * 1536;             // fp16 hi+lo planes H_p, ATT_p, X_p, G_p, xs_p (2 halves = 1 float each)
   f += 1000 * (1 + ST_COEF_STRIDE) + 64 + nE * rows * 32;
@@ -336,6 +340,7 @@ static int model_workspace(st_model* m, int B) {
   m->G = a.take<float>(nE * rows * 1024);
   m->O = a.take<float>(nE * rows * 1536);
   for (int k = 0; k < 4; ++k) m->wavbuf[k] = a.take<float>((size_t)cb * kWavLen[1] * 64);
+  for (int k = 0; k < 3; ++k) m->wavp[k] = a.take<__half>(2 * ((size_t)cb * kWavLen[1] + 16) * 64);
   m->atcat = a.take<float>((size_t)cb * 128 * 512);
   m->pooled = a.take<float>((size_t)cb * 32 * 512);
   m->scale_dev = a.take<float>(B);
@@ -356,7 +361,71 @@ static int model_workspace(st_model* m, int B) {
 }
 
 // WavEncoder + word path + mix + pool for `cb` clips -> pooled [cb*32, 512]   (denoiser.py:151-157)
+// WavEncoder on the tcgen05 engine with the activations chained as fp16 hi/lo planes: every conv streams the planes its
+// producer's epilogue wrote, the conv shortcut and conv1 of a block share one operand, and an fp32 copy is written only
+// where it is a residual (identity shortcuts of blocks 2 and 4, the conv shortcuts' outputs) or the result.  Only the
+// raw-audio convs of block 0 (C_in = 2) are one exact-fp32 direct-convolution pass (wav_first_kernel).
+static int encode_wav_tc(st_model* m, const float* audio, int cb, cudaStream_t s) {
+  const float* in_f = audio;          // fp32 view of the block input (null when nobody needs it)
+  const __half* in_p = nullptr;       // plane view of the block input
+  long long in_ps = 0;
+  int pin = -1, fin = -1;             // which wavp / wavbuf the block input occupies
+  for (int i = 0; i < 6; ++i) {
+    const int cin = kWav[i][0], cout = kWav[i][1], stride = kWav[i][2], pad = kWav[i][3], ds = kWav[i][4];
+    const int Lin = kWavLen[i], Lout = kWavLen[i + 1];
+    const bool last = (i == 5);
+    const bool next_identity = !last && !kWav[i + 1][4];          // the next block adds its input back: keep an fp32 copy
+    int fb[3], nf = 0, pb[2], np = 0;
+    for (int k = 0; k < 4 && nf < 3; ++k) if (k != fin) fb[nf++] = k;
+    for (int k = 0; k < 3 && np < 2; ++k) if (k != pin) pb[np++] = k;
+    float* h1_f = m->wavbuf[fb[0]];
+    float* sc = m->wavbuf[fb[1]];
+    float* out_f = last ? m->atcat : m->wavbuf[fb[2]];
+    __half* h1_p = m->wavp[pb[0]];
+    __half* out_p = m->wavp[pb[1]];
+    const long long h1_ps = ((long long)cb * Lout + 16) * cout, out_ps = h1_ps;
+    GemmP p;
+    p.A = in_f; p.W = m->wav[i][0].w; p.bias = m->wav[i][0].b;
+    p.M = cb * Lout; p.N = cout; p.K = 15 * cin; p.ldw = m->wav[i][0].ldw;
+    p.Lout = Lout; p.Lin = Lin; p.C = cin; p.stride = stride; p.pad = pad; p.dil = 1;
+    p.a_batch = (long long)Lin * cin; p.lda = cin; p.ldo = cout; p.act = ACT_LRELU;
+    GemmP q = p;                                                   // conv shortcut: same operand, same geometry
+    q.W = m->wav[i][2].w; q.bias = m->wav[i][2].b; q.ldw = m->wav[i][2].ldw; q.out = sc; q.act = ACT_NONE;
+    if (i == 0) {
+      // raw-audio side: conv1 and the conv shortcut in one exact-fp32 pass (30-tap dot products), conv1 straight to planes
+      ST_TRY(wav_first(audio, m->wav[0][0].w, m->wav[0][0].b, m->wav[0][2].w, m->wav[0][2].b, m->wav[0][0].ldw, cb, Lin, Lout, stride, pad,
+                       h1_p, h1_ps, sc, s));
+    } else {
+      p.a_planes = in_p; p.a_plane_stride = in_ps; q.a_planes = in_p; q.a_plane_stride = in_ps;
+      p.o_planes = h1_p; p.o_plane_stride = h1_ps; p.o_planes_ld = cout;
+    }
+    if (i > 0) ST_TRY(gemm(p, s));
+    const float* shortcut = in_f;
+    if (ds) { if (i > 0) ST_TRY(gemm(q, s)); shortcut = sc; }
+    GemmP c2;
+    c2.A = h1_f; c2.W = m->wav[i][1].w; c2.bias = m->wav[i][1].b;
+    c2.M = cb * Lout; c2.N = cout; c2.K = 15 * cout; c2.ldw = m->wav[i][1].ldw;
+    c2.Lout = Lout; c2.Lin = Lout; c2.C = cout; c2.stride = 1; c2.pad = 7; c2.dil = 1;
+    c2.a_batch = (long long)Lout * cout; c2.lda = cout; c2.ldo = last ? 512 : cout;
+    c2.res = shortcut; c2.res_mode = RES_PRE; c2.ldr = cout; c2.res_div = 1; c2.act = ACT_LRELU;
+    c2.A = nullptr; c2.a_planes = h1_p; c2.a_plane_stride = h1_ps;
+    c2.out = (last || next_identity) ? out_f : nullptr;
+    if (!last) { c2.o_planes = out_p; c2.o_plane_stride = out_ps; c2.o_planes_ld = cout; }
+    ST_TRY(gemm(c2, s));
+    in_f = (last || next_identity) ? out_f : nullptr;
+    fin = (last || !next_identity) ? -1 : fb[2];
+    in_p = out_p; in_ps = out_ps; pin = pb[1];
+  }
+  return ST_OK;
+}
+
 static int encode_audio_words(st_model* m, const float* audio, const int32_t* word, int cb, int null_inputs, cudaStream_t s) {
+  if (st_get_engine() == ST_ENGINE_TC && g_wav_planes) {
+    ST_TRY(encode_wav_tc(m, audio, cb, s));
+    ST_TRY(gather_words(word, m->word_table, m->atcat + 256, 512, cb * 128, null_inputs, s));
+    ST_TRY(avgpool4(m->atcat, m->pooled, cb * 32, 512, s));
+    return ST_OK;
+  }
   const float* in = audio;
   int in_buf = -1;
   for (int i = 0; i < 6; ++i) {

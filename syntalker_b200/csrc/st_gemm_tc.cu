@@ -1268,7 +1268,8 @@ bool tc_supported(const GemmP& p) {
   const int mode = conv_mode(p);
   if (mode < 0) return false;
   if (mode == 0) return (p.K % TC_BK) == 0;
-  if (mode == 3 && p.a_planes) return false;      // the flat strided view is only built over the split scratch
+  // the flat strided view reads up to stride - 1 rows past the tensor: caller-owned planes must carry that slack
+  if (mode == 3 && p.a_planes && p.a_plane_stride < ((long long)(p.M / p.Lout) * p.Lin + 16) * p.C) return false;
   return true;
 }
 

@@ -160,6 +160,8 @@ int profile_end(double* ms, double* flops, int64_t* n);
 // ---- other kernels --------------------------------------------------------------------------------------
 // y (fp32) and / or planes (fp16 hi/lo of y * kActScale, [2][rows][512]) may be null
 int layernorm512(const float* x, const float* gamma, const float* beta, float* y, __half* planes, int rows, cudaStream_t s);
+int wav_first(const float* audio, const float* w1, const float* b1, const float* wd, const float* bd, int ldw, int cb, int Lin, int Lout,
+              int stride, int pad, __half* h1_planes, long long plane_stride, float* sc, cudaStream_t s);   // block 0 of the WavEncoder: conv1 -> planes, conv shortcut -> fp32
 int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStream_t s);   // qkv [nseq*32,1536] -> out [nseq*32,512]
 void tc_forget_weights(const float* W);
 int tc_split(const float* a, int lda, int M, int K, __half* planes, cudaStream_t s);   // fp32 -> hi/lo planes of a*kActScale

@@ -26,6 +26,16 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// packed fp32 pair FMA (sm_100): (d0, d1) += (a0, a1) * (b0, b1)
+__device__ __forceinline__ void ffma2k(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  unsigned long long a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(d0), "f"(d1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
+}
+
 __device__ __forceinline__ void split16(float v, __half& hi, __half& lo) {
   v = fminf(fmaxf(v * kActScale, -65000.0f), 65000.0f);
   hi = __float2half_rn(v);
@@ -275,6 +285,96 @@ __global__ void __launch_bounds__(256) layernorm512_kernel(const float* __restri
 
 int layernorm512(const float* x, const float* gamma, const float* beta, float* y, __half* planes, int rows, cudaStream_t s) {
   launch_k(layernorm512_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, gamma, beta, y, planes, rows);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+
+// =========================================================================================================
+// 2b. First WavEncoder block, raw-audio side (denoiser.py:308-315 block 0, layer.py:159-163): conv1 (k15, stride 5,
+//     pad 1700, BatchNorm folded, LeakyReLU) and the conv shortcut (same geometry, no activation) share their input
+//     window, so one pass computes both: C_in = 2 makes this a 30-tap dot product per output, FMA / HBM-write bound,
+//     not a GEMM.  A warp walks output positions; lane l owns channels 2l, 2l+1 of both convs (120 weights in
+//     registers), the 30 inputs of a position are broadcast reads from a staged window.  conv1 leaves fp16 hi/lo
+//     planes for the tcgen05 conv that follows, the shortcut stays fp32 (it is a residual).
+// =========================================================================================================
+constexpr int WF_POS = 256;                 // output positions per staged window
+constexpr int WF_WIN = 4;                   // windows per CTA (the per-CTA weight fetch is amortised over 1024 positions)
+__global__ void __launch_bounds__(256) wav_first_kernel(const float* __restrict__ audio, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                        const float* __restrict__ wd, const float* __restrict__ bd, int ldw, int Lin, int Lout,
+                                                        int stride, int pad, __half* __restrict__ h1_planes, long long plane_stride,
+                                                        float* __restrict__ sc) {
+  pdl_wait();
+  trace_stamp(10);
+  pdl_launch();
+  __shared__ __align__(16) float xs[(WF_POS * 5 + 16) * 2];
+  __shared__ __align__(16) float ws[2][30][64];                  // [conv][tap*2 + c_in][channel]: transposed so that lanes read consecutive words
+  const int clip = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 2 * 64 * 30; i += 256) {
+    const int cv = i / (64 * 30), r = i - cv * 64 * 30, ch = r / 30, k = r - ch * 30;
+    ws[cv][k][ch] = __ldg((cv ? wd : w1) + (long long)ch * ldw + k);
+  }
+  __syncthreads();
+  float wa[2][30], wb[2][30];
+#pragma unroll
+  for (int k = 0; k < 30; ++k) {
+    const float2 u = *reinterpret_cast<const float2*>(&ws[0][k][2 * lane]), v = *reinterpret_cast<const float2*>(&ws[1][k][2 * lane]);
+    wa[0][k] = u.x; wa[1][k] = u.y; wb[0][k] = v.x; wb[1][k] = v.y;
+  }
+  const float ba0 = __ldg(b1 + 2 * lane), ba1 = __ldg(b1 + 2 * lane + 1), bb0 = __ldg(bd + 2 * lane), bb1 = __ldg(bd + 2 * lane + 1);
+  const float* a = audio + (long long)clip * Lin * 2;
+  const int nwin = (WF_POS - 1) * stride + 15;
+  for (int win = 0; win < WF_WIN; ++win) {
+    const int t0 = (blockIdx.x * WF_WIN + win) * WF_POS;
+    if (t0 >= Lout) break;
+    const int l0 = t0 * stride - pad;                            // first input position of the window
+    __syncthreads();                                             // the previous window is consumed
+    for (int i = threadIdx.x; i < nwin; i += 256) {
+      const int l = l0 + i;
+      float2 v = make_float2(0.f, 0.f);
+      if (l >= 0 && l < Lin) v = __ldg(reinterpret_cast<const float2*>(a) + l);
+      reinterpret_cast<float2*>(xs)[i] = v;
+    }
+    __syncthreads();
+    // two output positions per iteration (8 independent packed-FMA chains per warp)
+    for (int tt = warp; tt < WF_POS; tt += 16) {
+      const int tA = t0 + tt, tB = tA + 8;
+      if (tA >= Lout) break;
+      const float2* xa = reinterpret_cast<const float2*>(xs) + tt * stride;
+      const float2* xb = xa + 8 * stride;
+      float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};   // (conv1 ch0, conv1 ch1, shortcut ch0, shortcut ch1)
+#pragma unroll
+      for (int j = 0; j < 15; ++j) {
+        const float2 x = xa[j], y = xb[j];                          // (c_in 0, c_in 1) of input position j: broadcast reads
+        ffma2k(accA[0], accA[1], x.x, x.x, wa[0][2 * j], wa[1][2 * j]);     ffma2k(accA[2], accA[3], x.x, x.x, wb[0][2 * j], wb[1][2 * j]);
+        ffma2k(accB[0], accB[1], y.x, y.x, wa[0][2 * j], wa[1][2 * j]);     ffma2k(accB[2], accB[3], y.x, y.x, wb[0][2 * j], wb[1][2 * j]);
+        ffma2k(accA[0], accA[1], x.y, x.y, wa[0][2 * j + 1], wa[1][2 * j + 1]); ffma2k(accA[2], accA[3], x.y, x.y, wb[0][2 * j + 1], wb[1][2 * j + 1]);
+        ffma2k(accB[0], accB[1], y.y, y.y, wa[0][2 * j + 1], wa[1][2 * j + 1]); ffma2k(accB[2], accB[3], y.y, y.y, wb[0][2 * j + 1], wb[1][2 * j + 1]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int t = u ? tB : tA;
+        if (t >= Lout) break;
+        const float* acc = u ? accB : accA;
+        float a0 = acc[0] + ba0, a1 = acc[1] + ba1;
+        a0 = a0 > 0.f ? a0 : a0 * 0.01f; a1 = a1 > 0.f ? a1 : a1 * 0.01f;
+        const long long row = (long long)clip * Lout + t;
+        __half h0, l0h, h1, l1h;
+        split16(a0, h0, l0h); split16(a1, h1, l1h);
+        *reinterpret_cast<__half2*>(h1_planes + row * 64 + 2 * lane) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2*>(h1_planes + plane_stride + row * 64 + 2 * lane) = __halves2half2(l0h, l1h);
+        *reinterpret_cast<float2*>(sc + row * 64 + 2 * lane) = make_float2(acc[2] + bb0, acc[3] + bb1);
+      }
+    }
+  }
+}
+
+int wav_first(const float* audio, const float* w1, const float* b1, const float* wd, const float* bd, int ldw, int cb, int Lin, int Lout,
+              int stride, int pad, __half* h1_planes, long long plane_stride, float* sc, cudaStream_t s) {
+  if (stride != 5) { set_error("wav_first: built for the stride-5 first block"); return ST_EINVAL; }
+  launch_k(wav_first_kernel, dim3((Lout + WF_POS * WF_WIN - 1) / (WF_POS * WF_WIN), cb), dim3(256), 0, s, audio, w1, b1, wd, bd, ldw, Lin, Lout, stride, pad,
+           h1_planes, plane_stride, sc);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
