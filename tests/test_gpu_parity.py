@@ -400,6 +400,22 @@ def test_long_clip_window_loop_vs_oracle(W, models, vq_w, vqs, engine):
         lc.run(audio[:, :1000].contiguous().cuda(), word.cuda(), seed0.cuda(), x_init.cuda())       # audio too short for 3 windows
 
 
+def test_host_pipeline_equals_device_path(models, vqs, engine):
+    """st_generate_330_host (pinned host buffers in, H2D / D2H inside) must equal the device-resident call bit for bit, also when
+    its staging buffers are reused by a second call."""
+    B = 20
+    inp = synth.make_inputs(B, seed=77)
+    d10 = create_gaussian_diffusion(timestep_respacing="ddim10")
+    win = Window330(models["beatx"], d10, vqs[78], vqs[180], vqs[57], B=B, use_ddim=True)
+    pin = {k: inp[k].contiguous().pin_memory() for k in ("audio", "word", "seed", "noise")}
+    for _ in range(2):                                        # second call reuses the staging buffers (ordering against the first)
+        pose_h, trans_h = win.run(pin["audio"], pin["word"], pin["seed"], pin["noise"], want_sample=True)
+    pose_h, trans_h, sample_h = pose_h.clone(), trans_h.clone(), win.h["sample"].clone()
+    pose_d, trans_d, sample_d = win.run_device(inp["audio"].cuda(), inp["word"].cuda(), inp["seed"].cuda(), inp["noise"].cuda())
+    assert torch.equal(sample_h, sample_d.cpu())
+    assert torch.equal(pose_h, pose_d.cpu()) and torch.equal(trans_h, trans_d.cpu())
+
+
 # ---- 6. end to end through the host-buffer C-ABI call ----------------------------------------------------------------
 def test_e2e_config1_vs_golden(golden, models, vqs, engine):
     g = golden("e2e_config1")
