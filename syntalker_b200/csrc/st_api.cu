@@ -178,6 +178,8 @@ struct st_model {
   int32_t* t_model_dev = nullptr;
   float* coef_dev = nullptr;
   cudaStream_t loop_stream = nullptr;       // graphs cannot be captured on the legacy default stream
+  cudaStream_t dec_stream[2] = {nullptr, nullptr};   // the three body parts decode side by side (fork / join around st_rvq_decode x3)
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   std::map<std::string, cudaGraphExec_t> graphs;
   std::map<std::string, int64_t> graph_nodes;
@@ -186,6 +188,7 @@ struct st_model {
 
 static bool g_use_graphs = true;
 static bool g_rank_simt = false;
+static bool g_decode_streams = true;   // st_debug_probe bit 256: decode the three body parts one after the other
 static bool g_wav_planes = true;   // st_debug_probe bit 128: WavEncoder with fp32 activations and a split pass per conv
 static bool g_fused_attn = true;   // st_debug_probe bit 32 turns the fused qkv + attention kernel off
 
@@ -195,6 +198,7 @@ extern "C" int st_debug_probe(int flags) {
   st::g_tc_fast = !(flags & 16);
   g_fused_attn = !(flags & 32);
   g_rank_simt = (flags & 64) != 0;
+  g_decode_streams = !(flags & 256);
   g_wav_planes = !(flags & 128);
   return ST_OK;
 }
@@ -302,6 +306,7 @@ extern "C" void st_model_destroy(st_model* m) {
   cudaDeviceSynchronize();
   for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
   if (m->loop_stream) cudaStreamDestroy(m->loop_stream);
+  if (m->dec_stream[0]) { for (int k = 0; k < 2; ++k) { cudaStreamDestroy(m->dec_stream[k]); cudaEventDestroy(m->ev_join[k]); } cudaEventDestroy(m->ev_fork); }
   if (m->ev_in) cudaEventDestroy(m->ev_in);
   if (m->ev_out) cudaEventDestroy(m->ev_out);
   m->w.release(); m->ws.release(); m->io.release(); m->stage.release(); m->longws.release();
@@ -877,7 +882,8 @@ static GemmP conv3(const float* in, const ConvW& w, float* out, int B, int Lin, 
 //   c0: relu(conv(x)) = h                       res block: h += conv1x1(relu(conv_k3_dil(relu(h))))
 //   x2 upsample + k3 conv = two 2-tap convs on the low-resolution rows (even / odd output rows, weights pre-summed by the
 //   packer): out[2u] = W0 in[u-1] + (W1+W2) in[u];  out[2u+1] = (W0+W1) in[u] + W2 in[u+1]
-static int decode_convs_tc(st_vq* v, const float* qsum, int B, int T4, float* rec, float* hA, float* hB, float* hC, cudaStream_t s) {
+static int decode_convs_tc(st_vq* v, const float* qsum, const __half* qsum_planes, int B, int T4, float* rec, float* hA, float* hB, float* hC,
+                           cudaStream_t s) {
   const size_t big = (size_t)B * T4 * 4 * 512;                 // elements of the largest activation [B, 4*T4, 512]
   __half* P[3];
   for (int k = 0; k < 3; ++k) P[k] = v->ws.take<__half>(2 * big);
@@ -886,6 +892,7 @@ static int decode_convs_tc(st_vq* v, const float* qsum, int B, int T4, float* re
   float* h = hA; float* nxt = hC;
   __half* Ph = P[0]; __half* Pt = P[1]; __half* Pn = P[2];
   GemmP p0 = conv3(qsum, v->c0, h, B, T, T, 512, 1, 0);
+  if (qsum_planes) { p0.a_planes = qsum_planes; p0.a_plane_stride = ps; }
   p0.act = ACT_RELU; p0.o_planes = Ph; p0.o_plane_stride = ps; p0.o_planes_ld = 512;
   ST_TRY(gemm(p0, s));
   const int dils[3] = {9, 3, 1};
@@ -934,7 +941,7 @@ extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, flo
   cudaStream_t s = (cudaStream_t)stream;
   const size_t rows = (size_t)B * T4;
   const size_t big = rows * 4 * 512;
-  ST_TRY(v->ws.reserve((rows * 512 * 3 + big * 3) * sizeof(float) + 3 * 2 * big * sizeof(__half) + 32 * 256));
+  ST_TRY(v->ws.reserve((rows * 512 * 3 + big * 3) * sizeof(float) + (3 * 2 * big + 4 * rows * 512) * sizeof(__half) + 40 * 256));
   float* r = v->ws.take<float>(rows * 512);
   float* dot = v->ws.take<float>(rows * 512);
   float* qsum = v->ws.take<float>(rows * 512);
@@ -942,15 +949,23 @@ extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, flo
   float* hB = v->ws.take<float>(big);
   float* hC = v->ws.take<float>(big);
   ST_TRY(copy_strided_scale(lat, lat_stride, lat_scale, r, (int)rows, 512, s));
-  // residual quantisation, 6 layers (residual_vq.py:132-152)
+  // residual quantisation, 6 layers (residual_vq.py:132-152).  tcgen05 engine: the residual travels as planes owned by this
+  // handle (vq_select writes the next layer's operand, and the quantised sum for the decoder's first conv), so nothing
+  // here touches the engine's shared split scratch and the three body parts may run on different streams.
+  const bool tc = st_get_engine() == ST_ENGINE_TC && !g_rank_simt;
+  __half* rp = tc ? v->ws.take<__half>(2 * rows * 512) : nullptr;
+  __half* qp = tc ? v->ws.take<__half>(2 * rows * 512) : nullptr;
+  if (tc) ST_TRY(tc_split(r, 512, (int)rows, 512, rp, s));
   for (int q = 0; q < 6; ++q) {
     GemmP p = linear(r, (int)rows, 512, v->cb[q], nullptr, dot, 512);
+    if (tc) { p.a_planes = rp; p.a_plane_stride = (long long)rows * 512; }
     ST_TRY(g_rank_simt ? gemm_simt(p, s) : gemm(p, s));   // split-fp16 products carry fp32-class error; bit 64 of st_debug_probe forces SIMT
-    ST_TRY(vq_select(dot, v->cnorm[q], v->cb[q], r, qsum, idx_out ? idx_out + q : nullptr, 6, (int)rows, q == 0, s));
+    ST_TRY(vq_select(dot, v->cnorm[q], v->cb[q], r, qsum, idx_out ? idx_out + q : nullptr, 6, (int)rows, q == 0, q < 5 ? rp : nullptr,
+                     q == 5 ? qp : nullptr, s));
   }
   if (residual_out) ST_CHECK_CUDA(cudaMemcpyAsync(residual_out, r, rows * 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   // decoder (encdec.py:51-68)
-  if (st_get_engine() == ST_ENGINE_TC) return decode_convs_tc(v, qsum, B, T4, rec, hA, hB, hC, s);
+  if (st_get_engine() == ST_ENGINE_TC) return decode_convs_tc(v, qsum, qp, B, T4, rec, hA, hB, hC, s);
   int T = T4;
   GemmP p0 = conv3(qsum, v->c0, hA, B, T, T, 512, 1, 0);
   p0.act = ACT_RELU;
@@ -1042,6 +1057,34 @@ extern "C" int st_sample_to_tokens(const float* sample, int B, int T, float scal
   return transpose_to_tokens(sample, tokens, B, 1536, T, scale, (cudaStream_t)stream);
 }
 
+
+// latent2origin of the three body parts (trainer:480-482).  The parts are independent and each launch covers only part of
+// the machine at window-batch sizes (64-256 CTAs), so they run on three streams: fork after `s`, join back into `s`.
+static int decode_three(st_model* m, st_vq* const vq[3], const float* tok, float latent_scale, int B, int T4, float* const rec[3], cudaStream_t s) {
+  const bool side = g_decode_streams && vq[0] != vq[1] && vq[1] != vq[2] && vq[0] != vq[2];
+  if (!side) {
+    for (int k = 0; k < 3; ++k) ST_TRY(st_rvq_decode(vq[k], tok + 512 * k, 1536, latent_scale, B, T4, rec[k], nullptr, nullptr, s));
+    return ST_OK;
+  }
+  if (!m->dec_stream[0]) {
+    for (int k = 0; k < 2; ++k) {
+      ST_CHECK_CUDA(cudaStreamCreateWithFlags(&m->dec_stream[k], cudaStreamNonBlocking));
+      ST_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_join[k], cudaEventDisableTiming));
+    }
+    ST_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  }
+  ST_CHECK_CUDA(cudaEventRecord(m->ev_fork, s));
+  for (int k = 0; k < 2; ++k) ST_CHECK_CUDA(cudaStreamWaitEvent(m->dec_stream[k], m->ev_fork, 0));
+  ST_TRY(st_rvq_decode(vq[1], tok + 512, 1536, latent_scale, B, T4, rec[1], nullptr, nullptr, m->dec_stream[0]));   // hands: the widest decoder first
+  ST_TRY(st_rvq_decode(vq[0], tok, 1536, latent_scale, B, T4, rec[0], nullptr, nullptr, s));
+  ST_TRY(st_rvq_decode(vq[2], tok + 1024, 1536, latent_scale, B, T4, rec[2], nullptr, nullptr, m->dec_stream[1]));
+  for (int k = 0; k < 2; ++k) {
+    ST_CHECK_CUDA(cudaEventRecord(m->ev_join[k], m->dec_stream[k]));
+    ST_CHECK_CUDA(cudaStreamWaitEvent(s, m->ev_join[k], 0));
+  }
+  return ST_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int st_generate_330(st_model* m, const st_schedule* sc, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
                                st_vq* vq_lower, const st_cond* cond, const float* x_init, const float* noise_tape,
@@ -1061,9 +1104,9 @@ extern "C" int st_generate_330(st_model* m, const st_schedule* sc, const st_guid
   float* xo = sample_out ? sample_out : d_x;
   ST_TRY(st_sample(m, sc, g, x_init, noise_tape, B, xo, stream));
   ST_TRY(transpose_to_tokens(xo, d_tok, B, 1536, 32, 1.0f, s));
-  ST_TRY(st_rvq_decode(vq_upper, d_tok, 1536, latent_scale, B, 32, d_up, nullptr, nullptr, stream));
-  ST_TRY(st_rvq_decode(vq_hands, d_tok + 512, 1536, latent_scale, B, 32, d_ha, nullptr, nullptr, stream));
-  ST_TRY(st_rvq_decode(vq_lower, d_tok + 1024, 1536, latent_scale, B, 32, d_lo, nullptr, nullptr, stream));
+  st_vq* const vq3[3] = {vq_upper, vq_hands, vq_lower};
+  float* const rec3[3] = {d_up, d_ha, d_lo};
+  ST_TRY(decode_three(m, vq3, d_tok, latent_scale, B, 32, rec3, s));
   ST_TRY(pose330(d_up, d_ha, d_lo, ms, ms + 330, ms + 660, ms + 663, jaw_aa, B, 128, rec_pose, rec_trans, s));
   return ST_OK;
 }
@@ -1180,9 +1223,9 @@ extern "C" int st_generate_long_330(st_model* m, const st_schedule* sc, const st
     ST_CHECK_CUDA(cudaMemcpy2DAsync(d_lat + (size_t)at * 1536, lat_pitch, m->xs + (size_t)first * 1536, tok_pitch,
                                     (size_t)ntok * 1536 * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
   }
-  ST_TRY(st_rvq_decode(vq_upper, d_lat, 1536, latent_scale, B, Ttot, d_up, nullptr, nullptr, stream));
-  ST_TRY(st_rvq_decode(vq_hands, d_lat + 512, 1536, latent_scale, B, Ttot, d_ha, nullptr, nullptr, stream));
-  ST_TRY(st_rvq_decode(vq_lower, d_lat + 1024, 1536, latent_scale, B, Ttot, d_lo, nullptr, nullptr, stream));
+  st_vq* const vq3[3] = {vq_upper, vq_hands, vq_lower};
+  float* const rec3[3] = {d_up, d_ha, d_lo};
+  ST_TRY(decode_three(m, vq3, d_lat, latent_scale, B, Ttot, rec3, s));
   ST_TRY(pose330(d_up, d_ha, d_lo, ms, ms + 330, ms + 660, ms + 663, jaw_aa, B, n, rec_pose, rec_trans, s));
   return ST_OK;
 }

@@ -212,7 +212,7 @@ int transpose_from_tokens(const float* tok, float* x, int B, int C, int T, cudaS
 int gather_words(const int32_t* word, const float* table, float* out, int ldo, int rows, int force_zero, cudaStream_t s);
 int avgpool4(const float* in, float* out, int rows_out, int cols, cudaStream_t s);                         // rows_out x cols, in has 4x rows
 int vq_select(const float* dot, const float* cnorm, const float* codebook, float* residual, float* qsum, int64_t* idx,
-              int idx_stride, int rows, int first, cudaStream_t s);
+              int idx_stride, int rows, int first, __half* r_planes, __half* q_planes, cudaStream_t s);   // planes: optional fp16 hi/lo copies of the new residual / of qsum
 int copy_strided_scale(const float* in, long long in_stride, float scale, float* out, int rows, int cols, cudaStream_t s);
 int pose330(const float* up, const float* ha, const float* lo, const float* mean, const float* std, const float* tmean,
             const float* tstd, const float* jaw, int B, int n, float* pose, float* trans, cudaStream_t s);

@@ -806,7 +806,7 @@ int copy_strided_scale(const float* in, long long in_stride, float scale, float*
 __global__ void __launch_bounds__(256) vq_select_kernel(const float* __restrict__ dot, const float* __restrict__ cnorm,
                                                         const float* __restrict__ codebook, float* __restrict__ residual,
                                                         float* __restrict__ qsum, int64_t* __restrict__ idx, int idx_stride,
-                                                        int rows, int first) {
+                                                        int rows, int first, __half* __restrict__ r_planes, __half* __restrict__ q_planes) {
   pdl_wait();
   trace_stamp(9);
   pdl_launch();
@@ -852,18 +852,22 @@ __global__ void __launch_bounds__(256) vq_select_kernel(const float* __restrict_
     nr.x = __fsub_rn(r[i].x, xq.x); nr.y = __fsub_rn(r[i].y, xq.y);
     nr.z = __fsub_rn(r[i].z, xq.z); nr.w = __fsub_rn(r[i].w, xq.w);
     rr[lane + 32 * i] = nr;
+    // tcgen05 engine: the next layer's ranking GEMM streams the new residual as fp16 hi/lo planes -- written here, no split pass
+    if (r_planes) store_planes4(r_planes + (long long)row * 512 + (lane + 32 * i) * 4, (long long)rows * 512, nr.x, nr.y, nr.z, nr.w);
     if (first) acc = make_float4(0.f + xq.x, 0.f + xq.y, 0.f + xq.z, 0.f + xq.w);
     else {
       const float4 old = qs[lane + 32 * i];
       acc = make_float4(__fadd_rn(old.x, xq.x), __fadd_rn(old.y, xq.y), __fadd_rn(old.z, xq.z), __fadd_rn(old.w, xq.w));
     }
     qs[lane + 32 * i] = acc;
+    if (q_planes) store_planes4(q_planes + (long long)row * 512 + (lane + 32 * i) * 4, (long long)rows * 512, acc.x, acc.y, acc.z, acc.w);
   }
 }
 
 int vq_select(const float* dot, const float* cnorm, const float* codebook, float* residual, float* qsum, int64_t* idx,
-              int idx_stride, int rows, int first, cudaStream_t s) {
-  launch_k(vq_select_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, dot, cnorm, codebook, residual, qsum, idx, idx_stride, rows, first);
+              int idx_stride, int rows, int first, __half* r_planes, __half* q_planes, cudaStream_t s) {
+  launch_k(vq_select_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, dot, cnorm, codebook, residual, qsum, idx, idx_stride, rows, first,
+           r_planes, q_planes);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
