@@ -317,15 +317,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           umma_commit(&empty_bar[s]);
           continue;
         }
+        if (BN <= 128) {
+          // the lo weight plane follows the hi plane in the stage: one MMA of width 2 BN forms a_hi.[w_hi ; w_lo] (main
+          // accumulator + first cross term), a second of width BN adds a_lo.w_hi (see the trunk kernel)
+          const uint32_t idesc_w = umma_idesc_f16(TC_BM, 2 * BN);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t dah = umma_desc_sw128(a_hi) + 2 * k, dal = umma_desc_sw128(a_lo) + 2 * k;
-          const uint64_t dwh = umma_desc_sw128(w_hi) + 2 * k, dwl = umma_desc_sw128(w_lo) + 2 * k;
-          // hi.hi goes to the main accumulator; the two 2^-11-sized cross terms go to their own accumulator so that
-          // the tensor core's truncating fp32 adds see a 3x shorter chain on the large sum (measured: error / 3)
-          umma_f16(tmem_base, dah, dwh, idesc, (kb | k) != 0);
-          umma_f16(tmem_base + BN, dah, dwl, idesc, (kb | k) != 0);
-          umma_f16(tmem_base + BN, dal, dwh, idesc, 1);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t dah = umma_desc_sw128(a_hi) + 2 * k, dal = umma_desc_sw128(a_lo) + 2 * k;
+            const uint64_t dwh = umma_desc_sw128(w_hi) + 2 * k;
+            umma_f16(tmem_base, dah, dwh, idesc_w, (kb | k) != 0);
+            umma_f16(tmem_base + BN, dal, dwh, idesc, 1);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t dah = umma_desc_sw128(a_hi) + 2 * k, dal = umma_desc_sw128(a_lo) + 2 * k;
+            const uint64_t dwh = umma_desc_sw128(w_hi) + 2 * k, dwl = umma_desc_sw128(w_lo) + 2 * k;
+            // hi.hi goes to the main accumulator; the two 2^-11-sized cross terms go to their own accumulator so that
+            // the tensor core's truncating fp32 adds see a 3x shorter chain on the large sum (measured: error / 3)
+            umma_f16(tmem_base, dah, dwh, idesc, (kb | k) != 0);
+            umma_f16(tmem_base + BN, dah, dwl, idesc, (kb | k) != 0);
+            umma_f16(tmem_base + BN, dal, dwh, idesc, 1);
+          }
         }
         umma_commit(&empty_bar[s]);     // slot reusable once these MMAs have read it
       }
