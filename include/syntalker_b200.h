@@ -212,6 +212,15 @@ typedef struct {
 int st_generate_330_host(st_model* m, const st_schedule* s, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
                          st_vq* vq_lower, const st_host_inputs* in, int B, float latent_scale, float* rec_pose_host,
                          float* rec_trans_host, float* sample_host /* nullable [B,1536,1,32] */, void* stream);
+/* The same call split in two, so that TWO window batches can be in flight: `slot` (0 or 1) names a staging set; _begin queues
+ * the H2D copies on an internal copy stream, the computation on `stream` and the D2H copies on a second copy stream, and
+ * returns; _wait blocks until the slot's results are in the host buffers given to _begin.  Inputs of batch i + 1 then cross
+ * PCIe while batch i computes.  The host buffers must stay valid (and pinned, for the copies to be asynchronous) until
+ * _wait returns; a slot must be waited for before it is reused (ST_ESTATE otherwise). */
+int st_generate_330_host_begin(st_model* m, const st_schedule* s, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
+                               st_vq* vq_lower, const st_host_inputs* in, int B, float latent_scale, float* rec_pose_host,
+                               float* rec_trans_host, float* sample_host /* nullable */, int slot, void* stream);
+int st_generate_330_host_wait(st_model* m, int slot);
 
 /* ---- long clip: the window loop ----------------------------------------------
  * Replaces: the `for i in range(0, roundt)` loop of _g_test with its seed hand-off and latent stitching, plus the single

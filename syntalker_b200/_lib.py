@@ -24,7 +24,7 @@ SYMBOLS = [
     "st_model_create", "st_model_destroy", "st_vq_create", "st_vq_destroy", "st_vq_out_dim",
     "st_schedule_create", "st_schedule_destroy", "st_cond_encode", "st_denoise", "st_sample",
     "st_rvq_decode", "st_pose_assemble_330", "st_pose_assemble_623", "st_sample_to_tokens",
-    "st_rvq_encode", "st_generate_330", "st_generate_330_host", "st_generate_long_330", "st_selftest_gemm", "st_bench_gemm", "st_profile_begin", "st_profile_end",
+    "st_rvq_encode", "st_generate_330", "st_generate_330_host", "st_generate_330_host_begin", "st_generate_330_host_wait", "st_generate_long_330", "st_selftest_gemm", "st_bench_gemm", "st_profile_begin", "st_profile_end",
 ]
 
 
@@ -95,6 +95,9 @@ def lib():
     L.st_generate_330.argtypes = [vp, vp, C.POINTER(StGuidance), vp, vp, vp, C.POINTER(StCond), vp, vp, vp, vp, i32, f32, vp, vp, vp, vp]
     L.st_generate_330_host.argtypes = [vp, vp, C.POINTER(StGuidance), vp, vp, vp, C.POINTER(StHostInputs), i32, f32,
                                        vp, vp, vp, vp]
+    L.st_generate_330_host_begin.argtypes = [vp, vp, C.POINTER(StGuidance), vp, vp, vp, C.POINTER(StHostInputs), i32, f32,
+                                             vp, vp, vp, i32, vp]
+    L.st_generate_330_host_wait.argtypes = [vp, i32]
     L.st_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     L.st_bench_gemm.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(C.c_double)]
     L.st_selftest_gemm.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp]

@@ -160,7 +160,11 @@ struct st_model {
   float* cst_null = nullptr;   // [32,512]
   bool null_ready = false;
   // workspace
-  Arena ws, io, stage, longws;
+  Arena ws, io, longws;
+  struct HostSlot { Arena stage; cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_done = nullptr; bool pending = false; };
+  HostSlot hslot[2];                        // staging sets of the host-buffer pipeline (two window batches in flight)
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_enter = nullptr;
   int ws_B = 0;
   float *cst_real = nullptr, *g2 = nullptr, *sv[3] = {nullptr, nullptr, nullptr};
   bool have_style[3] = {false, false, false};
@@ -309,7 +313,12 @@ extern "C" void st_model_destroy(st_model* m) {
   if (m->dec_stream[0]) { for (int k = 0; k < 2; ++k) { cudaStreamDestroy(m->dec_stream[k]); cudaEventDestroy(m->ev_join[k]); } cudaEventDestroy(m->ev_fork); }
   if (m->ev_in) cudaEventDestroy(m->ev_in);
   if (m->ev_out) cudaEventDestroy(m->ev_out);
-  m->w.release(); m->ws.release(); m->io.release(); m->stage.release(); m->longws.release();
+  m->w.release(); m->ws.release(); m->io.release(); m->longws.release();
+  for (int k = 0; k < 2; ++k) {
+    m->hslot[k].stage.release();
+    if (m->hslot[k].ev_h2d) { cudaEventDestroy(m->hslot[k].ev_h2d); cudaEventDestroy(m->hslot[k].ev_comp); cudaEventDestroy(m->hslot[k].ev_done); }
+  }
+  if (m->h2d_stream) { cudaStreamDestroy(m->h2d_stream); cudaStreamDestroy(m->d2h_stream); cudaEventDestroy(m->ev_enter); }
   if (m->cst_null) cudaFree(m->cst_null);
   delete m;
 }
@@ -1111,22 +1120,40 @@ extern "C" int st_generate_330(st_model* m, const st_schedule* sc, const st_guid
   return ST_OK;
 }
 
-extern "C" int st_generate_330_host(st_model* m, const st_schedule* sc, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
-                                    st_vq* vq_lower, const st_host_inputs* in, int B, float latent_scale, float* rec_pose_host,
-                                    float* rec_trans_host, float* sample_host, void* stream) {
+// Host-buffer pipeline.  `slot` (0 / 1) names one of two staging sets, so that two window batches can be in flight: the
+// inputs of batch i + 1 cross PCIe on the H2D stream and the results of batch i return on the D2H stream while the
+// compute stream works (the computations themselves are serialised on `stream`: they share the model's workspace).
+// st_generate_330_host_begin enqueues everything and returns; st_generate_330_host_wait blocks until the slot's results
+// are in the caller's host buffers.  A slot must be waited for before it is reused.
+extern "C" int st_generate_330_host_begin(st_model* m, const st_schedule* sc, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
+                                          st_vq* vq_lower, const st_host_inputs* in, int B, float latent_scale, float* rec_pose_host,
+                                          float* rec_trans_host, float* sample_host, int slot, void* stream) {
   ST_REQUIRE(m && sc && in && rec_pose_host && B > 0, "st_generate_330_host: null argument");
+  ST_REQUIRE(slot == 0 || slot == 1, "st_generate_330_host: slot must be 0 or 1");
   ST_REQUIRE(in->audio && in->word && in->seed && in->x_init && in->mean && in->std, "st_generate_330_host: missing host input");
+  st_model::HostSlot& hs = m->hslot[slot];
+  if (hs.pending) { set_error("st_generate_330_host: slot %d is still in flight (call st_generate_330_host_wait first)", slot); return ST_ESTATE; }
   cudaStream_t s = (cudaStream_t)stream;
+  if (!m->h2d_stream) {
+    ST_CHECK_CUDA(cudaStreamCreateWithFlags(&m->h2d_stream, cudaStreamNonBlocking));
+    ST_CHECK_CUDA(cudaStreamCreateWithFlags(&m->d2h_stream, cudaStreamNonBlocking));
+    ST_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_enter, cudaEventDisableTiming));
+  }
+  if (!hs.ev_h2d) {
+    ST_CHECK_CUDA(cudaEventCreateWithFlags(&hs.ev_h2d, cudaEventDisableTiming));
+    ST_CHECK_CUDA(cudaEventCreateWithFlags(&hs.ev_comp, cudaEventDisableTiming));
+    ST_CHECK_CUDA(cudaEventCreateWithFlags(&hs.ev_done, cudaEventDisableTiming));
+  }
   const size_t nx = (size_t)B * ST_LATENT * ST_TOKENS;
   const int sdim = m->style_dim;
   bool any_sigma = false;
   for (int k = 0; k < sc->S; ++k) any_sigma |= sc->coef[(size_t)k * ST_COEF_STRIDE + (sc->mode == ST_MODE_DDPM ? 2 : 4)] != 0.f;
   ST_REQUIRE(!any_sigma || in->noise_tape, "st_generate_330_host: schedule has sigma != 0 but noise_tape is NULL");
-  // staging lives in its own arena (m->io is used by st_generate_330)
+  // staging lives in the slot's own arena (m->io is used by st_generate_330)
   size_t f = (size_t)B * ST_AUDIO_LEN * 2 + (size_t)B * 128 + (size_t)B * 6144 + 3 * (size_t)B * (sdim ? sdim : 1) + nx * 2 +
              (any_sigma ? nx * sc->S : 0) + (size_t)B * 128 * (3 + 330 + 3) + 666 + 64 * 16;
-  ST_TRY(m->stage.reserve(f * sizeof(float) + 32 * 256));
-  Arena& a = m->stage;
+  ST_TRY(hs.stage.reserve(f * sizeof(float) + 32 * 256));
+  Arena& a = hs.stage;
   float* d_audio = a.take<float>((size_t)B * ST_AUDIO_LEN * 2);
   int32_t* d_word = a.take<int32_t>((size_t)B * 128);
   float* d_seed = a.take<float>((size_t)B * 6144);
@@ -1138,7 +1165,10 @@ extern "C" int st_generate_330_host(st_model* m, const st_schedule* sc, const st
   float* d_pose = a.take<float>((size_t)B * 128 * 330);
   float* d_trans = a.take<float>((size_t)B * 128 * 3);
   float* d_ms = a.take<float>(666);
-  auto h2d = [&](void* d, const void* h, size_t bytes) { return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s); };
+  // ---- inputs: H2D stream.  Not ordered behind `stream` (that is the point: the previous batch is still computing there);
+  // the slot's staging set is free because its previous use was waited for ----
+  cudaStream_t hi = m->h2d_stream, ho = m->d2h_stream;
+  auto h2d = [&](void* d, const void* h, size_t bytes) { return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, hi); };
   ST_CHECK_CUDA(h2d(d_audio, in->audio, (size_t)B * ST_AUDIO_LEN * 2 * sizeof(float)));
   ST_CHECK_CUDA(h2d(d_word, in->word, (size_t)B * 128 * sizeof(int32_t)));
   ST_CHECK_CUDA(h2d(d_seed, in->seed, (size_t)B * 6144 * sizeof(float)));
@@ -1150,7 +1180,7 @@ extern "C" int st_generate_330_host(st_model* m, const st_schedule* sc, const st
   ST_CHECK_CUDA(h2d(d_x, in->x_init, nx * sizeof(float)));
   if (d_tape) ST_CHECK_CUDA(h2d(d_tape, in->noise_tape, nx * sc->S * sizeof(float)));
   if (d_jaw) ST_CHECK_CUDA(h2d(d_jaw, in->jaw_aa, (size_t)B * 128 * 3 * sizeof(float)));
-  ST_CHECK_CUDA(cudaMemsetAsync(d_ms, 0, 666 * sizeof(float), s));
+  ST_CHECK_CUDA(cudaMemsetAsync(d_ms, 0, 666 * sizeof(float), hi));
   ST_CHECK_CUDA(h2d(d_ms, in->mean, 330 * sizeof(float)));
   ST_CHECK_CUDA(h2d(d_ms + 330, in->std, 330 * sizeof(float)));
   const bool want_trans = rec_trans_host && in->trans_mean && in->trans_std;
@@ -1158,18 +1188,42 @@ extern "C" int st_generate_330_host(st_model* m, const st_schedule* sc, const st
     ST_CHECK_CUDA(h2d(d_ms + 660, in->trans_mean, 3 * sizeof(float)));
     ST_CHECK_CUDA(h2d(d_ms + 663, in->trans_std, 3 * sizeof(float)));
   }
+  ST_CHECK_CUDA(cudaEventRecord(hs.ev_h2d, hi));
+  // ---- compute: the caller's stream ----
+  ST_CHECK_CUDA(cudaStreamWaitEvent(s, hs.ev_h2d, 0));
   st_cond c;
   c.audio = d_audio; c.word = d_word; c.seed = d_seed;
   for (int k = 0; k < 3; ++k) c.style[k] = d_style[k];
   ST_TRY(st_generate_330(m, sc, g, vq_upper, vq_hands, vq_lower, &c, d_x, d_tape, d_jaw, d_ms, B, latent_scale, d_pose,
                          want_trans ? d_trans : nullptr, d_s, stream));
-  if (sample_host) ST_CHECK_CUDA(cudaMemcpyAsync(sample_host, d_s, nx * sizeof(float), cudaMemcpyDeviceToHost, s));
-  ST_CHECK_CUDA(cudaMemcpyAsync(rec_pose_host, d_pose, (size_t)B * 128 * 330 * sizeof(float), cudaMemcpyDeviceToHost, s));
-  if (want_trans) ST_CHECK_CUDA(cudaMemcpyAsync(rec_trans_host, d_trans, (size_t)B * 128 * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-  ST_CHECK_CUDA(cudaStreamSynchronize(s));
+  ST_CHECK_CUDA(cudaEventRecord(hs.ev_comp, s));
+  // ---- results: D2H stream ----
+  ST_CHECK_CUDA(cudaStreamWaitEvent(ho, hs.ev_comp, 0));
+  if (sample_host) ST_CHECK_CUDA(cudaMemcpyAsync(sample_host, d_s, nx * sizeof(float), cudaMemcpyDeviceToHost, ho));
+  ST_CHECK_CUDA(cudaMemcpyAsync(rec_pose_host, d_pose, (size_t)B * 128 * 330 * sizeof(float), cudaMemcpyDeviceToHost, ho));
+  if (want_trans) ST_CHECK_CUDA(cudaMemcpyAsync(rec_trans_host, d_trans, (size_t)B * 128 * 3 * sizeof(float), cudaMemcpyDeviceToHost, ho));
+  ST_CHECK_CUDA(cudaEventRecord(hs.ev_done, ho));
+  hs.pending = true;
   return ST_OK;
 }
 
+extern "C" int st_generate_330_host_wait(st_model* m, int slot) {
+  ST_REQUIRE(m && (slot == 0 || slot == 1), "st_generate_330_host_wait: bad argument");
+  st_model::HostSlot& hs = m->hslot[slot];
+  if (!hs.pending) return ST_OK;
+  hs.pending = false;
+  ST_CHECK_CUDA(cudaEventSynchronize(hs.ev_done));
+  return ST_OK;
+}
+
+// one window batch, blocking: begin on slot 0 + wait
+extern "C" int st_generate_330_host(st_model* m, const st_schedule* sc, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
+                                    st_vq* vq_lower, const st_host_inputs* in, int B, float latent_scale, float* rec_pose_host,
+                                    float* rec_trans_host, float* sample_host, void* stream) {
+  ST_TRY(st_generate_330_host_wait(m, 0));
+  ST_TRY(st_generate_330_host_begin(m, sc, g, vq_upper, vq_hands, vq_lower, in, B, latent_scale, rec_pose_host, rec_trans_host, sample_host, 0, stream));
+  return st_generate_330_host_wait(m, 0);
+}
 
 // ---- long clip: the trainer's window loop on the device (diffusion_rvqvae_trainer.py:413-531) ------------------------
 // R windows of 128 frames, consecutive windows share pre_frames * 4 = 16 frames: window i reads words

@@ -103,13 +103,28 @@ class Window330:
 
     def run(self, audio, word, seed, x_init, y=None, styles=None, jaw_aa=None, noise_tape=None, want_sample=False):
         """All inputs are CPU tensors. Returns (rec_pose [B,128,330], rec_trans [B,128,3]) pinned CPU tensors."""
+        self.begin(0, audio, word, seed, x_init, y=y, styles=styles, jaw_aa=jaw_aa, noise_tape=noise_tape, want_sample=want_sample)
+        return self.wait(0)
+
+    def begin(self, slot, audio, word, seed, x_init, y=None, styles=None, jaw_aa=None, noise_tape=None, want_sample=False):
+        """Queue one window batch on staging set `slot` (0 / 1) and return: H2D on a copy stream, compute on the current
+        stream, D2H on a second copy stream (st_generate_330_host_begin). Two batches may be in flight, so the inputs of
+        batch i + 1 cross PCIe while batch i computes; `wait(slot)` returns the slot's pinned results."""
         B, h = self.B, self.h
+        pin = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype).pin_memory()
+        if "slots" not in h:
+            h["slots"] = [{"pose": h["pose"], "trans": h["trans"], "sample": h["sample"], "style": h["style"], "jaw": h["jaw"]},
+                          {"pose": pin(B, 128, 330), "trans": pin(B, 128, 3), "sample": pin(B, 1536, 1, 32),
+                           "style": [pin(*t.shape) for t in h["style"]], "jaw": pin(B, 128, 3)}]
+        hs = h["slots"][slot]
 
         def stage(name, t, dtype=torch.float32):
             """A caller's pinned, contiguous tensor of the right dtype is handed to the native call as it is; anything else is
-            copied into this object's pinned staging buffer first."""
+            copied into this object's pinned staging buffer first (slot 0 only: a second batch in flight needs its own memory)."""
             if t.dtype == dtype and t.is_pinned() and t.is_contiguous() and t.numel() == h[name].numel():
                 return t
+            if slot != 0:
+                raise ValueError(f"begin(slot=1) needs pinned, contiguous {dtype} inputs ('{name}' is not)")
             h[name].copy_(t.to(dtype).reshape(h[name].shape))
             return h[name]
 
@@ -126,13 +141,13 @@ class Window330:
         for k in range(3):
             if styles[k] is not None and self.base.variant != "beatx":
                 s = styles[k]
-                h["style"][k].copy_(s.expand(B, -1) if s.shape[0] == 1 else s)
-                inp.style[k] = h["style"][k].data_ptr()
-                nb += h["style"][k].numel() * 4
+                hs["style"][k].copy_(s.expand(B, -1) if s.shape[0] == 1 else s)
+                inp.style[k] = hs["style"][k].data_ptr()
+                nb += hs["style"][k].numel() * 4
             else:
                 inp.style[k] = None
         if jaw_aa is not None:
-            h["jaw"].copy_(jaw_aa); inp.jaw_aa = h["jaw"].data_ptr(); nb += h["jaw"].numel() * 4
+            hs["jaw"].copy_(jaw_aa); inp.jaw_aa = hs["jaw"].data_ptr(); nb += hs["jaw"].numel() * 4
         if noise_tape is not None:
             noise_tape = noise_tape.contiguous()
             inp.noise_tape = noise_tape.data_ptr(); nb += noise_tape.numel() * 4
@@ -140,15 +155,25 @@ class Window330:
         inp.mean, inp.std, inp.trans_mean, inp.trans_std = m["mean"].data_ptr(), m["std"].data_ptr(), m["trans_mean"].data_ptr(), m["trans_std"].data_ptr()
         g = self.wrapper.guidance(y) if self.wrapper is not None else Guidance(_lib.ST_CFG_NONE)
         sched, _ = self.diffusion._native(self.mode, self.eta)
+        hs["keep"] = (inp, g, noise_tape, t_audio, t_word, t_seed, t_x)       # alive until wait()
         with torch.cuda.device(self.base.device):
-            _lib.check(_lib.lib().st_generate_330_host(
+            _lib.check(_lib.lib().st_generate_330_host_begin(
                 self.base.handle, sched, C.byref(g.struct(B)), self.vqs[0].handle, self.vqs[1].handle, self.vqs[2].handle,
-                C.byref(inp), B, self.latent_scale, h["pose"].data_ptr(), h["trans"].data_ptr(),
-                h["sample"].data_ptr() if want_sample else None, _lib.stream_ptr()))
+                C.byref(inp), B, self.latent_scale, hs["pose"].data_ptr(), hs["trans"].data_ptr(),
+                hs["sample"].data_ptr() if want_sample else None, slot, _lib.stream_ptr()))
         self.base._cond_key.key = None          # the native call re-encoded the cache from its own staging buffers
         self.h2d_bytes = nb
-        self.d2h_bytes = (h["pose"].numel() + h["trans"].numel() + (h["sample"].numel() if want_sample else 0)) * 4
-        return h["pose"], h["trans"]
+        self.d2h_bytes = (hs["pose"].numel() + hs["trans"].numel() + (hs["sample"].numel() if want_sample else 0)) * 4
+
+    def wait(self, slot):
+        """Block until the batch queued on `slot` is complete; returns its (rec_pose, rec_trans) pinned CPU tensors."""
+        hs = self.h["slots"][slot] if "slots" in self.h else None
+        with torch.cuda.device(self.base.device):
+            _lib.check(_lib.lib().st_generate_330_host_wait(self.base.handle, slot))
+        if hs is None:
+            raise _lib.StError("wait() before begin()")
+        hs.pop("keep", None)
+        return hs["pose"], hs["trans"]
 
 
 class LongClip330:

@@ -414,6 +414,18 @@ def test_host_pipeline_equals_device_path(models, vqs, engine):
     pose_d, trans_d, sample_d = win.run_device(inp["audio"].cuda(), inp["word"].cuda(), inp["seed"].cuda(), inp["noise"].cuda())
     assert torch.equal(sample_h, sample_d.cpu())
     assert torch.equal(pose_h, pose_d.cpu()) and torch.equal(trans_h, trans_d.cpu())
+    # two batches in flight on the two staging sets (begin / wait): each returns its own batch's result
+    inp2 = synth.make_inputs(B, seed=78)
+    pin2 = {k: inp2[k].contiguous().pin_memory() for k in ("audio", "word", "seed", "noise")}
+    win.begin(0, pin["audio"], pin["word"], pin["seed"], pin["noise"])
+    win.begin(1, pin2["audio"], pin2["word"], pin2["seed"], pin2["noise"])
+    with pytest.raises(_lib.StError):
+        win.begin(1, pin2["audio"], pin2["word"], pin2["seed"], pin2["noise"])      # slot 1 is still in flight
+    p0, t0 = win.wait(0)
+    p0 = p0.clone()
+    p1, t1 = win.wait(1)
+    pose_d2, _, _ = win.run_device(inp2["audio"].cuda(), inp2["word"].cuda(), inp2["seed"].cuda(), inp2["noise"].cuda())
+    assert torch.equal(p0, pose_d.cpu()) and torch.equal(p1, pose_d2.cpu())
 
 
 # ---- 6. end to end through the host-buffer C-ABI call ----------------------------------------------------------------
