@@ -173,6 +173,8 @@ struct st_model {
   float *wavbuf[4] = {nullptr, nullptr, nullptr, nullptr}, *atcat = nullptr, *pooled = nullptr;
   __half* wavp[3] = {nullptr, nullptr, nullptr};   // WavEncoder activations as fp16 hi/lo planes (tcgen05 engine), 16 slack rows each
   float *scale_dev = nullptr, *scale2_dev = nullptr;
+  std::vector<float> scale_last, scale2_last;          // host copies of what scale_dev / scale2_dev hold
+  unsigned long long sched_id = 0;                     // schedule whose tables t_model_dev / coef_dev hold
   int64_t* t_tmp = nullptr;
   // fp16 hi/lo operand planes for the tcgen05 engine
   __half *H_p = nullptr, *ATT_p = nullptr, *G_p = nullptr, *X_p = nullptr, *xs_p = nullptr;
@@ -208,6 +210,7 @@ extern "C" int st_debug_probe(int flags) {
 }
 
 struct st_schedule {
+  unsigned long long id = 0;     // unique per st_schedule_create (a destroyed schedule's address may be reused)
   int S = 0, mode = 0;
   std::vector<int32_t> t_model;
   std::vector<float> coef;
@@ -371,6 +374,7 @@ static int model_workspace(st_model* m, int B) {
   m->coef_dev = a.take<float>(1000 * ST_COEF_STRIDE);
   m->ws_B = B;
   m->cond_B = 0;   // the cache lived in the old block
+  m->scale_last.clear(); m->scale2_last.clear(); m->sched_id = 0;
   return ST_OK;
 }
 
@@ -667,11 +671,19 @@ static int upload_scales(st_model* m, const Plan& pl, const st_guidance* g, int 
   sp->o = m->O;
   sp->scale = nullptr; sp->scale2 = nullptr;
   for (int k = 0; k < 3; ++k) { sp->part_sa[k] = pl.part_sa[k]; sp->part_sp[k] = pl.part_sp[k]; sp->part_ua[k] = pl.part_ua[k]; }
+  // The scales come from pageable host memory, and a pageable cudaMemcpyAsync first drains the stream on the host side: in
+  // steady state (same values as the last call) the device copy is reused, so the host keeps running ahead of the GPU.
+  auto upload = [&](float* dst, const float* src, std::vector<float>& last) -> int {
+    if ((int)last.size() == B && memcmp(last.data(), src, B * sizeof(float)) == 0) return ST_OK;
+    ST_CHECK_CUDA(cudaMemcpyAsync(dst, src, B * sizeof(float), cudaMemcpyHostToDevice, s));
+    last.assign(src, src + B);
+    return ST_OK;
+  };
   if (pl.cfg_mode == ST_CFG_TEXT || pl.cfg_mode == ST_CFG_TWO) {
-    ST_CHECK_CUDA(cudaMemcpyAsync(m->scale_dev, g->scale, B * sizeof(float), cudaMemcpyHostToDevice, s));
+    ST_TRY(upload(m->scale_dev, g->scale, m->scale_last));
     sp->scale = m->scale_dev;
     if (pl.cfg_mode == ST_CFG_TWO) {
-      ST_CHECK_CUDA(cudaMemcpyAsync(m->scale2_dev, g->scale2, B * sizeof(float), cudaMemcpyHostToDevice, s));
+      ST_TRY(upload(m->scale2_dev, g->scale2, m->scale2_last));
       sp->scale2 = m->scale2_dev;
     }
   }
@@ -698,7 +710,9 @@ extern "C" int st_schedule_create(int S, int mode, const int32_t* t_model, const
   ST_REQUIRE(S > 0 && t_model && coef && out, "st_schedule_create: null argument or S <= 0");
   ST_REQUIRE(mode == ST_MODE_DDPM || mode == ST_MODE_DDIM, "st_schedule_create: unknown mode %d", mode);
   for (int k = 0; k < S; ++k) ST_REQUIRE(t_model[k] >= 0 && t_model[k] < ST_MAX_T, "t_model[%d]=%d out of [0,%d)", k, t_model[k], ST_MAX_T);
+  static unsigned long long next_id = 0;
   st_schedule* sc = new st_schedule();
+  sc->id = ++next_id;
   sc->S = S; sc->mode = mode;
   sc->t_model.assign(t_model, t_model + S);
   sc->coef.assign(coef, coef + (size_t)S * ST_COEF_STRIDE);
@@ -740,8 +754,11 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
   StepP sp;
   ST_TRY(upload_scales(m, pl, g, B, &sp, s));
   sp.mode = sc->mode;
-  ST_CHECK_CUDA(cudaMemcpyAsync(m->t_model_dev, sc->t_model.data(), sc->S * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-  ST_CHECK_CUDA(cudaMemcpyAsync(m->coef_dev, sc->coef.data(), (size_t)sc->S * ST_COEF_STRIDE * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (m->sched_id != sc->id) {     // the schedule's tables, once per schedule
+    ST_CHECK_CUDA(cudaMemcpyAsync(m->t_model_dev, sc->t_model.data(), sc->S * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    ST_CHECK_CUDA(cudaMemcpyAsync(m->coef_dev, sc->coef.data(), (size_t)sc->S * ST_COEF_STRIDE * sizeof(float), cudaMemcpyHostToDevice, s));
+    m->sched_id = sc->id;
+  }
   ST_TRY(init_loop(m->loop, sc->S, noise_tape, s));
   ST_TRY(transpose_to_tokens(x_init, m->xs, B, 1536, 32, 1.0f, s));
   if (st_get_engine() == ST_ENGINE_TC) ST_TRY(tc_split(m->xs, 1536, B * 32, 1536, m->xs_p, s));
