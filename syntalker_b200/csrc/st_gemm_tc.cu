@@ -682,6 +682,12 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);   // REDUX result lives in a uniform register
   pdl_launch();     // dependents may be scheduled; they still wait for this grid's completion before touching memory
+  if (ep.attn) {
+    // the attention epilogue writes into the peer CTA's shared memory: both CTAs of the cluster must be running before
+    // either does (co-scheduling guarantees residency, not that the peer has started)
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
 
   if (warp == 0) {
     if (elect_one()) {
