@@ -119,6 +119,25 @@ def test_denoise_batch_independence_and_ragged_batches(models):
         assert maxabs(part, full[sl]) < 2e-5
 
 
+def test_denoise_multi_wave_tile_widths(W, models, engine):
+    """More rows than one wave of 128 x 64 tiles (B = 40 with CFG: 2 560 rows): the tile-width model switches the 512-wide
+    layers to 128-wide tiles (LayerNorm partials then come 4 per CTA). Rows must equal the small-batch run and the oracle."""
+    m = ClassifierFreeSampleModel(models["beatx_motionclip"])
+    B = 40
+    inp = synth.make_inputs(B, seed=19, variant="beatx_motionclip")
+    t = torch.full((B,), 480, dtype=torch.int64).cuda()
+    y = y_of(inp); y["scale"] = torch.ones(1) * 2.0
+    full = m(inp["noise"].cuda(), t, y)
+    sl = slice(37, 39)
+    sub = {k: v[sl] for k, v in inp.items()}
+    ys = y_of(sub); ys["scale"] = torch.ones(1) * 2.0
+    part = m(sub["noise"].cuda(), t[sl], ys)
+    assert maxabs(part, full[sl]) < 2e-5
+    yo = {k: sub[k] for k in ("audio", "word", "seed", "style_feature")}; yo["scale"] = torch.ones(1) * 2.0
+    ref = omdm.cfg_text(lambda a, b, c: omdm.mdm_forward(W["beatx_motionclip"], a, b, c, "beatx_motionclip"), sub["noise"], t[sl].cpu(), yo)
+    assert maxabs(full[sl], ref) < 1e-4
+
+
 def test_denoise_rejects_bad_arguments(models):
     m = models["beatx"]
     inp = synth.make_inputs(1, seed=1)
