@@ -81,7 +81,9 @@ inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bl
 }
 #ifdef __CUDACC__
 // Debug trace (st_debug_trace): CTA (0,0) thread 0 of every kernel stamps %globaltimer and a kernel id at entry.
-static __device__ unsigned long long* g_trace_buf = nullptr;   // per translation unit (no -rdc); [cap][2] = (ns, id); slot 0 = counter
+// In constant memory: every kernel reads this pointer at entry, and as a plain __device__ variable that read was an L2
+// round trip on the critical path of every launch (23 % of the trunk kernel's stall samples under ncu).
+static __constant__ unsigned long long* g_trace_buf = nullptr;   // per translation unit (no -rdc); [cap][2] = (ns, id); slot 0 = counter
 __device__ __forceinline__ void trace_stamp(int id, bool any_thread = false) {
   unsigned long long* t = g_trace_buf;
   if (t && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (any_thread || threadIdx.x == 0)) {
