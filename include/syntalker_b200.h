@@ -79,6 +79,8 @@ int st_set_graphs(int on);
 int st_set_pdl(int on);
 /* Debug: device buffer of >= 64 int64 receiving clock64() stamps of CTA (0,0) of every tcgen05 GEMM launch; NULL = off. */
 int st_debug_timeline(long long* dev_buf);
+/* Debug: only trunk-kernel launches with this N and K record the timeline (0, 0 = every launch). */
+int st_debug_timeline_select(int N, int K);
 /* Debug: device buffer of 120000 uint64; every kernel's first thread appends (%globaltimer ns, kernel id); slot 0 = count. NULL = off. */
 int st_debug_trace(unsigned long long* dev_buf);
 /* debug: timing-only variants of the tcgen05 GEMM main loop (results are garbage when flags != 0) */

@@ -238,7 +238,9 @@ extern "C" int st_set_engine(int engine) {
 extern "C" int st_get_engine(void) { return g_engine; }
 namespace st { extern long long* g_tc_dbg; extern int g_tc_probe; extern bool g_tc_fast; }
 extern "C" int st_debug_probe(int flags);
+namespace st { extern int g_tc_dbg_n, g_tc_dbg_k; }
 extern "C" int st_debug_timeline(long long* dev_buf) { st::g_tc_dbg = dev_buf; return ST_OK; }
+extern "C" int st_debug_timeline_select(int N, int K) { st::g_tc_dbg_n = N; st::g_tc_dbg_k = K; return ST_OK; }
 extern "C" int st_debug_trace(unsigned long long* dev_buf) {
   ST_TRY(st::set_trace_kernels(dev_buf));
   return st::set_trace_tc(dev_buf);

@@ -703,10 +703,6 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       pdl_wait();
       trace_stamp(1, true);
       if (dbg) dbg[1] = clock64();
-      if (ep.has_res) {
-        mbar_expect_tx(res_bar, NCH * FAST_BOX_F32);
-        for (int c = 0; c < NCH; ++c) tma_load_2d(res_tile + c * FAST_BOX_F32, &tmO, res_bar, n0 + c * 32, m0);
-      }
       int s = 0;
       uint32_t ph = 0;                       // ring pass parity
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -727,6 +723,12 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_4d(st, &tmA, &full_bar[s], cb * TC_BK, j * ep.dil - ep.pad, m0 / ep.T, 0);
           }
           if (dbg && kb < 16) dbg[8 + kb] = clock64();
+        }
+        // the residual tile is only needed by the epilogue: it is requested behind the first ring pass of operands, not
+        // in front of it (all 128 CTAs start at once, and the first K block's arrival is what the tensor pipe waits for)
+        if (ep.has_res && kb == pre - 1) {
+          mbar_expect_tx(res_bar, NCH * FAST_BOX_F32);
+          for (int c = 0; c < NCH; ++c) tma_load_2d(res_tile + c * FAST_BOX_F32, &tmO, res_bar, n0 + c * 32, m0);
         }
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
@@ -1034,10 +1036,18 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int j = 0; j < 32; ++j) { const float dd = x[j] - mj; qd += dd * dd; }
         if (row_ok) *reinterpret_cast<float2*>(ep.stats_out + ((long long)grow * 16 + blockIdx.x * NCH + c) * 2) = make_float2(mj, qd);
       }
+      // Results leave as soon as a staging box is complete, not at the end of the epilogue: the TMA store of a box drains
+      // (all 128 CTAs write 4-12 MB at once) while the planes of the same chunk / the next chunk are still being computed.
       if (ep.has_out) {
         const uint32_t orow = out_base + (uint32_t)(c * FAST_BOX_F32 + r * 128);
 #pragma unroll
         for (int q = 0; q < 8; ++q) sts128(orow + (((uint32_t)q ^ sw) << 4), make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
+        fence_proxy_async();                                          // staging writes -> visible to the TMA engine
+        asm volatile("bar.sync %0, 128;" ::"r"(6 + cpart) : "memory");   // the four warps that own fp32 box c
+        if (lg == 0 && lane == 0) {
+          tma_store_2d(&tmO, out_base + c * FAST_BOX_F32, n0 + c * 32, m0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
       if (ep.has_planes) {
         const uint32_t prow = pl_base + (uint32_t)((c >> 1) * FAST_BOX_PL + r * 128);
@@ -1050,19 +1060,18 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           sts128u(prow + off, make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
           sts128u(prow + TC_A_PLANE + off, make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7])));
         }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");                // both column halves of plane box c / 2 (all eight warps)
+        if (warp == 4 && lane == 0) {
+          tma_store_3d(&tmP, pl_base + (c >> 1) * FAST_BOX_PL, n0 + (c >> 1) * 64, m0, 0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
     }
     tc_fence_before();
-    fence_proxy_async();                                            // staging writes -> visible to the TMA engine
-    asm volatile("bar.sync 1, 256;" ::: "memory");                  // the eight epilogue warps
     if (dbg && threadIdx.x == 64) dbg[6] = clock64();
-    if (warp == 2 && elect_one()) {
-      if (ep.has_out)
-        for (int c = 0; c < NCH; ++c) tma_store_2d(&tmO, out_base + c * FAST_BOX_F32, n0 + c * 32, m0);
-      if (ep.has_planes)
-        for (int b = 0; b < (BN >> 6); ++b) tma_store_3d(&tmP, pl_base + b * FAST_BOX_PL, n0 + b * 64, m0, 0);
-      tma_store_commit_wait();
-    }
+    // the staging memory must outlive the TMA engine's reads: each issuing thread waits for its own bulk groups
+    if (lg == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (dbg && threadIdx.x == 64) dbg[4] = clock64();
     }
   }
@@ -1202,6 +1211,7 @@ static std::unordered_map<const float*, WPlanes> g_wplanes;
 static std::mutex g_w_mu;
 long long* g_tc_dbg = nullptr;  // set by st_debug_timeline
 int g_tc_probe = 0;             // set by st_debug_probe
+int g_tc_dbg_n = 0, g_tc_dbg_k = 0;   // st_debug_timeline_select: only launches with this N, K record the timeline (0 = all)
 bool g_tc_fast = true;          // trunk kernel for the shapes it takes (st_debug_probe bit 16 turns it off)
 static Arena g_scratch;          // activation planes of the GEMM in flight (stream order serialises reuse)
 
@@ -1437,7 +1447,7 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   ep.ln_stats = p.ln_stats; ep.stats_out = p.stats_out;
   ep.scale = w->inv_scale / kActScale;
   ep.act = p.act; ep.has_res = p.res ? 1 : 0; ep.has_out = p.out ? 1 : 0; ep.has_planes = p.o_planes ? 1 : 0;
-  ep.M = p.M; ep.N = p.N; ep.dbg = g_tc_dbg; ep.probe = g_tc_probe; ep.attn = p.attn;
+  ep.M = p.M; ep.N = p.N; ep.dbg = (g_tc_dbg_n == 0 || (g_tc_dbg_n == p.N && g_tc_dbg_k == p.K)) ? g_tc_dbg : nullptr; ep.probe = g_tc_probe; ep.attn = p.attn;
   ep.mode = cmode; ep.T = p.Lout; ep.kb_per_tap = cmode == 0 ? 1 : p.C / TC_BK; ep.dil = p.dil; ep.pad = p.pad;
   ep.planes_relu = p.o_planes_relu;
   static bool attr = false;
