@@ -768,7 +768,11 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
   // captures one step into a CUDA graph; from then on every step is one graph launch.  Capture and replay run
   // on the model's own stream (the caller's may be the legacy default stream, which cannot capture), fenced
   // against the caller's stream with events on both sides.
-  const std::string key = plan_key(pl, B, sc->mode);
+  // G consecutive steps per graph (the largest of 50, 25, 20, 10, 5, 4, 2, 1 that divides S): kernels of consecutive steps
+  // inside one graph hand over through programmatic edges like the kernels of one step; a graph launch boundary costs ~4 us
+  int G = 1;
+  for (int c : {50, 25, 20, 10, 5, 4, 2}) if (sc->S % c == 0) { G = c; break; }
+  const std::string key = plan_key(pl, B, sc->mode) + " G" + std::to_string(G);
   cudaGraphExec_t exec = nullptr;
   const bool graphs_ok = g_use_graphs && !st::profiling();
   cudaStream_t ls = s;
@@ -787,7 +791,8 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
       cudaGraph_t graph = nullptr;
       const int64_t l0 = g_launches;
       ST_CHECK_CUDA(cudaStreamBeginCapture(ls, cudaStreamCaptureModeRelaxed));
-      const int r = one_step(m, pl, sp, B, ls);
+      int r = ST_OK;
+      for (int i = 0; i < G && r == ST_OK; ++i) r = one_step(m, pl, sp, B, ls);
       m->graph_nodes[key] = g_launches - l0;     // kernels per replay; capturing itself executed nothing
       g_launches = l0;
       cudaError_t ce = cudaStreamEndCapture(ls, &graph);
@@ -798,9 +803,10 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
       m->graphs[key] = exec;
     }
   }
-  for (int k = sc->S - 1; k >= 0; --k) {
-    if (exec) { ST_CHECK_CUDA(cudaGraphLaunch(exec, ls)); g_launches += m->graph_nodes[key]; }
-    else ST_TRY(one_step(m, pl, sp, B, ls));
+  if (exec) {
+    for (int k = 0; k < sc->S / G; ++k) { ST_CHECK_CUDA(cudaGraphLaunch(exec, ls)); g_launches += m->graph_nodes[key]; }
+  } else {
+    for (int k = sc->S - 1; k >= 0; --k) ST_TRY(one_step(m, pl, sp, B, ls));
   }
   if (ls != s) {
     ST_CHECK_CUDA(cudaEventRecord(m->ev_out, ls));
