@@ -87,3 +87,23 @@ def test_layernorm_folded_into_linear():
         ref = F.linear(F.layer_norm(x, (512,), W[p + "norm2.weight"], W[p + "norm2.bias"], 1e-5), W[p + "mlp.fc1.weight"], W[p + "mlp.fc1.bias"])
         got = rstd * (x @ P[f"blk.{i}.fc1.wg"].t() - mu * P[f"blk.{i}.fc1.s"]) + P[f"blk.{i}.fc1.c"]
         assert float((ref - got).abs().max()) < 2e-5
+
+
+def test_gelu_single_branch_erf_table_and_error():
+    """The GELU of the trunk kernel's epilogue uses a fitted single-branch erf (tests/fit_erf.py): the table compiled into the
+    kernel is the fitted one, and its fp32 evaluation is as close to float64 as the reference's own fp32 nn.GELU."""
+    import os, re, sys
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import fit_erf
+    src = open(os.path.join(here, "..", "syntalker_b200", "csrc", "st_gemm_tc.cu")).read()
+    m = re.search(r"kErfQ\[11\] = \{([^}]*)\}", src)
+    table = [float(v.strip().rstrip("f")) for v in m.group(1).split(",")]
+    assert table == fit_erf.COEF
+    assert np.allclose(fit_erf.fit(), fit_erf.COEF, rtol=0, atol=1e-8)
+    max_abs, _ = fit_erf.errors()
+    assert max_abs < 8e-7
+    x = torch.linspace(-10, 10, 200001)
+    ref64 = x.double() * 0.5 * (1 + torch.erf(x.double() / 2 ** 0.5))
+    assert float((torch.nn.functional.gelu(x).double() - ref64).abs().max()) > max_abs      # the reference's fp32 GELU is no closer
