@@ -71,6 +71,8 @@ class ClockSampler(threading.Thread):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import atexit
+            atexit.register(lambda p=self.proc: p.poll() is None and p.kill())      # never leave the sampler behind
             for line in self.proc.stdout:
                 c = [x.strip() for x in line.split(",")]
                 if len(c) >= 8:
