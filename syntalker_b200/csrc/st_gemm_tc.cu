@@ -1232,7 +1232,10 @@ long long* g_tc_dbg = nullptr;  // set by st_debug_timeline
 int g_tc_probe = 0;             // set by st_debug_probe
 int g_tc_dbg_n = 0, g_tc_dbg_k = 0;   // st_debug_timeline_select: only launches with this N, K record the timeline (0 = all)
 bool g_tc_fast = true;          // trunk kernel for the shapes it takes (st_debug_probe bit 16 turns it off)
-static Arena g_scratch;          // activation planes of the GEMM in flight (stream order serialises reuse)
+// Activation planes of a GEMM whose operand is still fp32: one arena PER STREAM.  Stream order serialises the reuse on one
+// stream; two handles driven on two streams at once (the library is re-entrant per handle) must not share it.
+static std::map<cudaStream_t, Arena> g_scratch;
+static std::mutex g_scratch_mu;
 
 static int split_launch(const float* a, int lda, int M, int K, int Kp, float scale, int relu, __half* planes, cudaStream_t s) {
   const long long n = (long long)M * (Kp >> 2);
@@ -1495,14 +1498,19 @@ int gemm_tc(const GemmP& p, cudaStream_t s) {
     // operand still fp32: split it into the scratch planes first (stream order serialises reuse of the scratch)
     pstride = (rows + 16) * Ka;                           // slack rows keep the strided flat view inside the buffer
     const size_t need = (size_t)2 * pstride * sizeof(__half) + 1024;
-    if (need > g_scratch.cap) {
+    Arena* sc = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(g_scratch_mu);
+      sc = &g_scratch[s];                                 // std::map nodes are stable: the pointer survives later insertions
+    }
+    if (need > sc->cap) {
       cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
       cudaStreamIsCapturing(s, &cap);
       if (cap != cudaStreamCaptureStatusNone) { set_error("split scratch must be sized before graph capture"); return ST_ESTATE; }
-      ST_TRY(g_scratch.reserve(need + need / 2));
-      ST_CHECK_CUDA(cudaMemsetAsync(g_scratch.base, 0, g_scratch.cap, s));
+      ST_TRY(sc->reserve(need + need / 2));
+      ST_CHECK_CUDA(cudaMemsetAsync(sc->base, 0, sc->cap, s));
     }
-    __half* sp = reinterpret_cast<__half*>(g_scratch.base);
+    __half* sp = reinterpret_cast<__half*>(sc->base);
     const long long n4 = rows * (Ka >> 2);
 launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, s, p.A, p.lda, (int)rows, Ka, Ka, kActScale, p.a_relu, sp, pstride);
     ST_CHECK_LAUNCH();

@@ -447,6 +447,41 @@ def test_host_pipeline_equals_device_path(models, vqs, engine):
     assert torch.equal(p0, pose_d.cpu()) and torch.equal(p1, pose_d2.cpu())
 
 
+def test_two_handles_on_two_streams_are_independent(W, vq_w, engine):
+    """the library is re-entrant per handle and stream-ordered. Two model / decoder handle sets driven on two
+    streams at once (no synchronisation between them) must each return, bit for bit, what they return alone."""
+    B = 8
+    d10 = create_gaussian_diffusion(timestep_respacing="ddim10")
+    sets = []
+    for seed in (91, 92):
+        m = ClassifierFreeSampleModel(MDM(None).load_state_dict(W["beatx_motionclip"]))
+        v = [RVQVAE(None, d).load_state_dict(vq_w[d]) for d in synth.PART_DIMS_BEATX]
+        inp = synth.make_inputs(B, seed=seed, variant="beatx_motionclip")
+        d_in = {k: inp[k].cuda().contiguous() for k in ("audio", "word", "seed", "noise", "style_feature")}
+        y = {"scale": torch.ones(1) * 2.0, "style_feature": d_in["style_feature"]}
+        sets.append((Window330(m, d10, *v, B=B, use_ddim=True), d_in, y))
+    run = lambda s: s[0].run_device(s[1]["audio"], s[1]["word"], s[1]["seed"], s[1]["noise"], y=s[2])
+    alone = []
+    for s in sets:
+        for _ in range(3):                                    # eager, graph capture, graph replay
+            out = run(s)
+        torch.cuda.synchronize()
+        alone.append([t.clone() for t in out])
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream())
+    outs = [None, None]
+    for _ in range(3):
+        for k in (0, 1):
+            with torch.cuda.stream(streams[k]):
+                outs[k] = run(sets[k])
+    torch.cuda.synchronize()
+    for k in (0, 1):
+        for a, b in zip(alone[k], outs[k]):
+            assert torch.equal(a, b)
+    assert not torch.equal(outs[0][0], outs[1][0])
+
+
 # ---- 6. end to end through the host-buffer C-ABI call ----------------------------------------------------------------
 def test_e2e_config1_vs_golden(golden, models, vqs, engine):
     g = golden("e2e_config1")
