@@ -34,10 +34,14 @@ E_COND, E_TRUNK, E_DEC = 4.677e9, 1.2342e9 + 0.0336e9, 3.899e9
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, averaged over the launches of the
-    committed `ncu --set full` capture (profiles/r1b_ncu_gemm_tc_fast_full.csv; cold-cache replays). None if absent."""
+    committed `ncu --set full` capture (profiles/r1c_ncu_gemm_tc_fast_full.csv, else the r1b one; cold-cache replays).
+    None if absent."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r1b_ncu_gemm_tc_fast_full.csv")
-    if not os.path.exists(p):
+    for name in ("r1c_ncu_gemm_tc_fast_full.csv", "r1b_ncu_gemm_tc_fast_full.csv"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            break
+    else:
         return None
     rows = list(csv.reader(open(p)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -315,6 +319,57 @@ def main():
                     "ms_per_step": float(toth.item()) / args.steps, "ms_per_step_blocking_call": serial_ms,
                     "pipeline": "two window batches in flight (begin / wait on two staging sets): H2D of step i+1 and D2H of step i-1 overlap the computation of step i"},
             "roofline": roof}
+    # ---- extra (not the headline): TWO window batches of the same configuration in flight on two handle sets / two streams.
+    # Every layer of the loop is one wave of 128 CTAs on 148 SMs and a quarter of a layer's time is hand-over between
+    # dependent kernels; a second, independent window batch fills those gaps (tests/concurrency_probe.py).  `value` and
+    # `e2e` above stay one batch at a time -- this object reports what a caller with >= 64 clips queued gets.
+    if world == 1 and not os.environ.get("ST_NO_TWO_IN_FLIGHT"):
+        try:
+            model_b = MDM(None).load_state_dict(synth.mdm_state_dict("beatx_motionclip", seed=0))
+            vqs_b = [RVQVAE(None, d).load_state_dict(synth.rvq_state_dict(d, seed=0)) for d in synth.PART_DIMS_BEATX]
+            win_b = Window330(ClassifierFreeSampleModel(model_b), diff, *vqs_b, B=B, use_ddim=True)
+            outs_b = tuple(torch.empty_like(t) for t in outs)
+            sets = [(win, outs), (win_b, outs_b)]
+            streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+            main_s = torch.cuda.current_stream()
+
+            def two(n, host):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for st in streams:
+                    st.wait_stream(main_s)
+                for i in range(n):
+                    w_i, o_i = sets[i % 2]
+                    with torch.cuda.stream(streams[i % 2]):
+                        flush.zero_()
+                        if host:
+                            slot = (i // 2) % 2                        # both staging sets of both handle sets: four batches queued
+                            if i >= 4:
+                                w_i.wait(slot)
+                            w_i.begin(slot, pinned["audio"], pinned["word"], pinned["seed"], pinned["noise"], y=y_host)
+                        else:
+                            w_i.run_device(d_in["audio"], d_in["word"], d_in["seed"], d_in["noise"], y=y_dev, out=o_i)
+                if host:
+                    for i in range(max(0, n - 4), n):
+                        sets[i % 2][0].wait((i // 2) % 2)
+                for st in streams:
+                    main_s.wait_stream(st)
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1)
+
+            n2 = max(2, args.steps + args.steps % 2)
+            two(4, False)
+            t_dev = two(n2, False)
+            same = bool(torch.equal(outs[0], outs_b[0]))               # same inputs, same weights: the two handle sets must agree bit for bit
+            two(4, True)
+            t_host = two(n2, True)
+            line["two_in_flight"] = {"value": B * 128 * n2 / (t_dev / 1000), "e2e": B * 128 * n2 / (t_host / 1000), "unit": UNIT, "steps": n2,
+                                     "ms_per_step": t_dev / n2, "e2e_ms_per_step": t_host / n2, "results_bitwise_equal": same,
+                                     "what": "two independent 32-clip window batches in flight (two handle sets, two streams); not the headline"}
+        except Exception as e:                                         # the extra must never cost the headline line
+            line["two_in_flight"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cpu_reference_sample(2, 1, threads)

@@ -107,12 +107,17 @@ int profile_end(double* ms, double* flops, int64_t* n) {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   const int64_t l0 = g_launches;
+  // the replay stream's split scratch is sized for the largest fp32 operand before the capture starts
+  size_t need = 0;
+  for (const GemmP& p : g_prof_list)
+    if (g_engine == ST_ENGINE_TC && tc_supported(p)) need = std::max(need, tc_scratch_need(p));
+  if (need) ST_TRY(tc_scratch_reserve(s, need));
   ST_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
   int r = ST_OK;
   for (const GemmP& p : g_prof_list) { r = gemm_dispatch(p, s); if (r != ST_OK) break; }
   cudaError_t ce = cudaStreamEndCapture(s, &graph);
   g_launches = l0;
-  if (r != ST_OK) { if (graph) cudaGraphDestroy(graph); cudaStreamDestroy(s); (void)cudaGetLastError(); return r; }
+  if (r != ST_OK) { if (graph) cudaGraphDestroy(graph); tc_scratch_release(s); cudaStreamDestroy(s); (void)cudaGetLastError(); return r; }
   ST_CHECK_CUDA(ce);
   ST_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
   cudaEvent_t e0, e1;
@@ -127,7 +132,7 @@ int profile_end(double* ms, double* flops, int64_t* n) {
   ST_CHECK_CUDA(cudaEventElapsedTime(&t, e0, e1));
   if (ms) *ms = t;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); cudaStreamDestroy(s);
+  cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); tc_scratch_release(s); cudaStreamDestroy(s);
   g_prof_list.clear();
   return ST_OK;
 }
@@ -314,8 +319,8 @@ extern "C" void st_model_destroy(st_model* m) {
   if (!m) return;
   cudaDeviceSynchronize();
   for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
-  if (m->loop_stream) cudaStreamDestroy(m->loop_stream);
-  if (m->dec_stream[0]) { for (int k = 0; k < 2; ++k) { cudaStreamDestroy(m->dec_stream[k]); cudaEventDestroy(m->ev_join[k]); } cudaEventDestroy(m->ev_fork); }
+  if (m->loop_stream) { tc_scratch_release(m->loop_stream); cudaStreamDestroy(m->loop_stream); }
+  if (m->dec_stream[0]) { for (int k = 0; k < 2; ++k) { tc_scratch_release(m->dec_stream[k]); cudaStreamDestroy(m->dec_stream[k]); cudaEventDestroy(m->ev_join[k]); } cudaEventDestroy(m->ev_fork); }
   if (m->ev_in) cudaEventDestroy(m->ev_in);
   if (m->ev_out) cudaEventDestroy(m->ev_out);
   m->w.release(); m->ws.release(); m->io.release(); m->longws.release();
@@ -1348,7 +1353,7 @@ extern "C" int st_bench_gemm(int M, int N, int K, int engine, int reps, const fl
   float t = 0.f;
   cudaEventElapsedTime(&t, e0, e1);
   *ms_per_launch = (double)t / reps;
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); cudaStreamDestroy(s);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); tc_scratch_release(s); cudaStreamDestroy(s);
   if (tc) { tc_forget_weights(W); cudaFree(planes); }
   return ST_OK;
 }

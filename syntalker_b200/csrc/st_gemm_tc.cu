@@ -1484,6 +1484,38 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   return ST_OK;
 }
 
+// bytes of split scratch a GEMM needs (0: its operand already arrives as planes)
+size_t tc_scratch_need(const GemmP& p) {
+  if (p.a_planes) return 0;
+  const int mode = conv_mode(p);
+  const int Ka = mode == 0 ? p.K : p.C;
+  const long long rows = mode == 0 ? p.M : (long long)(p.M / p.Lout) * p.Lin;
+  return (size_t)2 * (rows + 16) * Ka * sizeof(__half) + 1024;
+}
+// the stream's arena, grown to `need` (never during graph capture: captured launches keep the pointer)
+int tc_scratch_reserve(cudaStream_t s, size_t need, Arena** out) {
+  Arena* sc = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    sc = &g_scratch[s];                                   // std::map nodes are stable: the pointer survives later insertions
+  }
+  if (need > sc->cap) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);
+    if (cap != cudaStreamCaptureStatusNone) { set_error("split scratch must be sized before graph capture"); return ST_ESTATE; }
+    ST_TRY(sc->reserve(need + need / 2));
+    ST_CHECK_CUDA(cudaMemsetAsync(sc->base, 0, sc->cap, s));
+  }
+  if (out) *out = sc;
+  return ST_OK;
+}
+// a stream that is about to be destroyed gives its arena back (stream handles are reused by the driver)
+void tc_scratch_release(cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  auto it = g_scratch.find(s);
+  if (it != g_scratch.end()) { it->second.release(); g_scratch.erase(it); }
+}
+
 int gemm_tc(const GemmP& p, cudaStream_t s) {
   if (!tc_supported(p)) { set_error("gemm_tc: unsupported problem"); return ST_EUNSUPPORTED; }
   WPlanes* w = nullptr;
@@ -1497,19 +1529,8 @@ int gemm_tc(const GemmP& p, cudaStream_t s) {
   if (!planes) {
     // operand still fp32: split it into the scratch planes first (stream order serialises reuse of the scratch)
     pstride = (rows + 16) * Ka;                           // slack rows keep the strided flat view inside the buffer
-    const size_t need = (size_t)2 * pstride * sizeof(__half) + 1024;
     Arena* sc = nullptr;
-    {
-      std::lock_guard<std::mutex> lk(g_scratch_mu);
-      sc = &g_scratch[s];                                 // std::map nodes are stable: the pointer survives later insertions
-    }
-    if (need > sc->cap) {
-      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(s, &cap);
-      if (cap != cudaStreamCaptureStatusNone) { set_error("split scratch must be sized before graph capture"); return ST_ESTATE; }
-      ST_TRY(sc->reserve(need + need / 2));
-      ST_CHECK_CUDA(cudaMemsetAsync(sc->base, 0, sc->cap, s));
-    }
+    ST_TRY(tc_scratch_reserve(s, tc_scratch_need(p), &sc));
     __half* sp = reinterpret_cast<__half*>(sc->base);
     const long long n4 = rows * (Ka >> 2);
 launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, s, p.A, p.lda, (int)rows, Ka, Ka, kActScale, p.a_relu, sp, pstride);

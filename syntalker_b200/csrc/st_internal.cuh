@@ -167,6 +167,11 @@ int wav_first(const float* audio, const float* w1, const float* b1, const float*
 int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStream_t s);   // qkv [nseq*32,1536] -> out [nseq*32,512]
 void tc_forget_weights(const float* W);
 int tc_split(const float* a, int lda, int M, int K, __half* planes, cudaStream_t s);   // fp32 -> hi/lo planes of a*kActScale
+// split scratch of the tcgen05 engine: one arena per stream (a GEMM whose operand is still fp32 splits it there first)
+struct Arena;
+size_t tc_scratch_need(const GemmP& p);
+int tc_scratch_reserve(cudaStream_t s, size_t need, Arena** out = nullptr);
+void tc_scratch_release(cudaStream_t s);
 int advance_loop(LoopState* ls, cudaStream_t s);
 int init_loop(LoopState* ls, int S, const float* tape, cudaStream_t s);
 struct TokensInP {
