@@ -160,6 +160,7 @@ struct st_model {
   ConvW wav[6][3];   // conv1, conv2, ds
   const float *word_table = nullptr, *w_cm = nullptr, *w_seed = nullptr, *bias_all = nullptr, *w_x = nullptr, *vt_table = nullptr;
   const float *w_style = nullptr, *null_sv = nullptr, *rope_cos = nullptr, *rope_sin = nullptr, *out_w = nullptr, *out_b = nullptr;
+  const float *w_xo = nullptr, *c_xo = nullptr;   // W_x W_out [512,512] and W_x b_out [512] (optional: z recursion of deterministic DDIM)
   BlkW blk[8];
   // constants for audio-masked evaluations (h3d): computed lazily
   float* cst_null = nullptr;   // [32,512]
@@ -202,6 +203,7 @@ static bool g_rank_simt = false;
 static bool g_decode_streams = true;   // st_debug_probe bit 256: decode the three body parts one after the other
 static bool g_wav_planes = true;   // st_debug_probe bit 128: WavEncoder with fp32 activations and a split pass per conv
 static bool g_fused_attn = true;   // st_debug_probe bit 32 turns the fused qkv + attention kernel off
+static bool g_zrec = true;         // st_debug_probe bit 512 turns the z recursion of deterministic DDIM off (state kept in x space)
 
 namespace st { extern int g_tc_probe; extern bool g_tc_fast; }
 extern "C" int st_debug_probe(int flags) {
@@ -211,6 +213,7 @@ extern "C" int st_debug_probe(int flags) {
   g_rank_simt = (flags & 64) != 0;
   g_decode_streams = !(flags & 256);
   g_wav_planes = !(flags & 128);
+  g_zrec = !(flags & 512);
   return ST_OK;
 }
 
@@ -284,6 +287,10 @@ static int model_resolve(st_model* m) {
   m->rope_sin = m->w.get("rope_sin", 32 * 32, &err);
   m->out_w = m->w.get("out.w", 1536 * 512, &err);
   m->out_b = m->w.get("out.b", 1536, &err);
+  if (m->w.dev.count("w_xo") && m->w.dev.count("c_xo")) {
+    m->w_xo = m->w.get("w_xo", 512 * 512, &err);
+    m->c_xo = m->w.get("c_xo", 512, &err);
+  }
   m->style_dim = m->variant == ST_VARIANT_BEATX_MOTIONCLIP ? 512 : m->variant == ST_VARIANT_H3D ? 256 : 0;
   if (m->style_dim) m->w_style = m->w.get("w_style", 512 * m->style_dim, &err);
   if (m->variant == ST_VARIANT_H3D) m->null_sv = m->w.get("null_sv", 512, &err);
@@ -594,18 +601,27 @@ static int make_plan(const st_model* m, const st_guidance* g, Plan* pl) {
 // ---- one trunk pass over the state m->xs for all planned evaluations -> m->O ---------------------------
 // SIMT engine: every activation stays fp32.  tcgen05 engine: LayerNorm, attention and the GELU epilogue emit the
 // fp16 hi/lo planes the next GEMM streams with TMA; only the residual stream, QKV and the outputs stay fp32.
-static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, int t_scalar, bool loop, cudaStream_t s) {
+// z = x . W_x^T for the state m->xs (tcgen05 engine: from the state planes m->xs_p)
+static int trunk_input(st_model* m, int B, cudaStream_t s) {
+  const int rows = B * 32;
+  GemmP pz = linear(m->xs, rows, 1536, m->w_x, nullptr, m->z, 512);
+  if (st_get_engine() == ST_ENGINE_TC) { pz.a_planes = m->xs_p; pz.a_plane_stride = (long long)rows * 1536; }
+  return gemm(pz, s);
+}
+
+// zstep (sampling loop of deterministic DDIM on the tcgen05 engine): the step starts from z (tokens_step applies the
+// recursion of the previous step's update) and ends in P = X . W_xo^T instead of the output GEMM unless it is the last
+static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, int t_scalar, bool loop, cudaStream_t s,
+                     bool zstep = false, bool last = true, const StepP* mix = nullptr) {
   const int rows = B * 32, R = pl.nE * rows;
   const bool tc = (st_get_engine() == ST_ENGINE_TC);
   const long long ps512 = (long long)R * 512, ps1024 = (long long)R * 1024;
-  GemmP pz = linear(m->xs, rows, 1536, m->w_x, nullptr, m->z, 512);
-  if (tc) {
-    // the state lives in the model's own planes (a captured step graph must not point into the engine's global split
+  if (!zstep) {
+    // the state lives in the model's own planes (a captured step graph must not point into the engine's split
     // scratch); inside the sampling loop step_update keeps them current, a single evaluation splits here
-    if (!loop) ST_TRY(tc_split(m->xs, 1536, rows, 1536, m->xs_p, s));
-    pz.a_planes = m->xs_p; pz.a_plane_stride = (long long)rows * 1536;
+    if (tc && !loop) ST_TRY(tc_split(m->xs, 1536, rows, 1536, m->xs_p, s));
+    ST_TRY(trunk_input(m, B, s));
   }
-  ST_TRY(gemm(pz, s));
   TokensInP tp;
   tp.z = m->z; tp.vt_table = m->vt_table; tp.t_dev = t_dev; tp.t_scalar = t_scalar; tp.g2 = m->g2;
   tp.ls = loop ? m->loop : nullptr; tp.t_model_dev = m->t_model_dev;
@@ -618,7 +634,14 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
     if (sv >= 0 && sv <= 2) tp.sv[e] = m->sv[sv];
     else if (sv == 3) { tp.sv[e] = m->null_sv; tp.sv_bcast[e] = 1; }
   }
-  ST_TRY(tokens_in(tp, s));
+  if (zstep) {
+    TokensStepP ts;
+    ts.t = tp; ts.z_rw = m->z; ts.P = m->H; ts.c_xo = m->c_xo; ts.coef_dev = m->coef_dev;
+    ts.cfg_mode = mix->cfg_mode; ts.scale = mix->scale; ts.scale2 = mix->scale2; ts.ls_adv = m->loop;
+    ST_TRY(tokens_step(ts, s));
+  } else {
+    ST_TRY(tokens_in(tp, s));
+  }
   for (int i = 0; i < 8; ++i) {
     const BlkW& b = m->blk[i];
     if (tc) {
@@ -664,6 +687,12 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
     GemmP p2 = linear(m->G, R, 1024, b.fc2w, b.fc2b, m->X, 512);
     p2.res = m->X; p2.res_mode = RES_POST; p2.ldr = 512;
     ST_TRY(gemm(p2, s));
+  }
+  if (zstep && !last) {
+    // the next step only needs W_x x_{k-1}: P = X (W_x W_out)^T per evaluation; tokens_step mixes and applies the update
+    GemmP px = linear(m->X, R, 512, m->w_xo, nullptr, m->H, 512);
+    px.a_planes = m->X_p; px.a_plane_stride = ps512;
+    return gemm(px, s);
   }
   GemmP po = linear(m->X, R, 512, m->out_w, m->out_b, m->O, 1536);
   if (tc) { po.a_planes = m->X_p; po.a_plane_stride = ps512; }
@@ -738,8 +767,9 @@ static std::string plan_key(const Plan& pl, int B, int mode) {
 
 // one diffusion step: trunk for every planned evaluation, CFG mix + sampler update, k -= 1  (all step-dependent
 // values are read from device memory, so the same launch sequence -- or its captured graph -- serves every step)
-static int one_step(st_model* m, const Plan& pl, const StepP& sp0, int B, cudaStream_t s) {
-  ST_TRY(run_trunk(m, pl, B, nullptr, 0, true, s));
+static int one_step(st_model* m, const Plan& pl, const StepP& sp0, int B, cudaStream_t s, bool zstep = false, bool last = true) {
+  ST_TRY(run_trunk(m, pl, B, nullptr, 0, true, s, zstep, last, &sp0));
+  if (zstep && !last) return ST_OK;   // the update is applied to z by the next step's tokens_step
   StepP sp = sp0;
   sp.xs = m->xs; sp.eps = nullptr; sp.ls = m->loop; sp.coef_dev = m->coef_dev;
   sp.xs_planes = st_get_engine() == ST_ENGINE_TC ? m->xs_p : nullptr;
@@ -777,7 +807,14 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
   // inside one graph hand over through programmatic edges like the kernels of one step; a graph launch boundary costs ~4 us
   int G = 1;
   for (int c : {50, 25, 20, 10, 5, 4, 2}) if (sc->S % c == 0) { G = c; break; }
-  const std::string key = plan_key(pl, B, sc->mode) + " G" + std::to_string(G);
+  // Deterministic DDIM on the tcgen05 engine keeps the loop in token space: x_{k-1} = alpha x0_hat + beta x_k is linear and the
+  // next step only needs W_x x_{k-1}, so between steps ONE 512 x 512 GEMM (W_x W_out, folded by the packer) replaces the
+  // 512 -> 1536 output GEMM, the state update and the 1536 -> 512 input GEMM; the state itself is formed once, by the last
+  // step (alpha_bar_prev = 1: x <- x0_hat).  The last step differs from the others, so a captured graph must hold the whole loop.
+  const bool zrec = g_zrec && st_get_engine() == ST_ENGINE_TC && sc->mode == ST_MODE_DDIM && !any_sigma && m->w_xo &&
+                    pl.cfg_mode != ST_CFG_BODYPART && (G == sc->S || !g_use_graphs);
+  if (zrec) ST_TRY(trunk_input(m, B, s));
+  const std::string key = plan_key(pl, B, sc->mode) + " G" + std::to_string(G) + (zrec ? " z" : "");
   cudaGraphExec_t exec = nullptr;
   const bool graphs_ok = g_use_graphs && !st::profiling();
   cudaStream_t ls = s;
@@ -797,7 +834,7 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
       const int64_t l0 = g_launches;
       ST_CHECK_CUDA(cudaStreamBeginCapture(ls, cudaStreamCaptureModeRelaxed));
       int r = ST_OK;
-      for (int i = 0; i < G && r == ST_OK; ++i) r = one_step(m, pl, sp, B, ls);
+      for (int i = 0; i < G && r == ST_OK; ++i) r = one_step(m, pl, sp, B, ls, zrec, i == G - 1);
       m->graph_nodes[key] = g_launches - l0;     // kernels per replay; capturing itself executed nothing
       g_launches = l0;
       cudaError_t ce = cudaStreamEndCapture(ls, &graph);
@@ -811,7 +848,7 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
   if (exec) {
     for (int k = 0; k < sc->S / G; ++k) { ST_CHECK_CUDA(cudaGraphLaunch(exec, ls)); g_launches += m->graph_nodes[key]; }
   } else {
-    for (int k = sc->S - 1; k >= 0; --k) ST_TRY(one_step(m, pl, sp, B, ls));
+    for (int k = sc->S - 1; k >= 0; --k) ST_TRY(one_step(m, pl, sp, B, ls, zrec, k == 0));
   }
   if (ls != s) {
     ST_CHECK_CUDA(cudaEventRecord(m->ev_out, ls));

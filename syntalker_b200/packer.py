@@ -129,6 +129,14 @@ def pack_mdm(sd: Dict[str, torch.Tensor], variant: str | None = None) -> Dict[st
             out[f"blk.{i}.qkv.{suf}p"] = out[f"blk.{i}.qkv.{suf}"][torch.from_numpy(perm)].contiguous()
     out["out.w"] = sd["output_process.poseFinal.weight"].detach().cpu().float().contiguous()
     out["out.b"] = sd["output_process.poseFinal.bias"].detach().cpu().float().contiguous()
+    # ---- deterministic DDIM keeps the loop in token space ("z recursion") ----
+    # x_{k-1} = a_k x0_hat + b_k x_k is linear (gaussian_diffusion.py:772-790 with sigma = 0), x0_hat = W_out h + b_out per
+    # evaluation (denoiser.py:287-301) and the next step only needs W_x x_{k-1}:
+    #   W_x x_{k-1} = a_k (W_x W_out) h_mix + a_k W_x b_out + b_k (W_x x_k)
+    # so between steps one 512 x 512 GEMM replaces the 512 -> 1536 output GEMM, the state update and the 1536 -> 512 input GEMM.
+    Wx64 = P @ Wb @ Wpe
+    out["w_xo"] = _t32(Wx64 @ _f64(sd["output_process.poseFinal.weight"]))
+    out["c_xo"] = _t32(Wx64 @ _f64(sd["output_process.poseFinal.bias"]))
     return out
 
 

@@ -33,17 +33,20 @@ def cond(P, audio, word, seed, null_audio=False):
     return cst, g2
 
 
-def trunk(P, x, t, cst, g2, sv=None):
-    """x [B,1536,1,32] -> model output [B,1536,1,32] for one evaluation."""
-    B = x.shape[0]
-    xs = x[:, :, 0, :].permute(0, 2, 1)                                            # [B,32,1536]
-    z = xs @ P["w_x"].t() + P["vt_table"][t][:, None, :] + cst + g2[:, None, :]
+def tokens(P, z, t, cst, g2, sv=None):
+    """z = W_x x_t [B,32,512] -> rotary-embedded tokens (the conditioning terms are step-invariant)."""
+    B = z.shape[0]
+    z = z + P["vt_table"][t][:, None, :] + cst + g2[:, None, :]
     if sv is not None:
         z = z + sv[:, None, :]
     zz = z.reshape(B, 32, 8, 64)
     cos, sin = P["rope_cos"][None, :, None, :], P["rope_sin"][None, :, None, :]
     x1, x2 = zz[..., :32], zz[..., 32:]
-    h = torch.cat([x1 * cos - x2 * sin, x2 * cos + x1 * sin], dim=-1).reshape(B, 32, 512)
+    return torch.cat([x1 * cos - x2 * sin, x2 * cos + x1 * sin], dim=-1).reshape(B, 32, 512)
+
+
+def blocks(P, h):
+    B = h.shape[0]
     for i in range(8):
         p = f"blk.{i}."
         a = F.layer_norm(h, (512,), P[p + "ln1.g"], P[p + "ln1.b"], 1e-5)
@@ -52,8 +55,31 @@ def trunk(P, x, t, cst, g2, sv=None):
         h = h + att.transpose(1, 2).reshape(B, 32, 512) @ P[p + "proj.w"].t() + P[p + "proj.b"]
         a = F.layer_norm(h, (512,), P[p + "ln2.g"], P[p + "ln2.b"], 1e-5)
         h = h + F.gelu(a @ P[p + "fc1.w"].t() + P[p + "fc1.b"]) @ P[p + "fc2.w"].t() + P[p + "fc2.b"]
+    return h
+
+
+def trunk(P, x, t, cst, g2, sv=None):
+    """x [B,1536,1,32] -> model output [B,1536,1,32] for one evaluation."""
+    xs = x[:, :, 0, :].permute(0, 2, 1)                                            # [B,32,1536]
+    h = blocks(P, tokens(P, xs @ P["w_x"].t(), t, cst, g2, sv))
     o = h @ P["out.w"].t() + P["out.b"]                                            # [B,32,1536]
     return o.permute(0, 2, 1).unsqueeze(2)
+
+
+def ddim_z_loop(P, coef, t_model, x_init, cst, g2, svs, scale):
+    """Deterministic DDIM with text CFG as the library runs it on the tcgen05 engine: the loop carries z = W_x x_k, not
+    x_k.  coef [S,5] = schedule.ddim_coefs rows {a, b, c1, c2, sigma = 0}; svs = (conditional, unconditional) style terms."""
+    S, B = len(t_model), x_init.shape[0]
+    z = x_init[:, :, 0, :].permute(0, 2, 1) @ P["w_x"].t()
+    for k in range(S - 1, -1, -1):
+        t = torch.full((B,), int(t_model[k]), dtype=torch.int64)
+        hs = [blocks(P, tokens(P, z, t, cst, g2, sv)) for sv in svs]
+        h_mix = hs[1] + scale * (hs[0] - hs[1])                                     # cfg_sampler.py:28 is linear
+        if k == 0:                                                                  # alpha_bar_prev = 1: x <- x0_hat
+            return (h_mix @ P["out.w"].t() + P["out.b"]).permute(0, 2, 1).unsqueeze(2)
+        a, b, c1, c2 = (float(v) for v in coef[k][:4])
+        alpha, beta = c1 - c2 / b, c2 * a / b                                       # x_{k-1} = alpha x0_hat + beta x_k
+        z = beta * z + alpha * (h_mix @ P["w_xo"].t() + P["c_xo"])
 
 
 def rvq_decoder(P, xq, out_dim):

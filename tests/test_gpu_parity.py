@@ -261,6 +261,42 @@ def test_ddim_last_step_returns_x0_and_python_loop_agrees(models):
     assert maxabs(native, x0_last[0]) < 2e-5
 
 
+def test_ddim_z_recursion_equals_the_x_space_loop(models):
+    """tcgen05 engine, deterministic DDIM: the loop carries z = W_x x_k (one 512 x 512 GEMM between steps instead of output GEMM,
+    state update and input GEMM).  With the recursion switched off (st_debug_probe bit 512) the same call
+    keeps the state in x space in the reference's rounding order; the two must agree far inside the parity tolerance, for
+    every guidance plan the recursion serves, eagerly (first call) and from the captured graph (later calls)."""
+    L = _lib.lib()
+    _lib.set_engine("tc")
+    B = 3
+    cases = []
+    inp = synth.make_inputs(B, seed=15)
+    cases.append((models["beatx"], {"y": y_of(inp)}, inp))
+    inp = synth.make_inputs(B, seed=16, variant="beatx_motionclip")
+    y = y_of(inp); y["scale"] = torch.tensor([2.0, 0.5, 3.0])
+    cases.append((ClassifierFreeSampleModel(models["beatx_motionclip"]), {"y": y}, inp))
+    inp = synth.make_inputs(B, seed=17, variant="h3d")
+    y = y_of(inp); y["style_feature"] = inp["style_upper"].cuda()
+    y["scale_audio"], y["scale_prompt"] = torch.ones(1) * 1.5, torch.ones(1) * 3.0
+    cases.append((TwoClassifierFreeSampleModel(models["h3d"]), {"y": y}, inp))
+    for resp in ("ddim10", "ddim2", [3]):      # [3]: no graph holds the whole loop -> x-space fallback
+        d = create_gaussian_diffusion(timestep_respacing=resp)
+        for w, kw, inp in cases:
+            run = lambda: d.ddim_sample_loop(w, (B, 1536, 1, 32), noise=inp["noise"].cuda(), clip_denoised=False, model_kwargs=kw)
+            try:
+                _lib.check(L.st_debug_probe(512))
+                ref = [run() for _ in range(3)][-1]
+            finally:
+                _lib.check(L.st_debug_probe(0))
+            n0 = _lib.launch_count()
+            outs = [run() for _ in range(3)]
+            n_z = (_lib.launch_count() - n0) // 3
+            assert torch.equal(outs[1], outs[2])
+            assert maxabs(outs[0], outs[2]) < 1e-6            # eager and graph run the same arithmetic
+            assert maxabs(outs[2], ref) < 5e-5
+            print(f"z recursion {resp}: max-abs vs x-space loop {maxabs(outs[2], ref):.2e}, launches per call {n_z}")
+
+
 def test_ddim50_cfg_vs_oracle(W, models, engine):
     """BASELINE config 2 at reduced batch: motionclip model, CFG 2.0, full DDIM-50, against the oracle."""
     inp = synth.make_inputs(2, seed=21, variant="beatx_motionclip")

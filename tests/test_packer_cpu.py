@@ -39,6 +39,29 @@ def test_packed_forward_matches_oracle(variant):
         assert float((ref_a - emu.trunk(P, inp["noise"], t, cstn, g2, sv)).abs().max()) < 1e-4
 
 
+def test_ddim_z_recursion_equals_the_reference_loop():
+    """Deterministic DDIM keeps the loop in token space (packer `w_xo`, `c_xo`): z_{k-1} = beta_k z_k + alpha_k (W_xo h_mix + c_xo)
+    must reproduce the reference's x-space loop with ClassifierFreeSampleModel (gaussian_diffusion.py:772-790, cfg_sampler.py:17-28)."""
+    from oracle import diffusion as odiff
+    from syntalker_b200 import schedule
+    variant = "beatx_motionclip"
+    W = synth.mdm_state_dict(variant, seed=0)
+    P = packer.pack_mdm(W)
+    inp = synth.make_inputs(2, seed=6, variant=variant)
+    y = {k: inp[k] for k in ("audio", "word", "seed", "style_feature")}
+    y["scale"] = torch.ones(1) * 2.0
+    fn = lambda x, t, yy: omdm.cfg_text(lambda a, b, c: omdm.mdm_forward(W, a, b, c, variant), x, t, yy)
+    sch = odiff.make_schedule(respacing="ddim4")
+    ref = odiff.ddim_sample_loop(sch, fn, inp["noise"], y)
+    betas, tmap = schedule.respace(schedule.get_named_beta_schedule("cosine", 1000), schedule.space_timesteps(1000, "ddim4"))
+    assert list(tmap) == list(sch.timestep_map)
+    coef = schedule.ddim_coefs(schedule.Tables(betas))
+    cst, g2 = emu.cond(P, inp["audio"], inp["word"], inp["seed"])
+    sv_c = inp["style_feature"] @ P["w_style"].t()
+    got = emu.ddim_z_loop(P, coef, tmap, inp["noise"], cst, g2, (sv_c, None), 2.0)
+    assert float((ref - got).abs().max()) < 1e-4
+
+
 def test_module_prefix_is_stripped():
     W = synth.mdm_state_dict("beatx", seed=0)
     Wm = {"module." + k: v for k, v in W.items()}
