@@ -83,7 +83,9 @@ int st_debug_timeline(long long* dev_buf);
 int st_debug_timeline_select(int N, int K);
 /* Debug: device buffer of 120000 uint64; every kernel's first thread appends (%globaltimer ns, kernel id); slot 0 = count. NULL = off. */
 int st_debug_trace(unsigned long long* dev_buf);
-/* debug: timing-only variants of the tcgen05 GEMM main loop (results are garbage when flags != 0) */
+/* debug / A-B switches.  bits 0-3: timing-only variants of the tcgen05 main loop (results are garbage); 16: trunk kernel off
+ * (generic tcgen05 kernel); 32: separate attention kernel; 64: RVQ code ranking on the SIMT engine; 128: WavEncoder with fp32
+ * activations; 256: body parts decode one after the other; 512: deterministic DDIM keeps its state in x space. */
 int st_debug_probe(int flags);
 
 /* ---- weights -------------------------------------------------------------------------------------
@@ -91,7 +93,8 @@ int st_debug_probe(int flags);
  * `packed` are the tensors syntalker_b200/packer.py derives from the reference state dict
  * (BatchNorm folded into the WavEncoder convs, input_process/2/3 folded into one 1536->512 matrix,
  * the timestep MLP tabulated for t = 0..999).  Names are checked; a missing or
- * mis-sized tensor is ST_EINVAL. */
+ * mis-sized tensor is ST_EINVAL.  Optional: "w_xo" [512,512] = W_x W_out and "c_xo" [512] = W_x b_out; with them the
+ * deterministic DDIM loop of the tcgen05 engine carries W_x x_k between steps instead of x_k (st_sample). */
 int st_model_create(const st_tensor* packed, int n, int variant, st_model** out);
 void st_model_destroy(st_model* m);
 
@@ -157,7 +160,11 @@ int st_denoise(st_model* m, const float* x, const int64_t* t, const st_guidance*
  * clip_denoised=False, no cond_fn -- the only way the trainers call it.  x_init: device [B,1536,1,32]
  * (the `noise` argument or th.randn(shape)).  noise_tape: device [S,B,1536,1,32] eps_k for k = S-1..0
  * stored in draw order (tape[0] is used at k=S-1), required when any sigma != 0, else may be NULL.
- * x_out may alias x_init.  Uses the cache of the last st_cond_encode. */
+ * x_out may alias x_init.  Uses the cache of the last st_cond_encode.
+ * Deterministic DDIM (every sigma = 0) on the tcgen05 engine with guidance NONE / TEXT / TWO runs the update in token space:
+ * x_{k-1} = alpha_k x0_hat + beta_k x_k is linear and the next step only needs W_x x_{k-1}, so between steps one 512x512
+ * GEMM replaces output GEMM + state update + input GEMM; the state is formed by the last step (x <- x0_hat,
+ * gaussian_diffusion.py:774-790 with alpha_bar_prev = 1).  Same result to ~1e-5; st_debug_probe(512) keeps the x-space loop. */
 int st_sample(st_model* m, const st_schedule* s, const st_guidance* g, const float* x_init, const float* noise_tape,
               int B, float* x_out, void* stream);
 
