@@ -161,6 +161,7 @@ struct st_model {
   const float *word_table = nullptr, *w_cm = nullptr, *w_seed = nullptr, *bias_all = nullptr, *w_x = nullptr, *vt_table = nullptr;
   const float *w_style = nullptr, *null_sv = nullptr, *rope_cos = nullptr, *rope_sin = nullptr, *out_w = nullptr, *out_b = nullptr;
   const float *w_xo = nullptr, *c_xo = nullptr;   // W_x W_out [512,512] and W_x b_out [512] (optional: z recursion of deterministic DDIM)
+  const float *w_xo2 = nullptr, *c_xo2 = nullptr; // [W_xo | W_xo W_fc2(block 7)] [512,1536] and W_xo b_fc2 [512] (optional: the last fc2 folded into that GEMM)
   BlkW blk[8];
   // constants for audio-masked evaluations (h3d): computed lazily
   float* cst_null = nullptr;   // [32,512]
@@ -204,6 +205,7 @@ static bool g_decode_streams = true;   // st_debug_probe bit 256: decode the thr
 static bool g_wav_planes = true;   // st_debug_probe bit 128: WavEncoder with fp32 activations and a split pass per conv
 static bool g_fused_attn = true;   // st_debug_probe bit 32 turns the fused qkv + attention kernel off
 static bool g_zrec = true;         // st_debug_probe bit 512 turns the z recursion of deterministic DDIM off (state kept in x space)
+static bool g_zrec_fc2 = true;     // st_debug_probe bit 1024: the last block's fc2 stays a layer of its own inside the z recursion
 
 namespace st { extern int g_tc_probe; extern bool g_tc_fast; }
 extern "C" int st_debug_probe(int flags) {
@@ -214,6 +216,7 @@ extern "C" int st_debug_probe(int flags) {
   g_decode_streams = !(flags & 256);
   g_wav_planes = !(flags & 128);
   g_zrec = !(flags & 512);
+  g_zrec_fc2 = !(flags & 1024);
   return ST_OK;
 }
 
@@ -290,6 +293,10 @@ static int model_resolve(st_model* m) {
   if (m->w.dev.count("w_xo") && m->w.dev.count("c_xo")) {
     m->w_xo = m->w.get("w_xo", 512 * 512, &err);
     m->c_xo = m->w.get("c_xo", 512, &err);
+  }
+  if (m->w_xo && m->w.dev.count("w_xo2") && m->w.dev.count("c_xo2")) {
+    m->w_xo2 = m->w.get("w_xo2", 512 * 1536, &err);
+    m->c_xo2 = m->w.get("c_xo2", 512, &err);
   }
   m->style_dim = m->variant == ST_VARIANT_BEATX_MOTIONCLIP ? 512 : m->variant == ST_VARIANT_H3D ? 256 : 0;
   if (m->style_dim) m->w_style = m->w.get("w_style", 512 * m->style_dim, &err);
@@ -616,6 +623,7 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   const int rows = B * 32, R = pl.nE * rows;
   const bool tc = (st_get_engine() == ST_ENGINE_TC);
   const long long ps512 = (long long)R * 512, ps1024 = (long long)R * 1024;
+  const bool fold_fc2 = zstep && !last && g_zrec_fc2 && m->w_xo2 != nullptr;
   if (!zstep) {
     // the state lives in the model's own planes (a captured step graph must not point into the engine's split
     // scratch); inside the sampling loop step_update keeps them current, a single evaluation splits here
@@ -667,6 +675,7 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
       p1.act = ACT_GELU; p1.a_planes = m->X_p; p1.a_plane_stride = ps512; p1.ln_stats = m->ln_stats; p1.ln_s = b.fc1_s; p1.ln_c = b.fc1_c;
       p1.o_planes = m->G_p; p1.o_plane_stride = ps1024; p1.o_planes_ld = 1024;
       ST_TRY(gemm(p1, s));
+      if (i == 7 && fold_fc2) continue;        // x + fc2(g) is linear in (x, g): folded into the GEMM that ends the step
       GemmP p2 = linear(m->G, R, 1024, b.fc2w, b.fc2b, m->X, 512);
       p2.res = m->X; p2.res_mode = RES_POST; p2.ldr = 512; p2.a_planes = m->G_p; p2.a_plane_stride = ps1024;
       p2.o_planes = m->X_p; p2.o_plane_stride = ps512; p2.o_planes_ld = 512; p2.stats_out = m->ln_stats;
@@ -690,6 +699,12 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   }
   if (zstep && !last) {
     // the next step only needs W_x x_{k-1}: P = X (W_x W_out)^T per evaluation; tokens_step mixes and applies the update
+    if (fold_fc2) {
+      // P = [X_mid | G] [W_xo | W_xo W_fc2]^T + W_xo b_fc2: the operand is the residual planes followed by the GELU planes
+      GemmP px = linear(m->X, R, 1536, m->w_xo2, m->c_xo2, m->H, 512);
+      px.a_planes = m->X_p; px.a_plane_stride = ps512; px.a2_planes = m->G_p; px.a2_plane_stride = ps1024; px.a2_K = 1024;
+      return gemm(px, s);
+    }
     GemmP px = linear(m->X, R, 512, m->w_xo, nullptr, m->H, 512);
     px.a_planes = m->X_p; px.a_plane_stride = ps512;
     return gemm(px, s);
@@ -814,7 +829,7 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
   const bool zrec = g_zrec && st_get_engine() == ST_ENGINE_TC && sc->mode == ST_MODE_DDIM && !any_sigma && m->w_xo &&
                     pl.cfg_mode != ST_CFG_BODYPART && (G == sc->S || !g_use_graphs);
   if (zrec) ST_TRY(trunk_input(m, B, s));
-  const std::string key = plan_key(pl, B, sc->mode) + " G" + std::to_string(G) + (zrec ? " z" : "");
+  const std::string key = plan_key(pl, B, sc->mode) + " G" + std::to_string(G) + (zrec ? (g_zrec_fc2 ? " zf" : " z") : "");
   cudaGraphExec_t exec = nullptr;
   const bool graphs_ok = g_use_graphs && !st::profiling();
   cudaStream_t ls = s;

@@ -579,6 +579,7 @@ struct FastEpi {
   // (4-D map {C, T, clips, 2}, T | 128): K block kb = (tap j, channel block cb), TMA zero-fills the padding
   int mode, T, kb_per_tap, dil, pad;
   int planes_relu;         // the planes carry max(result, 0)
+  int kb_split;            // mode 0: K blocks >= kb_split come from the second operand tensor (tmA2), counted from its column 0
   long long* dbg;
   int probe;
 };
@@ -650,7 +651,7 @@ constexpr int FAST_BOX_PL = 2 * TC_A_PLANE;      // one plane staging box: 2 pla
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, const FastEpi ep,
-                    const int num_kb, const int BN, const int STAGES) {
+                    const int num_kb, const int BN, const int STAGES, const __grid_constant__ CUtensorMap tmA2) {
   const int W_PLANE = BN * TC_BK * 2;
   const int STAGE_BYTES = 2 * TC_A_PLANE + 2 * W_PLANE;
   const int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
@@ -677,6 +678,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmW);
     if (ep.has_out || ep.has_res) tma_prefetch_desc(&tmO);
     if (ep.has_planes) tma_prefetch_desc(&tmP);
+    if (ep.kb_split < num_kb) tma_prefetch_desc(&tmA2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -736,7 +738,8 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_3d(st + 2 * TC_A_PLANE, &tmW, &full_bar[s], kb * TC_BK, n0, 0);
           }
           if (ep.mode == 0) {
-            tma_load_3d(st, &tmA, &full_bar[s], kb * TC_BK, m0, 0);
+            if (kb < ep.kb_split) tma_load_3d(st, &tmA, &full_bar[s], kb * TC_BK, m0, 0);
+            else tma_load_3d(st, &tmA2, &full_bar[s], (kb - ep.kb_split) * TC_BK, m0, 0);
           } else {
             const int j = kb / ep.kb_per_tap, cb = kb - j * ep.kb_per_tap;
             tma_load_4d(st, &tmA, &full_bar[s], cb * TC_BK, j * ep.dil - ep.pad, m0 / ep.T, 0);
@@ -1431,6 +1434,7 @@ static bool tc_fast_supported(const GemmP& p) {
   const int cmode = conv_mode(p);
   if ((cmode != 0 && cmode != 1) || (p.K % TC_BK) != 0 || (p.N % 64) != 0 || p.out_scale != 1.0f) return false;
   if (p.a_relu && p.a_planes) return false;          // a ReLU on the input is applied when the operand is split, or by the producer
+  if (p.a2_planes && (cmode != 0 || !p.a_planes || p.a2_K <= 0 || p.a2_K >= p.K || (p.a2_K % TC_BK) != 0)) return false;
   if (!p.out && !p.o_planes) return false;
   if (p.act != ACT_NONE && p.act != ACT_GELU && p.act != ACT_RELU) return false;
   if (p.res && (p.res != p.out || p.res_div != 1 || p.ldr != p.ldo || (p.res_mode == RES_PRE && p.act != ACT_NONE))) return false;
@@ -1457,8 +1461,11 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   const int smem = stages * stage + (p.attn ? ATT_SX_BYTES : res) + 2 * 192 * 4 + (2 * stages + 2) * 8 + 16 + 1024;
   const CUtensorMap *tmA = nullptr, *tmW = nullptr, *tmO = nullptr, *tmP = nullptr;
   const int cmode = conv_mode(p);
-  if (cmode == 0) ST_TRY(get_map_3d(&tmA, planes, pstride, p.M, p.K, TC_BM));
+  const CUtensorMap* tmA2 = nullptr;
+  if (cmode == 0) ST_TRY(get_map_3d(&tmA, planes, pstride, p.M, p.K - p.a2_K, TC_BM));
   else ST_TRY(get_map_4d(&tmA, planes, pstride, p.M / p.Lout, p.Lin, p.C));
+  if (p.a2_planes) ST_TRY(get_map_3d(&tmA2, p.a2_planes, p.a2_plane_stride, p.M, p.a2_K, TC_BM));
+  else tmA2 = tmA;
   ST_TRY(get_map_3d(&tmW, w->planes, (long long)p.N * w->Kp, p.N, w->Kp, BN));
   tmO = tmA; tmP = tmA;
   if (p.out) ST_TRY(get_map_2d_f32(&tmO, p.out, p.M, p.N, p.ldo));
@@ -1472,14 +1479,15 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   ep.M = p.M; ep.N = p.N; ep.dbg = (g_tc_dbg_n == 0 || (g_tc_dbg_n == p.N && g_tc_dbg_k == p.K)) ? g_tc_dbg : nullptr; ep.probe = g_tc_probe; ep.attn = p.attn;
   ep.mode = cmode; ep.T = p.Lout; ep.kb_per_tap = cmode == 0 ? 1 : p.C / TC_BK; ep.dil = p.dil; ep.pad = p.pad;
   ep.planes_relu = p.o_planes_relu;
+  ep.kb_split = p.a2_planes ? (p.K - p.a2_K) / TC_BK : 0x7fffffff;
   static bool attr = false;
   if (!attr) {
     ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM);
-  if (p.attn) launch_k_cluster(gemm_tc_fast_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, 2, *tmA, *tmW, *tmO, *tmP, ep, w->Kp / TC_BK, BN, stages);
-  else launch_k(gemm_tc_fast_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, *tmA, *tmW, *tmO, *tmP, ep, w->Kp / TC_BK, BN, stages);
+  if (p.attn) launch_k_cluster(gemm_tc_fast_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, 2, *tmA, *tmW, *tmO, *tmP, ep, w->Kp / TC_BK, BN, stages, *tmA2);
+  else launch_k(gemm_tc_fast_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, *tmA, *tmW, *tmO, *tmP, ep, w->Kp / TC_BK, BN, stages, *tmA2);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -1538,6 +1546,7 @@ launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 
     planes = sp;
   }
   if ((g_tc_fast || p.attn) && tc_fast_supported(p)) return gemm_tc_fast(p, w, planes, pstride, s);
+  if (p.a2_planes) { set_error("gemm_tc: a two-tensor operand is served by the trunk kernel only"); return ST_EUNSUPPORTED; }
   if (p.attn) { set_error("gemm_tc: fused attention needs the 1536 x 512 qkv layout"); return ST_EUNSUPPORTED; }
   if (p.ln_stats || p.stats_out) { set_error("gemm_tc: folded LayerNorm is served by the trunk kernel only"); return ST_EUNSUPPORTED; }
   const CUtensorMap* tmA = nullptr;

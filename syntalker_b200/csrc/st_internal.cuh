@@ -122,6 +122,10 @@ struct GemmP {
   // the result wanted as such planes for the next GEMM.  `out` may then be null.
   const __half* a_planes = nullptr;
   long long a_plane_stride = 0;   // elements between the hi and the lo plane
+  // trunk kernel only: the operand is the column-wise concatenation [a_planes (K - a2_K columns) | a2_planes (a2_K columns)]
+  const __half* a2_planes = nullptr;
+  long long a2_plane_stride = 0;
+  int a2_K = 0;
   __half* o_planes = nullptr;
   long long o_plane_stride = 0;
   int o_planes_ld = 0, o_planes_relu = 0;

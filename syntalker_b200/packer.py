@@ -137,6 +137,12 @@ def pack_mdm(sd: Dict[str, torch.Tensor], variant: str | None = None) -> Dict[st
     Wx64 = P @ Wb @ Wpe
     out["w_xo"] = _t32(Wx64 @ _f64(sd["output_process.poseFinal.weight"]))
     out["c_xo"] = _t32(Wx64 @ _f64(sd["output_process.poseFinal.bias"]))
+    # ... and the last block's fc2 folds into the same GEMM (x + fc2(g) is linear in (x, g), transformer.py:197-198):
+    #   W_xo (x_mid + W_fc2 g + b_fc2) = [W_xo | W_xo W_fc2] [x_mid ; g] + W_xo b_fc2           (K = 512 + 1024)
+    Wxo64 = Wx64 @ _f64(sd["output_process.poseFinal.weight"])
+    Wf2, bf2 = _f64(sd["mytimmblocks.7.mlp.fc2.weight"]), _f64(sd["mytimmblocks.7.mlp.fc2.bias"])
+    out["w_xo2"] = _t32(np.concatenate([Wxo64, Wxo64 @ Wf2], axis=1))
+    out["c_xo2"] = _t32(Wxo64 @ bf2)
     return out
 
 

@@ -45,7 +45,8 @@ def tokens(P, z, t, cst, g2, sv=None):
     return torch.cat([x1 * cos - x2 * sin, x2 * cos + x1 * sin], dim=-1).reshape(B, 32, 512)
 
 
-def blocks(P, h):
+def blocks(P, h, split_last=False):
+    """split_last: stop in front of the last block's fc2 and return (residual stream, GELU output) instead."""
     B = h.shape[0]
     for i in range(8):
         p = f"blk.{i}."
@@ -54,7 +55,10 @@ def blocks(P, h):
         att = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2) * 128 ** -0.5, dim=-1) @ qkv[2]
         h = h + att.transpose(1, 2).reshape(B, 32, 512) @ P[p + "proj.w"].t() + P[p + "proj.b"]
         a = F.layer_norm(h, (512,), P[p + "ln2.g"], P[p + "ln2.b"], 1e-5)
-        h = h + F.gelu(a @ P[p + "fc1.w"].t() + P[p + "fc1.b"]) @ P[p + "fc2.w"].t() + P[p + "fc2.b"]
+        g = F.gelu(a @ P[p + "fc1.w"].t() + P[p + "fc1.b"])
+        if split_last and i == 7:
+            return h, g
+        h = h + g @ P[p + "fc2.w"].t() + P[p + "fc2.b"]
     return h
 
 
@@ -73,13 +77,16 @@ def ddim_z_loop(P, coef, t_model, x_init, cst, g2, svs, scale):
     z = x_init[:, :, 0, :].permute(0, 2, 1) @ P["w_x"].t()
     for k in range(S - 1, -1, -1):
         t = torch.full((B,), int(t_model[k]), dtype=torch.int64)
-        hs = [blocks(P, tokens(P, z, t, cst, g2, sv)) for sv in svs]
-        h_mix = hs[1] + scale * (hs[0] - hs[1])                                     # cfg_sampler.py:28 is linear
         if k == 0:                                                                  # alpha_bar_prev = 1: x <- x0_hat
+            hs = [blocks(P, tokens(P, z, t, cst, g2, sv)) for sv in svs]
+            h_mix = hs[1] + scale * (hs[0] - hs[1])                                 # cfg_sampler.py:28 is linear
             return (h_mix @ P["out.w"].t() + P["out.b"]).permute(0, 2, 1).unsqueeze(2)
+        # every other step ends in ONE GEMM over [residual stream | GELU output] of the last block (K = 512 + 1024)
+        ps = [torch.cat(blocks(P, tokens(P, z, t, cst, g2, sv), split_last=True), dim=-1) @ P["w_xo2"].t() + P["c_xo2"] for sv in svs]
+        p_mix = ps[1] + scale * (ps[0] - ps[1])
         a, b, c1, c2 = (float(v) for v in coef[k][:4])
         alpha, beta = c1 - c2 / b, c2 * a / b                                       # x_{k-1} = alpha x0_hat + beta x_k
-        z = beta * z + alpha * (h_mix @ P["w_xo"].t() + P["c_xo"])
+        z = beta * z + alpha * (p_mix + P["c_xo"])
 
 
 def rvq_decoder(P, xq, out_dim):

@@ -288,13 +288,18 @@ def test_ddim_z_recursion_equals_the_x_space_loop(models):
                 ref = [run() for _ in range(3)][-1]
             finally:
                 _lib.check(L.st_debug_probe(0))
-            n0 = _lib.launch_count()
-            outs = [run() for _ in range(3)]
-            n_z = (_lib.launch_count() - n0) // 3
-            assert torch.equal(outs[1], outs[2])
-            assert maxabs(outs[0], outs[2]) < 1e-6            # eager and graph run the same arithmetic
-            assert maxabs(outs[2], ref) < 5e-5
-            print(f"z recursion {resp}: max-abs vs x-space loop {maxabs(outs[2], ref):.2e}, launches per call {n_z}")
+            for flags in (1024, 0):                           # 1024: the last block's fc2 not folded into the step's final GEMM
+                try:
+                    _lib.check(L.st_debug_probe(flags))
+                    n0 = _lib.launch_count()
+                    outs = [run() for _ in range(3)]
+                    n_z = (_lib.launch_count() - n0) // 3
+                finally:
+                    _lib.check(L.st_debug_probe(0))
+                assert torch.equal(outs[1], outs[2])
+                assert maxabs(outs[0], outs[2]) < 1e-6        # eager and graph run the same arithmetic
+                assert maxabs(outs[2], ref) < 5e-5
+                print(f"z recursion {resp} probe {flags}: max-abs vs x-space loop {maxabs(outs[2], ref):.2e}, launches per call {n_z}")
 
 
 def test_ddim50_cfg_vs_oracle(W, models, engine):
