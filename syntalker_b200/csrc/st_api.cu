@@ -616,10 +616,30 @@ static int trunk_input(st_model* m, int B, cudaStream_t s) {
   return gemm(pz, s);
 }
 
-// zstep (sampling loop of deterministic DDIM on the tcgen05 engine): the step starts from z (tokens_step applies the
-// recursion of the previous step's update) and ends in P = X . W_xo^T instead of the output GEMM unless it is the last
+// One step of the z recursion (sampling loop of deterministic DDIM on the tcgen05 engine): the step starts from z
+// (tokens_step applies the previous step's update) and ends in P = X . W_xo^T instead of the output GEMM unless it is the last.
+// The step's values are host-side here: the captured graph holds the whole loop, one set of nodes per step.
+struct ZStep {
+  bool on = false, first = false, last = true;
+  int t = 0;                 // original timestep fed to the denoiser (respace.py:124-129)
+  float alpha = 0.f, beta = 0.f;
+};
+static ZStep zstep_of(const st_schedule* sc, int k) {
+  ZStep z;
+  z.on = true; z.first = (k == sc->S - 1); z.last = (k == 0); z.t = sc->t_model[k];
+  if (!z.first) {
+    // the update that produced x_k ran with the coefficients of step k + 1: e = (a x - x0) / b, x <- c1 x0 + c2 e
+    const float* cf = &sc->coef[(size_t)(k + 1) * ST_COEF_STRIDE];
+    const double a = cf[0], b = cf[1], c1 = cf[2], c2 = cf[3];
+    z.alpha = (float)(c1 - c2 / b);
+    z.beta = (float)(c2 * a / b);
+  }
+  return z;
+}
+
 static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, int t_scalar, bool loop, cudaStream_t s,
-                     bool zstep = false, bool last = true, const StepP* mix = nullptr) {
+                     const ZStep& zs = ZStep(), const StepP* mix = nullptr) {
+  const bool zstep = zs.on, last = zs.last;
   const int rows = B * 32, R = pl.nE * rows;
   const bool tc = (st_get_engine() == ST_ENGINE_TC);
   const long long ps512 = (long long)R * 512, ps1024 = (long long)R * 1024;
@@ -644,8 +664,9 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   }
   if (zstep) {
     TokensStepP ts;
-    ts.t = tp; ts.z_rw = m->z; ts.P = m->H; ts.c_xo = m->c_xo; ts.coef_dev = m->coef_dev;
-    ts.cfg_mode = mix->cfg_mode; ts.scale = mix->scale; ts.scale2 = mix->scale2; ts.ls_adv = m->loop;
+    ts.t = tp; ts.z_rw = m->z; ts.P = m->H; ts.c_xo = m->c_xo; ts.vt = m->vt_table + (size_t)zs.t * 512;
+    ts.alpha = zs.alpha; ts.beta = zs.beta; ts.first = zs.first ? 1 : 0;
+    ts.cfg_mode = mix->cfg_mode; ts.scale = mix->scale; ts.scale2 = mix->scale2;
     ST_TRY(tokens_step(ts, s));
   } else {
     ST_TRY(tokens_in(tp, s));
@@ -782,11 +803,21 @@ static std::string plan_key(const Plan& pl, int B, int mode) {
 
 // one diffusion step: trunk for every planned evaluation, CFG mix + sampler update, k -= 1  (all step-dependent
 // values are read from device memory, so the same launch sequence -- or its captured graph -- serves every step)
-static int one_step(st_model* m, const Plan& pl, const StepP& sp0, int B, cudaStream_t s, bool zstep = false, bool last = true) {
-  ST_TRY(run_trunk(m, pl, B, nullptr, 0, true, s, zstep, last, &sp0));
-  if (zstep && !last) return ST_OK;   // the update is applied to z by the next step's tokens_step
+static int one_step(st_model* m, const Plan& pl, const StepP& sp0, int B, cudaStream_t s, const ZStep& zs = ZStep(),
+                    const st_schedule* sc = nullptr) {
+  ST_TRY(run_trunk(m, pl, B, nullptr, 0, true, s, zs, &sp0));
+  if (zs.on && !zs.last) return ST_OK;   // the update is applied to z by the next step's tokens_step
   StepP sp = sp0;
-  sp.xs = m->xs; sp.eps = nullptr; sp.ls = m->loop; sp.coef_dev = m->coef_dev;
+  sp.xs = m->xs; sp.eps = nullptr;
+  if (zs.on) {
+    // last step of the z recursion: the one real update, with step 0's coefficients as launch parameters (alpha_bar_prev = 1:
+    // x <- x0_hat whatever the stale state holds); the device-side loop state is not used by this loop
+    sp.ls = nullptr;
+    for (int q = 0; q < ST_COEF_STRIDE; ++q) sp.c[q] = sc->coef[q];
+    ST_TRY(step_update(sp, s));
+    return ST_OK;
+  }
+  sp.ls = m->loop; sp.coef_dev = m->coef_dev;
   sp.xs_planes = st_get_engine() == ST_ENGINE_TC ? m->xs_p : nullptr;
   sp.ls_advance = m->loop;          // the update's last CTA also moves the loop to the next step
   ST_TRY(step_update(sp, s));
@@ -829,7 +860,7 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
   const bool zrec = g_zrec && st_get_engine() == ST_ENGINE_TC && sc->mode == ST_MODE_DDIM && !any_sigma && m->w_xo &&
                     pl.cfg_mode != ST_CFG_BODYPART && (G == sc->S || !g_use_graphs);
   if (zrec) ST_TRY(trunk_input(m, B, s));
-  const std::string key = plan_key(pl, B, sc->mode) + " G" + std::to_string(G) + (zrec ? (g_zrec_fc2 ? " zf" : " z") : "");
+  const std::string key = plan_key(pl, B, sc->mode) + " G" + std::to_string(G) + (zrec ? (g_zrec_fc2 ? " zf" : " z") + std::to_string(sc->id) : std::string());   // the z recursion bakes the schedule into the graph
   cudaGraphExec_t exec = nullptr;
   const bool graphs_ok = g_use_graphs && !st::profiling();
   cudaStream_t ls = s;
@@ -849,7 +880,7 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
       const int64_t l0 = g_launches;
       ST_CHECK_CUDA(cudaStreamBeginCapture(ls, cudaStreamCaptureModeRelaxed));
       int r = ST_OK;
-      for (int i = 0; i < G && r == ST_OK; ++i) r = one_step(m, pl, sp, B, ls, zrec, i == G - 1);
+      for (int i = 0; i < G && r == ST_OK; ++i) r = zrec ? one_step(m, pl, sp, B, ls, zstep_of(sc, G - 1 - i), sc) : one_step(m, pl, sp, B, ls);
       m->graph_nodes[key] = g_launches - l0;     // kernels per replay; capturing itself executed nothing
       g_launches = l0;
       cudaError_t ce = cudaStreamEndCapture(ls, &graph);
@@ -863,7 +894,7 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
   if (exec) {
     for (int k = 0; k < sc->S / G; ++k) { ST_CHECK_CUDA(cudaGraphLaunch(exec, ls)); g_launches += m->graph_nodes[key]; }
   } else {
-    for (int k = sc->S - 1; k >= 0; --k) ST_TRY(one_step(m, pl, sp, B, ls, zrec, k == 0));
+    for (int k = sc->S - 1; k >= 0; --k) ST_TRY(zrec ? one_step(m, pl, sp, B, ls, zstep_of(sc, k), sc) : one_step(m, pl, sp, B, ls));
   }
   if (ls != s) {
     ST_CHECK_CUDA(cudaEventRecord(m->ev_out, ls));

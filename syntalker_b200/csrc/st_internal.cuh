@@ -200,19 +200,20 @@ struct TokensInP {
 int tokens_in(const TokensInP& p, cudaStream_t s);
 
 // Sampling loop, deterministic DDIM on the tcgen05 engine: the loop carries z = W_x x_k instead of x_k ("z recursion",
-// DESIGN.md §4).  One launch per step: z <- beta z + alpha (CFG-mix of P + c_xo) with the coefficients of step k + 1
-// (skipped at k = S - 1, where z comes from the input GEMM), then the tokens of step k like tokens_in; the last CTA
-// moves the loop on (k -= 1 unless k == 0: the final step ends in the full output GEMM + step_update).
+// DESIGN.md §4).  One launch per step: z <- beta z + alpha (CFG-mix of P + c_xo) with the coefficients of the PREVIOUS
+// step's update (skipped at the first step, where z comes from the input GEMM), then the tokens of this step like
+// tokens_in.  The step's values are launch parameters (the captured graph holds the whole loop, one node per step).
 struct TokensStepP {
-  TokensInP t;               // t.ls set; t.z is the state (read here, written through z_rw)
-  float* z_rw;               // [B*32,512]
-  const float* P;            // [nE*B*32,512] = last block's residual rows . W_xo^T of the previous step, eval-major
+  TokensInP t;               // conditioning terms, rotary tables, outputs (t.z, t.ls, t.t_dev, t.vt_table are not used)
+  float* z_rw;               // [B*32,512] state, updated in place
+  const float* P;            // [nE*B*32,512] = previous step's last-block rows through W_xo (W_xo2), eval-major
   const float* c_xo;         // [512] = W_x b_out
-  const float* coef_dev;     // [S][ST_COEF_STRIDE] DDIM rows {a, b, c1, c2, sigma = 0}
+  const float* vt;           // [512] row t_model[k] of the timestep table
+  float alpha, beta;         // x_k = alpha x0_hat + beta x_{k+1}
+  int first;                 // first step of the loop: z is taken as it is
   int cfg_mode;              // ST_CFG_NONE / ST_CFG_TEXT / ST_CFG_TWO (evaluation order as in step_update)
   const float* scale;        // device [B]
   const float* scale2;       // device [B] (TWO)
-  LoopState* ls_adv;
 };
 int tokens_step(const TokensStepP& p, cudaStream_t s);
 
