@@ -566,10 +566,12 @@ int tokens_in(const TokensInP& p, cudaStream_t s) {
   return ST_OK;
 }
 
-// ---- 4b. the same for a step of the z recursion: one warp per (row, half of the 512 columns) --------------------------
+// ---- 4b. the same for a step of the z recursion: TS_SPLIT warps per row, each over 8 / TS_SPLIT rotary groups of 64 columns ----
 // Everything that depends on the step (timestep row of the embedding table, alpha, beta) is a launch parameter: the captured
 // graph holds the whole loop, so every step's node carries its own values and the kernel starts without a chain of dependent
 // loads through the loop state.  All loads of a warp are issued before its first store.
+constexpr int TS_SPLIT = 4;                 // warps per row: each takes 8 / TS_SPLIT of the eight 64-column rotary groups
+constexpr int TS_NG = 8 / TS_SPLIT, TS_NV = 2 * TS_NG;
 __global__ void __launch_bounds__(256) tokens_step_kernel(TokensStepP q) {
   pdl_wait();
   trace_stamp(3);
@@ -578,67 +580,67 @@ __global__ void __launch_bounds__(256) tokens_step_kernel(TokensStepP q) {
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const long long rows_e = (long long)p.B * 32;
-  if (wid >= rows_e * 2) return;
-  const int row = (int)(wid >> 1), half = (int)(wid & 1);
+  if (wid >= rows_e * TS_SPLIT) return;
+  const int row = (int)(wid / TS_SPLIT), part = (int)(wid % TS_SPLIT);
   const int b = row >> 5, tau = row & 31;
   float* __restrict__ zr = q.z_rw + (long long)row * 512;
-  int col[8];
+  int col[TS_NV];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) { col[2 * g] = (half * 4 + g) * 64 + lane; col[2 * g + 1] = col[2 * g] + 32; }
-  float zv[8], vtv[8], g2v[8], cv[2][8], sw[2][8];
+  for (int g = 0; g < TS_NG; ++g) { col[2 * g] = (part * TS_NG + g) * 64 + lane; col[2 * g + 1] = col[2 * g] + 32; }
+  float zv[TS_NV], vtv[TS_NV], g2v[TS_NV], cv[2][TS_NV], sw[2][TS_NV];
   const float* __restrict__ vt = q.vt;
   const float* __restrict__ g2 = p.g2 + (long long)b * 512;
   auto load_eval = [&](int e, float* c, float* s_) {
     const float* __restrict__ cst = p.cst[e] + (long long)(p.cst_bcast[e] ? tau : row) * 512;
     const float* __restrict__ sv = p.sv[e] ? p.sv[e] + (p.sv_bcast[e] ? 0 : (long long)b * 512) : nullptr;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { c[i] = __ldg(cst + col[i]); s_[i] = sv ? __ldg(sv + col[i]) : 0.f; }
+    for (int i = 0; i < TS_NV; ++i) { c[i] = __ldg(cst + col[i]); s_[i] = sv ? __ldg(sv + col[i]) : 0.f; }
     return sv != nullptr;
   };
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { zv[i] = zr[col[i]]; vtv[i] = __ldg(vt + col[i]); g2v[i] = __ldg(g2 + col[i]); }
+  for (int i = 0; i < TS_NV; ++i) { zv[i] = zr[col[i]]; vtv[i] = __ldg(vt + col[i]); g2v[i] = __ldg(g2 + col[i]); }
   bool has_sv = load_eval(0, cv[0], sw[0]);
   const float cs = __ldg(p.rope_cos + tau * 32 + lane), sn = __ldg(p.rope_sin + tau * 32 + lane);
   if (!q.first) {
     // x_k = alpha x0_hat + beta x_{k+1}  (gaussian_diffusion.py:772-790, sigma = 0) applied to z = W_x x
     const float* __restrict__ P0 = q.P + (long long)row * 512;
     const long long pe = rows_e * 512;
-    float pm[8], cx[8];
+    float pm[TS_NV], cx[TS_NV];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cx[i] = __ldg(q.c_xo + col[i]);
+    for (int i = 0; i < TS_NV; ++i) cx[i] = __ldg(q.c_xo + col[i]);
     if (q.cfg_mode == ST_CFG_NONE) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pm[i] = __ldg(P0 + col[i]);
+      for (int i = 0; i < TS_NV; ++i) pm[i] = __ldg(P0 + col[i]);
     } else if (q.cfg_mode == ST_CFG_TEXT) {
       const float sc = __ldg(q.scale + b);            // eval 0 = conditional, eval 1 = unconditional (cfg_sampler.py:28)
-      float c[8], u[8];
+      float c[TS_NV], u[TS_NV];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { c[i] = __ldg(P0 + col[i]); u[i] = __ldg(P0 + pe + col[i]); }
+      for (int i = 0; i < TS_NV; ++i) { c[i] = __ldg(P0 + col[i]); u[i] = __ldg(P0 + pe + col[i]); }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pm[i] = u[i] + sc * (c[i] - u[i]);
+      for (int i = 0; i < TS_NV; ++i) pm[i] = u[i] + sc * (c[i] - u[i]);
     } else {
       const float sa = __ldg(q.scale + b), sp = __ldg(q.scale2 + b);   // eval 0 = uu, 1 = ut, 2 = ua (cfg_sampler.py:54)
-      float uu[8], ut[8], ua[8];
+      float uu[TS_NV], ut[TS_NV], ua[TS_NV];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { uu[i] = __ldg(P0 + col[i]); ut[i] = __ldg(P0 + pe + col[i]); ua[i] = __ldg(P0 + 2 * pe + col[i]); }
+      for (int i = 0; i < TS_NV; ++i) { uu[i] = __ldg(P0 + col[i]); ut[i] = __ldg(P0 + pe + col[i]); ua[i] = __ldg(P0 + 2 * pe + col[i]); }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pm[i] = uu[i] + sa * (ut[i] - uu[i]) + sp * (ua[i] - uu[i]);
+      for (int i = 0; i < TS_NV; ++i) pm[i] = uu[i] + sa * (ut[i] - uu[i]) + sp * (ua[i] - uu[i]);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) zv[i] = q.beta * zv[i] + q.alpha * (pm[i] + cx[i]);
+    for (int i = 0; i < TS_NV; ++i) zv[i] = q.beta * zv[i] + q.alpha * (pm[i] + cx[i]);
   }
-  float base[8];
+  float base[TS_NV];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) base[i] = zv[i] + vtv[i];
+  for (int i = 0; i < TS_NV; ++i) base[i] = zv[i] + vtv[i];
   for (int e = 0; e < p.nE; ++e) {
     const int cur = e & 1, nxt = cur ^ 1;
     const bool sv_cur = has_sv;
     if (e + 1 < p.nE) has_sv = load_eval(e + 1, cv[nxt], sw[nxt]);     // the next evaluation's terms are in flight during this one's stores
     const long long orow = (long long)e * rows_e + row;
-    float v[8];
+    float v[TS_NV];
     float sum = 0.f;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < TS_NG; ++g) {
       float x1 = base[2 * g] + cv[cur][2 * g] + g2v[2 * g];
       float x2 = base[2 * g + 1] + cv[cur][2 * g + 1] + g2v[2 * g + 1];
       if (sv_cur) { x1 += sw[cur][2 * g]; x2 += sw[cur][2 * g + 1]; }
@@ -648,34 +650,34 @@ __global__ void __launch_bounds__(256) tokens_step_kernel(TokensStepP q) {
     }
     float* xo = p.x + orow * 512;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xo[col[i]] = v[i];
+    for (int i = 0; i < TS_NV; ++i) xo[col[i]] = v[i];
     if (p.x_planes) {
       const long long ps = rows_e * p.nE * 512;
       __half* xp = p.x_planes + orow * 512;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { __half h, l; split16(v[i], h, l); xp[col[i]] = h; xp[ps + col[i]] = l; }
+      for (int i = 0; i < TS_NV; ++i) { __half h, l; split16(v[i], h, l); xp[col[i]] = h; xp[ps + col[i]] = l; }
     }
     if (p.stats) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float mean = sum * (1.0f / 256.0f);
+      const float mean = sum * (1.0f / (64.0f * TS_NG));
       float m2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; m2 += d * d; }
+      for (int i = 0; i < TS_NV; ++i) { const float d = v[i] - mean; m2 += d * d; }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
-      // eight identical partials (mean, M2/8) of this half row combine with the other half's to exactly (mean, M2)
-      if (lane < 8) *reinterpret_cast<float2*>(p.stats + (orow * 16 + half * 8 + lane) * 2) = make_float2(mean, m2 * 0.125f);
+      // 2 TS_NG identical partials (mean, M2 / (2 TS_NG)) of this part of the row combine with the other parts' to exactly (mean, M2)
+      if (lane < 2 * TS_NG) *reinterpret_cast<float2*>(p.stats + (orow * 16 + part * 2 * TS_NG + lane) * 2) = make_float2(mean, m2 * (0.5f / TS_NG));
     }
   }
   if (!q.first) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) zr[col[i]] = zv[i];
+    for (int i = 0; i < TS_NV; ++i) zr[col[i]] = zv[i];
   }
 }
 
 int tokens_step(const TokensStepP& p, cudaStream_t s) {
-  const long long n = (long long)2 * p.t.B * 32;      // warps
+  const long long n = (long long)TS_SPLIT * p.t.B * 32;      // warps
   launch_k(tokens_step_kernel, dim3((unsigned)((n + 7) / 8)), dim3(256), 0, s, p);
   ST_CHECK_LAUNCH();
   return ST_OK;
