@@ -876,6 +876,12 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
     auto it = m->graphs.find(key);
     if (it != m->graphs.end()) exec = it->second;
     else {
+      if (m->graphs.size() >= 64) {
+        // the z recursion keys its graphs by schedule: a caller that keeps creating schedules must not grow the cache for ever
+        ST_CHECK_CUDA(cudaStreamSynchronize(ls));
+        for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+        m->graphs.clear(); m->graph_nodes.clear();
+      }
       cudaGraph_t graph = nullptr;
       const int64_t l0 = g_launches;
       ST_CHECK_CUDA(cudaStreamBeginCapture(ls, cudaStreamCaptureModeRelaxed));
