@@ -70,20 +70,19 @@ def trunk(P, x, t, cst, g2, sv=None):
     return o.permute(0, 2, 1).unsqueeze(2)
 
 
-def ddim_z_loop(P, coef, t_model, x_init, cst, g2, svs, scale):
-    """Deterministic DDIM with text CFG as the library runs it on the tcgen05 engine: the loop carries z = W_x x_k, not
-    x_k.  coef [S,5] = schedule.ddim_coefs rows {a, b, c1, c2, sigma = 0}; svs = (conditional, unconditional) style terms."""
+def ddim_z_loop(P, coef, t_model, x_init, evals, mix):
+    """Deterministic DDIM as the library runs it on the tcgen05 engine: the loop carries z = W_x x_k, not x_k.
+    coef [S,5] = schedule.ddim_coefs rows {a, b, c1, c2, sigma = 0}; evals = [(cst, g2, sv), ...] one per planned evaluation in
+    the order of step_update; mix(list of per-evaluation tensors) = the guidance combination (linear, cfg_sampler.py:28,54)."""
     S, B = len(t_model), x_init.shape[0]
     z = x_init[:, :, 0, :].permute(0, 2, 1) @ P["w_x"].t()
     for k in range(S - 1, -1, -1):
         t = torch.full((B,), int(t_model[k]), dtype=torch.int64)
         if k == 0:                                                                  # alpha_bar_prev = 1: x <- x0_hat
-            hs = [blocks(P, tokens(P, z, t, cst, g2, sv)) for sv in svs]
-            h_mix = hs[1] + scale * (hs[0] - hs[1])                                 # cfg_sampler.py:28 is linear
+            h_mix = mix([blocks(P, tokens(P, z, t, *e)) for e in evals])
             return (h_mix @ P["out.w"].t() + P["out.b"]).permute(0, 2, 1).unsqueeze(2)
         # every other step ends in ONE GEMM over [residual stream | GELU output] of the last block (K = 512 + 1024)
-        ps = [torch.cat(blocks(P, tokens(P, z, t, cst, g2, sv), split_last=True), dim=-1) @ P["w_xo2"].t() + P["c_xo2"] for sv in svs]
-        p_mix = ps[1] + scale * (ps[0] - ps[1])
+        p_mix = mix([torch.cat(blocks(P, tokens(P, z, t, *e), split_last=True), dim=-1) @ P["w_xo2"].t() + P["c_xo2"] for e in evals])
         a, b, c1, c2 = (float(v) for v in coef[k][:4])
         alpha, beta = c1 - c2 / b, c2 * a / b                                       # x_{k-1} = alpha x0_hat + beta x_k
         z = beta * z + alpha * (p_mix + P["c_xo"])

@@ -39,26 +39,45 @@ def test_packed_forward_matches_oracle(variant):
         assert float((ref_a - emu.trunk(P, inp["noise"], t, cstn, g2, sv)).abs().max()) < 1e-4
 
 
-def test_ddim_z_recursion_equals_the_reference_loop():
-    """Deterministic DDIM keeps the loop in token space (packer `w_xo`, `c_xo`): z_{k-1} = beta_k z_k + alpha_k (W_xo h_mix + c_xo)
-    must reproduce the reference's x-space loop with ClassifierFreeSampleModel (gaussian_diffusion.py:772-790, cfg_sampler.py:17-28)."""
+@pytest.mark.parametrize("plan", ["none", "text", "two"])
+def test_ddim_z_recursion_equals_the_reference_loop(plan):
+    """Deterministic DDIM keeps the loop in token space (packer `w_xo`, `c_xo`, `w_xo2`, `c_xo2`):
+    z_{k-1} = beta_k z_k + alpha_k (W_xo h_mix + c_xo) must reproduce the reference's x-space loop (gaussian_diffusion.py:772-790)
+    without guidance (denoiser.MDM), under ClassifierFreeSampleModel (cfg_sampler.py:17-28) and under
+    TwoClassifierFreeSampleModel (cfg_sampler.py:38-54, denoiser_h3d)."""
     from oracle import diffusion as odiff
     from syntalker_b200 import schedule
-    variant = "beatx_motionclip"
+    variant = {"none": "beatx", "text": "beatx_motionclip", "two": "h3d"}[plan]
     W = synth.mdm_state_dict(variant, seed=0)
     P = packer.pack_mdm(W)
     inp = synth.make_inputs(2, seed=6, variant=variant)
-    y = {k: inp[k] for k in ("audio", "word", "seed", "style_feature")}
-    y["scale"] = torch.ones(1) * 2.0
-    fn = lambda x, t, yy: omdm.cfg_text(lambda a, b, c: omdm.mdm_forward(W, a, b, c, variant), x, t, yy)
+    y = {k: inp[k] for k in ("audio", "word", "seed")}
+    model = lambda a, b, c: omdm.mdm_forward(W, a, b, c, variant)
+    cst, g2 = emu.cond(P, inp["audio"], inp["word"], inp["seed"])
+    if plan == "none":
+        fn = model
+        evals, mix = [(cst, g2, None)], lambda o: o[0]
+    elif plan == "text":
+        y["style_feature"] = inp["style_feature"]
+        y["scale"] = torch.ones(1) * 2.0
+        fn = lambda x, t, yy: omdm.cfg_text(model, x, t, yy)
+        evals = [(cst, g2, inp["style_feature"] @ P["w_style"].t()), (cst, g2, None)]      # conditional, unconditional
+        mix = lambda o: o[1] + 2.0 * (o[0] - o[1])
+    else:
+        y["style_feature"] = inp["style_upper"]
+        y["scale_audio"], y["scale_prompt"] = torch.ones(1) * 1.5, torch.ones(1) * 3.0
+        fn = lambda x, t, yy: omdm.cfg_two(model, x, t, yy)
+        cst_n, _ = emu.cond(P, inp["audio"], inp["word"], inp["seed"], null_audio=True)
+        sv_null = P["null_sv"][None].expand(2, -1)
+        sv_real = inp["style_upper"] @ P["w_style"].t()
+        evals = [(cst_n, g2, sv_null), (cst, g2, sv_null), (cst_n, g2, sv_real)]           # uu, ut, ua
+        mix = lambda o: o[0] + 1.5 * (o[1] - o[0]) + 3.0 * (o[2] - o[0])
     sch = odiff.make_schedule(respacing="ddim4")
     ref = odiff.ddim_sample_loop(sch, fn, inp["noise"], y)
     betas, tmap = schedule.respace(schedule.get_named_beta_schedule("cosine", 1000), schedule.space_timesteps(1000, "ddim4"))
     assert list(tmap) == list(sch.timestep_map)
     coef = schedule.ddim_coefs(schedule.Tables(betas))
-    cst, g2 = emu.cond(P, inp["audio"], inp["word"], inp["seed"])
-    sv_c = inp["style_feature"] @ P["w_style"].t()
-    got = emu.ddim_z_loop(P, coef, tmap, inp["noise"], cst, g2, (sv_c, None), 2.0)
+    got = emu.ddim_z_loop(P, coef, tmap, inp["noise"], evals, mix)
     assert float((ref - got).abs().max()) < 1e-4
 
 
