@@ -87,6 +87,27 @@ res["two_streams_ms_per_batch"] = min(timed(two_streams) for _ in range(3)) / K
 torch.cuda.synchronize()
 res["two_streams_bitwise_equal"] = bool(torch.equal(A["out"][0], ref_A) and torch.equal(Bs["out"][0], ref_B))
 
+# more than two in flight (N_SETS=3 python tests/concurrency_probe.py): does a third batch still find gaps?
+n_sets = int(os.environ.get("N_SETS", "2"))
+if n_sets > 2:
+    sets = [A, Bs] + [make_set(32, 10 + i) for i in range(n_sets - 2)]
+    for s in sets[2:]:
+        for _ in range(3):
+            run(s)
+    strs = [torch.cuda.Stream() for _ in sets]
+
+    def n_streams():
+        for st in strs:
+            st.wait_stream(main)
+        for i in range(K * n_sets // 2):
+            with torch.cuda.stream(strs[i % n_sets]):
+                run(sets[i % n_sets])
+        for st in strs:
+            main.wait_stream(st)
+
+    n_streams()
+    res[f"{n_sets}_streams_ms_per_batch"] = min(timed(n_streams) for _ in range(3)) / (K * n_sets // 2)
+    del sets
 del Bs
 C64 = make_set(64, 3)
 for _ in range(3):
