@@ -204,6 +204,7 @@ static bool g_rank_simt = false;
 static bool g_decode_streams = true;   // st_debug_probe bit 256: decode the three body parts one after the other
 static bool g_wav_planes = true;   // st_debug_probe bit 128: WavEncoder with fp32 activations and a split pass per conv
 static bool g_fused_attn = true;   // st_debug_probe bit 32 turns the fused qkv + attention kernel off
+static bool g_attn_tc = false;     // st_debug_probe bit 2048: QK^T and PV of the fused attention on the tensor cores (attn == 2)
 static bool g_zrec = true;         // st_debug_probe bit 512 turns the z recursion of deterministic DDIM off (state kept in x space)
 static bool g_zrec_fc2 = true;     // st_debug_probe bit 1024: the last block's fc2 stays a layer of its own inside the z recursion
 
@@ -216,6 +217,7 @@ extern "C" int st_debug_probe(int flags) {
   g_decode_streams = !(flags & 256);
   g_wav_planes = !(flags & 128);
   g_zrec = !(flags & 512);
+  g_attn_tc = (flags & 2048) != 0;
   g_zrec_fc2 = !(flags & 1024);
   return ST_OK;
 }
@@ -680,7 +682,7 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
         // qkv GEMM + 32-token attention in one kernel (cluster of 2 CTAs per (4 sequences, head))
         GemmP pq = linear(m->X, R, 512, b.qkv_wgp, nullptr, nullptr, 1536);
         pq.a_planes = m->X_p; pq.a_plane_stride = ps512; pq.ln_stats = m->ln_stats; pq.ln_s = b.qkv_sp; pq.ln_c = b.qkv_cp;
-        pq.attn = 1; pq.o_planes = m->ATT_p; pq.o_plane_stride = ps512; pq.o_planes_ld = 512;
+        pq.attn = g_attn_tc ? 2 : 1; pq.o_planes = m->ATT_p; pq.o_plane_stride = ps512; pq.o_planes_ld = 512;
         ST_TRY(gemm(pq, s));
       } else {
         GemmP pq = linear(m->X, R, 512, b.qkv_wg, nullptr, m->QKV, 1536);

@@ -645,6 +645,12 @@ constexpr int ATT_LDS = 36;                      // score row stride (floats)
 constexpr int ATT_SX_BYTES = 128 * ATT_LDS * 4;  // partial scores written by the peer CTA of the cluster
 constexpr int ATT_KV_BYTES = 128 * ATT_LDK * 4;
 constexpr int ATT_PL_OFF = 124928;               // plane staging box behind Q, K, V and P (3 x 34816 + 18432 = 122880 -> 1024-aligned)
+// tensor-core attention (attn == 2): operand tiles in the (dead) ring memory, offsets from the ring base, all 128B-swizzled
+// K-major tiles with 128-byte rows.  Q / K: [128 tokens x 64 dims] hi, lo (K_hi and K_lo back to back = one N = 256 operand);
+// V^T per 64-key block: [64 dims hi ; 64 dims lo] x 64 keys (one N = 128 operand); P per 64-key block: [128 queries x 64 keys]
+// hi, lo; the result's plane staging box reuses the Q tiles.
+constexpr int ATT2_Q = 0, ATT2_K = 32768, ATT2_VT = 65536, ATT2_P = 98304, ATT2_O = 0;
+constexpr float kPScale = 1024.0f;               // softmax probabilities are split as (p * 1024): lo stays a normal fp16
 constexpr int FAST_BOX_F32 = 128 * 32 * 4;       // one fp32 staging box: 128 rows x 32 columns, 128B rows
 constexpr int FAST_BOX_PL = 2 * TC_A_PLANE;      // one plane staging box: 2 planes x 128 rows x 64 halfs
 
@@ -665,7 +671,10 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_bar = empty_bar + STAGES;
   uint64_t* res_bar = acc_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+  // tensor-core attention (attn == 2): operand tiles ready for Q K^T (256 arrivals), scores complete (commit), P and V^T
+  // ready (256 arrivals), P V complete (commit)
+  uint64_t* att_bar = res_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(att_bar + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
@@ -684,6 +693,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(acc_bar, 1);
     mbar_init(res_bar, 1);
+    mbar_init(&att_bar[0], 256); mbar_init(&att_bar[1], 1); mbar_init(&att_bar[2], 256); mbar_init(&att_bar[3], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -799,6 +809,44 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       umma_commit(acc_bar);
       if (dbg) dbg[2] = clock64();
     }
+    if (ep.attn == 2) {
+      // ===== tensor-core attention, MMA side: S = Q K^T over this CTA's 64 dims, then O = P V over the 128 keys of the tile
+      // (block diagonal P: a query row only carries the 32 keys of its own sequence) =====
+      const uint32_t s0 = smem_u32(smem);
+      __syncwarp();
+      if (elect_one()) {
+        mbar_wait(&att_bar[0], 0);
+        tc_fence_after();
+        const uint32_t id_cat = umma_idesc_f16(TC_BM, 256), id_n = umma_idesc_f16(TC_BM, 128);
+        const uint64_t dqh = umma_desc_sw128(s0 + ATT2_Q), dql = umma_desc_sw128(s0 + ATT2_Q + TC_A_PLANE), dk = umma_desc_sw128(s0 + ATT2_K);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          umma_f16(tmem_base, dqh + 2 * k, dk + 2 * k, id_cat, k != 0);        // columns [0,128) q_hi.k_hi, [128,256) q_hi.k_lo
+          umma_f16(tmem_base + 128, dql + 2 * k, dk + 2 * k, id_n, 1);         // + q_lo.k_hi
+        }
+        umma_commit(&att_bar[1]);
+      }
+      __syncwarp();
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // the score exchange of the epilogue warps
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      if (elect_one()) {
+        mbar_wait(&att_bar[2], 0);
+        tc_fence_after();
+        const uint32_t id_cat = umma_idesc_f16(TC_BM, 128), id_n = umma_idesc_f16(TC_BM, 64);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t dph = umma_desc_sw128(s0 + ATT2_P + kb * 32768), dpl = umma_desc_sw128(s0 + ATT2_P + kb * 32768 + TC_A_PLANE);
+          const uint64_t dv = umma_desc_sw128(s0 + ATT2_VT + kb * 16384);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            umma_f16(tmem_base + 384, dph + 2 * k, dv + 2 * k, id_cat, (kb | k) != 0);   // [384,448) p_hi.v_hi, [448,512) p_hi.v_lo
+            umma_f16(tmem_base + 448, dpl + 2 * k, dv + 2 * k, id_n, 1);                 // + p_lo.v_hi
+          }
+        }
+        umma_commit(&att_bar[3]);
+      }
+      __syncwarp();
+    }
   } else {
     // ===== epilogue: warps 2..9; TMEM lane group = warp % 4 (rows), the two warps of a group alternate 32-column chunks =====
     pdl_wait();
@@ -839,7 +887,158 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t out_base = stage0;                                                  // NCH fp32 boxes
     const uint32_t pl_base = stage0 + (ep.has_out ? NCH * FAST_BOX_F32 : 0);           // BN / 64 plane boxes
     const uint32_t res_base = smem_u32(res_tile);
-    if (ep.attn) {
+    if (ep.attn == 2) {
+      // ---- fused attention on the tensor cores (transformer.py:83-104).  Same tile as below: 4 sequences x 32 tokens, 64 of
+      // the 128 dims of q, k, v of one head.  q, k -> fp16 hi/lo operand tiles (thread = token row), v -> transposed tiles
+      // (dims x keys); S = Q K^T as three split MMAs into TMEM; each thread reads the 32 scores of its own row (the diagonal
+      // 32 x 32 block of its sequence), exchanges the partial sums over 64 dims with the cluster peer, runs the softmax in
+      // registers and writes its row of the block-diagonal P; O = P V as three split MMAs; the result leaves as planes.
+      const uint32_t sx = smem_u32(res_tile);
+      uint32_t sx_peer;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(sx_peer) : "r"(sx), "r"((uint32_t)((blockIdx.x & 1) ^ 1)));
+      const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
+      auto chunk = [&](int c, float* x) {                // 32 columns of chunk c of this thread's row, bias and folded LayerNorm applied
+        uint32_t v[32], vc[32];
+        tmem_ld32(trow + c * 32, v);
+        tmem_ld32(trow + BN + c * 32, vc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + t * 4);
+          const float4 s4 = *reinterpret_cast<const float4*>(lns_s + c * 32 + t * 4);
+          x[4 * t + 0] = (__uint_as_float(v[4 * t + 0]) + __uint_as_float(vc[4 * t + 0])) * sc + b4.x - u * s4.x;
+          x[4 * t + 1] = (__uint_as_float(v[4 * t + 1]) + __uint_as_float(vc[4 * t + 1])) * sc + b4.y - u * s4.y;
+          x[4 * t + 2] = (__uint_as_float(v[4 * t + 2]) + __uint_as_float(vc[4 * t + 2])) * sc + b4.z - u * s4.z;
+          x[4 * t + 3] = (__uint_as_float(v[4 * t + 3]) + __uint_as_float(vc[4 * t + 3])) * sc + b4.w - u * s4.w;
+        }
+      };
+      if (cpart == 0) {
+        // q0 q1 k0 k1 -> Q and K operand tiles (row r, 16-byte chunk (c & 1) * 4 + q, 128B swizzle)
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float x[32];
+          chunk(c, x);
+          const uint32_t row = stage0 + (uint32_t)((c < 2 ? ATT2_Q : ATT2_K) + r * 128);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __half h[8], l[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_f16(x[8 * q + e] * kActScale, h[e], l[e]);
+            const uint32_t off = (((uint32_t)((c & 1) * 4 + q)) ^ sw) << 4;
+            sts128u(row + off, make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
+            sts128u(row + TC_A_PLANE + off, make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7])));
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[0])) : "memory");
+      } else {
+        // v0 v1 -> registers (the score MMAs overwrite the qkv accumulators: every TMEM read is done before they start)
+        float xv[64];
+        chunk(4, xv);
+        chunk(5, xv + 32);
+        tc_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[0])) : "memory");
+        // V^T: element (dim d, key r) of the 64-key block r / 64; hi rows 0..63, lo rows 64..127 of the block's tile
+        const uint32_t kcol = (uint32_t)(r & 63);
+        const uint32_t vt = stage0 + (uint32_t)(ATT2_VT + (r >> 6) * 16384) + (kcol & 7) * 2;
+#pragma unroll
+        for (int d = 0; d < 64; ++d) {
+          __half h, l;
+          split_f16(xv[d] * kActScale, h, l);
+          const uint32_t a = vt + (uint32_t)(d * 128) + (((kcol >> 3) ^ (uint32_t)(d & 7)) << 4);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(__half_as_ushort(h)) : "memory");
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(a + 8192), "h"(__half_as_ushort(l)) : "memory");
+        }
+        // zeros of row r of P: the other sequence's 32 keys in its own 64-key block, all 64 keys of the other block
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          const uint32_t own = stage0 + (uint32_t)(ATT2_P + (lg >> 1) * 32768 + pl * TC_A_PLANE + r * 128);
+          const uint32_t oth = stage0 + (uint32_t)(ATT2_P + ((lg >> 1) ^ 1) * 32768 + pl * TC_A_PLANE + r * 128);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sts128u(own + ((((uint32_t)(((lg & 1) ^ 1) * 4 + q)) ^ sw) << 4), z4);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) sts128u(oth + (((uint32_t)q ^ sw) << 4), z4);
+        }
+        fence_proxy_async();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[2])) : "memory");
+      }
+      float sv[32];
+      if (cpart == 0) {
+        // partial scores of this row over the 64 local dims: diagonal block of the sequence, main + cross accumulator
+        mbar_wait(&att_bar[1], 0);
+        tc_fence_after();
+        uint32_t v[32], vc[32];
+        tmem_ld32(trow + lg * 32, v);
+        tmem_ld32(trow + 128 + lg * 32, vc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sv[j] = __uint_as_float(v[j]) + __uint_as_float(vc[j]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sx_peer + (uint32_t)(r * ATT_LDS + 4 * q) * 4), "f"(sv[4 * q]),
+                       "f"(sv[4 * q + 1]), "f"(sv[4 * q + 2]), "f"(sv[4 * q + 3]) : "memory");
+      }
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      if (cpart == 0) {
+        // softmax over the 32 keys of the row, in registers; operands were scaled by kActScale each
+        const float ssc = 0.08838834764831845f / (kActScale * kActScale);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 o4 = lds128(sx + (uint32_t)(r * ATT_LDS + 4 * q) * 4);
+          sv[4 * q] = (sv[4 * q] + o4.x) * ssc; sv[4 * q + 1] = (sv[4 * q + 1] + o4.y) * ssc;
+          sv[4 * q + 2] = (sv[4 * q + 2] + o4.z) * ssc; sv[4 * q + 3] = (sv[4 * q + 3] + o4.w) * ssc;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, sv[j]);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { sv[j] = expf(sv[j] - mx); sum += sv[j]; }
+        const float inv = kPScale / sum;
+        const uint32_t prow = stage0 + (uint32_t)(ATT2_P + (lg >> 1) * 32768 + r * 128);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __half h[8], l[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_f16(sv[8 * q + e] * inv, h[e], l[e]);
+          const uint32_t off = (((uint32_t)((lg & 1) * 4 + q)) ^ sw) << 4;
+          sts128u(prow + off, make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
+          sts128u(prow + TC_A_PLANE + off, make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7])));
+        }
+        fence_proxy_async();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[2])) : "memory");
+      }
+      // O: this thread's row, 32 of the CTA's 64 dims; accumulators carry (p * 1024) (v * 16), the planes want o * 16
+      mbar_wait(&att_bar[3], 0);
+      tc_fence_after();
+      {
+        uint32_t v[32], vc[32];
+        tmem_ld32(trow + 384 + cpart * 32, v);
+        tmem_ld32(trow + 448 + cpart * 32, vc);
+        tmem_ld_wait();
+        const uint32_t orow = stage0 + (uint32_t)(ATT2_O + r * 128);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __half h[8], l[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_f16((__uint_as_float(v[8 * q + e]) + __uint_as_float(vc[8 * q + e])) * (1.0f / kPScale), h[e], l[e]);
+          const uint32_t off = (((uint32_t)(cpart * 4 + q)) ^ sw) << 4;
+          sts128u(orow + off, make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
+          sts128u(orow + TC_A_PLANE + off, make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7])));
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && elect_one()) {
+        tma_store_3d(&tmP, stage0 + ATT2_O, blockIdx.x * 64, m0, 0);
+        tma_store_commit_wait();
+      }
+      if (dbg && threadIdx.x == 64) dbg[4] = clock64();
+    } else if (ep.attn) {
       // ---- fused attention (transformer.py:83-104).  This CTA holds, for 4 sequences x 32 tokens (TMEM lane group = one
       // sequence, lane = token), 64 of the 128 dims of q, k and v of one head; its cluster peer holds the other 64.
       // q, k, v go to shared memory (fp32); the two warps of a lane group then take 16 query rows each and work in
@@ -1097,8 +1296,8 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (dbg && threadIdx.x == 64) dbg[4] = clock64();
     }
   }
-  if (ep.attn && warp < 2) {
-    // the producer and MMA warps take part in the cluster barrier of the attention epilogue
+  if ((ep.attn == 1 && warp < 2) || (ep.attn == 2 && warp == 0)) {
+    // the producer and MMA warps take part in the cluster barrier of the attention epilogue (attn == 2: the MMA warp already has)
     __syncwarp();
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -1458,7 +1657,7 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   int stages = (232448 - 4096 - res) / stage;
   if (stages > 4) stages = 4;
   if (p.attn) { stages = 2; }
-  const int smem = stages * stage + (p.attn ? ATT_SX_BYTES : res) + 2 * 192 * 4 + (2 * stages + 2) * 8 + 16 + 1024;
+  const int smem = stages * stage + (p.attn ? ATT_SX_BYTES : res) + 2 * 192 * 4 + (2 * stages + 2 + 4) * 8 + 16 + 1024;
   const CUtensorMap *tmA = nullptr, *tmW = nullptr, *tmO = nullptr, *tmP = nullptr;
   const int cmode = conv_mode(p);
   const CUtensorMap* tmA2 = nullptr;
