@@ -932,6 +932,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_before();
         fence_proxy_async();
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[0])) : "memory");
+        if (dbg && threadIdx.x == 64) { dbg[40] = dbg[0]; dbg[41] = dbg[3]; dbg[42] = clock64(); }
       } else {
         // v0 v1 -> registers (the score MMAs overwrite the qkv accumulators: every TMEM read is done before they start)
         float xv[64];
@@ -979,9 +980,11 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int q = 0; q < 8; ++q)
           asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sx_peer + (uint32_t)(r * ATT_LDS + 4 * q) * 4), "f"(sv[4 * q]),
                        "f"(sv[4 * q + 1]), "f"(sv[4 * q + 2]), "f"(sv[4 * q + 3]) : "memory");
+        if (dbg && threadIdx.x == 64) dbg[43] = clock64();
       }
       asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
       asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      if (dbg && threadIdx.x == 64) dbg[44] = clock64();
       if (cpart == 0) {
         // softmax over the 32 keys of the row, in registers; operands were scaled by kActScale each
         const float ssc = 0.08838834764831845f / (kActScale * kActScale);
@@ -1010,10 +1013,12 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         fence_proxy_async();
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[2])) : "memory");
+        if (dbg && threadIdx.x == 64) dbg[45] = clock64();
       }
       // O: this thread's row, 32 of the CTA's 64 dims; accumulators carry (p * 1024) (v * 16), the planes want o * 16
       mbar_wait(&att_bar[3], 0);
       tc_fence_after();
+      if (dbg && threadIdx.x == 64) dbg[46] = clock64();
       {
         uint32_t v[32], vc[32];
         tmem_ld32(trow + 384 + cpart * 32, v);
@@ -1037,7 +1042,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_store_3d(&tmP, stage0 + ATT2_O, blockIdx.x * 64, m0, 0);
         tma_store_commit_wait();
       }
-      if (dbg && threadIdx.x == 64) dbg[4] = clock64();
+      if (dbg && threadIdx.x == 64) { dbg[47] = clock64(); dbg[4] = dbg[47]; }
     } else if (ep.attn) {
       // ---- fused attention (transformer.py:83-104).  This CTA holds, for 4 sequences x 32 tokens (TMEM lane group = one
       // sequence, lane = token), 64 of the 128 dims of q, k and v of one head; its cluster peer holds the other 64.
@@ -1531,11 +1536,8 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcEpi
   const int stage_bytes = 2 * TC_A_PLANE + 2 * BN * TC_BK * 2;
   const int stages = BN == 64 ? 4 : BN == 128 ? 3 : 2;
   const int smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
-  static bool attr = false;
-  if (!attr) {
-    ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * TC_A_PLANE + 2 * 64 * TC_BK * 2) + 9 * 8 + 16 + 1024));
-    attr = true;
-  }
+  static DeviceOnce attr;       // the attribute is per device (one process may drive models on several GPUs)
+  if (attr.first()) ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * TC_A_PLANE + 2 * 64 * TC_BK * 2) + 9 * 8 + 16 + 1024));
   dim3 grid((ep.N + BN - 1) / BN, mtiles);
   launch_k(gemm_tc_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, tmA, tmW, ep, num_kb, BN, stages);
   ST_CHECK_LAUNCH();
@@ -1679,11 +1681,8 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   ep.mode = cmode; ep.T = p.Lout; ep.kb_per_tap = cmode == 0 ? 1 : p.C / TC_BK; ep.dil = p.dil; ep.pad = p.pad;
   ep.planes_relu = p.o_planes_relu;
   ep.kb_split = p.a2_planes ? (p.K - p.a2_K) / TC_BK : 0x7fffffff;
-  static bool attr = false;
-  if (!attr) {
-    ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr = true;
-  }
+  static DeviceOnce attr;
+  if (attr.first()) ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM);
   if (p.attn) launch_k_cluster(gemm_tc_fast_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, 2, *tmA, *tmW, *tmO, *tmP, ep, w->Kp / TC_BK, BN, stages, *tmA2);
   else launch_k(gemm_tc_fast_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, *tmA, *tmW, *tmO, *tmP, ep, w->Kp / TC_BK, BN, stages, *tmA2);

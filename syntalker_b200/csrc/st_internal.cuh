@@ -79,6 +79,19 @@ inline cudaError_t launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bl
   cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
+// "once per device" latch for per-device function attributes (cudaFuncSetAttribute): first() is true the first time it is
+// called with a given current device.  A racing second thread may set the attribute twice, which is harmless.
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
 #ifdef __CUDACC__
 // Debug trace (st_debug_trace): CTA (0,0) thread 0 of every kernel stamps %globaltimer and a kernel id at entry.
 // In constant memory: every kernel reads this pointer at entry, and as a plain __device__ variable that read was an L2

@@ -7,6 +7,8 @@ from syntalker_b200.denoiser import MDM
 B = 64
 torch.set_grad_enabled(False)
 L = _lib.lib()
+if os.environ.get("ST_PROBE"):
+    _lib.check(L.st_debug_probe(int(os.environ["ST_PROBE"])))
 model = MDM(None).load_state_dict(synth.mdm_state_dict("beatx", seed=0))
 inp = synth.make_inputs(B, seed=1, variant="beatx")
 y = {k: inp[k].cuda() for k in ("audio", "word", "seed")}

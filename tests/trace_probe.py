@@ -11,6 +11,8 @@ from syntalker_b200.diffusion import create_gaussian_diffusion
 B = 32
 torch.set_grad_enabled(False)
 L = _lib.lib()
+if os.environ.get("ST_PROBE"):
+    _lib.check(L.st_debug_probe(int(os.environ["ST_PROBE"])))
 model = MDM(None).load_state_dict(synth.mdm_state_dict("beatx_motionclip", seed=0))
 w = ClassifierFreeSampleModel(model)
 diff = create_gaussian_diffusion(timestep_respacing="ddim5")
