@@ -203,6 +203,8 @@ def main():
     _lib.set_engine(args.engine)
     _lib.check(_lib.lib().st_set_pdl(int(os.environ.get("ST_PDL", "1"))))
     _lib.check(_lib.lib().st_set_graphs(int(os.environ.get("ST_GRAPHS", "1"))))
+    if os.environ.get("ST_PROBE"):          # A/B experiments only (st_debug_probe bits); the default run sets nothing
+        _lib.check(_lib.lib().st_debug_probe(int(os.environ["ST_PROBE"])))
     B = args.batch
     model = MDM(None).load_state_dict(synth.mdm_state_dict("beatx_motionclip", seed=0))
     wrapped = ClassifierFreeSampleModel(model)

@@ -204,7 +204,7 @@ static bool g_rank_simt = false;
 static bool g_decode_streams = true;   // st_debug_probe bit 256: decode the three body parts one after the other
 static bool g_wav_planes = true;   // st_debug_probe bit 128: WavEncoder with fp32 activations and a split pass per conv
 static bool g_fused_attn = true;   // st_debug_probe bit 32 turns the fused qkv + attention kernel off
-static bool g_attn_tc = false;     // st_debug_probe bit 2048: QK^T and PV of the fused attention on the tensor cores (attn == 2)
+static bool g_attn_tc = true;      // QK^T and PV of the fused attention as tcgen05 MMAs (attn == 2); st_debug_probe bit 2048 selects the packed-fp32 FMA epilogue
 static bool g_zrec = true;         // st_debug_probe bit 512 turns the z recursion of deterministic DDIM off (state kept in x space)
 static bool g_zrec_fc2 = true;     // st_debug_probe bit 1024: the last block's fc2 stays a layer of its own inside the z recursion
 
@@ -217,7 +217,7 @@ extern "C" int st_debug_probe(int flags) {
   g_decode_streams = !(flags & 256);
   g_wav_planes = !(flags & 128);
   g_zrec = !(flags & 512);
-  g_attn_tc = (flags & 2048) != 0;
+  g_attn_tc = !(flags & 2048);
   g_zrec_fc2 = !(flags & 1024);
   return ST_OK;
 }

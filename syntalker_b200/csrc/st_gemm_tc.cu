@@ -117,6 +117,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -139,6 +148,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// The same for an MN-major operand (cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>, canonical layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): rows of 64 contiguous MN elements (128 B, swizzled in groups of 8 rows),
+// one row per K index; LBO = bytes between 64-element groups along MN, SBO = bytes between groups of 8 K rows.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+constexpr uint32_t kIdescBMajorMN = 1u << 16;      // InstrDescriptor b_major_: B operand is MN-major
 // Instruction descriptor (InstrDescriptor): D = F32 (1 << 4), A = B = F16 (0), K-major both, N >> 3 at bit 17, M >> 4 at bit 24.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
@@ -187,6 +203,21 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   v = fminf(fmaxf(v, -65000.0f), 65000.0f);
   hi = __float2half_rn(v);
   lo = __float2half_rn(v - __half2float(hi));
+}
+
+// (a, b) -> packed fp16 pairs hi = rn(a, b) (saturating to the largest finite fp16), lo = rn((a, b) - hi): six instructions per
+// pair (F2FP.SATFINITE.PACK_AB, 2 HADD2.F32, 2 FADD, F2FP.PACK_AB) where the clamp + scalar form took ten.
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));       // low half <- a, high half <- b
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - f.y), "f"(a - f.x));
+}
+// eight consecutive values (times s) -> one 16-byte chunk of the hi plane and one of the lo plane
+__device__ __forceinline__ void split8_f16(const float* x, float s, uint4& h, uint4& l) {
+  split2_f16(x[0] * s, x[1] * s, h.x, l.x);
+  split2_f16(x[2] * s, x[3] * s, h.y, l.y);
+  split2_f16(x[4] * s, x[5] * s, h.z, l.z);
+  split2_f16(x[6] * s, x[7] * s, h.w, l.w);
 }
 
 // One binary for every tile width (BN = 64 / 128 / 192 and the ring depth are run-time values): the sampling loop
@@ -646,10 +677,11 @@ constexpr int ATT_SX_BYTES = 128 * ATT_LDS * 4;  // partial scores written by th
 constexpr int ATT_KV_BYTES = 128 * ATT_LDK * 4;
 constexpr int ATT_PL_OFF = 124928;               // plane staging box behind Q, K, V and P (3 x 34816 + 18432 = 122880 -> 1024-aligned)
 // tensor-core attention (attn == 2): operand tiles in the (dead) ring memory, offsets from the ring base, all 128B-swizzled
-// K-major tiles with 128-byte rows.  Q / K: [128 tokens x 64 dims] hi, lo (K_hi and K_lo back to back = one N = 256 operand);
-// V^T per 64-key block: [64 dims hi ; 64 dims lo] x 64 keys (one N = 128 operand); P per 64-key block: [128 queries x 64 keys]
-// hi, lo; the result's plane staging box reuses the Q tiles.
-constexpr int ATT2_Q = 0, ATT2_K = 32768, ATT2_VT = 65536, ATT2_P = 98304, ATT2_O = 0;
+// tiles with 128-byte rows.  Q / K / V: [128 tokens x 64 dims] hi, lo -- thread = token row writes its own row, no transposition:
+// K_hi and K_lo back to back are one K-major N = 256 operand of Q K^T, and V is the MN-major B operand of P V (rows = keys = K index,
+// the 64 dims of a row = N; V_hi ; V_lo one N = 128 operand with LBO = plane stride); P per 64-key block: [128 queries x 64 keys]
+// hi, lo, K-major; the result's plane staging box reuses the Q tiles.
+constexpr int ATT2_Q = 0, ATT2_K = 32768, ATT2_V = 65536, ATT2_P = 98304, ATT2_O = 0;
 constexpr float kPScale = 1024.0f;               // softmax probabilities are split as (p * 1024): lo stays a normal fp16
 constexpr int FAST_BOX_F32 = 128 * 32 * 4;       // one fp32 staging box: 128 rows x 32 columns, 128B rows
 constexpr int FAST_BOX_PL = 2 * TC_A_PLANE;      // one plane staging box: 2 planes x 128 rows x 64 halfs
@@ -832,15 +864,16 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (elect_one()) {
         mbar_wait(&att_bar[2], 0);
         tc_fence_after();
-        const uint32_t id_cat = umma_idesc_f16(TC_BM, 128), id_n = umma_idesc_f16(TC_BM, 64);
+        const uint32_t id_cat = umma_idesc_f16(TC_BM, 128) | kIdescBMajorMN, id_n = umma_idesc_f16(TC_BM, 64) | kIdescBMajorMN;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const uint64_t dph = umma_desc_sw128(s0 + ATT2_P + kb * 32768), dpl = umma_desc_sw128(s0 + ATT2_P + kb * 32768 + TC_A_PLANE);
-          const uint64_t dv = umma_desc_sw128(s0 + ATT2_VT + kb * 16384);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
-            umma_f16(tmem_base + 384, dph + 2 * k, dv + 2 * k, id_cat, (kb | k) != 0);   // [384,448) p_hi.v_hi, [448,512) p_hi.v_lo
-            umma_f16(tmem_base + 448, dpl + 2 * k, dv + 2 * k, id_n, 1);                 // + p_lo.v_hi
+            // keys 64 kb + 16 k .. + 16 of V (128 bytes per key row); N = [64 dims of V_hi ; 64 dims of V_lo]
+            const uint64_t dv = umma_desc_mn_sw128(s0 + ATT2_V + kb * 8192 + k * 2048, TC_A_PLANE, 1024);
+            umma_f16(tmem_base + 384, dph + 2 * k, dv, id_cat, (kb | k) != 0);   // [384,448) p_hi.v_hi, [448,512) p_hi.v_lo
+            umma_f16(tmem_base + 448, dpl + 2 * k, dv, id_n, 1);                 // + p_lo.v_hi
           }
         }
         umma_commit(&att_bar[3]);
@@ -888,133 +921,121 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t pl_base = stage0 + (ep.has_out ? NCH * FAST_BOX_F32 : 0);           // BN / 64 plane boxes
     const uint32_t res_base = smem_u32(res_tile);
     if (ep.attn == 2) {
-      // ---- fused attention on the tensor cores (transformer.py:83-104).  Same tile as below: 4 sequences x 32 tokens, 64 of
-      // the 128 dims of q, k, v of one head.  q, k -> fp16 hi/lo operand tiles (thread = token row), v -> transposed tiles
-      // (dims x keys); S = Q K^T as three split MMAs into TMEM; each thread reads the 32 scores of its own row (the diagonal
-      // 32 x 32 block of its sequence), exchanges the partial sums over 64 dims with the cluster peer, runs the softmax in
-      // registers and writes its row of the block-diagonal P; O = P V as three split MMAs; the result leaves as planes.
+      // ---- fused attention on the tensor cores (transformer.py:83-104).  The tile: 4 sequences x 32 tokens (TMEM lane group =
+      // sequence, lane = token), 64 of the 128 dims of q, k, v of one head; the cluster peer holds the other 64 dims.
+      //  1. thread = token row: q, k, v -> fp16 hi/lo operand tiles (row-major, 128B swizzle; the two warps of a lane group take
+      //     the column halves [0,32) / [32,64) of each of q, k, v), plus the zeros of its row of the block-diagonal P
+      //  2. MMA warp: S = Q K^T as three split MMAs into TMEM columns [0,256) (the qkv accumulators are dead by then)
+      //  3. thread (row, key half): 16 partial scores of its row's own sequence -> the peer CTA (distributed shared memory),
+      //     cluster barrier, add the peer's partial sums over the other 64 dims
+      //  4. softmax over the row's 32 keys: each warp reduces its 16 keys, the pair merges (max, sum) through shared memory;
+      //     P (times 1024) -> hi/lo tiles
+      //  5. MMA warp: O = P V as three split MMAs (V is the MN-major B operand) into columns [384,512)
+      //  6. thread (row, dim half): 32 dims of O -> plane staging (over the dead Q tiles) -> one TMA store
       const uint32_t sx = smem_u32(res_tile);
       uint32_t sx_peer;
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(sx_peer) : "r"(sx), "r"((uint32_t)((blockIdx.x & 1) ^ 1)));
       const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
-      auto chunk = [&](int c, float* x) {                // 32 columns of chunk c of this thread's row, bias and folded LayerNorm applied
+#pragma unroll 1
+      for (int cc = 0; cc < 3; ++cc) {
+        const int c = 2 * cc + cpart;                    // chunks [q0 q1 k0 k1 v0 v1]: this warp's half of q, k, v
         uint32_t v[32], vc[32];
         tmem_ld32(trow + c * 32, v);
         tmem_ld32(trow + BN + c * 32, vc);
         tmem_ld_wait();
+        const uint32_t row = stage0 + (uint32_t)(cc * 32768 + r * 128);                 // ATT2_Q / ATT2_K / ATT2_V
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + t * 4);
-          const float4 s4 = *reinterpret_cast<const float4*>(lns_s + c * 32 + t * 4);
-          x[4 * t + 0] = (__uint_as_float(v[4 * t + 0]) + __uint_as_float(vc[4 * t + 0])) * sc + b4.x - u * s4.x;
-          x[4 * t + 1] = (__uint_as_float(v[4 * t + 1]) + __uint_as_float(vc[4 * t + 1])) * sc + b4.y - u * s4.y;
-          x[4 * t + 2] = (__uint_as_float(v[4 * t + 2]) + __uint_as_float(vc[4 * t + 2])) * sc + b4.z - u * s4.z;
-          x[4 * t + 3] = (__uint_as_float(v[4 * t + 3]) + __uint_as_float(vc[4 * t + 3])) * sc + b4.w - u * s4.w;
-        }
-      };
-      if (cpart == 0) {
-        // q0 q1 k0 k1 -> Q and K operand tiles (row r, 16-byte chunk (c & 1) * 4 + q, 128B swizzle)
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          float x[32];
-          chunk(c, x);
-          const uint32_t row = stage0 + (uint32_t)((c < 2 ? ATT2_Q : ATT2_K) + r * 128);
+        for (int q = 0; q < 4; ++q) {
+          float x[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            __half h[8], l[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) split_f16(x[8 * q + e] * kActScale, h[e], l[e]);
-            const uint32_t off = (((uint32_t)((c & 1) * 4 + q)) ^ sw) << 4;
-            sts128u(row + off, make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
-            sts128u(row + TC_A_PLANE + off, make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7])));
+          for (int t = 0; t < 2; ++t) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + q * 8 + t * 4);
+            const float4 s4 = *reinterpret_cast<const float4*>(lns_s + c * 32 + q * 8 + t * 4);
+            const int j = 8 * q + 4 * t;
+            x[4 * t + 0] = (__uint_as_float(v[j + 0]) + __uint_as_float(vc[j + 0])) * sc + b4.x - u * s4.x;
+            x[4 * t + 1] = (__uint_as_float(v[j + 1]) + __uint_as_float(vc[j + 1])) * sc + b4.y - u * s4.y;
+            x[4 * t + 2] = (__uint_as_float(v[j + 2]) + __uint_as_float(vc[j + 2])) * sc + b4.z - u * s4.z;
+            x[4 * t + 3] = (__uint_as_float(v[j + 3]) + __uint_as_float(vc[j + 3])) * sc + b4.w - u * s4.w;
           }
+          uint4 h, l;
+          split8_f16(x, kActScale, h, l);
+          const uint32_t off = (((uint32_t)(cpart * 4 + q)) ^ sw) << 4;
+          sts128u(row + off, h);
+          sts128u(row + TC_A_PLANE + off, l);
         }
-        tc_fence_before();
-        fence_proxy_async();
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[0])) : "memory");
-        if (dbg && threadIdx.x == 64) { dbg[40] = dbg[0]; dbg[41] = dbg[3]; dbg[42] = clock64(); }
-      } else {
-        // v0 v1 -> registers (the score MMAs overwrite the qkv accumulators: every TMEM read is done before they start)
-        float xv[64];
-        chunk(4, xv);
-        chunk(5, xv + 32);
-        tc_fence_before();
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[0])) : "memory");
-        // V^T: element (dim d, key r) of the 64-key block r / 64; hi rows 0..63, lo rows 64..127 of the block's tile
-        const uint32_t kcol = (uint32_t)(r & 63);
-        const uint32_t vt = stage0 + (uint32_t)(ATT2_VT + (r >> 6) * 16384) + (kcol & 7) * 2;
-#pragma unroll
-        for (int d = 0; d < 64; ++d) {
-          __half h, l;
-          split_f16(xv[d] * kActScale, h, l);
-          const uint32_t a = vt + (uint32_t)(d * 128) + (((kcol >> 3) ^ (uint32_t)(d & 7)) << 4);
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(__half_as_ushort(h)) : "memory");
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(a + 8192), "h"(__half_as_ushort(l)) : "memory");
-        }
-        // zeros of row r of P: the other sequence's 32 keys in its own 64-key block, all 64 keys of the other block
-        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
-          const uint32_t own = stage0 + (uint32_t)(ATT2_P + (lg >> 1) * 32768 + pl * TC_A_PLANE + r * 128);
-          const uint32_t oth = stage0 + (uint32_t)(ATT2_P + ((lg >> 1) ^ 1) * 32768 + pl * TC_A_PLANE + r * 128);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) sts128u(own + ((((uint32_t)(((lg & 1) ^ 1) * 4 + q)) ^ sw) << 4), z4);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) sts128u(oth + (((uint32_t)q ^ sw) << 4), z4);
-        }
-        fence_proxy_async();
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[2])) : "memory");
       }
-      float sv[32];
-      if (cpart == 0) {
-        // partial scores of this row over the 64 local dims: diagonal block of the sequence, main + cross accumulator
-        mbar_wait(&att_bar[1], 0);
-        tc_fence_after();
-        uint32_t v[32], vc[32];
-        tmem_ld32(trow + lg * 32, v);
-        tmem_ld32(trow + 128 + lg * 32, vc);
+      {
+        // zeros of row r of plane `cpart` of P: the other sequence's 32 keys in the row's own 64-key block, all 64 keys of the other
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t own = stage0 + (uint32_t)(ATT2_P + (lg >> 1) * 32768 + cpart * TC_A_PLANE + r * 128);
+        const uint32_t oth = stage0 + (uint32_t)(ATT2_P + ((lg >> 1) ^ 1) * 32768 + cpart * TC_A_PLANE + r * 128);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sts128u(own + ((((uint32_t)(((lg & 1) ^ 1) * 4 + q)) ^ sw) << 4), z4);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sts128u(oth + (((uint32_t)q ^ sw) << 4), z4);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[0])) : "memory");
+      if (dbg && threadIdx.x == 64) { dbg[40] = dbg[0]; dbg[41] = dbg[3]; dbg[42] = clock64(); }
+      // partial scores of this row over the 64 local dims: keys [16 cpart, +16) of the sequence's diagonal block
+      float sv[16];
+      const uint32_t srow = (uint32_t)(r * ATT_LDS + cpart * 16) * 4;
+      mbar_wait(&att_bar[1], 0);
+      tc_fence_after();
+      {
+        uint32_t v[16], vc[16];
+        tmem_ld16(trow + lg * 32 + cpart * 16, v);
+        tmem_ld16(trow + 128 + lg * 32 + cpart * 16, vc);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sv[j] = __uint_as_float(v[j]) + __uint_as_float(vc[j]);
+        for (int j = 0; j < 16; ++j) sv[j] = __uint_as_float(v[j]) + __uint_as_float(vc[j]);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sx_peer + (uint32_t)(r * ATT_LDS + 4 * q) * 4), "f"(sv[4 * q]),
+        for (int q = 0; q < 4; ++q)
+          asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sx_peer + srow + 16 * q), "f"(sv[4 * q]),
                        "f"(sv[4 * q + 1]), "f"(sv[4 * q + 2]), "f"(sv[4 * q + 3]) : "memory");
-        if (dbg && threadIdx.x == 64) dbg[43] = clock64();
       }
+      if (dbg && threadIdx.x == 64) dbg[43] = clock64();
       asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
       asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
       if (dbg && threadIdx.x == 64) dbg[44] = clock64();
-      if (cpart == 0) {
-        // softmax over the 32 keys of the row, in registers; operands were scaled by kActScale each
-        const float ssc = 0.08838834764831845f / (kActScale * kActScale);
-        float mx = -INFINITY;
+      {
+        // softmax over the 32 keys of the row; the operands were scaled by kActScale each, exp(x) = 2^(x log2 e)
+        const float ssc = 0.08838834764831845f * 1.4426950408889634f / (kActScale * kActScale);
+        float mw = -INFINITY;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 o4 = lds128(sx + (uint32_t)(r * ATT_LDS + 4 * q) * 4);
+        for (int q = 0; q < 4; ++q) {
+          const float4 o4 = lds128(sx + srow + 16 * q);
           sv[4 * q] = (sv[4 * q] + o4.x) * ssc; sv[4 * q + 1] = (sv[4 * q + 1] + o4.y) * ssc;
           sv[4 * q + 2] = (sv[4 * q + 2] + o4.z) * ssc; sv[4 * q + 3] = (sv[4 * q + 3] + o4.w) * ssc;
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, sv[j]);
-        float sum = 0.f;
+        for (int j = 0; j < 16; ++j) mw = fmaxf(mw, sv[j]);
+        float lw = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { sv[j] = expf(sv[j] - mx); sum += sv[j]; }
-        const float inv = kPScale / sum;
+        for (int j = 0; j < 16; ++j) { sv[j] = exp2f(sv[j] - mw); lw += sv[j]; }
+        // merge with the partner warp's 16 keys: (max, sum) pairs meet in the four spare floats of the row's score slot
+        const uint32_t mrow = sx + (uint32_t)(r * ATT_LDS + 32) * 4;
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(mrow + 8 * cpart), "f"(mw), "f"(lw) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory");
+        float mo, lo_;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(mo), "=f"(lo_) : "r"(mrow + 8 * (cpart ^ 1)) : "memory");
+        const float m = fmaxf(mw, mo);
+        const float fw = exp2f(mw - m), fo = exp2f(mo - m);
+        const float inv = fw * kPScale / (lw * fw + lo_ * fo);
         const uint32_t prow = stage0 + (uint32_t)(ATT2_P + (lg >> 1) * 32768 + r * 128);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          __half h[8], l[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) split_f16(sv[8 * q + e] * inv, h[e], l[e]);
-          const uint32_t off = (((uint32_t)((lg & 1) * 4 + q)) ^ sw) << 4;
-          sts128u(prow + off, make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
-          sts128u(prow + TC_A_PLANE + off, make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7])));
+        for (int q = 0; q < 2; ++q) {
+          uint4 h, l;
+          split8_f16(sv + 8 * q, inv, h, l);
+          const uint32_t off = (((uint32_t)((lg & 1) * 4 + cpart * 2 + q)) ^ sw) << 4;
+          sts128u(prow + off, h);
+          sts128u(prow + TC_A_PLANE + off, l);
         }
         fence_proxy_async();
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[2])) : "memory");
-        if (dbg && threadIdx.x == 64) dbg[45] = clock64();
       }
+      if (dbg && threadIdx.x == 64) dbg[45] = clock64();
       // O: this thread's row, 32 of the CTA's 64 dims; accumulators carry (p * 1024) (v * 16), the planes want o * 16
       mbar_wait(&att_bar[3], 0);
       tc_fence_after();
@@ -1027,12 +1048,14 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t orow = stage0 + (uint32_t)(ATT2_O + r * 128);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          __half h[8], l[8];
+          float x[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) split_f16((__uint_as_float(v[8 * q + e]) + __uint_as_float(vc[8 * q + e])) * (1.0f / kPScale), h[e], l[e]);
+          for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[8 * q + e]) + __uint_as_float(vc[8 * q + e]);
+          uint4 h, l;
+          split8_f16(x, 1.0f / kPScale, h, l);
           const uint32_t off = (((uint32_t)(cpart * 4 + q)) ^ sw) << 4;
-          sts128u(orow + off, make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
-          sts128u(orow + TC_A_PLANE + off, make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7])));
+          sts128u(orow + off, h);
+          sts128u(orow + TC_A_PLANE + off, l);
         }
       }
       tc_fence_before();
@@ -1277,14 +1300,17 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (ep.has_planes) {
         const uint32_t prow = pl_base + (uint32_t)((c >> 1) * FAST_BOX_PL + r * 128);
+        if (ep.planes_relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);      // only the planes carry the ReLU; x is not used after them
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          __half h[8], l[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) split_f16((ep.planes_relu ? fmaxf(x[8 * q + e], 0.f) : x[8 * q + e]) * kActScale, h[e], l[e]);
+          uint4 h, l;
+          split8_f16(x + 8 * q, kActScale, h, l);
           const uint32_t off = (((uint32_t)((c & 1) * 4 + q)) ^ sw) << 4;
-          sts128u(prow + off, make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
-          sts128u(prow + TC_A_PLANE + off, make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7])));
+          sts128u(prow + off, h);
+          sts128u(prow + TC_A_PLANE + off, l);
         }
         fence_proxy_async();
         asm volatile("bar.sync 1, 256;" ::: "memory");                // both column halves of plane box c / 2 (all eight warps)

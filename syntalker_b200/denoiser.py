@@ -26,14 +26,20 @@ def _dev_f32(t: torch.Tensor, name: str, device) -> torch.Tensor:
 
 class CondKey:
     """Identity of the y tensors last encoded, so a Python-side step loop (the reference's own
-    gaussian_diffusion loop calling model(x,t,y) once per step) pays for the conditioning once."""
+    gaussian_diffusion loop calling model(x,t,y) once per step) pays for the conditioning once.
+
+    The key is (data_ptr, _version, shape, dtype, device) of the CALLER's tensors, and `held` keeps strong references to
+    exactly those tensors for as long as the key is current: an address can only be handed to a new tensor after the old one
+    is freed, so while they are held a matching key really means "the same, unmodified tensors" (without the references the
+    allocator recycles the addresses of freed batches at version 0 and a different batch would hit the cache)."""
 
     def __init__(self):
         self.key = None
+        self.held = None
 
     @staticmethod
     def of(*tensors):
-        return tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None for t in tensors)
+        return tuple((t.data_ptr(), t._version, tuple(t.shape), t.dtype, str(t.device)) if t is not None else None for t in tensors)
 
 
 class MDM:
@@ -128,6 +134,10 @@ class MDM:
             styles = [sf, None, None] if not isinstance(sf, dict) else \
                 [sf.get("upper_mask"), sf.get("hands_mask"), sf.get("lower_mask")]
         sdim = 512 if self.variant == "beatx_motionclip" else 256
+        originals = (y["audio"], y["word"], y["seed"]) + tuple(s if self.variant != "beatx" else None for s in styles)
+        key = CondKey.of(*originals) + (B,)
+        if not force and key == self._cond_key.key:
+            return B
         st = []
         for s in styles:
             if s is None or self.variant == "beatx":
@@ -139,9 +149,6 @@ class MDM:
             if tuple(s.shape) != (B, sdim):
                 raise ValueError(f"style vector must be [B,{sdim}], got {tuple(s.shape)}")
             st.append(s)
-        key = CondKey.of(y["audio"], y["word"], y["seed"], *st) + (B,)
-        if not force and key == self._cond_key.key:
-            return B
         c = _lib.StCond()
         c.audio, c.word, c.seed = audio.data_ptr(), word.data_ptr(), seed.data_ptr()
         for k in range(3):
@@ -150,6 +157,7 @@ class MDM:
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().st_cond_encode(self.handle, C.byref(c), B, _lib.stream_ptr()))
         self._cond_key.key = key
+        self._cond_key.held = originals
         return B
 
     # ---- the model call ----
@@ -162,9 +170,11 @@ class MDM:
         if tuple(x.shape) != (B, LATENT_C, 1, N_TOKENS):
             raise ValueError(f"x must be [{B},{LATENT_C},1,{N_TOKENS}], got {tuple(x.shape)}")
         xs = _dev_f32(x, "x", self.device)
+        if timesteps.numel() != B:
+            raise ValueError(f"timesteps must be [B={B}], got {tuple(timesteps.shape)}")
+        if timesteps.device.type == "cpu" and B and (int(timesteps.min()) < 0 or int(timesteps.max()) >= 1000):
+            raise ValueError("timesteps must lie in [0,1000)")    # device tensors are clamped by the kernel instead: no sync per call
         t = timesteps.to(self.device).to(torch.int64).contiguous()
-        if t.numel() != B or int(t.min()) < 0 or int(t.max()) >= 1000:
-            raise ValueError("timesteps must be [B] with values in [0,1000)")
         g = _guidance
         if g is None:
             g = Guidance(_lib.ST_CFG_NONE, flags=(_lib.ST_FLAG_UNCOND if y.get("uncond", False) else 0) |

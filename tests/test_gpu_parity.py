@@ -303,8 +303,9 @@ def test_ddim_z_recursion_equals_the_x_space_loop(models):
 
 
 def test_attention_on_tensor_cores_equals_the_fma_attention(W, models):
-    """st_debug_probe bit 2048: Q K^T and P V of the fused qkv + attention kernel as split-fp16 tcgen05 MMAs (block-diagonal P,
-    softmax in registers from the TMEM rows) instead of packed fp32 FMAs. Same evaluation, both ways, and against the oracle."""
+    """The fused qkv + attention kernel forms Q K^T and P V as split-fp16 tcgen05 MMAs (block-diagonal P, V as the MN-major B
+    operand, softmax in registers from the TMEM rows); st_debug_probe bit 2048 selects the packed-fp32 FMA epilogue it replaced.
+    Same evaluation and the same DDIM-10 loop both ways, and the default against the oracle (transformer.py:83-104)."""
     L = _lib.lib()
     _lib.set_engine("tc")
     m = ClassifierFreeSampleModel(models["beatx_motionclip"])
@@ -312,22 +313,22 @@ def test_attention_on_tensor_cores_equals_the_fma_attention(W, models):
     inp = synth.make_inputs(B, seed=23, variant="beatx_motionclip")
     t = torch.tensor([980, 700, 400, 100, 20, 0]).cuda()
     y = y_of(inp); y["scale"] = torch.ones(1) * 2.0
-    ref = m(inp["noise"].cuda(), t, y)
+    d = create_gaussian_diffusion(timestep_respacing="ddim10")
+    run_loop = lambda: [d.ddim_sample_loop(m, (B, 1536, 1, 32), noise=inp["noise"].cuda(), clip_denoised=False, model_kwargs={"y": y}) for _ in range(3)][-1]
+    got = m(inp["noise"].cuda(), t, y)
+    loop = run_loop()
     try:
         _lib.check(L.st_debug_probe(2048))
-        got = m(inp["noise"].cuda(), t, y)
-        d = create_gaussian_diffusion(timestep_respacing="ddim10")
-        loop = [d.ddim_sample_loop(m, (B, 1536, 1, 32), noise=inp["noise"].cuda(), clip_denoised=False, model_kwargs={"y": y}) for _ in range(3)][-1]
+        ref = m(inp["noise"].cuda(), t, y)
+        loop_ref = run_loop()
     finally:
         _lib.check(L.st_debug_probe(0))
-    print(f"tensor-core attention vs FMA attention: max-abs {maxabs(got, ref):.2e}")
+    print(f"tensor-core attention vs FMA attention: evaluation max-abs {maxabs(got, ref):.2e}, DDIM-10 loop max-abs {maxabs(loop, loop_ref):.2e}")
     assert maxabs(got, ref) < 2e-5
+    assert maxabs(loop, loop_ref) < 1e-4
     yo = {k: inp[k][:2] for k in ("audio", "word", "seed", "style_feature")}; yo["scale"] = torch.ones(1) * 2.0
     oref = omdm.cfg_text(lambda a, b, c: omdm.mdm_forward(W["beatx_motionclip"], a, b, c, "beatx_motionclip"), inp["noise"][:2], t[:2].cpu(), yo)
     assert maxabs(got[:2], oref) < 1e-4
-    d = create_gaussian_diffusion(timestep_respacing="ddim10")
-    loop_ref = [d.ddim_sample_loop(m, (B, 1536, 1, 32), noise=inp["noise"].cuda(), clip_denoised=False, model_kwargs={"y": y}) for _ in range(3)][-1]
-    assert maxabs(loop, loop_ref) < 1e-4
 
 
 def test_ddim50_cfg_vs_oracle(W, models, engine):
