@@ -85,8 +85,13 @@ int st_debug_timeline_select(int N, int K);
 int st_debug_trace(unsigned long long* dev_buf);
 /* debug / A-B switches.  bits 0-3: timing-only variants of the tcgen05 main loop (results are garbage); 16: trunk kernel off
  * (generic tcgen05 kernel); 32: separate attention kernel; 64: RVQ code ranking on the SIMT engine; 128: WavEncoder with fp32
- * activations; 256: body parts decode one after the other; 512: deterministic DDIM keeps its state in x space. */
+ * activations; 256: body parts decode one after the other; 512: the sampling loop keeps its state in x space (no z recursion);
+ * 1024: the last block's fc2 stays a layer of its own inside the z recursion; 2048: packed-fp32 FMA attention epilogue instead of
+ * the tcgen05 Q K^T / P V. */
 int st_debug_probe(int flags);
+/* Parity-test taps of the last st_cond_encode: atcat_out [B,128,512] = [WavEncoder output | word features]
+ * per frame (models/denoiser.py:151-155, B <= 32), cst_out [B*32,512] = the hoisted conditioning constant.  Either may be NULL. */
+int st_debug_cond_taps(st_model* m, float* atcat_out, float* cst_out, int B, void* stream);
 
 /* ---- weights -------------------------------------------------------------------------------------
  * Replaces: MDM(args) construction + load_checkpoints (train.py:85-94, utils/other_tools.py:771-790).
@@ -134,6 +139,7 @@ typedef struct {
 #define ST_CFG_TEXT 1       /* ClassifierFreeSampleModel            :17-28   scale[B] */
 #define ST_CFG_TWO 2        /* TwoClassifierFreeSampleModel          :38-54   scale_audio[B], scale_prompt[B]; style[0] is the prompt */
 #define ST_CFG_BODYPART 3   /* TwoClassifierFreeSampleModel_Bodypart :67-117  audio_scale 1, prompt_scale 4 unless overridden */
+#define ST_CFG_BODYPART1 4  /* ClassifierFreeSampleModel_Bodypart :125-167: per prompted part u + scale (ua_part - u), u = (null prompt, audio) */
 #define ST_FLAG_UNCOND 1
 #define ST_FLAG_UNCOND_AUDIO 2
 typedef struct {
@@ -161,12 +167,25 @@ int st_denoise(st_model* m, const float* x, const int64_t* t, const st_guidance*
  * (the `noise` argument or th.randn(shape)).  noise_tape: device [S,B,1536,1,32] eps_k for k = S-1..0
  * stored in draw order (tape[0] is used at k=S-1), required when any sigma != 0, else may be NULL.
  * x_out may alias x_init.  Uses the cache of the last st_cond_encode.
- * Deterministic DDIM (every sigma = 0) on the tcgen05 engine with guidance NONE / TEXT / TWO runs the update in token space:
- * x_{k-1} = alpha_k x0_hat + beta_k x_k is linear and the next step only needs W_x x_{k-1}, so between steps one 512x512
- * GEMM replaces output GEMM + state update + input GEMM; the state is formed by the last step (x <- x0_hat,
- * gaussian_diffusion.py:774-790 with alpha_bar_prev = 1).  Same result to ~1e-5; st_debug_probe(512) keeps the x-space loop. */
+ * On the tcgen05 engine with guidance NONE / TEXT / TWO the update runs in token space ("z recursion"):
+ * x_{k-1} = alpha_k x0_hat + beta_k x_k + sigma_k eps_k is linear and the next step only needs W_x x_{k-1}, so between steps one
+ * 512x512 GEMM replaces output GEMM + state update + input GEMM (the noise enters as W_x eps_k, formed for a chunk of steps at
+ * a time); the state is formed by the last step (DDIM: x <- x0_hat, gaussian_diffusion.py:774-790 with alpha_bar_prev = 1;
+ * DDPM: coef1 = 1, coef2 = 0, sigma = 0 at t = 0, :383,:556).  Same result to ~1e-5; st_debug_probe(512) keeps the x-space loop. */
 int st_sample(st_model* m, const st_schedule* s, const st_guidance* g, const float* x_init, const float* noise_tape,
               int B, float* x_out, void* stream);
+
+/* The same loop in pieces, for callers that hand the per-step noise over in chunks instead of one [S,B,1536,1,32] tape (the
+ * reference draws one th.randn_like(x) per step, gaussian_diffusion.py:541,781; a 1000-step tape at B = 32 is 6.3 GB):
+ *   st_sample_begin(...);  repeat { st_sample_run(m, n, noise_chunk ( [n,B,1536,1,32] in draw order, or NULL ), stream); }
+ *   until S steps have run;  st_sample_end(m, x_out, stream).
+ * st_sample_chunk(s) is the number of steps one captured graph holds; pieces that are multiples of it (and aligned to it) replay
+ * graphs, other sizes run step by step, and a loop that needs noise on the z recursion only accepts multiples.  The schedule and
+ * the guidance scales must stay alive until st_sample_end.  One loop per model handle at a time. */
+int st_sample_chunk(const st_schedule* s);
+int st_sample_begin(st_model* m, const st_schedule* s, const st_guidance* g, const float* x_init, int B, void* stream);
+int st_sample_run(st_model* m, int n_steps, const float* noise_chunk, void* stream);
+int st_sample_end(st_model* m, float* x_out, void* stream);
 
 /* ---- RVQ-VAE decode ------------------------------------------------------------------------------
  * Replaces: vq.latent2origin(x)[0] (models/vq/model.py:102-109).  lat: device [B,T4,512] already

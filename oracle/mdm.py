@@ -117,12 +117,14 @@ def mdm_forward(W, x, t, y, variant="beatx", taps=None):
 
 # ---- classifier-free-guidance wrappers (diffusion/cfg_sampler.py) ------------------------------------
 
-def cfg_text(model_fn, x, t, y):
-    """ClassifierFreeSampleModel.forward, cfg_sampler.py:17-28."""
+def cfg_text(model_fn, x, t, y, eval_metric=False):
+    """ClassifierFreeSampleModel.forward, cfg_sampler.py:17-28 (eval=True returns the unconditional output, :25-26)."""
     yc = dict(y); yc["uncond_audio"] = True
     out = model_fn(x, t, yc)
     yu = dict(yc); yu["uncond"] = True
     out_u = model_fn(x, t, yu)
+    if eval_metric:
+        return out_u
     return out_u + y["scale"].view(-1, 1, 1, 1) * (out - out_u)
 
 
@@ -157,3 +159,26 @@ def cfg_bodypart(model_fn, x, t, y, audio_scale=1.0, prompt_scale=4.0):
         sl = PART_SLICES[key]
         out[:, sl] = out[:, sl] + o[:, sl]
     return out
+
+
+def cfg_bodypart1(model_fn, x, t, y, eval_metric=False):
+    """ClassifierFreeSampleModel_Bodypart.forward, cfg_sampler.py:133-167: per prompted part one evaluation with that prompt and the
+    audio masked, one evaluation with the null prompt (audio kept); out_uncond + scale * (out - out_uncond)."""
+    yu = dict(y); yu["uncond"] = True
+    if eval_metric:                                                       # :143-146
+        yu["style_feature"] = y["style_feature"]["lower_mask"]
+        return model_fn(x, t, yu)
+    out = torch.zeros_like(x)
+    covered = torch.zeros(x.shape[1], dtype=torch.bool)
+    for key, value in y["style_feature"].items():
+        if value is None:
+            continue
+        yp = dict(y); yp["style_feature"] = value; yp["uncond_audio"] = True
+        o = model_fn(x, t, yp)
+        sl = PART_SLICES[key]
+        out[:, sl] = out[:, sl] + o[:, sl]
+        covered[sl] = True
+    yu["style_feature"] = torch.zeros(1, 256)
+    out_u = model_fn(x, t, yu)
+    out[:, ~covered] = out[:, ~covered] + out_u[:, ~covered]
+    return out_u + y["scale"].view(-1, 1, 1, 1) * (out - out_u)

@@ -14,15 +14,15 @@ LIB_PATH = os.path.join(_HERE, "libsyntalker_b200.so")
 ST_VARIANT = {"beatx": 0, "beatx_motionclip": 1, "h3d": 2}
 ST_ENGINE_SIMT, ST_ENGINE_TC = 0, 1
 ST_MODE_DDPM, ST_MODE_DDIM = 0, 1
-ST_CFG_NONE, ST_CFG_TEXT, ST_CFG_TWO, ST_CFG_BODYPART = 0, 1, 2, 3
+ST_CFG_NONE, ST_CFG_TEXT, ST_CFG_TWO, ST_CFG_BODYPART, ST_CFG_BODYPART1 = 0, 1, 2, 3, 4
 ST_FLAG_UNCOND, ST_FLAG_UNCOND_AUDIO = 1, 2
 ST_COEF_STRIDE = 5
 
 # every symbol include/syntalker_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "st_last_error", "st_abi_version", "st_launch_count", "st_set_engine", "st_get_engine", "st_set_graphs", "st_set_pdl", "st_debug_timeline", "st_debug_timeline_select", "st_debug_trace", "st_debug_probe",
+    "st_last_error", "st_abi_version", "st_launch_count", "st_set_engine", "st_get_engine", "st_set_graphs", "st_set_pdl", "st_debug_timeline", "st_debug_timeline_select", "st_debug_trace", "st_debug_probe", "st_debug_cond_taps",
     "st_model_create", "st_model_destroy", "st_vq_create", "st_vq_destroy", "st_vq_out_dim",
-    "st_schedule_create", "st_schedule_destroy", "st_cond_encode", "st_denoise", "st_sample",
+    "st_schedule_create", "st_schedule_destroy", "st_cond_encode", "st_denoise", "st_sample", "st_sample_chunk", "st_sample_begin", "st_sample_run", "st_sample_end",
     "st_rvq_decode", "st_pose_assemble_330", "st_pose_assemble_623", "st_sample_to_tokens",
     "st_rvq_encode", "st_generate_330", "st_generate_330_host", "st_generate_330_host_begin", "st_generate_330_host_wait", "st_generate_long_330", "st_selftest_gemm", "st_bench_gemm", "st_profile_begin", "st_profile_end",
 ]
@@ -74,6 +74,7 @@ def lib():
     L.st_debug_timeline.argtypes = [vp]
     L.st_debug_timeline_select.argtypes = [i32, i32]
     L.st_debug_trace.argtypes = [vp]
+    L.st_debug_cond_taps.argtypes = [vp, vp, vp, i32, vp]
     L.st_model_create.argtypes = [C.POINTER(StTensor), i32, i32, C.POINTER(vp)]
     L.st_model_destroy.argtypes = [vp]
     L.st_model_destroy.restype = None
@@ -87,6 +88,10 @@ def lib():
     L.st_cond_encode.argtypes = [vp, C.POINTER(StCond), i32, vp]
     L.st_denoise.argtypes = [vp, vp, vp, C.POINTER(StGuidance), vp, i32, vp]
     L.st_sample.argtypes = [vp, vp, C.POINTER(StGuidance), vp, vp, i32, vp, vp]
+    L.st_sample_chunk.argtypes = [vp]
+    L.st_sample_begin.argtypes = [vp, vp, C.POINTER(StGuidance), vp, i32, vp]
+    L.st_sample_run.argtypes = [vp, i32, vp, vp]
+    L.st_sample_end.argtypes = [vp, vp, vp]
     L.st_rvq_decode.argtypes = [vp, vp, i64, f32, i32, i32, vp, vp, vp, vp]
     L.st_rvq_encode.argtypes = [vp, vp, i32, i32, vp, vp]
     L.st_generate_long_330.argtypes = [vp, vp, C.POINTER(StGuidance), vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp]

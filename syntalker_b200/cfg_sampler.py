@@ -94,7 +94,21 @@ class TwoClassifierFreeSampleModel_Bodypart(_Wrapper):
 
 
 class ClassifierFreeSampleModel_Bodypart(_Wrapper):
-    """cfg_sampler.py:125-167. Not used by any trainer on the hot path (SURVEY.md §3.3 uses the Two* variant)."""
+    """cfg_sampler.py:125-167: per prompted body part one evaluation (that prompt, audio masked), one evaluation with the null
+    prompt (audio kept) = out_uncond; parts without a prompt keep out_uncond; out_uncond + scale * (out - out_uncond).
+    eval=True returns model(x, t, uncond=True) (:143-146)."""
+
+    def __init__(self, model, eval=False):
+        super().__init__(model, eval)
+        self.latent_dim = 1536
+
+    def styles(self, y):
+        sf = y["style_feature"]
+        if self.eval_metric:
+            return [sf["lower_mask"], None, None]
+        return [sf.get("upper_mask"), sf.get("hands_mask"), sf.get("lower_mask")]
 
     def guidance(self, y):
-        raise NotImplementedError("ClassifierFreeSampleModel_Bodypart is not wired: no caller on the sampling path uses it")
+        if self.eval_metric:
+            return Guidance(_lib.ST_CFG_NONE, flags=_lib.ST_FLAG_UNCOND)
+        return Guidance(_lib.ST_CFG_BODYPART1, scale=y["scale"])

@@ -154,6 +154,14 @@ struct BlkW {
 };
 struct EvalSpec { int cst_null; int sv_src; };   // sv_src: -1 none, 0..2 = style k, 3 = null embedding
 
+struct Plan {
+  int nE = 1;
+  EvalSpec ev[ST_MAX_EVALS];
+  int cfg_mode = ST_CFG_NONE;
+  float part_sa[3] = {0, 0, 0}, part_sp[3] = {0, 0, 0};
+  int part_ua[3] = {-1, -1, -1};
+};
+
 struct st_model {
   int variant = 0, device = 0, style_dim = 0;
   Weights w;
@@ -194,6 +202,19 @@ struct st_model {
   cudaStream_t dec_stream[2] = {nullptr, nullptr};   // the three body parts decode side by side (fork / join around st_rvq_decode x3)
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // the sampling loop in flight between st_sample_begin and st_sample_end
+  struct ActiveLoop {
+    bool on = false;
+    const st_schedule* sc = nullptr;
+    Plan pl;
+    StepP sp;
+    int B = 0, G = 1, k = -1;      // k: next step to run, S-1 .. 0; -1 when the loop is complete
+    bool zrec = false, any_sigma = false;
+    std::string key;               // graph key of this loop without the chunk index
+  } act;
+  Arena zws;                        // z recursion with noise: W_x eps of one chunk of steps + the staging of its tape
+  float *zeps = nullptr, *zcarry[2] = {nullptr, nullptr}, *ntok = nullptr;
+  int zws_B = 0, zws_G = 0, ntok_steps = 0;
   std::map<std::string, cudaGraphExec_t> graphs;
   std::map<std::string, int64_t> graph_nodes;
   std::map<std::string, int> warmed;
@@ -339,7 +360,7 @@ extern "C" void st_model_destroy(st_model* m) {
   if (m->dec_stream[0]) { for (int k = 0; k < 2; ++k) { tc_scratch_release(m->dec_stream[k]); cudaStreamDestroy(m->dec_stream[k]); cudaEventDestroy(m->ev_join[k]); } cudaEventDestroy(m->ev_fork); }
   if (m->ev_in) cudaEventDestroy(m->ev_in);
   if (m->ev_out) cudaEventDestroy(m->ev_out);
-  m->w.release(); m->ws.release(); m->io.release(); m->longws.release();
+  m->w.release(); m->ws.release(); m->io.release(); m->longws.release(); m->zws.release();
   for (int k = 0; k < 2; ++k) {
     m->hslot[k].stage.release();
     if (m->hslot[k].ev_h2d) { cudaEventDestroy(m->hslot[k].ev_h2d); cudaEventDestroy(m->hslot[k].ev_comp); cudaEventDestroy(m->hslot[k].ev_done); }
@@ -463,7 +484,7 @@ static int encode_wav_tc(st_model* m, const float* audio, int cb, cudaStream_t s
 static int encode_audio_words(st_model* m, const float* audio, const int32_t* word, int cb, int null_inputs, cudaStream_t s) {
   if (st_get_engine() == ST_ENGINE_TC && g_wav_planes) {
     ST_TRY(encode_wav_tc(m, audio, cb, s));
-    ST_TRY(gather_words(word, m->word_table, m->atcat + 256, 512, cb * 128, null_inputs, s));
+    ST_TRY(gather_words(word, m->word_table, m->atcat + 256, 512, cb * 128, null_inputs, (int)(m->w.numel.at("word_table") / 256), s));
     ST_TRY(avgpool4(m->atcat, m->pooled, cb * 32, 512, s));
     return ST_OK;
   }
@@ -501,7 +522,7 @@ static int encode_audio_words(st_model* m, const float* audio, const int32_t* wo
     in = outb;
     in_buf = last ? -1 : free_b[2];
   }
-  ST_TRY(gather_words(word, m->word_table, m->atcat + 256, 512, cb * 128, null_inputs, s));
+  ST_TRY(gather_words(word, m->word_table, m->atcat + 256, 512, cb * 128, null_inputs, (int)(m->w.numel.at("word_table") / 256), s));
   ST_TRY(avgpool4(m->atcat, m->pooled, cb * 32, 512, s));
   return ST_OK;
 }
@@ -545,15 +566,21 @@ extern "C" int st_cond_encode(st_model* m, const st_cond* c, int B, void* stream
   return ST_OK;
 }
 
-// ---- guidance -> evaluation list ---------------------------------------------------------------------
-struct Plan {
-  int nE = 1;
-  EvalSpec ev[ST_MAX_EVALS];
-  int cfg_mode = ST_CFG_NONE;
-  float part_sa[3] = {0, 0, 0}, part_sp[3] = {0, 0, 0};
-  int part_ua[3] = {-1, -1, -1};
-};
+// Stage taps of the conditioning encoder for parity tests: the last st_cond_encode's [WavEncoder output |
+// word features] rows, [B,128,512] (denoiser.py:151-155, before mix_audio_text), and the hoisted conditioning constant
+// W_cm pool4(.) + biases, [B*32,512].  Either pointer may be NULL.  atcat covers one encoder chunk, so B <= 32.
+extern "C" int st_debug_cond_taps(st_model* m, float* atcat_out, float* cst_out, int B, void* stream) {
+  ST_REQUIRE(m && B > 0 && m->cond_B == B, "st_debug_cond_taps: the conditioning cache does not hold B=%d", B);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (atcat_out) {
+    ST_REQUIRE(B <= kCondChunk, "st_debug_cond_taps: the encoder staging holds one chunk of %d clips", kCondChunk);
+    ST_CHECK_CUDA(cudaMemcpyAsync(atcat_out, m->atcat, (size_t)B * 128 * 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  if (cst_out) ST_CHECK_CUDA(cudaMemcpyAsync(cst_out, m->cst_real, (size_t)B * 32 * 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return ST_OK;
+}
 
+// ---- guidance -> evaluation list ---------------------------------------------------------------------
 static int make_plan(const st_model* m, const st_guidance* g, Plan* pl) {
   const int mode = g ? g->mode : ST_CFG_NONE;
   const int flags = g ? g->flags : 0;
@@ -584,7 +611,20 @@ static int make_plan(const st_model* m, const st_guidance* g, Plan* pl) {
     p.ev[1] = EvalSpec{an, v == ST_VARIANT_H3D ? 3 : -1};
     return ST_OK;
   }
-  ST_REQUIRE(v == ST_VARIANT_H3D, "CFG_TWO / CFG_BODYPART are defined for the h3d model only");
+  ST_REQUIRE(v == ST_VARIANT_H3D, "CFG_TWO / CFG_BODYPART / CFG_BODYPART1 are defined for the h3d model only");
+  if (mode == ST_CFG_BODYPART1) {
+    // ClassifierFreeSampleModel_Bodypart (cfg_sampler.py:133-167): out_uncond = (null prompt, audio kept); per prompted part one
+    // evaluation (that prompt, audio masked); unprompted parts keep out_uncond; out_uncond + scale * (out - out_uncond)
+    ST_REQUIRE(g->scale, "CFG_BODYPART1 needs scale[B]");
+    p.cfg_mode = ST_CFG_BODYPART1;
+    p.ev[0] = EvalSpec{0, 3};
+    p.nE = 1;
+    for (int k = 0; k < 3; ++k) {
+      p.part_ua[k] = -1;
+      if (m->have_style[k]) { p.ev[p.nE] = EvalSpec{1, k}; p.part_ua[k] = p.nE; p.nE++; }
+    }
+    return ST_OK;
+  }
   p.ev[0] = EvalSpec{1, 3};    // uu: prompt null, audio null
   p.ev[1] = EvalSpec{0, 3};    // ut: prompt null, audio real
   if (mode == ST_CFG_TWO) {
@@ -624,17 +664,26 @@ static int trunk_input(st_model* m, int B, cudaStream_t s) {
 struct ZStep {
   bool on = false, first = false, last = true;
   int t = 0;                 // original timestep fed to the denoiser (respace.py:124-129)
-  float alpha = 0.f, beta = 0.f;
+  float alpha = 0.f, beta = 0.f, sigma = 0.f;
+  const float* zeps = nullptr;   // W_x eps of the update that produced this step's state (sigma != 0 only)
 };
-static ZStep zstep_of(const st_schedule* sc, int k) {
+// x_k = alpha x0_hat + beta x_{k+1} + sigma eps_{k+1}: the update that produced x_k ran with the coefficients of step k + 1.
+//   DDIM (gaussian_diffusion.py:772-790): e = (a x - x0) / b, x <- c1 x0 + c2 e + sigma eps   =>  alpha = c1 - c2 / b, beta = c2 a / b
+//   DDPM (:383, :556):                    x <- coef1 x0 + coef2 x + sigma eps                 =>  alpha = coef1, beta = coef2
+static ZStep zstep_of(const st_schedule* sc, int k, const float* zeps_prev = nullptr) {
   ZStep z;
   z.on = true; z.first = (k == sc->S - 1); z.last = (k == 0); z.t = sc->t_model[k];
   if (!z.first) {
-    // the update that produced x_k ran with the coefficients of step k + 1: e = (a x - x0) / b, x <- c1 x0 + c2 e
     const float* cf = &sc->coef[(size_t)(k + 1) * ST_COEF_STRIDE];
-    const double a = cf[0], b = cf[1], c1 = cf[2], c2 = cf[3];
-    z.alpha = (float)(c1 - c2 / b);
-    z.beta = (float)(c2 * a / b);
+    if (sc->mode == ST_MODE_DDIM) {
+      const double a = cf[0], b = cf[1], c1 = cf[2], c2 = cf[3];
+      z.alpha = (float)(c1 - c2 / b);
+      z.beta = (float)(c2 * a / b);
+      z.sigma = cf[4];
+    } else {
+      z.alpha = cf[0]; z.beta = cf[1]; z.sigma = cf[2];
+    }
+    z.zeps = z.sigma != 0.f ? zeps_prev : nullptr;
   }
   return z;
 }
@@ -668,6 +717,7 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
     TokensStepP ts;
     ts.t = tp; ts.z_rw = m->z; ts.P = m->H; ts.c_xo = m->c_xo; ts.vt = m->vt_table + (size_t)zs.t * 512;
     ts.alpha = zs.alpha; ts.beta = zs.beta; ts.first = zs.first ? 1 : 0;
+    ts.sigma = zs.zeps ? zs.sigma : 0.f; ts.zeps = zs.zeps;
     ts.cfg_mode = mix->cfg_mode; ts.scale = mix->scale; ts.scale2 = mix->scale2;
     ST_TRY(tokens_step(ts, s));
   } else {
@@ -753,7 +803,7 @@ static int upload_scales(st_model* m, const Plan& pl, const st_guidance* g, int 
     last.assign(src, src + B);
     return ST_OK;
   };
-  if (pl.cfg_mode == ST_CFG_TEXT || pl.cfg_mode == ST_CFG_TWO) {
+  if (pl.cfg_mode == ST_CFG_TEXT || pl.cfg_mode == ST_CFG_TWO || pl.cfg_mode == ST_CFG_BODYPART1) {
     ST_TRY(upload(m->scale_dev, g->scale, m->scale_last));
     sp->scale = m->scale_dev;
     if (pl.cfg_mode == ST_CFG_TWO) {
@@ -826,47 +876,95 @@ static int one_step(st_model* m, const Plan& pl, const StepP& sp0, int B, cudaSt
   return ST_OK;
 }
 
-extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* g, const float* x_init, const float* noise_tape,
-                         int B, float* x_out, void* stream) {
-  ST_REQUIRE(m && sc && x_init && x_out && B > 0, "st_sample: null argument or B <= 0");
+static bool schedule_has_sigma(const st_schedule* sc) {
+  for (int k = 0; k < sc->S; ++k)
+    if (sc->coef[(size_t)k * ST_COEF_STRIDE + (sc->mode == ST_MODE_DDPM ? 2 : 4)] != 0.f) return true;
+  return false;
+}
+// steps per captured graph: the largest of 50, 25, 20, 10, 5, 4, 2, 1 that divides S.  Kernels of consecutive steps inside one
+// graph hand over through programmatic edges like the kernels of one step; a graph launch boundary costs ~4 us.
+static int chunk_steps(const st_schedule* sc) {
+  for (int c : {50, 25, 20, 10, 5, 4, 2}) if (sc->S % c == 0) return c;
+  return 1;
+}
+extern "C" int st_sample_chunk(const st_schedule* sc) { return sc ? chunk_steps(sc) : 0; }
+
+// W_x eps for `n` steps of the caller's tape ([n,B,1536,1,32], draw order) -> dst [n][B*32][512]: transposed to token-major in
+// pieces of <= ntok_steps steps, then one GEMM per piece (the noise does not depend on the chain: this runs ahead of the steps)
+static int prep_zeps(st_model* m, const float* tape, int n, int B, float* dst, cudaStream_t s) {
+  const size_t per = (size_t)B * 1536 * 32;
+  for (int i = 0; i < n; i += m->ntok_steps) {
+    const int c = (n - i) < m->ntok_steps ? (n - i) : m->ntok_steps;
+    ST_TRY(transpose_to_tokens(tape + (size_t)i * per, m->ntok, c * B, 1536, 32, 1.0f, s));
+    GemmP p = linear(m->ntok, c * B * 32, 1536, m->w_x, nullptr, dst + (size_t)i * B * 32 * 512, 512);
+    ST_TRY(gemm(p, s));
+  }
+  return ST_OK;
+}
+
+// ---- the sampling loop as begin / run / end: the caller may hand the per-step noise over in chunks (the reference draws one
+// randn_like per step, gaussian_diffusion.py:541,781; a 1000-step tape at B = 32 is 6.3 GB) --------------------------------
+extern "C" int st_sample_begin(st_model* m, const st_schedule* sc, const st_guidance* g, const float* x_init, int B, void* stream) {
+  ST_REQUIRE(m && sc && x_init && B > 0, "st_sample_begin: null argument or B <= 0");
   if (m->cond_B != B) { set_error("st_sample: B=%d but the conditioning cache holds B=%d (call st_cond_encode first)", B, m->cond_B); return ST_ESTATE; }
   cudaStream_t s = (cudaStream_t)stream;
-  Plan pl;
-  ST_TRY(make_plan(m, g, &pl));
-  bool any_sigma = false;
-  for (int k = 0; k < sc->S; ++k) any_sigma |= sc->coef[(size_t)k * ST_COEF_STRIDE + (sc->mode == ST_MODE_DDPM ? 2 : 4)] != 0.f;
-  ST_REQUIRE(!any_sigma || noise_tape, "st_sample: schedule has sigma != 0 but noise_tape is NULL");
-  StepP sp;
-  ST_TRY(upload_scales(m, pl, g, B, &sp, s));
-  sp.mode = sc->mode;
+  st_model::ActiveLoop& a = m->act;
+  a.on = false;
+  ST_TRY(make_plan(m, g, &a.pl));
+  a.any_sigma = schedule_has_sigma(sc);
+  ST_TRY(upload_scales(m, a.pl, g, B, &a.sp, s));
+  a.sp.mode = sc->mode;
   if (m->sched_id != sc->id) {     // the schedule's tables, once per schedule
     ST_CHECK_CUDA(cudaMemcpyAsync(m->t_model_dev, sc->t_model.data(), sc->S * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ST_CHECK_CUDA(cudaMemcpyAsync(m->coef_dev, sc->coef.data(), (size_t)sc->S * ST_COEF_STRIDE * sizeof(float), cudaMemcpyHostToDevice, s));
     m->sched_id = sc->id;
   }
-  ST_TRY(init_loop(m->loop, sc->S, noise_tape, s));
+  ST_TRY(init_loop(m->loop, sc->S, sc->S - 1, nullptr, s));
   ST_TRY(transpose_to_tokens(x_init, m->xs, B, 1536, 32, 1.0f, s));
   if (st_get_engine() == ST_ENGINE_TC) ST_TRY(tc_split(m->xs, 1536, B * 32, 1536, m->xs_p, s));
-  // The first call with a given plan runs eagerly (it creates weight planes, tensor maps, scratch); the second
-  // captures one step into a CUDA graph; from then on every step is one graph launch.  Capture and replay run
-  // on the model's own stream (the caller's may be the legacy default stream, which cannot capture), fenced
-  // against the caller's stream with events on both sides.
-  // G consecutive steps per graph (the largest of 50, 25, 20, 10, 5, 4, 2, 1 that divides S): kernels of consecutive steps
-  // inside one graph hand over through programmatic edges like the kernels of one step; a graph launch boundary costs ~4 us
-  int G = 1;
-  for (int c : {50, 25, 20, 10, 5, 4, 2}) if (sc->S % c == 0) { G = c; break; }
-  // Deterministic DDIM on the tcgen05 engine keeps the loop in token space: x_{k-1} = alpha x0_hat + beta x_k is linear and the
-  // next step only needs W_x x_{k-1}, so between steps ONE 512 x 512 GEMM (W_x W_out, folded by the packer) replaces the
-  // 512 -> 1536 output GEMM, the state update and the 1536 -> 512 input GEMM; the state itself is formed once, by the last
-  // step (alpha_bar_prev = 1: x <- x0_hat).  The last step differs from the others, so a captured graph must hold the whole loop.
-  const bool zrec = g_zrec && st_get_engine() == ST_ENGINE_TC && sc->mode == ST_MODE_DDIM && !any_sigma && m->w_xo &&
-                    pl.cfg_mode != ST_CFG_BODYPART && (G == sc->S || !g_use_graphs);
-  if (zrec) ST_TRY(trunk_input(m, B, s));
-  const std::string key = plan_key(pl, B, sc->mode) + " G" + std::to_string(G) + (zrec ? (g_zrec_fc2 ? " zf" : " z") + std::to_string(sc->id) : std::string());   // the z recursion bakes the schedule into the graph
-  cudaGraphExec_t exec = nullptr;
+  a.G = chunk_steps(sc);
+  // The tcgen05 engine keeps the loop in token space ("z recursion"): x_{k-1} = alpha x0_hat + beta x_k + sigma eps_k is linear and
+  // the next step only needs W_x x_{k-1}, so between steps ONE 512 x 512 GEMM (W_x W_out, folded by the packer) replaces the
+  // 512 -> 1536 output GEMM, the state update and the 1536 -> 512 input GEMM; the noise enters as W_x eps_k, formed for a whole
+  // chunk of steps ahead of them; the state itself is formed once, by the last step (alpha_bar_prev = 1: x <- x0_hat, coef2 = 0,
+  // sigma = 0).  The steps differ (coefficients are launch parameters), so a captured graph holds one specific chunk of the loop.
+  a.zrec = g_zrec && st_get_engine() == ST_ENGINE_TC && m->w_xo && a.pl.cfg_mode != ST_CFG_BODYPART && a.pl.cfg_mode != ST_CFG_BODYPART1;
+  if (a.zrec) ST_TRY(trunk_input(m, B, s));
+  if (a.zrec && a.any_sigma && (m->zws_B != B || m->zws_G != a.G)) {
+    for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);      // captured z-step nodes point into the old block
+    m->graphs.clear(); m->warmed.clear(); m->graph_nodes.clear();
+    const size_t rows = (size_t)B * 32;
+    int ns = (int)(32768 / rows);
+    ns = ns < 1 ? 1 : (ns > a.G ? a.G : ns);
+    ST_TRY(m->zws.reserve(((size_t)(a.G + 1) * rows * 512 + (size_t)ns * rows * 1536) * sizeof(float) + 8 * 256));
+    m->zeps = m->zws.take<float>((size_t)(a.G > 1 ? a.G - 1 : 1) * rows * 512);
+    m->zcarry[0] = m->zws.take<float>(rows * 512);
+    m->zcarry[1] = m->zws.take<float>(rows * 512);
+    m->ntok = m->zws.take<float>((size_t)ns * rows * 1536);
+    m->ntok_steps = ns; m->zws_B = B; m->zws_G = a.G;
+  }
+  a.key = plan_key(a.pl, B, sc->mode) + " G" + std::to_string(a.G) + (a.zrec ? (g_zrec_fc2 ? " zf" : " z") + std::to_string(sc->id) : std::string());
+  a.sc = sc; a.B = B; a.k = sc->S - 1; a.on = true;
+  return ST_OK;
+}
+
+extern "C" int st_sample_run(st_model* m, int n_steps, const float* noise_chunk, void* stream) {
+  ST_REQUIRE(m && n_steps > 0, "st_sample_run: null argument or n_steps <= 0");
+  st_model::ActiveLoop& a = m->act;
+  ST_REQUIRE(a.on, "st_sample_run: no sampling loop in flight (call st_sample_begin first)");
+  const st_schedule* sc = a.sc;
+  const int B = a.B, S = sc->S, G = a.G;
+  ST_REQUIRE(n_steps <= a.k + 1, "st_sample_run: %d steps requested, %d left", n_steps, a.k + 1);
+  ST_REQUIRE(!a.any_sigma || noise_chunk, "st_sample_run: the schedule has sigma != 0 but no noise was given");
+  const bool znoise = a.zrec && a.any_sigma;
+  ST_REQUIRE(!znoise || ((S - 1 - a.k) % G == 0 && n_steps % G == 0),
+             "st_sample_run: with noise the loop advances in whole chunks of %d steps (st_sample_chunk)", G);
+  cudaStream_t s = (cudaStream_t)stream;
   const bool graphs_ok = g_use_graphs && !st::profiling();
+  // Capture and replay run on the model's own stream (the caller's may be the legacy default stream, which cannot capture),
+  // fenced against the caller's stream with events on both sides.
   cudaStream_t ls = s;
-  if (graphs_ok && m->warmed[key] >= 1) {
+  if (graphs_ok) {
     if (!m->loop_stream) {
       ST_CHECK_CUDA(cudaStreamCreateWithFlags(&m->loop_stream, cudaStreamNonBlocking));
       ST_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_in, cudaEventDisableTiming));
@@ -875,42 +973,90 @@ extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* 
     ls = m->loop_stream;
     ST_CHECK_CUDA(cudaEventRecord(m->ev_in, s));
     ST_CHECK_CUDA(cudaStreamWaitEvent(ls, m->ev_in, 0));
-    auto it = m->graphs.find(key);
-    if (it != m->graphs.end()) exec = it->second;
-    else {
-      if (m->graphs.size() >= 64) {
-        // the z recursion keys its graphs by schedule: a caller that keeps creating schedules must not grow the cache for ever
-        ST_CHECK_CUDA(cudaStreamSynchronize(ls));
-        for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
-        m->graphs.clear(); m->graph_nodes.clear();
-      }
-      cudaGraph_t graph = nullptr;
-      const int64_t l0 = g_launches;
-      ST_CHECK_CUDA(cudaStreamBeginCapture(ls, cudaStreamCaptureModeRelaxed));
-      int r = ST_OK;
-      for (int i = 0; i < G && r == ST_OK; ++i) r = zrec ? one_step(m, pl, sp, B, ls, zstep_of(sc, G - 1 - i), sc) : one_step(m, pl, sp, B, ls);
-      m->graph_nodes[key] = g_launches - l0;     // kernels per replay; capturing itself executed nothing
-      g_launches = l0;
-      cudaError_t ce = cudaStreamEndCapture(ls, &graph);
-      if (r != ST_OK) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return r; }
-      ST_CHECK_CUDA(ce);
-      ST_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-      cudaGraphDestroy(graph);
-      m->graphs[key] = exec;
-    }
   }
-  if (exec) {
-    for (int k = 0; k < sc->S / G; ++k) { ST_CHECK_CUDA(cudaGraphLaunch(exec, ls)); g_launches += m->graph_nodes[key]; }
-  } else {
-    for (int k = sc->S - 1; k >= 0; --k) ST_TRY(zrec ? one_step(m, pl, sp, B, ls, zstep_of(sc, k), sc) : one_step(m, pl, sp, B, ls));
+  const size_t per = (size_t)B * 1536 * 32, zrows = (size_t)B * 32 * 512;
+  int done = 0;
+  while (done < n_steps) {
+    const int pos = S - 1 - a.k;                       // steps already taken
+    const bool aligned = (pos % G) == 0 && (n_steps - done) >= G;
+    const int g = aligned ? G : 1;
+    const int chunk = pos / G;
+    const float* noise = noise_chunk ? noise_chunk + (size_t)done * per : nullptr;
+    const float* carry_in = nullptr;
+    if (znoise) {
+      // W_x eps of this chunk's steps: step k_hi - j in slot j; the last step's goes to the carry the NEXT chunk's first step reads
+      carry_in = m->zcarry[chunk & 1];
+      if (G > 1) ST_TRY(prep_zeps(m, noise, G - 1, B, m->zeps, ls));
+      ST_TRY(prep_zeps(m, noise + (size_t)(G - 1) * per, 1, B, m->zcarry[(chunk + 1) & 1], ls));
+    } else if (a.any_sigma) {
+      // x-space loop: step_update reads eps of step k at tape + (S - 1 - k) * per (device-side loop state)
+      ST_TRY(init_loop(m->loop, S, a.k, noise - (size_t)pos * per, ls));
+    }
+    auto zs_of = [&](int k) {
+      const int j = (S - 1 - k) - chunk * G;            // index inside the chunk
+      return zstep_of(sc, k, znoise ? (j == 0 ? carry_in : m->zeps + (size_t)(j - 1) * zrows) : nullptr);
+    };
+    cudaGraphExec_t exec = nullptr;
+    const std::string key = a.key + (a.zrec ? " c" + std::to_string(chunk) : std::string());
+    if (aligned && graphs_ok && m->warmed[key] >= 1) {
+      auto it = m->graphs.find(key);
+      if (it != m->graphs.end()) exec = it->second;
+      else {
+        if (m->graphs.size() >= 96) {
+          // the z recursion keys its graphs by schedule and chunk: a caller that keeps creating schedules must not grow the cache for ever
+          ST_CHECK_CUDA(cudaStreamSynchronize(ls));
+          for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+          m->graphs.clear(); m->graph_nodes.clear();
+        }
+        cudaGraph_t graph = nullptr;
+        const int64_t l0 = g_launches;
+        ST_CHECK_CUDA(cudaStreamBeginCapture(ls, cudaStreamCaptureModeRelaxed));
+        int r = ST_OK;
+        for (int i = 0; i < G && r == ST_OK; ++i) r = a.zrec ? one_step(m, a.pl, a.sp, B, ls, zs_of(a.k - i), sc) : one_step(m, a.pl, a.sp, B, ls);
+        m->graph_nodes[key] = g_launches - l0;     // kernels per replay; capturing itself executed nothing
+        g_launches = l0;
+        cudaError_t ce = cudaStreamEndCapture(ls, &graph);
+        if (r != ST_OK) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return r; }
+        ST_CHECK_CUDA(ce);
+        ST_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        m->graphs[key] = exec;
+      }
+    }
+    if (exec) {
+      ST_CHECK_CUDA(cudaGraphLaunch(exec, ls));
+      g_launches += m->graph_nodes[key];
+    } else {
+      for (int i = 0; i < g; ++i) ST_TRY(a.zrec ? one_step(m, a.pl, a.sp, B, ls, zs_of(a.k - i), sc) : one_step(m, a.pl, a.sp, B, ls));
+    }
+    if (aligned) m->warmed[key] += 1;
+    a.k -= g;
+    done += g;
   }
   if (ls != s) {
     ST_CHECK_CUDA(cudaEventRecord(m->ev_out, ls));
     ST_CHECK_CUDA(cudaStreamWaitEvent(s, m->ev_out, 0));
   }
-  m->warmed[key] += 1;
-  ST_TRY(transpose_from_tokens(m->xs, x_out, B, 1536, 32, s));
   return ST_OK;
+}
+
+extern "C" int st_sample_end(st_model* m, float* x_out, void* stream) {
+  ST_REQUIRE(m && x_out, "st_sample_end: null argument");
+  st_model::ActiveLoop& a = m->act;
+  ST_REQUIRE(a.on, "st_sample_end: no sampling loop in flight");
+  ST_REQUIRE(a.k < 0, "st_sample_end: %d steps of the loop have not run", a.k + 1);
+  a.on = false;
+  return transpose_from_tokens(m->xs, x_out, a.B, 1536, 32, (cudaStream_t)stream);
+}
+
+// the whole loop in one call; noise_tape = [S,B,1536,1,32] in draw order (t = S-1 .. 0) or NULL when every sigma is 0
+extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* g, const float* x_init, const float* noise_tape,
+                         int B, float* x_out, void* stream) {
+  ST_REQUIRE(m && sc && x_init && x_out && B > 0, "st_sample: null argument or B <= 0");
+  ST_REQUIRE(!schedule_has_sigma(sc) || noise_tape, "st_sample: schedule has sigma != 0 but noise_tape is NULL");
+  ST_TRY(st_sample_begin(m, sc, g, x_init, B, stream));
+  ST_TRY(st_sample_run(m, sc->S, noise_tape, stream));
+  return st_sample_end(m, x_out, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -190,7 +190,7 @@ size_t tc_scratch_need(const GemmP& p);
 int tc_scratch_reserve(cudaStream_t s, size_t need, Arena** out = nullptr);
 void tc_scratch_release(cudaStream_t s);
 int advance_loop(LoopState* ls, cudaStream_t s);
-int init_loop(LoopState* ls, int S, const float* tape, cudaStream_t s);
+int init_loop(LoopState* ls, int S, int k, const float* tape, cudaStream_t s);   // k: the step the loop stands at; tape + (S-1-k')*B*1536*32 = eps of step k'
 struct TokensInP {
   const float* z;            // [B*32,512] = x_t . Wx^T
   const float* vt_table;     // [1000,512]
@@ -222,7 +222,9 @@ struct TokensStepP {
   const float* P;            // [nE*B*32,512] = previous step's last-block rows through W_xo (W_xo2), eval-major
   const float* c_xo;         // [512] = W_x b_out
   const float* vt;           // [512] row t_model[k] of the timestep table
-  float alpha, beta;         // x_k = alpha x0_hat + beta x_{k+1}
+  float alpha, beta;         // x_k = alpha x0_hat + beta x_{k+1} + sigma eps_{k+1}
+  float sigma;               // 0: deterministic step (zeps is not read)
+  const float* zeps;         // [B*32,512] = W_x eps_{k+1} (DDPM / DDIM with eta > 0), or null
   int first;                 // first step of the loop: z is taken as it is
   int cfg_mode;              // ST_CFG_NONE / ST_CFG_TEXT / ST_CFG_TWO (evaluation order as in step_update)
   const float* scale;        // device [B]
@@ -251,7 +253,7 @@ int step_update(const StepP& p, cudaStream_t s);
 
 int transpose_to_tokens(const float* x, float* tok, int B, int C, int T, float scale, cudaStream_t s);     // [B,C,T]->[B,T,C]
 int transpose_from_tokens(const float* tok, float* x, int B, int C, int T, cudaStream_t s);                // [B,T,C]->[B,C,T]
-int gather_words(const int32_t* word, const float* table, float* out, int ldo, int rows, int force_zero, cudaStream_t s);
+int gather_words(const int32_t* word, const float* table, float* out, int ldo, int rows, int force_zero, int n_words, cudaStream_t s);
 int avgpool4(const float* in, float* out, int rows_out, int cols, cudaStream_t s);                         // rows_out x cols, in has 4x rows
 int vq_select(const float* dot, const float* cnorm, const float* codebook, float* residual, float* qsum, int64_t* idx,
               int idx_stride, int rows, int first, __half* r_planes, __half* q_planes, cudaStream_t s);   // planes: optional fp16 hi/lo copies of the new residual / of qsum

@@ -625,6 +625,15 @@ __global__ void __launch_bounds__(256) tokens_step_kernel(TokensStepP q) {
     }
 #pragma unroll
     for (int i = 0; i < TS_NV; ++i) zv[i] = q.beta * zv[i] + q.alpha * (pm[i] + cx[i]);
+    if (q.sigma != 0.f) {
+      // stochastic step (DDPM gaussian_diffusion.py:556, DDIM with eta > 0 :781-790): + sigma W_x eps, the noise already in token space
+      const float* __restrict__ ze = q.zeps + (long long)row * 512;
+      float nz[TS_NV];
+#pragma unroll
+      for (int i = 0; i < TS_NV; ++i) nz[i] = __ldg(ze + col[i]);
+#pragma unroll
+      for (int i = 0; i < TS_NV; ++i) zv[i] = fmaf(q.sigma, nz[i], zv[i]);
+    }
   }
   float base[TS_NV];
 #pragma unroll
@@ -709,6 +718,16 @@ __global__ void __launch_bounds__(256) step_update_kernel(StepP p) {
     const float cv[4] = {c.x, c.y, c.z, c.w}, uv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) x0[q] = __fadd_rn(uv[q], __fmul_rn(sc, __fsub_rn(cv[q], uv[q])));
+  } else if (p.cfg_mode == ST_CFG_BODYPART1) {
+    // eval 0 = out_uncond (no prompt, audio), eval >= 1 = (prompt of a part, no audio); cfg_sampler.py:149-167
+    const float4 u = ld(0);
+    const int ua_e = p.part_ua[col / 512];
+    const float sc = p.scale[b];
+    const float uv[4] = {u.x, u.y, u.z, u.w};
+    float cv[4] = {uv[0], uv[1], uv[2], uv[3]};       // a part without a prompt keeps out_uncond: u + scale * (u - u)
+    if (ua_e >= 0) { const float4 c = ld(ua_e); cv[0] = c.x; cv[1] = c.y; cv[2] = c.z; cv[3] = c.w; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x0[q] = __fadd_rn(uv[q], __fmul_rn(sc, __fsub_rn(cv[q], uv[q])));
   } else {
     // eval 0 = uu (no prompt, no audio), eval 1 = ut (no prompt, audio), eval >= 2 = ua (prompt, no audio)
     const float4 uu = ld(0), ut = ld(1);
@@ -782,19 +801,19 @@ __global__ void advance_loop_kernel(LoopState* ls) {
   pdl_launch();
   ls->k -= 1;
 }
-__global__ void init_loop_kernel(LoopState* ls, int S, const float* tape) {
+__global__ void init_loop_kernel(LoopState* ls, int S, int k, const float* tape) {
   pdl_wait();
   trace_stamp(10);
   pdl_launch();
-  ls->k = S - 1; ls->S = S; ls->tape = tape; ls->done = 0;
+  ls->k = k; ls->S = S; ls->tape = tape; ls->done = 0;
 }
 int advance_loop(LoopState* ls, cudaStream_t s) {
   launch_k(advance_loop_kernel, dim3(1), dim3(1), 0, s, ls);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
-int init_loop(LoopState* ls, int S, const float* tape, cudaStream_t s) {
-  launch_k(init_loop_kernel, dim3(1), dim3(1), 0, s, ls, S, tape);
+int init_loop(LoopState* ls, int S, int k, const float* tape, cudaStream_t s) {
+  launch_k(init_loop_kernel, dim3(1), dim3(1), 0, s, ls, S, k, tape);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -848,20 +867,22 @@ int transpose_from_tokens(const float* tok, float* x, int B, int C, int T, cudaS
 //    denoiser.py:152-153) and the 4-frame average pool (denoiser.py:157).
 // =========================================================================================================
 __global__ void __launch_bounds__(256) gather_words_kernel(const int32_t* __restrict__ word, const float* __restrict__ table,
-                                                           float* __restrict__ out, int ldo, int rows, int force_zero) {
+                                                           float* __restrict__ out, int ldo, int rows, int force_zero, int n_words) {
   pdl_wait();
   trace_stamp(10);
   pdl_launch();
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;    // rows x 64 float4
   if (gid >= (long long)rows * 64) return;
   const int r = (int)(gid >> 6), c4 = (int)(gid & 63);
-  const int w = force_zero ? 0 : word[r];
+  // nn.Embedding raises on an id outside the table (denoiser.py:152); the host mirror checks CPU tensors, and an id that
+  // reaches the device anyway is clamped to <unk>-like row n_words - 1 / row 0 rather than read out of bounds
+  const int w = force_zero ? 0 : min(max(word[r], 0), n_words - 1);
   const float4 v = __ldg(reinterpret_cast<const float4*>(table + (long long)w * 256) + c4);
   *reinterpret_cast<float4*>(out + (long long)r * ldo + c4 * 4) = v;
 }
-int gather_words(const int32_t* word, const float* table, float* out, int ldo, int rows, int force_zero, cudaStream_t s) {
+int gather_words(const int32_t* word, const float* table, float* out, int ldo, int rows, int force_zero, int n_words, cudaStream_t s) {
   const long long n = (long long)rows * 64;
-  launch_k(gather_words_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, word, table, out, ldo, rows, force_zero);
+  launch_k(gather_words_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, word, table, out, ldo, rows, force_zero, n_words);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }

@@ -56,6 +56,7 @@ class MDM:
         self._h = None
         self._cond_key = CondKey()
         self._keep = None
+        self._vocab_rows = 0
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -70,6 +71,7 @@ class MDM:
                 raise RuntimeError(f"state dict is for variant '{found}' but the model was built as '{self.variant}'")
             self.variant = found
         packed = packer.pack_mdm(sd, self.variant)
+        self._vocab_rows = int(sd["text_pre_encoder_body.weight"].shape[0])
         arr, keep = _lib.tensor_array(packed)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -125,6 +127,8 @@ class MDM:
         word = y["word"]
         if tuple(word.shape) != (B, N_FRAMES):
             raise ValueError(f"y['word'] must be [B,{N_FRAMES}], got {tuple(word.shape)}")
+        if word.device.type == "cpu" and word.numel() and (int(word.min()) < 0 or int(word.max()) >= self._vocab_rows):
+            raise IndexError(f"y['word'] holds ids outside [0,{self._vocab_rows}) (nn.Embedding would raise, denoiser.py:152)")
         word = word.to(dev, non_blocking=True).to(torch.int32).contiguous()
         seed = _dev_f32(y["seed"], "seed", dev)
         if seed.numel() != B * 4 * LATENT_C:

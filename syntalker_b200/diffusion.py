@@ -106,24 +106,31 @@ class SpacedDiffusion(_sch.Tables):
             S = self.num_timesteps
             sig_col = 2 if mode == _lib.ST_MODE_DDPM else 4
             need_noise = bool(np.any(coef[:, sig_col] != 0))
-            tape = None
+            out = torch.empty_like(img)
+            L, h, gs = _lib.lib(), base.handle, g.struct(B)
             if noise_tape is not None:           # extension: caller-supplied eps_k, [S,B,1536,1,32] in draw order
                 tape = _dev_f32(noise_tape, "noise_tape", dev)
                 if tuple(tape.shape) != (S, B, 1536, 1, 32):
                     raise ValueError(f"noise_tape must be [{S},{B},1536,1,32], got {tuple(tape.shape)}")
-            elif need_noise or consume_rng:
-                # the reference draws th.randn_like(x) once per step, t = S-1..0, also at t == 0 (:541, :781)
-                tape = torch.empty((S, B, 1536, 1, 32), device=dev, dtype=torch.float32) if need_noise else None
-                for i in range(S):
-                    if need_noise:
-                        tape[i].normal_()
+                _lib.check(L.st_sample(h, sched, C.byref(gs), img.data_ptr(), tape.data_ptr(), B, out.data_ptr(), _lib.stream_ptr()))
+            elif need_noise:
+                # the reference draws th.randn_like(x) once per step, t = S-1..0, also at t == 0 (:541, :781): same draws, same
+                # order, handed to the native loop one chunk of steps at a time (a whole 1000-step tape would be B x 197 MB)
+                G = int(L.st_sample_chunk(sched))
+                buf = torch.empty((G, B, 1536, 1, 32), device=dev, dtype=torch.float32)
+                _lib.check(L.st_sample_begin(h, sched, C.byref(gs), img.data_ptr(), B, _lib.stream_ptr()))
+                for _ in range(S // G):
+                    for i in range(G):
+                        buf[i].normal_()
                         if const_noise:
-                            tape[i] = tape[i][[0]].repeat(B, 1, 1, 1)
-                    else:
+                            buf[i] = buf[i][[0]].repeat(B, 1, 1, 1)      # gaussian_diffusion.py:543-544
+                    _lib.check(L.st_sample_run(h, G, buf.data_ptr(), _lib.stream_ptr()))
+                _lib.check(L.st_sample_end(h, out.data_ptr(), _lib.stream_ptr()))
+            else:
+                if consume_rng:                  # ddim_sample draws an (unused, sigma = 0) randn_like every step (:781)
+                    for _ in range(S):
                         torch.empty_like(img).normal_()
-            out = torch.empty_like(img)
-            _lib.check(_lib.lib().st_sample(base.handle, sched, C.byref(g.struct(B)), img.data_ptr(),
-                                           tape.data_ptr() if tape is not None else None, B, out.data_ptr(), _lib.stream_ptr()))
+                _lib.check(L.st_sample(h, sched, C.byref(gs), img.data_ptr(), None, B, out.data_ptr(), _lib.stream_ptr()))
         return out
 
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
@@ -136,7 +143,10 @@ class SpacedDiffusion(_sch.Tables):
 
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
                          device=None, progress=False, eta=0.0, skip_timesteps=0, init_image=None, randomize_class=False,
-                         cond_fn_with_grad=False, dump_steps=None, const_noise=False, consume_rng=False):
+                         cond_fn_with_grad=False, dump_steps=None, const_noise=False, consume_rng=True):
+        """`consume_rng` (extension, default True like the reference): draw the per-step randn_like the reference's ddim_sample
+        draws even at eta = 0 (gaussian_diffusion.py:781), so that the torch generator stands where it would after the reference's
+        loop (e.g. the next window's start noise); False skips those S small launches."""
         if dump_steps is not None:
             raise NotImplementedError()          # gaussian_diffusion.py:912-913
         if const_noise is True:

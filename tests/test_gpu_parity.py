@@ -13,7 +13,8 @@ from oracle import mdm as omdm
 from oracle import pose as opose
 from oracle import rvq as orvq
 from syntalker_b200 import _lib, synth
-from syntalker_b200.cfg_sampler import ClassifierFreeSampleModel, TwoClassifierFreeSampleModel, TwoClassifierFreeSampleModel_Bodypart
+from syntalker_b200.cfg_sampler import (ClassifierFreeSampleModel, ClassifierFreeSampleModel_Bodypart, TwoClassifierFreeSampleModel,
+                                        TwoClassifierFreeSampleModel_Bodypart)
 from syntalker_b200.denoiser import MDM
 from syntalker_b200.denoiser_h3d import MDM as MDM_H3D
 from syntalker_b200.diffusion import create_gaussian_diffusion
@@ -344,7 +345,14 @@ def test_ddim50_cfg_vs_oracle(W, models, engine):
 
 
 # ---- 4. RVQ decode ----------------------------------------------------------------------------------------------
-def near_tie_mask(Wq, lat, idx_ref, tol=2e-2):
+NEAR_TIE = 1e-2
+# The reference ranks codes by the fp32 value (|r|^2 - 2 r.c) + |c|^2 at |d| ~ 1.3e4, where one fp32 ulp is 9.8e-4: each distance carries
+# two roundings at that magnitude (<= 1 ulp together) plus the fp32 accumulation error of the 512-term dot product times 2 (measured
+# <= 2e-3 for both the reference's sgemm and the split-fp16 tensor-core product), so two implementations that are both correct to fp32
+# may order a pair of codes differently when the exact gap is below ~ 2 x (1 ulp + 2e-3) = 6e-3; 1e-2 leaves a 1.7x margin.
+
+
+def near_tie_mask(Wq, lat, idx_ref, tol=NEAR_TIE):
     """Searches whose top-2 distance gap (fp64, residual chain of the reference decisions) is below tol."""
     B, T, _ = lat.shape
     r = lat.reshape(-1, 512).double()
@@ -356,6 +364,66 @@ def near_tie_mask(Wq, lat, idx_ref, tol=2e-2):
         ties[:, q] = (s[:, 1] - s[:, 0]) < tol
         r = r - cb[idx_ref.reshape(-1, 6)[:, q]]
     return ties.reshape(B, T, 6)
+
+
+def top2_gap(Wq, lat, idx_ref):
+    """fp64 top-2 distance gap of every search along the reference's residual chain, [B,T,6]."""
+    B, T, _ = lat.shape
+    r = lat.reshape(-1, 512).double()
+    gaps = torch.zeros(B * T, 6, dtype=torch.float64)
+    for q in range(6):
+        cb = Wq[f"quantizer.layers.{q}.codebook"].double()
+        d = (r ** 2).sum(-1, keepdim=True) - 2 * r @ cb.t() + (cb ** 2).sum(-1)[None]
+        s_, _ = torch.sort(d, dim=-1)
+        gaps[:, q] = s_[:, 1] - s_[:, 0]
+        r = r - cb[idx_ref.reshape(-1, 6)[:, q]]
+    return gaps.reshape(B, T, 6)
+
+
+def decode_with_flip_accounting(sample_gpu, vq_ws, vq_handles, dims, tag, tie_tol=NEAR_TIE, rec_tol=2e-4):
+    """parity of the decode is governed by code-index flips, so account for every one of them.  The GPU's OWN latent
+    is decoded by the oracle and by the C-ABI; every index mismatch must sit on a search whose fp64 top-2 gap is a near-tie
+    (listed), and every (clip, body part) without a flip must match to rec_tol.  A flip changes one code vector, which the
+    decoder's dilated convs (receptive field ~ the whole 32-token clip) spread over that clip's part -- and over nothing else.
+    Returns (recs_ref, clean [B,3] bool): oracle decodes of the GPU latent and which (clip, part) pairs are flip-free."""
+    lats = opose.sample_to_parts(sample_gpu.cpu(), 5.0)
+    recs_ref, clean, flips = [], [], []
+    for p_, (d, lat) in enumerate(zip(dims, lats)):
+        rec_ref, idx_ref = orvq.latent2origin(vq_ws[d], lat)
+        rec, _, _, idx = vq_handles[d].latent2origin(lat.cuda().clone(), return_indices=True)
+        mism = idx.cpu() != idx_ref
+        if mism.any():
+            gaps = top2_gap(vq_ws[d], lat, idx_ref)
+            # a flip changes the residual, so later layers of the same token may differ legitimately: only the FIRST differing
+            # layer of a token has to be a near-tie
+            first = mism & (mism.int().cumsum(-1) == 1)
+            for b, t_, q in first.nonzero().tolist():
+                flips.append((p_, b, t_, q, float(gaps[b, t_, q])))
+            assert bool((gaps[first] < tie_tol).all()), f"{tag}: code index differs where the fp64 top-2 gap is not a near-tie: {flips}"
+        ok = ~mism.any(dim=-1).any(dim=-1)
+        if ok.any():
+            assert maxabs(rec.cpu()[ok], rec_ref[ok]) < rec_tol, f"{tag}: decode of equal codes differs (part {p_})"
+        recs_ref.append(rec_ref); clean.append(ok)
+    n_search = sum(l.shape[0] * l.shape[1] * 6 for l in lats)
+    print(f"{tag}: #index mismatches {len(flips)} of {n_search} searches (first differing layer per token); "
+          f"fp64 top-2 gaps of the flips {[f'{g:.1e}' for *_, g in flips]}")
+    return recs_ref, torch.stack(clean, dim=1)
+
+
+# 330-d columns of each body part (diffusion_rvqvae_trainer.py:199-219): joint j -> columns 6j .. 6j+5
+PART_COLS_330 = [[6 * j + c for j in J for c in range(6)] for J in
+                 ([3, 6, 9, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21], list(range(25, 55)), [0, 1, 2, 4, 5, 7, 8, 10, 11])]
+
+
+def assert_pose_parity_on_clean_parts(pose, pose_ref, clean, part_cols, tag, tol=1e-3):
+    """max-abs < tol on every (clip, body part) whose codes all agree; the flipped pairs are reported, not tolerated silently."""
+    worst = 0.0
+    for b in range(pose.shape[0]):
+        for p_ in range(3):
+            if clean[b, p_]:
+                worst = max(worst, maxabs(pose[b][:, part_cols[p_]], pose_ref[b][:, part_cols[p_]]))
+    print(f"{tag}: pose max-abs on the {int(clean.sum())}/{clean.numel()} flip-free (clip, part) pairs {worst:.2e}")
+    assert worst < tol, tag
 
 
 def test_rvq_decode_vs_golden(golden, vq_w, vqs, engine):
@@ -591,13 +659,32 @@ def test_e2e_config2_shape_properties(W, vq_w, models, vqs, engine):
     Wm = W["beatx_motionclip"]
     fn = lambda x, t, yy: omdm.cfg_text(lambda a, b, c: omdm.mdm_forward(Wm, a, b, c, "beatx_motionclip"), x, t, yy)
     s_ref = odiff.ddim_sample_loop(odiff.make_schedule(use_ddim=True), fn, inp["noise"][:2], yo)
-    assert maxabs(sample[:2], s_ref) < 1e-3
+    lat_err = maxabs(sample[:2], s_ref)
+    print(f"config2 parity: latent max-abs vs the oracle loop {lat_err:.2e}")
+    assert lat_err < 3e-4
+    ms = load_mean_std()
+    # (1) all 32 clips: decode + assembly at the GPU's own latent, every code-index flip accounted for
+    recs_ref, clean = decode_with_flip_accounting(sample, vq_w, vqs, synth.PART_DIMS_BEATX, "config2 decode at the GPU latent")
+    pose_ref, trans_ref = opose.assemble_330(recs_ref[0], recs_ref[1], recs_ref[2], ms, None)
+    assert_pose_parity_on_clean_parts(pose, pose_ref, clean, PART_COLS_330, "config2 B=32")
+    ok_lo = clean[:, 2]
+    assert maxabs(trans[ok_lo], trans_ref[ok_lo]) < 1e-3
+    # (2) clips 0..1 end to end against the oracle's own latent: the latent error may move a search across a near-tie; the gap
+    # such a flip can bridge grows with the latent error (|c1 - c2| ~ 32, x5 latent scale)
     lats = opose.sample_to_parts(s_ref, 5.0)
     outs = [orvq.latent2origin(vq_w[dd], l) for dd, l in zip(synth.PART_DIMS_BEATX, lats)]
-    pose_ref, _ = opose.assemble_330(outs[0][0], outs[1][0], outs[2][0], load_mean_std(), None)
-    bad = np.abs(pose[:2].numpy() - pose_ref.numpy()) > 1e-3
-    print(f"config2 parity: latent max-abs {maxabs(sample[:2], s_ref):.2e}, pose elements over 1e-3: {bad.mean():.2e}")
-    assert bad.mean() < 2e-2        # an index flip at an fp32 near-tie moves one 4-frame block of one body part
+    pose_e2e, _ = opose.assemble_330(outs[0][0], outs[1][0], outs[2][0], ms, None)
+    clean2 = []
+    for dd, l, (_, idx_ref) in zip(synth.PART_DIMS_BEATX, opose.sample_to_parts(sample[:2], 5.0), outs):
+        _, _, _, idx = vqs[dd].latent2origin(l.cuda().clone(), return_indices=True)
+        mism = idx.cpu() != idx_ref
+        first = mism & (mism.int().cumsum(-1) == 1)
+        if first.any():
+            assert bool((top2_gap(vq_w[dd], lats[len(clean2)], idx_ref)[first] < NEAR_TIE + 400 * lat_err).all())
+        clean2.append(~mism.any(dim=-1).any(dim=-1))
+    clean2 = torch.stack(clean2, dim=1)
+    print(f"config2 end to end vs the oracle latent: {int((~clean2).sum())} of {clean2.numel()} (clip, part) pairs hold a flipped code")
+    assert_pose_parity_on_clean_parts(pose[:2], pose_e2e, clean2, PART_COLS_330, "config2 end to end, clips 0..1")
 
 
 # ---- 7. the other BASELINE configurations ------------------------------------------------------------------------
@@ -620,9 +707,148 @@ def test_config4_h3d_bodypart_pipeline_vs_oracle(W, models, engine):
     assert maxabs(sample, s_ref) < 1e-3
     lats = opose.sample_to_parts(s_ref, 5.0)
     outs = [orvq.latent2origin(vq_w[dd], l) for dd, l in zip(synth.PART_DIMS_H3D, lats)]
-    pose_ref = opose.assemble_623(outs[0][0], outs[1][0], outs[2][0])
-    bad = np.abs(pose.cpu().numpy() - pose_ref.numpy()) > 1e-3
-    assert bad.mean() < 2e-2          # zero unless a code index sits on an fp32 near-tie
+    vqh = dict(zip(synth.PART_DIMS_H3D, vqs_h))
+    recs_ref, clean = decode_with_flip_accounting(sample, vq_w, vqh, synth.PART_DIMS_H3D, "config4 decode at the GPU latent")
+    pose_ref = opose.assemble_623(recs_ref[0], recs_ref[1], recs_ref[2])
+    part_cols = [list(m_) for m_ in opose.h3d_masks()]
+    assert_pose_parity_on_clean_parts(pose.cpu(), pose_ref, clean, part_cols, "config4 B=2")
+
+
+# ---- 7b. round 2: fixtures generated by the real reference for the corners round 1 held against the oracle only ------------
+def test_cfg_two_and_h3d_text_cfg_vs_reference_golden(golden, models, engine):
+    """TwoClassifierFreeSampleModel (cfg_sampler.py:31-54, per-clip prompt scales) and ClassifierFreeSampleModel over denoiser_h3d,
+    also with eval=True (what h3d_diffusion_new_trainer.py:922 builds), against tests/golden/make_golden_r2.py."""
+    m = models["h3d"]
+    inp = synth.make_inputs(2, seed=3, variant="h3d")
+    y = cuda({k: inp[k] for k in ("audio", "word", "seed")}); y["style_feature"] = inp["style_upper"].cuda()
+    g = golden("cfg_two")
+    t = torch.from_numpy(g["t"]).cuda()
+    y2 = dict(y); y2["scale_audio"] = torch.from_numpy(g["scale_audio"]); y2["scale_prompt"] = torch.from_numpy(g["scale_prompt"])
+    assert maxabs(TwoClassifierFreeSampleModel(m)(inp["noise"].cuda(), t, y2), g["out"]) < 1e-4
+    g = golden("cfg_h3d_text")
+    y3 = dict(y); y3["scale"] = torch.from_numpy(g["scale"])
+    assert maxabs(ClassifierFreeSampleModel(m)(inp["noise"].cuda(), t, y3), g["out"]) < 1e-4
+    assert maxabs(ClassifierFreeSampleModel(m, eval=True)(inp["noise"].cuda(), t, y3), g["out_eval"]) < 1e-4
+
+
+def test_cfg_bodypart_single_scale_vs_reference_golden(golden, models, engine):
+    """ClassifierFreeSampleModel_Bodypart (cfg_sampler.py:125-167): 1 + (#prompted parts) evaluations, and its eval=True shortcut."""
+    inp = synth.make_inputs(1, seed=4, variant="h3d")
+    g = golden("cfg_bodypart1")
+    y = cuda({k: inp[k] for k in ("audio", "word", "seed")})
+    y["style_feature"] = {"upper_mask": inp["style_upper"].cuda(), "hands_mask": None, "lower_mask": inp["style_lower"].cuda()}
+    y["scale"] = torch.from_numpy(g["scale"])
+    t = torch.from_numpy(g["t"]).cuda()
+    assert maxabs(ClassifierFreeSampleModel_Bodypart(models["h3d"])(inp["noise"].cuda(), t, y), g["out"]) < 1e-4
+    assert maxabs(ClassifierFreeSampleModel_Bodypart(models["h3d"], eval=True)(inp["noise"].cuda(), t, y), g["out_eval"]) < 1e-4
+    # and inside the sampling loop (x-space loop: body-part guidance mixes per channel range)
+    d = create_gaussian_diffusion(timestep_respacing="ddim10")
+    yo = {k: inp[k] for k in ("audio", "word", "seed")}
+    yo["style_feature"] = {"upper_mask": inp["style_upper"], "hands_mask": None, "lower_mask": inp["style_lower"]}
+    yo["scale"] = torch.from_numpy(g["scale"])
+    # (h3d weights via the module-level fixture of the oracle tests would be a second copy: rebuild the dict here)
+    Wh = synth.mdm_state_dict("h3d", seed=0)
+    fn = lambda x, tt, yy: omdm.cfg_bodypart1(lambda a, b, c: omdm.mdm_forward(Wh, a, b, c, "h3d"), x, tt, yy)
+    ref = odiff.ddim_sample_loop(odiff.make_schedule(respacing="ddim10"), fn, inp["noise"], yo)
+    out = d.ddim_sample_loop(ClassifierFreeSampleModel_Bodypart(models["h3d"]), (1, 1536, 1, 32), noise=inp["noise"].cuda(),
+                             clip_denoised=False, model_kwargs={"y": y})
+    assert maxabs(out, ref) < 3e-4
+
+
+def test_h3d_decoders_and_623_scatter_vs_reference_golden(golden, engine):
+    """latent2origin of the HumanML3D decoders (D = 156 / 360 / 107) and the 623-d scatter (h3d_diffusion_new_trainer.py:194-221,
+    604-607) against the real reference's output."""
+    g = golden("h3d_decode")
+    recs = []
+    for d in synth.PART_DIMS_H3D:
+        vq = RVQVAE(None, d).load_state_dict(synth.rvq_state_dict(d, seed=0))
+        rec, _, _, idx = vq.latent2origin(torch.from_numpy(g[f"lat{d}"]).cuda(), return_indices=True)
+        assert np.array_equal(idx.cpu().numpy(), g[f"idx{d}"])
+        assert maxabs(rec, g[f"rec{d}"]) < 1e-4
+        recs.append(rec)
+    pose = pose_assemble_623(*recs)
+    assert pose.shape == (2, 128, 623) and maxabs(pose, g["rec_pose"]) < 1e-4
+    # the scatter itself is exact: feeding the reference's decodes reproduces its 623-d tensor bit for bit
+    exact = pose_assemble_623(*[torch.from_numpy(g[f"rec{d}"]).cuda() for d in synth.PART_DIMS_H3D])
+    assert torch.equal(exact.cpu(), torch.from_numpy(g["rec_pose"]))
+
+
+def ddpm_tape(seed, S, shape):
+    """eps_k in draw order, as tests/golden/make_golden_r2.py fed them to the reference's p_sample_loop."""
+    gen = torch.Generator().manual_seed(int(seed))
+    return torch.stack([torch.randn(shape, generator=gen) for _ in range(S)])
+
+
+def test_ddpm1000_vs_reference_golden(golden, models, engine):
+    """BASELINE config 3's loop against the REAL reference: B = 1, create_gaussian_diffusion() (1000 steps) through the reference's
+    own p_sample_loop (gaussian_diffusion.py:505-557, 607-739) with its 1000 noise draws replayed.  tcgen05 engine: the z recursion
+    (noise enters as W_x eps, formed per chunk of 50 steps) AND the x-space loop (probe 512); SIMT engine: x space in exact fp32.
+    Then the same loop fed in chunks through st_sample_begin / _run / _end."""
+    g = golden("ddpm1000")
+    m = models["beatx"]
+    inp = synth.make_inputs(1, seed=1, variant="beatx")
+    kw = {"y": y_of(inp)}
+    d = create_gaussian_diffusion()
+    assert d.num_timesteps == 1000
+    tape = ddpm_tape(g["seed"], 1000, (1, 1536, 1, 32)).cuda()
+    L = _lib.lib()
+    ref = g["x_after_999"]
+    run = lambda: d.p_sample_loop(m, (1, 1536, 1, 32), noise=inp["noise"].cuda(), clip_denoised=False, model_kwargs=kw, noise_tape=tape)
+    outs = [run() for _ in range(3)]           # eager, capture, replay
+    for i, o in enumerate(outs):
+        print(f"DDPM-1000 [{engine}] pass {i}: final sample max-abs vs the reference {maxabs(o, ref):.2e} (|x| <= {np.abs(ref).max():.1f})")
+        assert maxabs(o, ref) < 5e-4
+    if engine == "tc":
+        try:
+            _lib.check(L.st_debug_probe(512))
+            xs = [run() for _ in range(3)][-1]
+        finally:
+            _lib.check(L.st_debug_probe(0))
+        print(f"DDPM-1000 [tc, x-space loop]: max-abs vs the reference {maxabs(xs, ref):.2e}, vs the z recursion {maxabs(xs, outs[-1]):.2e}")
+        assert maxabs(xs, ref) < 5e-4
+    # the chunked entry points: same steps, noise handed over 50 steps at a time
+    import ctypes as C
+    from syntalker_b200.denoiser import Guidance
+    sched, _ = d._native(_lib.ST_MODE_DDPM, 0.0)
+    G = int(L.st_sample_chunk(sched))
+    assert G == 50
+    m.encode_cond(kw["y"], force=True)
+    x0 = inp["noise"].cuda().contiguous()
+    out = torch.empty_like(x0)
+    gs = Guidance(_lib.ST_CFG_NONE).struct(1)
+    _lib.check(L.st_sample_begin(m.handle, sched, C.byref(gs), x0.data_ptr(), 1, _lib.stream_ptr()))
+    for c in range(1000 // G):
+        _lib.check(L.st_sample_run(m.handle, G, tape[c * G:(c + 1) * G].contiguous().data_ptr(), _lib.stream_ptr()))
+    with pytest.raises(_lib.StError):
+        L_rc = L.st_sample_run(m.handle, 1, tape.data_ptr(), _lib.stream_ptr())     # nothing left to run
+        _lib.check(L_rc)
+    _lib.check(L.st_sample_end(m.handle, out.data_ptr(), _lib.stream_ptr()))
+    assert torch.equal(out, outs[-1])
+
+
+def test_cond_encode_stage_taps_vs_reference_golden(golden, models, W, engine):
+    """st_cond_encode as a stage of its own.  WavEncoder output (denoiser.py:151, 304-322) against the tap the
+    real reference left in mdm_beatx.npz; the word features and the hoisted conditioning constant against the oracle."""
+    import ctypes as C
+    g = golden("mdm_beatx")
+    m = models["beatx"]
+    inp = synth.make_inputs(2, seed=1, variant="beatx")
+    m.encode_cond(cuda({k: inp[k] for k in ("audio", "word", "seed")}), force=True)
+    at = torch.empty(2, 128, 512, device="cuda"); cst = torch.empty(64, 512, device="cuda")
+    _lib.check(_lib.lib().st_debug_cond_taps(m.handle, at.data_ptr(), cst.data_ptr(), 2, _lib.stream_ptr()))
+    wav = at[:, :, :256]
+    print(f"cond encode [{engine}]: WavEncoder tap max-abs vs the reference {maxabs(wav[:, ::8], g['wav']):.2e}")
+    assert maxabs(wav[:, ::8], g["wav"]) < 1e-4
+    Wb = W["beatx"]
+    word = torch.nn.functional.linear(Wb["text_pre_encoder_body.weight"][inp["word"].long()], Wb["text_encoder_body.weight"], Wb["text_encoder_body.bias"])
+    assert maxabs(at[:, :, 256:], word) < 1e-4
+    assert maxabs(wav, omdm.wav_encoder(Wb, inp["audio"])) < 1e-4            # every frame, against the oracle
+    # the hoisted constant (packer.py fold of denoiser.py:155-170): W_cm pool4([wav | word]) + bias_all, from the oracle's stage outputs
+    from syntalker_b200 import packer
+    pk = packer.pack_mdm(Wb, "beatx")
+    pooled = torch.cat([omdm.wav_encoder(Wb, inp["audio"]), word], dim=2).reshape(2, 32, 4, 512).mean(dim=2)
+    cst_ref = (pooled.double() @ pk["w_cm"].double().t() + pk["bias_all"].double()).float().reshape(64, 512)
+    assert maxabs(cst, cst_ref) < 1e-4
 
 
 def test_config3_ddpm1000_properties(models):
@@ -641,17 +867,23 @@ def test_config3_ddpm1000_properties(models):
     assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
 
 
-def test_config5_decode_only_large_batch(vq_w, vqs):
-    """BASELINE config 5 (RVQ decode-only) at B=256 x 128 frames: row-block independence and agreement with the
-    oracle on a slice; the full B=1024 shape is exercised by profiles/ runs."""
+def test_config5_decode_only_full_batch(vq_w, vqs):
+    """BASELINE config 5 (RVQ decode-only) at its real size, B = 1024 x 128 frames, all three body parts: row-block independence,
+    and slices of the batch against the oracle with every code-index flip accounted for."""
     g = torch.Generator().manual_seed(61)
-    lat = 5.0 * torch.randn(256, 32, 512, generator=g)
+    B = 1024
+    lat = 5.0 * torch.randn(B, 32, 512, generator=g)
+    sl = [0, 1, 2, 3, 500, 501, 1022, 1023]
     for d in synth.PART_DIMS_BEATX:
-        rec = vqs[d].latent2origin(lat.cuda().clone())[0]
-        assert rec.shape == (256, 128, d) and torch.isfinite(rec).all()
-        part = vqs[d].latent2origin(lat[100:104].cuda().clone())[0]
-        assert maxabs(part, rec[100:104]) < 2e-5
-    rec_ref, idx_ref = orvq.latent2origin(vq_w[78], lat[:8])
-    rec8, _, _, idx8 = vqs[78].latent2origin(lat[:8].cuda().clone(), return_indices=True)
-    clean = ~(idx8.cpu() != idx_ref).any(dim=-1).any(dim=-1)
-    assert clean.float().mean() > 0.8 and maxabs(rec8.cpu()[clean], rec_ref[clean]) < 3e-4
+        rec, _, _, idx = vqs[d].latent2origin(lat.cuda().clone(), return_indices=True)
+        assert rec.shape == (B, 128, d) and torch.isfinite(rec).all()
+        part = vqs[d].latent2origin(lat[700:704].cuda().clone())[0]
+        assert maxabs(part, rec[700:704]) < 2e-5
+        rec_ref, idx_ref = orvq.latent2origin(vq_w[d], lat[sl])
+        mism = idx.cpu()[sl] != idx_ref
+        first = mism & (mism.int().cumsum(-1) == 1)
+        if first.any():
+            assert bool((top2_gap(vq_w[d], lat[sl], idx_ref)[first] < NEAR_TIE).all())
+        clean = ~mism.any(dim=-1).any(dim=-1)
+        print(f"config5 D={d}: {int(first.sum())} flips in {len(sl) * 32 * 6} checked searches")
+        assert clean.float().mean() >= 0.75 and maxabs(rec.cpu()[sl][clean], rec_ref[clean]) < 3e-4
