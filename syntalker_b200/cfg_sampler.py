@@ -7,44 +7,49 @@ de-duplicated evaluations as one batched pass and mixes them with the reference'
 """
 from __future__ import annotations
 
+import torch
+
 from . import _lib
 from .denoiser import Guidance
 
 mask_dict = {"upper_mask": list(range(0, 512)), "hands_mask": list(range(512, 1024)), "lower_mask": list(range(1024, 1536))}
 
 
-class _Wrapper:
+def unwrap(model):
+    """(base MDM, outermost CFG wrapper or None) behind any nesting of nn.DataParallel / DDP (`.module`, train.py:87-94) and the
+    CFG wrappers (`.model`): the trainers wrap the DataParallel model in a CFG wrapper (h3d_diffusion_new_trainer.py:922)."""
+    wrapper, m = None, model
+    for _ in range(16):
+        if isinstance(m, _Wrapper):
+            wrapper = wrapper or m
+            m = m.model
+        elif hasattr(m, "module") and isinstance(m, torch.nn.Module) and not isinstance(m, _mdm_type()):
+            m = m.module
+        else:
+            break
+    return m, wrapper
+
+
+def _mdm_type():
+    from .denoiser import MDM
+    return MDM
+
+
+class _Wrapper(torch.nn.Module):
     def __init__(self, model, eval=False):
+        super().__init__()
         self.model = model
         self.eval_metric = eval
 
-    def parameters(self):
-        return self.model.parameters()
-
-    def eval(self):
-        return self
-
-    def to(self, *a, **k):
-        return self
-
-    def cuda(self, *a, **k):
-        return self
-
     @property
     def base(self):
-        m = self.model
-        while isinstance(m, _Wrapper):
-            m = m.model
-        return m
+        return unwrap(self)[0]
 
     def guidance(self, y):
         raise NotImplementedError
 
     def styles(self, y):
         return None
-
-    def __call__(self, x, timesteps, y=None):
-        return self.forward(x, timesteps, y)
 
     def forward(self, x, timesteps, y=None):
         base = self.base

@@ -509,7 +509,9 @@ __global__ void __launch_bounds__(256) tokens_in_kernel(TokensInP p) {
   const int e = (int)(wid / rows_e);
   const int row = (int)(wid - e * rows_e);          // b*32 + tau
   const int b = row >> 5, tau = row & 31;
-  const int t = p.ls ? p.t_model_dev[p.ls->k] : (p.t_dev ? (int)p.t_dev[b] : p.t_scalar);
+  // a timestep that reaches the device out of range is clamped into the table (the host mirror validates CPU tensors; checking a
+  // device tensor would cost a synchronisation per model call)
+  const int t = p.ls ? p.t_model_dev[p.ls->k] : min(max(p.t_dev ? (int)p.t_dev[b] : p.t_scalar, 0), ST_MAX_T - 1);
   const float* vt = p.vt_table + (long long)t * 512;
   const float* cst = p.cst[e] + (long long)(p.cst_bcast[e] ? tau : row) * 512;
   const float* g2 = p.g2 + (long long)b * 512;

@@ -42,43 +42,123 @@ class CondKey:
         return tuple((t.data_ptr(), t._version, tuple(t.shape), t.dtype, str(t.device)) if t is not None else None for t in tensors)
 
 
-class MDM:
+_BUFFER_KEYS = ("running_mean", "running_var", "num_batches_tracked", ".pe", "inv_freq")   # buffers of the reference module; the rest are parameters
+
+
+def _mangle(k: str) -> str:
+    return k.replace(".", "/")          # nn.Module refuses '.' in parameter names; state_dict() / named_parameters() hand back the original keys
+
+
+class MDM(torch.nn.Module):
+    """An `nn.Module` like the reference's: it holds the reference state dict (same keys, same shapes) as parameters / buffers on its
+    device, so `next(model.parameters()).device` (gaussian_diffusion.py:697), `state_dict()` / `load_state_dict()` (with or without the
+    `module.` prefix, utils/other_tools.py:771-790), `named_parameters()`, `.cuda()` / `.to()`, `.eval()` and wrapping in
+    `nn.DataParallel` / DDP (train.py:87-94) behave as they do for `models.denoiser.MDM`.  The arithmetic never touches those
+    tensors: `load_state_dict` packs them (packer.py) into the native handle, and `forward` runs in libsyntalker_b200.so."""
     variant_default = "beatx"
 
     def __init__(self, args=None, state_dict=None, device: Optional[torch.device] = None):
+        super().__init__()
         self.args = args
         use_mc = bool(getattr(args, "use_motionclip", False)) if args is not None else False
         self.variant = "beatx_motionclip" if (use_mc and self.variant_default == "beatx") else self.variant_default
-        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) \
+        self._device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) \
             if torch.cuda.is_available() else torch.device("cpu")
         self.use_motionclip = self.variant != "beatx"
-        self.training = False
         self._h = None
+        self._h_device = None
+        self._keys = []                # reference state-dict keys in order
         self._cond_key = CondKey()
         self._keep = None
         self._vocab_rows = 0
+        self.eval()
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
-    # ---- nn.Module-like surface the trainers touch (train.py:85-94, other_tools.py:771-790) ----
-    def load_state_dict(self, state_dict, strict: bool = True):
-        if self.device.type != "cuda":
+    @property
+    def device(self):
+        return self._device
+
+    # ---- nn.Module surface the trainers touch (train.py:85-94, other_tools.py:771-790) ----
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        self._load(packer.strip_module_prefix(state_dict), strict)
+        return self
+
+    def _load(self, sd, strict=True):
+        if self._device.type != "cuda":
             raise _lib.StError("syntalker_b200.MDM needs a CUDA device: there is no CPU path")
-        sd = packer.strip_module_prefix(state_dict)
         found = packer.detect_variant(sd)
         if found != self.variant:
             if strict and self.args is not None:
                 raise RuntimeError(f"state dict is for variant '{found}' but the model was built as '{self.variant}'")
             self.variant = found
-        packed = packer.pack_mdm(sd, self.variant)
+            self.use_motionclip = found != "beatx"
+        for k in self._keys:                                   # drop a previous load
+            (self._parameters if _mangle(k) in self._parameters else self._buffers).pop(_mangle(k), None)
+        self._keys = list(sd.keys())
+        for k, v in sd.items():
+            t = v.detach().to(self._device)
+            if any(k.endswith(b) for b in _BUFFER_KEYS) or not t.is_floating_point():
+                self.register_buffer(_mangle(k), t.clone())
+            else:
+                self.register_parameter(_mangle(k), torch.nn.Parameter(t.clone(), requires_grad=False))
         self._vocab_rows = int(sd["text_pre_encoder_body.weight"].shape[0])
+        self._build()
+
+    def _build(self):
+        """(Re)create the native handle from the tensors this module holds, on the device they live on."""
+        sd = self._ref_state()
+        packed = packer.pack_mdm(sd, self.variant)
         arr, keep = _lib.tensor_array(packed)
         h = C.c_void_p()
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self._device):
             _lib.check(_lib.lib().st_model_create(arr, len(packed), _lib.ST_VARIANT[self.variant], C.byref(h)))
         self._free()
-        self._h = h
+        self._h, self._h_device = h, self._device
         self._cond_key = CondKey()
+
+    def _ref_state(self):
+        out = {}
+        for k in self._keys:
+            m = _mangle(k)
+            out[k] = self._parameters[m] if m in self._parameters else self._buffers[m]
+        return out
+
+    # state_dict(): the reference's keys (this hook also serves wrappers, which add their own prefix: 'module.', 'model.')
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        for k, v in self._ref_state().items():
+            destination[prefix + k] = v if keep_vars else v.detach()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        sub = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)}
+        if not sub:
+            if strict:
+                missing_keys.append(prefix + "*")
+            return
+        try:
+            self._load(sub, strict)
+        except Exception as e:      # nn.Module.load_state_dict reports, it does not raise from the hooks
+            error_msgs.append(str(e))
+
+    def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
+        for k in self._keys:
+            if _mangle(k) in self._parameters:
+                yield (prefix + ("." if prefix else "") + k, self._parameters[_mangle(k)])
+
+    def named_buffers(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
+        for k in self._keys:
+            if _mangle(k) in self._buffers:
+                yield (prefix + ("." if prefix else "") + k, self._buffers[_mangle(k)])
+
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn, recurse) if recurse is not True else super()._apply(fn)
+        # .cuda() / .to(device): the native handle lives on one device; follow the tensors (dtype changes are not followed: the
+        # path computes in its own arithmetic whatever the storage type of the reference tensors)
+        if self._keys:
+            dev = self._ref_state()[self._keys[0]].device
+            if dev.type == "cuda" and dev != self._h_device:
+                self._device = dev
+                self._build()
         return self
 
     def _free(self):
@@ -92,23 +172,10 @@ class MDM:
         except Exception:
             pass
 
-    def parameters(self):
-        yield torch.empty(0, device=self.device)
-
-    def eval(self):
-        self.training = False
-        return self
-
     def train(self, mode=True):
         if mode:
             raise NotImplementedError("syntalker_b200.MDM is the sampling path only (SURVEY.md §8: training is out of scope)")
-        return self
-
-    def to(self, *a, **k):
-        return self
-
-    def cuda(self, *a, **k):
-        return self
+        return super().train(False)
 
     @property
     def handle(self):
@@ -165,9 +232,6 @@ class MDM:
         return B
 
     # ---- the model call ----
-    def __call__(self, x, timesteps, y=None, uncond_info=False):
-        return self.forward(x, timesteps, y)
-
     def forward(self, x, timesteps, y=None, _guidance=None):
         y = dict(y or {})
         B = self.encode_cond(y)

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib, schedule as _sch
-from .cfg_sampler import _Wrapper
+from .cfg_sampler import _Wrapper, unwrap
 from .denoiser import MDM, Guidance, _dev_f32
 
 
@@ -71,11 +71,11 @@ class SpacedDiffusion(_sch.Tables):
 
     @staticmethod
     def _split(model):
-        base = model.base if isinstance(model, _Wrapper) else model
+        base, wrapper = unwrap(model)
         if not isinstance(base, MDM):
-            raise TypeError("model must be a syntalker_b200 MDM (optionally inside a syntalker_b200 CFG wrapper); "
-                            "a torch nn.Module cannot be run by the native sampler and there is no fallback")
-        return base, (model if isinstance(model, _Wrapper) else None)
+            raise TypeError("model must be a syntalker_b200 MDM (optionally inside nn.DataParallel / DDP and / or a syntalker_b200 CFG "
+                            "wrapper); any other torch nn.Module cannot be run by the native sampler and there is no fallback")
+        return base, wrapper
 
     def _run(self, mode, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, eta, skip_timesteps,
              init_image, randomize_class, cond_fn_with_grad, const_noise, consume_rng, noise_tape=None):

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .cfg_sampler import _Wrapper
+from .cfg_sampler import _Wrapper, unwrap
 from .denoiser import Guidance
 
 
@@ -53,8 +53,7 @@ class Window330:
     """Pinned host staging + one st_generate_330_host call per window batch."""
 
     def __init__(self, model, diffusion, vq_upper, vq_hands, vq_lower, B, use_ddim=True, eta=0.0, latent_scale=5.0, ms=None):
-        self.base = model.base if isinstance(model, _Wrapper) else model
-        self.wrapper = model if isinstance(model, _Wrapper) else None
+        self.base, self.wrapper = unwrap(model)          # through nn.DataParallel / DDP and the CFG wrappers
         self.diffusion, self.B = diffusion, B
         self.vqs = (vq_upper, vq_hands, vq_lower)
         self.mode = _lib.ST_MODE_DDIM if use_ddim else _lib.ST_MODE_DDPM
@@ -186,8 +185,7 @@ class LongClip330:
     HOP_AUDIO = (16000 // 30) * 112
 
     def __init__(self, model, diffusion, vq_upper, vq_hands, vq_lower, use_ddim=True, eta=0.0, latent_scale=5.0, ms=None):
-        self.base = model.base if isinstance(model, _Wrapper) else model
-        self.wrapper = model if isinstance(model, _Wrapper) else None
+        self.base, self.wrapper = unwrap(model)          # through nn.DataParallel / DDP and the CFG wrappers
         self.diffusion = diffusion
         self.vqs = (vq_upper, vq_hands, vq_lower)
         self.mode = _lib.ST_MODE_DDIM if use_ddim else _lib.ST_MODE_DDPM
