@@ -219,6 +219,17 @@ int st_pose_assemble_623(const float* rec_upper, const float* rec_hands, const f
 /* sample [B,1536,1,T] -> token-major [B,T,1536] * scale (trainer:457 `squeeze().permute(1,0)` batched). */
 int st_sample_to_tokens(const float* sample, int B, int T, float scale, float* tokens, void* stream);
 
+/* ---- evaluation tail (the part that needs neither SMPL-X nor the VAESKConv evaluator weights) ----------
+ * st_pose_330_to_aa165: rec_pose [frames,330] (55 joints x 6d) -> poses [frames,165] axis-angle, the `poses` array of the result
+ *   files (diffusion_rvqvae_trainer.py:621-622: rotation_6d_to_matrix -> matrix_to_axis_angle; np.savez format :702-710).
+ * st_moments_accumulate: acc (device float64 [1 + D + D*D] = n, sum x, sum x x^T) += the moments of x [N,D]; the FID of the
+ *   reference (dataloaders/data_tools.py:1615-1625: np.mean, np.cov of all latents) follows from the summed statistics, so ranks
+ *   all-reduce `acc` (NCCL sum) instead of gathering latents.
+ * st_l1div_accumulate: acc (device float64 [2] = sum, counter) += L1div.run(x [n,J]) (utils/metric.py:16-22), one sequence per call. */
+int st_pose_330_to_aa165(const float* rec_pose, int64_t frames, float* poses_aa, void* stream);
+int st_moments_accumulate(const float* x, int64_t N, int D, double* acc, void* stream);
+int st_l1div_accumulate(const float* x, int n, int J, double* acc, void* stream);
+
 /* ---- whole window, device buffers ----------------------------------------------------------------
  * cond encode -> sample -> x latent_scale -> latent2origin x3 -> 330-d, everything resident in HBM.
  * ms: device [666] = mean[330] | std[330] | trans_mean[3] | trans_std[3].  sample_out (nullable) receives

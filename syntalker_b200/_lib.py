@@ -23,7 +23,7 @@ SYMBOLS = [
     "st_last_error", "st_abi_version", "st_launch_count", "st_set_engine", "st_get_engine", "st_set_graphs", "st_set_pdl", "st_debug_timeline", "st_debug_timeline_select", "st_debug_trace", "st_debug_probe", "st_debug_cond_taps",
     "st_model_create", "st_model_destroy", "st_vq_create", "st_vq_destroy", "st_vq_out_dim",
     "st_schedule_create", "st_schedule_destroy", "st_cond_encode", "st_denoise", "st_sample", "st_sample_chunk", "st_sample_begin", "st_sample_run", "st_sample_end",
-    "st_rvq_decode", "st_pose_assemble_330", "st_pose_assemble_623", "st_sample_to_tokens",
+    "st_rvq_decode", "st_pose_assemble_330", "st_pose_assemble_623", "st_sample_to_tokens", "st_pose_330_to_aa165", "st_moments_accumulate", "st_l1div_accumulate",
     "st_rvq_encode", "st_generate_330", "st_generate_330_host", "st_generate_330_host_begin", "st_generate_330_host_wait", "st_generate_long_330", "st_selftest_gemm", "st_bench_gemm", "st_profile_begin", "st_profile_end",
 ]
 
@@ -98,6 +98,9 @@ def lib():
     L.st_pose_assemble_330.argtypes = [vp] * 8 + [i32, i32, vp, vp, vp]
     L.st_pose_assemble_623.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.st_sample_to_tokens.argtypes = [vp, i32, i32, f32, vp, vp]
+    L.st_pose_330_to_aa165.argtypes = [vp, i64, vp, vp]
+    L.st_moments_accumulate.argtypes = [vp, i64, i32, vp, vp]
+    L.st_l1div_accumulate.argtypes = [vp, i32, i32, vp, vp]
     L.st_generate_330.argtypes = [vp, vp, C.POINTER(StGuidance), vp, vp, vp, C.POINTER(StCond), vp, vp, vp, vp, i32, f32, vp, vp, vp, vp]
     L.st_generate_330_host.argtypes = [vp, vp, C.POINTER(StGuidance), vp, vp, vp, C.POINTER(StHostInputs), i32, f32,
                                        vp, vp, vp, vp]

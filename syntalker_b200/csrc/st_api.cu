@@ -1328,6 +1328,20 @@ extern "C" int st_pose_assemble_623(const float* rec_upper, const float* rec_han
   ST_REQUIRE(rec_upper && rec_hands && rec_lower && rec_pose && B > 0 && n > 0, "st_pose_assemble_623: null argument");
   return pose623(rec_upper, rec_hands, rec_lower, B, n, rec_pose, (cudaStream_t)stream);
 }
+// ---- evaluation tail: result-file pose vector and the rank-reducible metric statistics --------------------
+extern "C" int st_pose_330_to_aa165(const float* rec_pose, int64_t frames, float* poses_aa, void* stream) {
+  ST_REQUIRE(rec_pose && poses_aa && frames > 0, "st_pose_330_to_aa165: null argument");
+  return pose_aa165(rec_pose, frames, poses_aa, (cudaStream_t)stream);
+}
+extern "C" int st_moments_accumulate(const float* x, int64_t N, int D, double* acc, void* stream) {
+  ST_REQUIRE(x && acc && N > 0 && D > 0 && D <= 4096, "st_moments_accumulate: null argument or bad shape");
+  return moments_accumulate(x, N, D, acc, (cudaStream_t)stream);
+}
+extern "C" int st_l1div_accumulate(const float* x, int n, int J, double* acc, void* stream) {
+  ST_REQUIRE(x && acc && n > 0 && J > 0, "st_l1div_accumulate: null argument or bad shape");
+  return l1div_accumulate(x, n, J, acc, (cudaStream_t)stream);
+}
+
 extern "C" int st_sample_to_tokens(const float* sample, int B, int T, float scale, float* tokens, void* stream) {
   ST_REQUIRE(sample && tokens && B > 0 && T > 0, "st_sample_to_tokens: null argument");
   return transpose_to_tokens(sample, tokens, B, 1536, T, scale, (cudaStream_t)stream);

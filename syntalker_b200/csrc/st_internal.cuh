@@ -261,6 +261,9 @@ int copy_strided_scale(const float* in, long long in_stride, float scale, float*
 int pose330(const float* up, const float* ha, const float* lo, const float* mean, const float* std, const float* tmean,
             const float* tstd, const float* jaw, int B, int n, float* pose, float* trans, cudaStream_t s);
 int pose623(const float* up, const float* ha, const float* lo, int B, int n, float* pose, cudaStream_t s);
+int pose_aa165(const float* pose, long long frames, float* aa, cudaStream_t s);
+int moments_accumulate(const float* x, long long N, int D, double* acc, cudaStream_t s);
+int l1div_accumulate(const float* x, int n, int J, double* acc, cudaStream_t s);
 
 // ---- device memory helpers ------------------------------------------------------------------------------
 struct Arena {

@@ -1039,7 +1039,14 @@ __device__ void aa_to_6d(const float aa[3], float out[6]) {
   out[5] = two_s * (j * k - i * r);
 }
 
+__device__ void sixd_to_aa(const float d6[6], float aa[3]);
 __device__ void sixd_roundtrip(const float d6[6], float out[6]) {
+  float aa[3];
+  sixd_to_aa(d6, aa);
+  aa_to_6d(aa, out);
+}
+// rotation_6d_to_matrix -> matrix_to_quaternion -> quaternion_to_axis_angle (utils/rotation_conversions.py:511-532, 96-118, 470-508)
+__device__ void sixd_to_aa(const float d6[6], float aa[3]) {
   // rotation_6d_to_matrix
   const float n1 = fmaxf(sqrtf(d6[0] * d6[0] + d6[1] * d6[1] + d6[2] * d6[2]), 1e-12f);
   const float b1[3] = {d6[0] / n1, d6[1] / n1, d6[2] / n1};
@@ -1062,8 +1069,7 @@ __device__ void sixd_roundtrip(const float d6[6], float out[6]) {
   const float half = atan2f(nrm, o0);
   const float angle = 2.0f * half;
   const float s = half_sinc(angle, half);
-  const float aa[3] = {o1 / s, o2 / s, o3 / s};
-  aa_to_6d(aa, out);
+  aa[0] = o1 / s; aa[1] = o2 / s; aa[2] = o3 / s;
 }
 
 __global__ void __launch_bounds__(256) pose330_kernel(const float* __restrict__ up, const float* __restrict__ ha,
@@ -1126,6 +1132,83 @@ int pose330(const float* up, const float* ha, const float* lo, const float* mean
     launch_k(trans_kernel, dim3((B * 3 + 127) / 128), dim3(128), 0, s, lo, tmean, tstd, B, n, trans);
     ST_CHECK_LAUNCH();
   }
+  return ST_OK;
+}
+
+// =========================================================================================================
+// 9b. Evaluation tail (the part that needs no SMPL-X): the 330-d features as the 165-d axis-angle vector of the
+//     result files (diffusion_rvqvae_trainer.py:621-622, 702-710), and the sufficient statistics of the two metrics that reduce over
+//     ranks -- first / second moments of the FID latents (dataloaders/data_tools.py:1615-1625: np.mean, np.cov) and the L1 diversity
+//     sums (utils/metric.py:12-27) -- accumulated in float64 so that per-rank partial sums add up exactly enough for an all-reduce.
+// =========================================================================================================
+__global__ void __launch_bounds__(256) pose_aa165_kernel(const float* __restrict__ pose, long long nj, float* __restrict__ aa) {
+  pdl_wait();
+  trace_stamp(10);
+  pdl_launch();
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;     // (frame, joint)
+  if (gid >= nj) return;
+  float d6[6], a[3];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) d6[q] = pose[gid * 6 + q];
+  sixd_to_aa(d6, a);
+  aa[gid * 3] = a[0]; aa[gid * 3 + 1] = a[1]; aa[gid * 3 + 2] = a[2];
+}
+int pose_aa165(const float* pose, long long frames, float* aa, cudaStream_t s) {
+  const long long nj = frames * 55;
+  launch_k(pose_aa165_kernel, dim3((unsigned)((nj + 255) / 256)), dim3(256), 0, s, pose, nj, aa);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+// acc = [n | s1[D] | s2[D][D]] (float64): n += N, s1[j] += sum_i x[i][j], s2[j][k] += sum_i x[i][j] x[i][k].  Block (j, k-tile of 64):
+// every (j, k) has exactly one writer and a fixed summation order, so the result is deterministic.
+__global__ void __launch_bounds__(64) moments_kernel(const float* __restrict__ x, long long N, int D, double* __restrict__ acc) {
+  pdl_wait();
+  trace_stamp(10);
+  pdl_launch();
+  const int j = blockIdx.x, k = blockIdx.y * 64 + threadIdx.x;
+  if (k >= D) return;
+  double s2 = 0.0, s1 = 0.0;
+  for (long long i = 0; i < N; ++i) {
+    const double xj = (double)x[i * D + j], xk = (double)x[i * D + k];
+    s2 = fma(xj, xk, s2);
+    s1 += xk;
+  }
+  acc[1 + D + (long long)j * D + k] += s2;
+  if (j == 0) acc[1 + k] += s1;
+  if (j == 0 && k == 0) acc[0] += (double)N;
+}
+int moments_accumulate(const float* x, long long N, int D, double* acc, cudaStream_t s) {
+  launch_k(moments_kernel, dim3(D, (D + 63) / 64), dim3(64), 0, s, x, N, D, acc);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+// L1div.run(results [n,J]) (utils/metric.py:16-22): counter += n; sum += sum_ij |x_ij - mean_j|.  acc = [sum, counter] (float64).
+__global__ void __launch_bounds__(256) l1div_kernel(const float* __restrict__ x, int n, int J, double* __restrict__ acc) {
+  pdl_wait();
+  trace_stamp(10);
+  pdl_launch();
+  __shared__ double part[256];
+  double tot = 0.0;
+  for (int j = threadIdx.x; j < J; j += 256) {
+    double m = 0.0;
+    for (int i = 0; i < n; ++i) m += (double)x[(long long)i * J + j];
+    m /= (double)n;
+    const float mf = (float)m;                                     // the reference's mean is a float32 array (np.mean of float32)
+    for (int i = 0; i < n; ++i) tot += (double)fabsf(x[(long long)i * J + j] - mf);
+  }
+  part[threadIdx.x] = tot;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { acc[0] += part[0]; acc[1] += (double)n; }
+}
+int l1div_accumulate(const float* x, int n, int J, double* acc, cudaStream_t s) {
+  launch_k(l1div_kernel, dim3(1), dim3(256), 0, s, x, n, J, acc);
+  ST_CHECK_LAUNCH();
   return ST_OK;
 }
 
