@@ -674,6 +674,7 @@ __device__ __forceinline__ float gelu_sb(float x) {
 constexpr int ATT_LDK = 68;                      // K / V staging row stride (floats): conflict-free float4 stores for lane = row
 constexpr int ATT_LDS = 36;                      // score row stride (floats)
 constexpr int ATT_SX_BYTES = 128 * ATT_LDS * 4;  // partial scores written by the peer CTA of the cluster
+constexpr int ATT_SX_TX = 128 * 32 * 4;          // bytes of them (32 scores per row; the row stride has 4 spare floats)
 constexpr int ATT_KV_BYTES = 128 * ATT_LDK * 4;
 constexpr int ATT_PL_OFF = 124928;               // plane staging box behind Q, K, V and P (3 x 34816 + 18432 = 122880 -> 1024-aligned)
 // tensor-core attention (attn == 2): operand tiles in the (dead) ring memory, offsets from the ring base, all 128B-swizzled
@@ -705,8 +706,9 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* res_bar = acc_bar + 1;
   // tensor-core attention (attn == 2): operand tiles ready for Q K^T (256 arrivals), scores complete (commit), P and V^T
   // ready (256 arrivals), P V complete (commit)
+  // [4]: the peer CTA's partial scores have landed in this CTA's score buffer (st.async complete_tx, 16 KB)
   uint64_t* att_bar = res_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(att_bar + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(att_bar + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
@@ -726,7 +728,9 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     mbar_init(acc_bar, 1);
     mbar_init(res_bar, 1);
     mbar_init(&att_bar[0], 256); mbar_init(&att_bar[1], 1); mbar_init(&att_bar[2], 256); mbar_init(&att_bar[3], 1);
+    mbar_init(&att_bar[4], 1);
     fence_barrier_init();
+    if (ep.attn == 2) mbar_expect_tx(&att_bar[4], ATT_SX_TX);      // the one arrival; the phase completes when the peer's 16 KB are in
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, TMEM_COLS);
@@ -849,18 +853,20 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (elect_one()) {
         mbar_wait(&att_bar[0], 0);
         tc_fence_after();
-        const uint32_t id_cat = umma_idesc_f16(TC_BM, 256), id_n = umma_idesc_f16(TC_BM, 128);
-        const uint64_t dqh = umma_desc_sw128(s0 + ATT2_Q), dql = umma_desc_sw128(s0 + ATT2_Q + TC_A_PLANE), dk = umma_desc_sw128(s0 + ATT2_K);
+        const uint32_t id_n = umma_idesc_f16(TC_BM, 128);
+        const uint64_t dqh = umma_desc_sw128(s0 + ATT2_Q), dql = umma_desc_sw128(s0 + ATT2_Q + TC_A_PLANE);
+        const uint64_t dkh = umma_desc_sw128(s0 + ATT2_K), dkl = umma_desc_sw128(s0 + ATT2_K + TC_A_PLANE);
+        // the v columns of the qkv accumulators ([128,192) and [320,384)) are still being read while these run: the scores go
+        // to [0,128) (q, k main: dead) and [384,512) (free)
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
-          umma_f16(tmem_base, dqh + 2 * k, dk + 2 * k, id_cat, k != 0);        // columns [0,128) q_hi.k_hi, [128,256) q_hi.k_lo
-          umma_f16(tmem_base + 128, dql + 2 * k, dk + 2 * k, id_n, 1);         // + q_lo.k_hi
+          umma_f16(tmem_base, dqh + 2 * k, dkh + 2 * k, id_n, k != 0);         // [0,128)   q_hi.k_hi
+          umma_f16(tmem_base + 384, dqh + 2 * k, dkl + 2 * k, id_n, k != 0);   // [384,512) q_hi.k_lo
+          umma_f16(tmem_base + 384, dql + 2 * k, dkh + 2 * k, id_n, 1);        //         + q_lo.k_hi
         }
         umma_commit(&att_bar[1]);
       }
       __syncwarp();
-      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // the score exchange of the epilogue warps
-      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
       if (elect_one()) {
         mbar_wait(&att_bar[2], 0);
         tc_fence_after();
@@ -872,8 +878,8 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < TC_BK / 16; ++k) {
             // keys 64 kb + 16 k .. + 16 of V (128 bytes per key row); N = [64 dims of V_hi ; 64 dims of V_lo]
             const uint64_t dv = umma_desc_mn_sw128(s0 + ATT2_V + kb * 8192 + k * 2048, TC_A_PLANE, 1024);
-            umma_f16(tmem_base + 384, dph + 2 * k, dv, id_cat, (kb | k) != 0);   // [384,448) p_hi.v_hi, [448,512) p_hi.v_lo
-            umma_f16(tmem_base + 448, dpl + 2 * k, dv, id_n, 1);                 // + p_lo.v_hi
+            umma_f16(tmem_base + 128, dph + 2 * k, dv, id_cat, (kb | k) != 0);   // [128,192) p_hi.v_hi, [192,256) p_hi.v_lo (all of qkv is dead)
+            umma_f16(tmem_base + 192, dpl + 2 * k, dv, id_n, 1);                 // + p_lo.v_hi
           }
         }
         umma_commit(&att_bar[3]);
@@ -935,9 +941,17 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t sx = smem_u32(res_tile);
       uint32_t sx_peer;
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(sx_peer) : "r"(sx), "r"((uint32_t)((blockIdx.x & 1) ^ 1)));
+      uint32_t sxbar_peer;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(sxbar_peer) : "r"(smem_u32(&att_bar[4])), "r"((uint32_t)((blockIdx.x & 1) ^ 1)));
       const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < 3; ++cc) {
+        if (cc == 2) {
+          // q and k are in place: the score MMAs run while v is converted
+          tc_fence_before();
+          fence_proxy_async();
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[0])) : "memory");
+        }
         const int c = 2 * cc + cpart;                    // chunks [q0 q1 k0 k1 v0 v1]: this warp's half of q, k, v
         uint32_t v[32], vc[32];
         tmem_ld32(trow + c * 32, v);
@@ -974,9 +988,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int q = 0; q < 8; ++q) sts128u(oth + (((uint32_t)q ^ sw) << 4), z4);
       }
-      tc_fence_before();
-      fence_proxy_async();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[0])) : "memory");
+      tc_fence_before();                                 // this thread's reads of the v accumulators precede the P V MMAs (att_bar[2])
       if (dbg && threadIdx.x == 64) { dbg[40] = dbg[0]; dbg[41] = dbg[3]; dbg[42] = clock64(); }
       // partial scores of this row over the 64 local dims: keys [16 cpart, +16) of the sequence's diagonal block
       float sv[16];
@@ -986,18 +998,19 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       {
         uint32_t v[16], vc[16];
         tmem_ld16(trow + lg * 32 + cpart * 16, v);
-        tmem_ld16(trow + 128 + lg * 32 + cpart * 16, vc);
+        tmem_ld16(trow + 384 + lg * 32 + cpart * 16, vc);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) sv[j] = __uint_as_float(v[j]) + __uint_as_float(vc[j]);
+        // to the peer's score buffer; every store also counts its 16 bytes on the peer's barrier, so the receiver waits for data,
+        // not for a cluster-wide barrier
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sx_peer + srow + 16 * q), "f"(sv[4 * q]),
-                       "f"(sv[4 * q + 1]), "f"(sv[4 * q + 2]), "f"(sv[4 * q + 3]) : "memory");
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                       ::"r"(sx_peer + srow + 16 * q), "f"(sv[4 * q]), "f"(sv[4 * q + 1]), "f"(sv[4 * q + 2]), "f"(sv[4 * q + 3]), "r"(sxbar_peer) : "memory");
       }
       if (dbg && threadIdx.x == 64) dbg[43] = clock64();
-      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      mbar_wait(&att_bar[4], 0);
       if (dbg && threadIdx.x == 64) dbg[44] = clock64();
       {
         // softmax over the 32 keys of the row; the operands were scaled by kActScale each, exp(x) = 2^(x log2 e)
@@ -1032,6 +1045,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           sts128u(prow + off, h);
           sts128u(prow + TC_A_PLANE + off, l);
         }
+        tc_fence_before();
         fence_proxy_async();
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&att_bar[2])) : "memory");
       }
@@ -1042,8 +1056,8 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (dbg && threadIdx.x == 64) dbg[46] = clock64();
       {
         uint32_t v[32], vc[32];
-        tmem_ld32(trow + 384 + cpart * 32, v);
-        tmem_ld32(trow + 448 + cpart * 32, vc);
+        tmem_ld32(trow + 128 + cpart * 32, v);
+        tmem_ld32(trow + 192 + cpart * 32, vc);
         tmem_ld_wait();
         const uint32_t orow = stage0 + (uint32_t)(ATT2_O + r * 128);
 #pragma unroll
@@ -1327,8 +1341,9 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (dbg && threadIdx.x == 64) dbg[4] = clock64();
     }
   }
-  if ((ep.attn == 1 && warp < 2) || (ep.attn == 2 && warp == 0)) {
-    // the producer and MMA warps take part in the cluster barrier of the attention epilogue (attn == 2: the MMA warp already has)
+  if (ep.attn == 1 && warp < 2) {
+    // the producer and MMA warps take part in the cluster barrier of the FMA attention epilogue (the tensor-core one exchanges
+    // its scores through st.async + an mbarrier instead)
     __syncwarp();
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -1685,7 +1700,7 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   int stages = (232448 - 4096 - res) / stage;
   if (stages > 4) stages = 4;
   if (p.attn) { stages = 2; }
-  const int smem = stages * stage + (p.attn ? ATT_SX_BYTES : res) + 2 * 192 * 4 + (2 * stages + 2 + 4) * 8 + 16 + 1024;
+  const int smem = stages * stage + (p.attn ? ATT_SX_BYTES : res) + 2 * 192 * 4 + (2 * stages + 2 + 5) * 8 + 16 + 1024;
   const CUtensorMap *tmA = nullptr, *tmW = nullptr, *tmO = nullptr, *tmP = nullptr;
   const int cmode = conv_mode(p);
   const CUtensorMap* tmA2 = nullptr;
