@@ -291,6 +291,10 @@ int st_bench_gemm(int M, int N, int K, int engine, int reps, const float* A, con
 /* ---- self test (no oracle involved): split-fp16 tcgen05 GEMM vs the SIMT fp32 GEMM on device ----- */
 int st_selftest_gemm(int M, int N, int K, int engine, const float* A, const float* W, const float* bias, float* out,
                      void* stream);
+/* The same for a stride-1 "same" Conv1d over channels-last activations (implicit GEMM): A [B,L,C], W [N, taps*C] tap-major as the
+ * packer lays conv weights out (row stride rounded up to 4 floats), out [B*L, N]. */
+int st_selftest_conv(int B, int L, int C, int N, int taps, int dil, int engine, const float* A, const float* W, const float* bias,
+                     float* out, void* stream);
 
 #ifdef __cplusplus
 }

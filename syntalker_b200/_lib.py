@@ -24,7 +24,7 @@ SYMBOLS = [
     "st_model_create", "st_model_destroy", "st_vq_create", "st_vq_destroy", "st_vq_out_dim",
     "st_schedule_create", "st_schedule_destroy", "st_cond_encode", "st_denoise", "st_sample", "st_sample_chunk", "st_sample_begin", "st_sample_run", "st_sample_end",
     "st_rvq_decode", "st_pose_assemble_330", "st_pose_assemble_623", "st_sample_to_tokens", "st_pose_330_to_aa165", "st_moments_accumulate", "st_l1div_accumulate",
-    "st_rvq_encode", "st_generate_330", "st_generate_330_host", "st_generate_330_host_begin", "st_generate_330_host_wait", "st_generate_long_330", "st_selftest_gemm", "st_bench_gemm", "st_profile_begin", "st_profile_end",
+    "st_rvq_encode", "st_generate_330", "st_generate_330_host", "st_generate_330_host_begin", "st_generate_330_host_wait", "st_generate_long_330", "st_selftest_gemm", "st_selftest_conv", "st_bench_gemm", "st_profile_begin", "st_profile_end",
 ]
 
 
@@ -110,6 +110,7 @@ def lib():
     L.st_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     L.st_bench_gemm.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(C.c_double)]
     L.st_selftest_gemm.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.st_selftest_conv.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     if L.st_abi_version() != 1:
         raise StError("libsyntalker_b200.so ABI version mismatch")
     _lib = L

@@ -199,6 +199,8 @@ struct st_model {
   int32_t* t_model_dev = nullptr;
   float* coef_dev = nullptr;
   cudaStream_t loop_stream = nullptr;       // graphs cannot be captured on the legacy default stream
+  cudaStream_t chain_stream = nullptr;      // second evaluation chain of a step (experiment, st_debug_probe bit 4096)
+  cudaEvent_t ev_cfork = nullptr, ev_cjoin = nullptr;
   cudaStream_t dec_stream[2] = {nullptr, nullptr};   // the three body parts decode side by side (fork / join around st_rvq_decode x3)
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -227,10 +229,12 @@ static bool g_wav_planes = true;   // st_debug_probe bit 128: WavEncoder with fp
 static bool g_fused_attn = true;   // st_debug_probe bit 32 turns the fused qkv + attention kernel off
 static bool g_attn_tc = true;      // QK^T and PV of the fused attention as tcgen05 MMAs (attn == 2); st_debug_probe bit 2048 selects the packed-fp32 FMA epilogue
 static bool g_zrec = true;         // st_debug_probe bit 512 turns the z recursion of deterministic DDIM off (state kept in x space)
+static bool g_dual_chain = false;  // st_debug_probe bit 4096 (experiment): the evaluations of a step as two chains on two streams
 static bool g_zrec_fc2 = true;     // st_debug_probe bit 1024: the last block's fc2 stays a layer of its own inside the z recursion
 
-namespace st { extern int g_tc_probe; extern bool g_tc_fast; }
+namespace st { extern int g_tc_probe; extern bool g_tc_fast; extern bool g_tc_taps; }
 extern "C" int st_debug_probe(int flags) {
+  st::g_tc_taps = !(flags & 8192);
   st::g_tc_probe = flags & 15;
   st::g_tc_fast = !(flags & 16);
   g_fused_attn = !(flags & 32);
@@ -239,6 +243,7 @@ extern "C" int st_debug_probe(int flags) {
   g_wav_planes = !(flags & 128);
   g_zrec = !(flags & 512);
   g_attn_tc = !(flags & 2048);
+  g_dual_chain = (flags & 4096) != 0;
   g_zrec_fc2 = !(flags & 1024);
   return ST_OK;
 }
@@ -358,6 +363,7 @@ extern "C" void st_model_destroy(st_model* m) {
   for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
   if (m->loop_stream) { tc_scratch_release(m->loop_stream); cudaStreamDestroy(m->loop_stream); }
   if (m->dec_stream[0]) { for (int k = 0; k < 2; ++k) { tc_scratch_release(m->dec_stream[k]); cudaStreamDestroy(m->dec_stream[k]); cudaEventDestroy(m->ev_join[k]); } cudaEventDestroy(m->ev_fork); }
+  if (m->chain_stream) { tc_scratch_release(m->chain_stream); cudaStreamDestroy(m->chain_stream); cudaEventDestroy(m->ev_cfork); cudaEventDestroy(m->ev_cjoin); }
   if (m->ev_in) cudaEventDestroy(m->ev_in);
   if (m->ev_out) cudaEventDestroy(m->ev_out);
   m->w.release(); m->ws.release(); m->io.release(); m->longws.release(); m->zws.release();
@@ -723,38 +729,81 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   } else {
     ST_TRY(tokens_in(tp, s));
   }
-  for (int i = 0; i < 8; ++i) {
-    const BlkW& b = m->blk[i];
-    if (tc) {
-      // tcgen05 engine: 5 launches per block.  LayerNorm never runs as a kernel: the GEMM that consumes it reads the raw
-      // residual planes and applies (mean, 1/sigma) in its epilogue from the row statistics its producer left.
+  // tcgen05 engine: the 8 blocks (and the GEMM that ends a z step) for evaluations [e0, e0 + ne) on stream cs.  4 launches per
+  // block.  LayerNorm never runs as a kernel: the GEMM that consumes it reads the raw residual planes and applies (mean, 1/sigma)
+  // in its epilogue from the row statistics its producer left.  Evaluations are stacked along the rows, so a subset is a row range
+  // of every buffer (the plane stride stays that of the whole stack).
+  auto chain_tc = [&](int e0, int ne, cudaStream_t cs) -> int {
+    const int Rc = ne * rows;
+    const size_t r0 = (size_t)e0 * rows;
+    float* X = m->X + r0 * 512; float* P = m->H + r0 * 512; float* stats = m->ln_stats + r0 * 32;
+    __half* X_p = m->X_p + r0 * 512; __half* ATT_p = m->ATT_p + r0 * 512; __half* G_p = m->G_p + r0 * 1024;
+    for (int i = 0; i < 8; ++i) {
+      const BlkW& b = m->blk[i];
       if (g_fused_attn) {
         // qkv GEMM + 32-token attention in one kernel (cluster of 2 CTAs per (4 sequences, head))
-        GemmP pq = linear(m->X, R, 512, b.qkv_wgp, nullptr, nullptr, 1536);
-        pq.a_planes = m->X_p; pq.a_plane_stride = ps512; pq.ln_stats = m->ln_stats; pq.ln_s = b.qkv_sp; pq.ln_c = b.qkv_cp;
-        pq.attn = g_attn_tc ? 2 : 1; pq.o_planes = m->ATT_p; pq.o_plane_stride = ps512; pq.o_planes_ld = 512;
-        ST_TRY(gemm(pq, s));
+        GemmP pq = linear(X, Rc, 512, b.qkv_wgp, nullptr, nullptr, 1536);
+        pq.a_planes = X_p; pq.a_plane_stride = ps512; pq.ln_stats = stats; pq.ln_s = b.qkv_sp; pq.ln_c = b.qkv_cp;
+        pq.attn = g_attn_tc ? 2 : 1; pq.o_planes = ATT_p; pq.o_plane_stride = ps512; pq.o_planes_ld = 512;
+        ST_TRY(gemm(pq, cs));
       } else {
-        GemmP pq = linear(m->X, R, 512, b.qkv_wg, nullptr, m->QKV, 1536);
-        pq.a_planes = m->X_p; pq.a_plane_stride = ps512; pq.ln_stats = m->ln_stats; pq.ln_s = b.qkv_s; pq.ln_c = b.qkv_c;
-        ST_TRY(gemm(pq, s));
-        ST_TRY(attention32(m->QKV, nullptr, m->ATT_p, pl.nE * B, s));
+        GemmP pq = linear(X, Rc, 512, b.qkv_wg, nullptr, m->QKV + r0 * 1536, 1536);
+        pq.a_planes = X_p; pq.a_plane_stride = ps512; pq.ln_stats = stats; pq.ln_s = b.qkv_s; pq.ln_c = b.qkv_c;
+        ST_TRY(gemm(pq, cs));
+        ST_TRY(attention32(m->QKV + r0 * 1536, nullptr, ATT_p, ne * B, cs, ps512));
       }
-      GemmP pp = linear(m->ATT, R, 512, b.projw, b.projb, m->X, 512);
-      pp.res = m->X; pp.res_mode = RES_POST; pp.ldr = 512; pp.a_planes = m->ATT_p; pp.a_plane_stride = ps512;
-      pp.o_planes = m->X_p; pp.o_plane_stride = ps512; pp.o_planes_ld = 512; pp.stats_out = m->ln_stats;
-      ST_TRY(gemm(pp, s));
-      GemmP p1 = linear(m->X, R, 512, b.fc1_wg, nullptr, nullptr, 1024);
-      p1.act = ACT_GELU; p1.a_planes = m->X_p; p1.a_plane_stride = ps512; p1.ln_stats = m->ln_stats; p1.ln_s = b.fc1_s; p1.ln_c = b.fc1_c;
-      p1.o_planes = m->G_p; p1.o_plane_stride = ps1024; p1.o_planes_ld = 1024;
-      ST_TRY(gemm(p1, s));
+      GemmP pp = linear(nullptr, Rc, 512, b.projw, b.projb, X, 512);
+      pp.res = X; pp.res_mode = RES_POST; pp.ldr = 512; pp.a_planes = ATT_p; pp.a_plane_stride = ps512;
+      pp.o_planes = X_p; pp.o_plane_stride = ps512; pp.o_planes_ld = 512; pp.stats_out = stats;
+      ST_TRY(gemm(pp, cs));
+      GemmP p1 = linear(X, Rc, 512, b.fc1_wg, nullptr, nullptr, 1024);
+      p1.act = ACT_GELU; p1.a_planes = X_p; p1.a_plane_stride = ps512; p1.ln_stats = stats; p1.ln_s = b.fc1_s; p1.ln_c = b.fc1_c;
+      p1.o_planes = G_p; p1.o_plane_stride = ps1024; p1.o_planes_ld = 1024;
+      ST_TRY(gemm(p1, cs));
       if (i == 7 && fold_fc2) continue;        // x + fc2(g) is linear in (x, g): folded into the GEMM that ends the step
-      GemmP p2 = linear(m->G, R, 1024, b.fc2w, b.fc2b, m->X, 512);
-      p2.res = m->X; p2.res_mode = RES_POST; p2.ldr = 512; p2.a_planes = m->G_p; p2.a_plane_stride = ps1024;
-      p2.o_planes = m->X_p; p2.o_plane_stride = ps512; p2.o_planes_ld = 512; p2.stats_out = m->ln_stats;
-      ST_TRY(gemm(p2, s));
-      continue;
+      GemmP p2 = linear(nullptr, Rc, 1024, b.fc2w, b.fc2b, X, 512);
+      p2.res = X; p2.res_mode = RES_POST; p2.ldr = 512; p2.a_planes = G_p; p2.a_plane_stride = ps1024;
+      p2.o_planes = X_p; p2.o_plane_stride = ps512; p2.o_planes_ld = 512; p2.stats_out = stats;
+      ST_TRY(gemm(p2, cs));
     }
+    if (zstep && !last) {
+      // the next step only needs W_x x_{k-1}: P = X (W_x W_out)^T per evaluation; tokens_step mixes and applies the update
+      if (fold_fc2) {
+        // P = [X_mid | G] [W_xo | W_xo W_fc2]^T + W_xo b_fc2: the operand is the residual planes followed by the GELU planes
+        GemmP px = linear(X, Rc, 1536, m->w_xo2, m->c_xo2, P, 512);
+        px.a_planes = X_p; px.a_plane_stride = ps512; px.a2_planes = G_p; px.a2_plane_stride = ps1024; px.a2_K = 1024;
+        return gemm(px, cs);
+      }
+      GemmP px = linear(X, Rc, 512, m->w_xo, nullptr, P, 512);
+      px.a_planes = X_p; px.a_plane_stride = ps512;
+      return gemm(px, cs);
+    }
+    GemmP po = linear(X, Rc, 512, m->out_w, m->out_b, m->O + r0 * 1536, 1536);
+    po.a_planes = X_p; po.a_plane_stride = ps512;
+    return gemm(po, cs);
+  };
+  if (tc) {
+    if (g_dual_chain && pl.nE >= 2 && loop) {
+      // EXPERIMENT (st_debug_probe bit 4096): the evaluations of a step are independent until the guidance mix, so they run as two
+      // chains on two streams (fork after the token prologue, join before the next one): 2 x 64 CTAs per layer side by side
+      if (!m->chain_stream) {
+        ST_CHECK_CUDA(cudaStreamCreateWithFlags(&m->chain_stream, cudaStreamNonBlocking));
+        ST_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_cfork, cudaEventDisableTiming));
+        ST_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_cjoin, cudaEventDisableTiming));
+      }
+      const int na = pl.nE / 2;
+      ST_CHECK_CUDA(cudaEventRecord(m->ev_cfork, s));
+      ST_CHECK_CUDA(cudaStreamWaitEvent(m->chain_stream, m->ev_cfork, 0));
+      ST_TRY(chain_tc(na, pl.nE - na, m->chain_stream));
+      ST_TRY(chain_tc(0, na, s));
+      ST_CHECK_CUDA(cudaEventRecord(m->ev_cjoin, m->chain_stream));
+      ST_CHECK_CUDA(cudaStreamWaitEvent(s, m->ev_cjoin, 0));
+      return ST_OK;
+    }
+    return chain_tc(0, pl.nE, s);
+  }
+  for (int i = 0; i < 8; ++i) {
+    const BlkW& b = m->blk[i];
     ST_TRY(layernorm512(m->X, b.ln1g, b.ln1b, m->H, nullptr, R, s));
     GemmP pq = linear(m->H, R, 512, b.qkv, nullptr, m->QKV, 1536);
     ST_TRY(gemm(pq, s));
@@ -770,20 +819,7 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
     p2.res = m->X; p2.res_mode = RES_POST; p2.ldr = 512;
     ST_TRY(gemm(p2, s));
   }
-  if (zstep && !last) {
-    // the next step only needs W_x x_{k-1}: P = X (W_x W_out)^T per evaluation; tokens_step mixes and applies the update
-    if (fold_fc2) {
-      // P = [X_mid | G] [W_xo | W_xo W_fc2]^T + W_xo b_fc2: the operand is the residual planes followed by the GELU planes
-      GemmP px = linear(m->X, R, 1536, m->w_xo2, m->c_xo2, m->H, 512);
-      px.a_planes = m->X_p; px.a_plane_stride = ps512; px.a2_planes = m->G_p; px.a2_plane_stride = ps1024; px.a2_K = 1024;
-      return gemm(px, s);
-    }
-    GemmP px = linear(m->X, R, 512, m->w_xo, nullptr, m->H, 512);
-    px.a_planes = m->X_p; px.a_plane_stride = ps512;
-    return gemm(px, s);
-  }
   GemmP po = linear(m->X, R, 512, m->out_w, m->out_b, m->O, 1536);
-  if (tc) { po.a_planes = m->X_p; po.a_plane_stride = ps512; }
   ST_TRY(gemm(po, s));
   return ST_OK;
 }
@@ -1607,6 +1643,27 @@ extern "C" int st_bench_gemm(int M, int N, int K, int engine, int reps, const fl
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); tc_scratch_release(s); cudaStreamDestroy(s);
   if (tc) { tc_forget_weights(W); cudaFree(planes); }
   return ST_OK;
+}
+
+// stride-1 "same" Conv1d over channels-last activations as the engine runs it (implicit GEMM): A [B, L, C], W [N, taps * C]
+// (tap-major, packer layout), out [B * L, N].  engine 0 = SIMT, 1 = tcgen05 (weight planes rebuilt on every call).
+extern "C" int st_selftest_conv(int B, int L, int C, int N, int taps, int dil, int engine, const float* A, const float* W,
+                                const float* bias, float* out, void* stream) {
+  ST_REQUIRE(A && W && out && B > 0 && L > 0 && C > 0 && N > 0 && taps > 0 && dil > 0, "st_selftest_conv: null argument");
+  GemmP p;
+  p.A = A; p.W = W; p.bias = bias; p.out = out;
+  p.M = B * L; p.N = N; p.K = taps * C; p.ldw = (p.K + 3) & ~3;
+  p.Lout = L; p.Lin = L; p.C = C; p.stride = 1; p.pad = dil * (taps - 1) / 2; p.dil = dil;
+  p.a_batch = (long long)L * C; p.lda = C; p.ldo = N;
+  if (engine == ST_ENGINE_TC) {
+    if (!tc_supported(p)) { set_error("st_selftest_conv: shape not supported by the tcgen05 engine"); return ST_EUNSUPPORTED; }
+    tc_forget_weights(W);
+    const int r = gemm_tc(p, (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    tc_forget_weights(W);
+    return r;
+  }
+  return gemm_simt(p, (cudaStream_t)stream);
 }
 
 extern "C" int st_selftest_gemm(int M, int N, int K, int engine, const float* A, const float* W, const float* bias, float* out,

@@ -148,6 +148,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// A K-major tile whose first row is NOT the first row of a 1024-byte swizzle atom (a conv tap reads the staged rows shifted by
+// tap * dilation) takes the same descriptor with the shifted start address and the base-offset field left 0: the hardware derives the
+// swizzle phase of a row from the absolute shared-memory address, like the TMA engine that wrote it.  Measured (tests/conv_probe.py):
+// integer-valued operands reproduce the per-tap-fetch result bit for bit at every shift; setting bits [49,52) to (address >> 7) & 7,
+// as the PTX ISA text on the matrix descriptor suggests for unaligned starts, reads the wrong rows.
 // The same for an MN-major operand (cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>, canonical layout
 // ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): rows of 64 contiguous MN elements (128 B, swizzled in groups of 8 rows),
 // one row per K index; LBO = bytes between 64-element groups along MN, SBO = bytes between groups of 8 K rows.
@@ -163,6 +168,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) { return (1u
 // ---------------------------------------------------------------------------------------------------------
 constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane group)
 constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;   // bytes of one A plane tile (128 rows x 128 B)
+constexpr int TAPS_ROWS = 152;                  // staged rows of a conv tile: 128 outputs + (taps - 1) * dilation <= 24 of halo
+constexpr int TAPS_SLOT = 2 * TAPS_ROWS * 128;  // hi + lo plane of one channel block, 38 912 B (a multiple of the 1024 B swizzle atom per plane)
 
 struct TcEpi {
   float* out;            // [M, ldo] fp32 or null
@@ -181,7 +188,10 @@ struct TcEpi {
   //  mode 1  conv, clips packed    4-D map {C, T, clips, 2}, T | 128   coords (cb*64, j*dil - pad, m0/T, 0)
   //  mode 2  conv, long clips      4-D map {C, Lin, B, 2}              coords (cb*64, t0 + j*dil - pad, b, 0)      tile -> (b, t0)
   //  mode 3  strided conv, pad 0   3-D map {s*C, ceil(B*Lin/s), 2}     coords ((G%s)*C + cb*64, G/s, 0), G = b*Lin + t0*s + j
+  //  mode 4  conv, long clips, rows staged ONCE per channel block (4-D map {C, Lin, B, 2}, box {64, 152, 1, 2} at t0 - pad): the
+  //          MMAs of tap j read them through a descriptor shifted by j*dil rows; only the weight tiles stream per (tap, block)
   int mode, T, kb_per_tap, dil, pad, stride, C, Lin, Lout, tpc;
+  int a_slots;           // mode 4: staged row slots (1 or 2)
   const float* ln_stats; // consumer: [rows][8][2] partial (mean, M2) of each 512-wide input row, or null
   const float* ln_s;     //           [N] column sums of the gamma-scaled weight
   const float* ln_c;     //           [N] W beta + bias
@@ -223,7 +233,7 @@ __device__ __forceinline__ void split8_f16(const float* x, float s, uint4& h, ui
 // One binary for every tile width (BN = 64 / 128 / 192 and the ring depth are run-time values): the sampling loop
 // alternates GEMMs of different widths back to back, and separate template instantiations evicted each other from
 // the instruction cache at every launch (the in-chain cost of a GEMM was ~4 us above its same-kernel-chain cost).
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcEpi ep, const int num_kb,
                const int BN, const int STAGES) {
   const int W_PLANE = BN * TC_BK * 2;
@@ -231,10 +241,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // main + correction accumulators
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  // mode 4 (staged taps): [2 row slots of 2 planes x 152 rows][STAGES weight slots]; otherwise [STAGES slots of A | W]
+  const bool taps_mode = ep.mode == 4;
+  const int NSLOT = ep.a_slots;                  // 1 when the conv has a single channel block (C = 64), else 2
+  const int ring_bytes = taps_mode ? NSLOT * TAPS_SLOT + STAGES * 2 * W_PLANE : STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ring_bytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* afull_bar = acc_bar + 1;            // mode 4: row slot filled / free
+  uint64_t* aempty_bar = afull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;                    // n fastest: CTAs that share an A tile run together
@@ -260,6 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(acc_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -279,7 +296,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   trace_stamp(1);
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
-  if (warp == 0) {
+  if (warp == 0 && taps_mode) {
+    if (elect_one()) {
+      // ===== TMA producer, staged taps: the rows [t0 - pad, t0 - pad + 152) of a channel block once, then one weight tile per tap =====
+      const int taps = num_kb / ep.kb_per_tap;
+      int n = 0;
+      for (int cb = 0; cb < ep.kb_per_tap; ++cb) {
+        const int as = cb % NSLOT;
+        mbar_wait(&aempty_bar[as], ((cb / NSLOT) & 1) ^ 1);
+        mbar_expect_tx(&afull_bar[as], TAPS_SLOT);
+        tma_load_4d(smem + as * TAPS_SLOT, &tmA, &afull_bar[as], cb * TC_BK, t0 - ep.pad, clip_b, 0);
+        for (int j = 0; j < taps; ++j, ++n) {
+          const int s = n % STAGES;
+          mbar_wait(&empty_bar[s], ((n / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], 2 * W_PLANE);
+          tma_load_3d(smem + NSLOT * TAPS_SLOT + s * 2 * W_PLANE, &tmW, &full_bar[s], (j * ep.kb_per_tap + cb) * TC_BK, n0, 0);
+        }
+      }
+    }
+  } else if (warp == 1 && taps_mode) {
+    if (elect_one()) {
+      // ===== MMA issuer, staged taps =====
+      const int taps = num_kb / ep.kb_per_tap;
+      const uint32_t idesc = umma_idesc_f16(TC_BM, BN), idesc_w = umma_idesc_f16(TC_BM, 2 * BN);
+      int n = 0;
+      for (int cb = 0; cb < ep.kb_per_tap; ++cb) {
+        const int as = cb % NSLOT;
+        mbar_wait(&afull_bar[as], (cb / NSLOT) & 1);
+        tc_fence_after();
+        const uint32_t rows_hi = smem_u32(smem + as * TAPS_SLOT), rows_lo = rows_hi + TAPS_SLOT / 2;
+        for (int j = 0; j < taps; ++j, ++n) {
+          const int s = n % STAGES;
+          mbar_wait(&full_bar[s], (n / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t shift = (uint32_t)(j * ep.dil) * 128;                    // tap j: the same rows, j*dil positions further on
+          const uint32_t w_hi = smem_u32(smem + NSLOT * TAPS_SLOT + s * 2 * W_PLANE), w_lo = w_hi + W_PLANE;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t dah = umma_desc_sw128(rows_hi + shift) + 2 * k, dal = umma_desc_sw128(rows_lo + shift) + 2 * k;
+            const uint64_t dwh = umma_desc_sw128(w_hi) + 2 * k, dwl = umma_desc_sw128(w_lo) + 2 * k;
+            const uint32_t acc = (n | k) != 0;
+            if (BN <= 128) {
+              umma_f16(tmem_base, dah, dwh, idesc_w, acc);                        // a_hi.[w_hi ; w_lo]
+              umma_f16(tmem_base + BN, dal, dwh, idesc, 1);                        // + a_lo.w_hi
+            } else {
+              umma_f16(tmem_base, dah, dwh, idesc, acc);
+              umma_f16(tmem_base + BN, dah, dwl, idesc, acc);
+              umma_f16(tmem_base + BN, dal, dwh, idesc, 1);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&aempty_bar[as]);
+      }
+      umma_commit(acc_bar);
+    }
+  } else if (warp == 0) {
     if (elect_one()) {
       // ===== TMA producer =====
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -1480,6 +1552,7 @@ long long* g_tc_dbg = nullptr;  // set by st_debug_timeline
 int g_tc_probe = 0;             // set by st_debug_probe
 int g_tc_dbg_n = 0, g_tc_dbg_k = 0;   // st_debug_timeline_select: only launches with this N, K record the timeline (0 = all)
 bool g_tc_fast = true;          // trunk kernel for the shapes it takes (st_debug_probe bit 16 turns it off)
+bool g_tc_taps = true;          // staged-taps conv mode of the generic kernel (st_debug_probe bit 8192 turns it off)
 // Activation planes of a GEMM whose operand is still fp32: one arena PER STREAM.  Stream order serialises the reuse on one
 // stream; two handles driven on two streams at once (the library is re-entrant per handle) must not share it.
 static std::map<cudaStream_t, Arena> g_scratch;
@@ -1572,14 +1645,34 @@ bool tc_supported(const GemmP& p) {
   return true;
 }
 
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcEpi& ep, int num_kb, int mtiles, int BN, cudaStream_t s) {
-  // ring depth: as many stages as fit beside the barriers in 227 KB (4 / 3 / 2 for BN = 64 / 128 / 192)
-  const int stage_bytes = 2 * TC_A_PLANE + 2 * BN * TC_BK * 2;
-  const int stages = BN == 64 ? 4 : BN == 128 ? 3 : 2;
-  const int smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, TcEpi ep, int num_kb, int mtiles, int BN, cudaStream_t s) {
+  // ring depth: as many stages as fit beside the barriers in 227 KB (4 / 3 / 2 for BN = 64 / 128 / 192).  A tall grid of 64-wide
+  // tiles (the WavEncoder convs: thousands of tiles, K = 15 taps) instead runs TWO CTAs per SM on half the ring: set-up and epilogue
+  // of one tile then overlap the main loop of the other (the kernel has one tile per CTA and no other overlap between tiles).
+  const int w_slot = 2 * BN * TC_BK * 2;
+  const int stage_bytes = 2 * TC_A_PLANE + w_slot;
+  const int ntiles = (ep.N + BN - 1) / BN;
+  const bool two_per_sm = BN == 64 && (long long)mtiles * ntiles > 2 * 148;
+  const int budget = two_per_sm ? 112 * 1024 : 227 * 1024 - 2048;
+  int stages, ring;
+  if (ep.mode == 4) {                     // staged taps: one or two row slots + a ring of weight tiles only
+    ep.a_slots = ep.kb_per_tap == 1 ? 1 : 2;
+    stages = (budget - ep.a_slots * TAPS_SLOT) / w_slot;
+    stages = stages > 4 ? 4 : stages;
+    ring = ep.a_slots * TAPS_SLOT + stages * w_slot;
+  } else {
+    ep.a_slots = 0;
+    stages = budget / stage_bytes;
+    stages = stages > 4 ? 4 : stages;
+    ring = stages * stage_bytes;
+  }
+  if (stages < 2) { set_error("launch_tc: no room for a two-stage ring (BN=%d mode=%d)", BN, ep.mode); return ST_EINVAL; }
+  const int epi_tile = (TC_BM * (BN + 4) + TC_BM) * 4;       // the epilogue's fp32 tile reuses the ring
+  if (ring < epi_tile) { set_error("launch_tc: ring of %d B cannot hold the epilogue tile (%d B)", ring, epi_tile); return ST_EINVAL; }
+  const int smem = ring + (2 * stages + 5) * 8 + 16 + 1024;
   static DeviceOnce attr;       // the attribute is per device (one process may drive models on several GPUs)
-  if (attr.first()) ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (2 * TC_A_PLANE + 2 * 64 * TC_BK * 2) + 9 * 8 + 16 + 1024));
-  dim3 grid((ep.N + BN - 1) / BN, mtiles);
+  if (attr.first()) ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  dim3 grid(ntiles, mtiles);
   launch_k(gemm_tc_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, tmA, tmW, ep, num_kb, BN, stages);
   ST_CHECK_LAUNCH();
   return ST_OK;
@@ -1606,8 +1699,8 @@ static int get_map_strided(const CUtensorMap** out, const __half* base, long lon
   return ST_OK;
 }
 // 4-D long-clip view {C, Lin, B, 2}, box {64, 128, 1, 2}
-static int get_map_long(const CUtensorMap** out, const __half* base, long long plane_stride, int B, int Lin, int C) {
-  MapKey key{base, plane_stride, C, Lin, B, -2};
+static int get_map_long(const CUtensorMap** out, const __half* base, long long plane_stride, int B, int Lin, int C, int box_rows = TC_BM) {
+  MapKey key{base, plane_stride, C, Lin, B, -2 - box_rows};
   std::lock_guard<std::mutex> lk(g_tc_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = &it->second; return ST_OK; }
@@ -1615,7 +1708,7 @@ static int get_map_long(const CUtensorMap** out, const __half* base, long long p
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ST_ECUDA; }
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Lin, (cuuint64_t)B, 2};
   cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Lin * C * 2, (cuuint64_t)plane_stride * 2};
-  cuuint32_t box[4] = {TC_BK, TC_BM, 1, 2};
+  cuuint32_t box[4] = {TC_BK, (cuuint32_t)box_rows, 1, 2};
   cuuint32_t est[4] = {1, 1, 1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1791,11 +1884,15 @@ launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, 
   const CUtensorMap* tmA = nullptr;
   const CUtensorMap* tmW = nullptr;
   TcEpi ep;
-  ep.mode = mode; ep.T = p.Lout; ep.kb_per_tap = mode == 0 ? 1 : p.C / TC_BK; ep.dil = p.dil; ep.pad = p.pad; ep.stride = p.stride;
+  // a stride-1 conv over long clips whose taps reach at most 24 rows beyond the tile stages its rows once per channel block and
+  // shifts the operand descriptor per tap (mode 4) instead of fetching the same rows once per tap (st_debug_probe bit 8192: off)
+  const int taps = mode == 0 ? 1 : p.K / p.C;
+  const bool staged = g_tc_taps && mode == 2 && taps > 1 && (taps - 1) * p.dil + TC_BM <= TAPS_ROWS;
+  ep.mode = staged ? 4 : mode; ep.T = p.Lout; ep.kb_per_tap = mode == 0 ? 1 : p.C / TC_BK; ep.dil = p.dil; ep.pad = p.pad; ep.stride = p.stride;
   ep.C = p.C; ep.Lin = p.Lin; ep.Lout = p.Lout; ep.tpc = (p.Lout + TC_BM - 1) / TC_BM;
   if (mode == 0) ST_TRY(get_map_3d(&tmA, planes, pstride, (int)rows, Ka, TC_BM));
   else if (mode == 1) ST_TRY(get_map_4d(&tmA, planes, pstride, nclips, p.Lin, p.C));
-  else if (mode == 2) ST_TRY(get_map_long(&tmA, planes, pstride, nclips, p.Lin, p.C));
+  else if (mode == 2) ST_TRY(get_map_long(&tmA, planes, pstride, nclips, p.Lin, p.C, staged ? TAPS_ROWS : TC_BM));
   else ST_TRY(get_map_strided(&tmA, planes, pstride, rows, p.C, p.stride));
   // tile width: keep the grid at one wave of <= 148 CTAs (1 CTA per SM) whenever the shape allows it
   const int mt = mode >= 2 ? nclips * ((p.Lout + TC_BM - 1) / TC_BM) : (p.M + TC_BM - 1) / TC_BM;

@@ -181,7 +181,7 @@ int profile_end(double* ms, double* flops, int64_t* n);
 int layernorm512(const float* x, const float* gamma, const float* beta, float* y, __half* planes, int rows, cudaStream_t s);
 int wav_first(const float* audio, const float* w1, const float* b1, const float* wd, const float* bd, int ldw, int cb, int Lin, int Lout,
               int stride, int pad, __half* h1_planes, long long plane_stride, float* sc, cudaStream_t s);   // block 0 of the WavEncoder: conv1 -> planes, conv shortcut -> fp32
-int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStream_t s);   // qkv [nseq*32,1536] -> out [nseq*32,512]
+int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStream_t s, long long plane_stride = 0);   // qkv [nseq*32,1536] -> out [nseq*32,512]
 void tc_forget_weights(const float* W);
 int tc_split(const float* a, int lda, int M, int K, __half* planes, cudaStream_t s);   // fp32 -> hi/lo planes of a*kActScale
 // split scratch of the tcgen05 engine: one arena per stream (a GEMM whose operand is still fp32 splits it there first)

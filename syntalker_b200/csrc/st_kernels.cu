@@ -482,11 +482,11 @@ __global__ void __launch_bounds__(256) attention32_kernel(const float* __restric
   }
 }
 
-int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStream_t s) {
+int attention32(const float* qkv, float* out, __half* planes, int nseq, cudaStream_t s, long long plane_stride) {
   constexpr int smem = (80 * ATT_LD + 32 * 20) * sizeof(float);
   static DeviceOnce attr_set;   // the attribute is per device
   if (attr_set.first()) ST_CHECK_CUDA(cudaFuncSetAttribute(attention32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  launch_k(attention32_kernel, dim3(nseq, 4, 2), dim3(256), smem, s, qkv, out, planes, (long long)nseq * 32 * 512);
+  launch_k(attention32_kernel, dim3(nseq, 4, 2), dim3(256), smem, s, qkv, out, planes, plane_stride ? plane_stride : (long long)nseq * 32 * 512);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }

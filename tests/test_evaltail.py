@@ -96,7 +96,10 @@ def test_native_accumulators_vs_oracle():
     aa = evaltail.poses_aa165(pose.to(dev)).cpu()
     aa_ref = ometrics.poses_aa165(pose)
     d = (aa - aa_ref).abs()
-    assert float(d.max()) < 1e-3 and float((d > 1e-5).float().mean()) < 1e-3      # ill-conditioned near pi like the 330-d round trip
+    assert float(d.max()) < 1e-3 and float((d > 1e-5).float().mean()) < 1e-2      # the axis-angle vector is ill-conditioned near pi ...
+    from oracle import pose as opose
+    R, R_ref = opose.axis_angle_to_matrix(aa.reshape(-1, 3)), opose.axis_angle_to_matrix(aa_ref.reshape(-1, 3))
+    assert float((R - R_ref).abs().max()) < 2e-5                                   # ... the rotation it encodes is not
     # one sequence through the whole tail with stand-in callables
     enc = lambda p: p.reshape(p.shape[0], -1, 8 * 330)[..., :240]
     fid2, l12 = evaltail.FIDAccumulator(240, dev), evaltail.L1divAccumulator(dev)
