@@ -73,6 +73,10 @@ int st_abi_version(void);
 int64_t st_launch_count(void);
 int st_set_engine(int engine);
 int st_get_engine(void);
+/* The engine of ONE handle (-1 = follow the process default of st_set_engine again).  Every call runs on the engine of the handle it is
+ * made on, so two handles driven from two host threads may use different engines; the st_debug_* switches stay process-wide. */
+int st_model_set_engine(st_model* m, int engine);
+int st_vq_set_engine(st_vq* v, int engine);
 /* The sampling loop replays one captured CUDA graph per diffusion step (default on); 0 = launch every kernel eagerly. */
 int st_set_graphs(int on);
 /* Programmatic dependent launch between consecutive kernels (default on); 0 = plain stream order. */

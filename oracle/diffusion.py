@@ -76,9 +76,10 @@ def _ext(arr, k, B):
     return torch.full((B, 1, 1, 1), float(np.float32(arr[k])), dtype=torch.float32)
 
 
-def ddim_sample_loop(sched, model_fn, noise, y, eta=0.0, tap=None):
+def ddim_sample_loop(sched, model_fn, noise, y, eta=0.0, tap=None, step_noise=None):
     """gaussian_diffusion.py:937-1002 with ddim_sample:741-791; clip_denoised=False, no cond_fn.
-    model_fn(x, t_original, y) -> x0 prediction. The unused per-step randn_like is not drawn."""
+    model_fn(x, t_original, y) -> x0 prediction. step_noise(k, x) supplies the randn_like(x) of step k (:781); it only
+    matters when eta > 0 (sigma = 0 otherwise), so with eta = 0 it may be omitted and is then not drawn."""
     x = noise
     B = x.shape[0]
     for k in range(sched.num_timesteps - 1, -1, -1):
@@ -88,6 +89,8 @@ def ddim_sample_loop(sched, model_fn, noise, y, eta=0.0, tap=None):
         ab, abp = _ext(sched.alphas_cumprod, k, B), _ext(sched.alphas_cumprod_prev, k, B)
         sigma = eta * torch.sqrt((1 - abp) / (1 - ab)) * torch.sqrt(1 - ab / abp)
         x = x0 * torch.sqrt(abp) + torch.sqrt(1 - abp - sigma ** 2) * eps
+        if step_noise is not None:
+            x = x + (0.0 if k == 0 else 1.0) * sigma * step_noise(k, x)                  # :786-790, no noise when t == 0
         if tap is not None:
             tap(k, x0, x)
     return x

@@ -20,7 +20,7 @@ ST_COEF_STRIDE = 5
 
 # every symbol include/syntalker_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "st_last_error", "st_abi_version", "st_launch_count", "st_set_engine", "st_get_engine", "st_set_graphs", "st_set_pdl", "st_debug_timeline", "st_debug_timeline_select", "st_debug_trace", "st_debug_probe", "st_debug_cond_taps",
+    "st_last_error", "st_abi_version", "st_launch_count", "st_set_engine", "st_get_engine", "st_model_set_engine", "st_vq_set_engine", "st_set_graphs", "st_set_pdl", "st_debug_timeline", "st_debug_timeline_select", "st_debug_trace", "st_debug_probe", "st_debug_cond_taps",
     "st_model_create", "st_model_destroy", "st_vq_create", "st_vq_destroy", "st_vq_out_dim",
     "st_schedule_create", "st_schedule_destroy", "st_cond_encode", "st_denoise", "st_sample", "st_sample_chunk", "st_sample_begin", "st_sample_run", "st_sample_end",
     "st_rvq_decode", "st_pose_assemble_330", "st_pose_assemble_623", "st_sample_to_tokens", "st_pose_330_to_aa165", "st_moments_accumulate", "st_l1div_accumulate",
@@ -69,6 +69,8 @@ def lib():
     L.st_launch_count.restype = i64
     L.st_set_engine.argtypes = [i32]
     L.st_get_engine.restype = i32
+    L.st_model_set_engine.argtypes = [vp, i32]
+    L.st_vq_set_engine.argtypes = [vp, i32]
     L.st_set_graphs.argtypes = [i32]
     L.st_set_pdl.argtypes = [i32]
     L.st_debug_timeline.argtypes = [vp]

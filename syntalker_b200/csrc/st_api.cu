@@ -10,7 +10,17 @@ namespace st {
 thread_local char g_err[1024] = "";
 thread_local int64_t g_launches = 0;
 bool g_pdl = true;
-static int g_engine = ST_ENGINE_TC;   // the product engine; SIMT is the exact-fp32 anchor (st_set_engine)
+static int g_engine = ST_ENGINE_TC;   // process default: the product engine; SIMT is the exact-fp32 anchor (st_set_engine)
+// The engine a call runs on belongs to the HANDLE it was made on (st_model_set_engine / st_vq_set_engine; -1 = follow the process
+// default): every entry point opens an EngineScope for its handle, and the code below asks cur_engine().  A handle is driven by
+// one host thread at a time, so a thread-local scope is exact, and two handles on two threads may use different engines.
+static thread_local int t_engine = -1;
+static int cur_engine() { return t_engine >= 0 ? t_engine : g_engine; }
+struct EngineScope {
+  int prev;
+  explicit EngineScope(int e) : prev(t_engine) { if (e >= 0) t_engine = e; }
+  ~EngineScope() { t_engine = prev; }
+};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -75,7 +85,7 @@ static std::vector<GemmP> g_prof_list;
 static double g_prof_flops = 0.0;
 
 static int gemm_dispatch(const GemmP& p, cudaStream_t s) {
-  if (g_engine == ST_ENGINE_TC && tc_supported(p)) return gemm_tc(p, s);
+  if (cur_engine() == ST_ENGINE_TC && tc_supported(p)) return gemm_tc(p, s);
   return gemm_simt(p, s);
 }
 
@@ -110,7 +120,7 @@ int profile_end(double* ms, double* flops, int64_t* n) {
   // the replay stream's split scratch is sized for the largest fp32 operand before the capture starts
   size_t need = 0;
   for (const GemmP& p : g_prof_list)
-    if (g_engine == ST_ENGINE_TC && tc_supported(p)) need = std::max(need, tc_scratch_need(p));
+    if (cur_engine() == ST_ENGINE_TC && tc_supported(p)) need = std::max(need, tc_scratch_need(p));
   if (need) ST_TRY(tc_scratch_reserve(s, need));
   ST_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
   int r = ST_OK;
@@ -164,6 +174,7 @@ struct Plan {
 
 struct st_model {
   int variant = 0, device = 0, style_dim = 0;
+  int engine = -1;                  // -1: the process default (st_set_engine) at the time of each call
   Weights w;
   ConvW wav[6][3];   // conv1, conv2, ds
   const float *word_table = nullptr, *w_cm = nullptr, *w_seed = nullptr, *bias_all = nullptr, *w_x = nullptr, *vt_table = nullptr;
@@ -257,6 +268,7 @@ struct st_schedule {
 
 struct st_vq {
   int out_dim = 0, ldw_last = 0;
+  int engine = -1;
   Weights w;
   const float *cb[6], *cnorm[6];
   ConvW c0, res1[2][3], res2[2][3], up[2], up_eo[2][2], c4, c6;
@@ -354,6 +366,18 @@ extern "C" int st_model_create(const st_tensor* packed, int n, int variant, st_m
   if (r == ST_OK) r = model_resolve(m);
   if (r != ST_OK) { m->w.release(); delete m; return r; }
   *out = m;
+  return ST_OK;
+}
+
+// engine of ONE handle: ST_ENGINE_SIMT / ST_ENGINE_TC, or -1 to follow the process default again
+extern "C" int st_model_set_engine(st_model* m, int engine) {
+  ST_REQUIRE(m && (engine == -1 || engine == ST_ENGINE_SIMT || engine == ST_ENGINE_TC), "st_model_set_engine: bad argument");
+  m->engine = engine;
+  return ST_OK;
+}
+extern "C" int st_vq_set_engine(st_vq* v, int engine) {
+  ST_REQUIRE(v && (engine == -1 || engine == ST_ENGINE_SIMT || engine == ST_ENGINE_TC), "st_vq_set_engine: bad argument");
+  v->engine = engine;
   return ST_OK;
 }
 
@@ -488,7 +512,7 @@ static int encode_wav_tc(st_model* m, const float* audio, int cb, cudaStream_t s
 }
 
 static int encode_audio_words(st_model* m, const float* audio, const int32_t* word, int cb, int null_inputs, cudaStream_t s) {
-  if (st_get_engine() == ST_ENGINE_TC && g_wav_planes) {
+  if (cur_engine() == ST_ENGINE_TC && g_wav_planes) {
     ST_TRY(encode_wav_tc(m, audio, cb, s));
     ST_TRY(gather_words(word, m->word_table, m->atcat + 256, 512, cb * 128, null_inputs, (int)(m->w.numel.at("word_table") / 256), s));
     ST_TRY(avgpool4(m->atcat, m->pooled, cb * 32, 512, s));
@@ -547,6 +571,7 @@ static int ensure_null_consts(st_model* m, cudaStream_t s) {
 }
 
 extern "C" int st_cond_encode(st_model* m, const st_cond* c, int B, void* stream) {
+  EngineScope es(m ? m->engine : -1);
   ST_REQUIRE(m && c && B > 0, "st_cond_encode: null argument or B <= 0");
   ST_REQUIRE(c->audio && c->word && c->seed, "st_cond_encode: audio, word and seed are required");
   cudaStream_t s = (cudaStream_t)stream;
@@ -576,6 +601,7 @@ extern "C" int st_cond_encode(st_model* m, const st_cond* c, int B, void* stream
 // word features] rows, [B,128,512] (denoiser.py:151-155, before mix_audio_text), and the hoisted conditioning constant
 // W_cm pool4(.) + biases, [B*32,512].  Either pointer may be NULL.  atcat covers one encoder chunk, so B <= 32.
 extern "C" int st_debug_cond_taps(st_model* m, float* atcat_out, float* cst_out, int B, void* stream) {
+  EngineScope es(m ? m->engine : -1);
   ST_REQUIRE(m && B > 0 && m->cond_B == B, "st_debug_cond_taps: the conditioning cache does not hold B=%d", B);
   cudaStream_t s = (cudaStream_t)stream;
   if (atcat_out) {
@@ -660,7 +686,7 @@ static int make_plan(const st_model* m, const st_guidance* g, Plan* pl) {
 static int trunk_input(st_model* m, int B, cudaStream_t s) {
   const int rows = B * 32;
   GemmP pz = linear(m->xs, rows, 1536, m->w_x, nullptr, m->z, 512);
-  if (st_get_engine() == ST_ENGINE_TC) { pz.a_planes = m->xs_p; pz.a_plane_stride = (long long)rows * 1536; }
+  if (cur_engine() == ST_ENGINE_TC) { pz.a_planes = m->xs_p; pz.a_plane_stride = (long long)rows * 1536; }
   return gemm(pz, s);
 }
 
@@ -698,7 +724,7 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
                      const ZStep& zs = ZStep(), const StepP* mix = nullptr) {
   const bool zstep = zs.on, last = zs.last;
   const int rows = B * 32, R = pl.nE * rows;
-  const bool tc = (st_get_engine() == ST_ENGINE_TC);
+  const bool tc = (cur_engine() == ST_ENGINE_TC);
   const long long ps512 = (long long)R * 512, ps1024 = (long long)R * 1024;
   const bool fold_fc2 = zstep && !last && g_zrec_fc2 && m->w_xo2 != nullptr;
   if (!zstep) {
@@ -851,6 +877,7 @@ static int upload_scales(st_model* m, const Plan& pl, const st_guidance* g, int 
 }
 
 extern "C" int st_denoise(st_model* m, const float* x, const int64_t* t, const st_guidance* g, float* out, int B, void* stream) {
+  EngineScope es(m ? m->engine : -1);
   ST_REQUIRE(m && x && t && out && B > 0, "st_denoise: null argument or B <= 0");
   if (m->cond_B != B) { set_error("st_denoise: B=%d but the conditioning cache holds B=%d (call st_cond_encode first)", B, m->cond_B); return ST_ESTATE; }
   cudaStream_t s = (cudaStream_t)stream;
@@ -883,7 +910,7 @@ extern "C" void st_schedule_destroy(st_schedule* s) { delete s; }
 
 static std::string plan_key(const Plan& pl, int B, int mode) {
   char buf[256];
-  int n = snprintf(buf, sizeof buf, "B%d m%d e%d c%d n%d", B, mode, st_get_engine(), pl.cfg_mode, pl.nE);
+  int n = snprintf(buf, sizeof buf, "B%d m%d e%d c%d n%d", B, mode, cur_engine(), pl.cfg_mode, pl.nE);
   for (int e = 0; e < pl.nE; ++e) n += snprintf(buf + n, sizeof buf - n, " %d:%d", pl.ev[e].cst_null, pl.ev[e].sv_src);
   for (int k = 0; k < 3; ++k) n += snprintf(buf + n, sizeof buf - n, " p%g/%g/%d", pl.part_sa[k], pl.part_sp[k], pl.part_ua[k]);
   return buf;
@@ -906,7 +933,7 @@ static int one_step(st_model* m, const Plan& pl, const StepP& sp0, int B, cudaSt
     return ST_OK;
   }
   sp.ls = m->loop; sp.coef_dev = m->coef_dev;
-  sp.xs_planes = st_get_engine() == ST_ENGINE_TC ? m->xs_p : nullptr;
+  sp.xs_planes = cur_engine() == ST_ENGINE_TC ? m->xs_p : nullptr;
   sp.ls_advance = m->loop;          // the update's last CTA also moves the loop to the next step
   ST_TRY(step_update(sp, s));
   return ST_OK;
@@ -941,6 +968,7 @@ static int prep_zeps(st_model* m, const float* tape, int n, int B, float* dst, c
 // ---- the sampling loop as begin / run / end: the caller may hand the per-step noise over in chunks (the reference draws one
 // randn_like per step, gaussian_diffusion.py:541,781; a 1000-step tape at B = 32 is 6.3 GB) --------------------------------
 extern "C" int st_sample_begin(st_model* m, const st_schedule* sc, const st_guidance* g, const float* x_init, int B, void* stream) {
+  EngineScope es(m ? m->engine : -1);
   ST_REQUIRE(m && sc && x_init && B > 0, "st_sample_begin: null argument or B <= 0");
   if (m->cond_B != B) { set_error("st_sample: B=%d but the conditioning cache holds B=%d (call st_cond_encode first)", B, m->cond_B); return ST_ESTATE; }
   cudaStream_t s = (cudaStream_t)stream;
@@ -957,14 +985,14 @@ extern "C" int st_sample_begin(st_model* m, const st_schedule* sc, const st_guid
   }
   ST_TRY(init_loop(m->loop, sc->S, sc->S - 1, nullptr, s));
   ST_TRY(transpose_to_tokens(x_init, m->xs, B, 1536, 32, 1.0f, s));
-  if (st_get_engine() == ST_ENGINE_TC) ST_TRY(tc_split(m->xs, 1536, B * 32, 1536, m->xs_p, s));
+  if (cur_engine() == ST_ENGINE_TC) ST_TRY(tc_split(m->xs, 1536, B * 32, 1536, m->xs_p, s));
   a.G = chunk_steps(sc);
   // The tcgen05 engine keeps the loop in token space ("z recursion"): x_{k-1} = alpha x0_hat + beta x_k + sigma eps_k is linear and
   // the next step only needs W_x x_{k-1}, so between steps ONE 512 x 512 GEMM (W_x W_out, folded by the packer) replaces the
   // 512 -> 1536 output GEMM, the state update and the 1536 -> 512 input GEMM; the noise enters as W_x eps_k, formed for a whole
   // chunk of steps ahead of them; the state itself is formed once, by the last step (alpha_bar_prev = 1: x <- x0_hat, coef2 = 0,
   // sigma = 0).  The steps differ (coefficients are launch parameters), so a captured graph holds one specific chunk of the loop.
-  a.zrec = g_zrec && st_get_engine() == ST_ENGINE_TC && m->w_xo && a.pl.cfg_mode != ST_CFG_BODYPART && a.pl.cfg_mode != ST_CFG_BODYPART1;
+  a.zrec = g_zrec && cur_engine() == ST_ENGINE_TC && m->w_xo && a.pl.cfg_mode != ST_CFG_BODYPART && a.pl.cfg_mode != ST_CFG_BODYPART1;
   if (a.zrec) ST_TRY(trunk_input(m, B, s));
   if (a.zrec && a.any_sigma && (m->zws_B != B || m->zws_G != a.G)) {
     for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);      // captured z-step nodes point into the old block
@@ -985,6 +1013,7 @@ extern "C" int st_sample_begin(st_model* m, const st_schedule* sc, const st_guid
 }
 
 extern "C" int st_sample_run(st_model* m, int n_steps, const float* noise_chunk, void* stream) {
+  EngineScope es(m ? m->engine : -1);
   ST_REQUIRE(m && n_steps > 0, "st_sample_run: null argument or n_steps <= 0");
   st_model::ActiveLoop& a = m->act;
   ST_REQUIRE(a.on, "st_sample_run: no sampling loop in flight (call st_sample_begin first)");
@@ -1077,6 +1106,7 @@ extern "C" int st_sample_run(st_model* m, int n_steps, const float* noise_chunk,
 }
 
 extern "C" int st_sample_end(st_model* m, float* x_out, void* stream) {
+  EngineScope es(m ? m->engine : -1);
   ST_REQUIRE(m && x_out, "st_sample_end: null argument");
   st_model::ActiveLoop& a = m->act;
   ST_REQUIRE(a.on, "st_sample_end: no sampling loop in flight");
@@ -1088,6 +1118,7 @@ extern "C" int st_sample_end(st_model* m, float* x_out, void* stream) {
 // the whole loop in one call; noise_tape = [S,B,1536,1,32] in draw order (t = S-1 .. 0) or NULL when every sigma is 0
 extern "C" int st_sample(st_model* m, const st_schedule* sc, const st_guidance* g, const float* x_init, const float* noise_tape,
                          int B, float* x_out, void* stream) {
+  EngineScope es(m ? m->engine : -1);
   ST_REQUIRE(m && sc && x_init && x_out && B > 0, "st_sample: null argument or B <= 0");
   ST_REQUIRE(!schedule_has_sigma(sc) || noise_tape, "st_sample: schedule has sigma != 0 but noise_tape is NULL");
   ST_TRY(st_sample_begin(m, sc, g, x_init, B, stream));
@@ -1248,6 +1279,7 @@ static int decode_convs_tc(st_vq* v, const float* qsum, const __half* qsum_plane
 
 extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, float lat_scale, int B, int T4, float* rec,
                              int64_t* idx_out, float* residual_out, void* stream) {
+  EngineScope es(v ? v->engine : -1);
   ST_REQUIRE(v && lat && rec && B > 0 && T4 > 0, "st_rvq_decode: null argument or empty batch");
   ST_REQUIRE(lat_stride >= 512 && (lat_stride & 3) == 0, "st_rvq_decode: lat_stride=%lld", (long long)lat_stride);
   cudaStream_t s = (cudaStream_t)stream;
@@ -1264,7 +1296,7 @@ extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, flo
   // residual quantisation, 6 layers (residual_vq.py:132-152).  tcgen05 engine: the residual travels as planes owned by this
   // handle (vq_select writes the next layer's operand, and the quantised sum for the decoder's first conv), so nothing
   // here touches the engine's shared split scratch and the three body parts may run on different streams.
-  const bool tc = st_get_engine() == ST_ENGINE_TC && !g_rank_simt;
+  const bool tc = cur_engine() == ST_ENGINE_TC && !g_rank_simt;
   __half* rp = tc ? v->ws.take<__half>(2 * rows * 512) : nullptr;
   __half* qp = tc ? v->ws.take<__half>(2 * rows * 512) : nullptr;
   if (tc) ST_TRY(tc_split(r, 512, (int)rows, 512, rp, s));
@@ -1277,7 +1309,7 @@ extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, flo
   }
   if (residual_out) ST_CHECK_CUDA(cudaMemcpyAsync(residual_out, r, rows * 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   // decoder (encdec.py:51-68)
-  if (st_get_engine() == ST_ENGINE_TC) return decode_convs_tc(v, qsum, qp, B, T4, rec, hA, hB, hC, s);
+  if (cur_engine() == ST_ENGINE_TC) return decode_convs_tc(v, qsum, qp, B, T4, rec, hA, hB, hC, s);
   int T = T4;
   GemmP p0 = conv3(qsum, v->c0, hA, B, T, T, 512, 1, 0);
   p0.act = ACT_RELU;
@@ -1312,6 +1344,7 @@ extern "C" int st_rvq_decode(st_vq* v, const float* lat, int64_t lat_stride, flo
 // Channels-last implicit GEMMs through the engine dispatch: the D-channel input conv and the two strided convs run on the
 // exact-fp32 engine (C_in not a multiple of 64 / padded stride), the res blocks and the last conv on tcgen05.
 extern "C" int st_rvq_encode(st_vq* v, const float* pose, int B, int T, float* lat, void* stream) {
+  EngineScope es(v ? v->engine : -1);
   ST_REQUIRE(v && pose && lat && B > 0 && T > 0 && (T % 4) == 0, "st_rvq_encode: null argument or T not a multiple of 4");
   ST_REQUIRE(v->has_enc, "st_rvq_encode: the checkpoint this handle was created from has no encoder weights");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1416,6 +1449,7 @@ extern "C" int st_generate_330(st_model* m, const st_schedule* sc, const st_guid
                                st_vq* vq_lower, const st_cond* cond, const float* x_init, const float* noise_tape,
                                const float* jaw_aa, const float* ms, int B, float latent_scale, float* rec_pose, float* rec_trans,
                                float* sample_out, void* stream) {
+  EngineScope es(m ? m->engine : -1);
   ST_REQUIRE(m && sc && vq_upper && vq_hands && vq_lower && cond && x_init && ms && rec_pose && B > 0, "st_generate_330: null argument");
   ST_REQUIRE(vq_upper->out_dim == 78 && vq_hands->out_dim == 180 && vq_lower->out_dim == 57, "st_generate_330: decoders must be 78/180/57 wide");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1445,6 +1479,7 @@ extern "C" int st_generate_330(st_model* m, const st_schedule* sc, const st_guid
 extern "C" int st_generate_330_host_begin(st_model* m, const st_schedule* sc, const st_guidance* g, st_vq* vq_upper, st_vq* vq_hands,
                                           st_vq* vq_lower, const st_host_inputs* in, int B, float latent_scale, float* rec_pose_host,
                                           float* rec_trans_host, float* sample_host, int slot, void* stream) {
+  EngineScope es(m ? m->engine : -1);
   ST_REQUIRE(m && sc && in && rec_pose_host && B > 0, "st_generate_330_host: null argument");
   ST_REQUIRE(slot == 0 || slot == 1, "st_generate_330_host: slot must be 0 or 1");
   ST_REQUIRE(in->audio && in->word && in->seed && in->x_init && in->mean && in->std, "st_generate_330_host: missing host input");
@@ -1554,6 +1589,7 @@ extern "C" int st_generate_long_330(st_model* m, const st_schedule* sc, const st
                                     int64_t n_words, const float* seed0, const float* const* style, const float* x_init,
                                     const float* noise_tape, const float* jaw_aa, const float* ms, int B, int R,
                                     float latent_scale, float* rec_pose, float* rec_trans, float* latents_out, void* stream) {
+  EngineScope es(m ? m->engine : -1);
   ST_REQUIRE(m && sc && vq_upper && vq_hands && vq_lower && audio_long && word_long && seed0 && x_init && ms && rec_pose && B > 0 && R > 0,
              "st_generate_long_330: null argument");
   ST_REQUIRE(vq_upper->out_dim == 78 && vq_hands->out_dim == 180 && vq_lower->out_dim == 57, "st_generate_long_330: decoders must be 78/180/57 wide");

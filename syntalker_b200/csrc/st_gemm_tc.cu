@@ -743,6 +743,37 @@ __device__ __forceinline__ float gelu_sb(float x) {
   return fmaf(h, er, h);
 }
 
+// the same for two values at once: the degree-10 Horner chain runs as ten packed fma.rn.f32x2 (same roundings, so the results are
+// bit-identical to gelu_sb); the GELU layer's epilogue is instruction-issue bound and the polynomial is more than half of it
+__device__ __forceinline__ unsigned long long pack_f2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma_f2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void gelu_sb2(float& x0, float& x1) {
+  const float z0 = fminf(fabsf(x0) * 0.70710678118654752440f, 4.2f), z1 = fminf(fabsf(x1) * 0.70710678118654752440f, 4.2f);
+  const unsigned long long z = pack_f2(z0, z1);
+  unsigned long long q = pack_f2(-1.26982216e-07f, -1.26982216e-07f);
+  q = fma_f2(q, z, pack_f2(3.31221616e-06f, 3.31221616e-06f)); q = fma_f2(q, z, pack_f2(-3.83041166e-05f, -3.83041166e-05f));
+  q = fma_f2(q, z, pack_f2(2.56761395e-04f, 2.56761395e-04f)); q = fma_f2(q, z, pack_f2(-1.07292213e-03f, -1.07292213e-03f));
+  q = fma_f2(q, z, pack_f2(2.56001420e-03f, 2.56001420e-03f)); q = fma_f2(q, z, pack_f2(-2.98958275e-04f, -2.98958275e-04f));
+  q = fma_f2(q, z, pack_f2(-2.76306103e-02f, -2.76306103e-02f)); q = fma_f2(q, z, pack_f2(1.48284197e-01f, 1.48284197e-01f));
+  q = fma_f2(q, z, pack_f2(9.18446271e-01f, 9.18446271e-01f)); q = fma_f2(q, z, pack_f2(1.62790707e+00f, 1.62790707e+00f));
+  float q0, q1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(q));
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-(z0 * q0)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-(z1 * q1)));
+  const float h0 = 0.5f * x0, h1 = 0.5f * x1;
+  x0 = fmaf(h0, copysignf(1.0f - e0, x0), h0);
+  x1 = fmaf(h1, copysignf(1.0f - e1, x1), h1);
+}
+
 constexpr int ATT_LDK = 68;                      // K / V staging row stride (floats): conflict-free float4 stores for lane = row
 constexpr int ATT_LDS = 36;                      // score row stride (floats)
 constexpr int ATT_SX_BYTES = 128 * ATT_LDS * 4;  // partial scores written by the peer CTA of the cluster
@@ -1348,7 +1379,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (ep.act == ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = gelu_sb(x[j]);
+        for (int j = 0; j < 32; j += 2) gelu_sb2(x[j], x[j + 1]);
       } else if (ep.act == ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);

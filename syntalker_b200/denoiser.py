@@ -183,6 +183,12 @@ class MDM(torch.nn.Module):
             raise _lib.StError("MDM has no weights: call load_state_dict() first")
         return self._h
 
+    def set_engine(self, name):
+        """GEMM engine of THIS model ('simt' = exact fp32, 'tc' = tcgen05 split-fp16, None = follow _lib.set_engine's process default)."""
+        e = {"simt": _lib.ST_ENGINE_SIMT, "tc": _lib.ST_ENGINE_TC, None: -1}[name]
+        _lib.check(_lib.lib().st_model_set_engine(self.handle, e))
+        return self
+
     # ---- conditioning ----
     def encode_cond(self, y, styles=None, force: bool = False):
         """st_cond_encode on y['audio'], y['word'], y['seed'] (+ style vectors). Cached on tensor identity."""

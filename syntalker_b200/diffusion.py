@@ -143,7 +143,7 @@ class SpacedDiffusion(_sch.Tables):
 
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
                          device=None, progress=False, eta=0.0, skip_timesteps=0, init_image=None, randomize_class=False,
-                         cond_fn_with_grad=False, dump_steps=None, const_noise=False, consume_rng=True):
+                         cond_fn_with_grad=False, dump_steps=None, const_noise=False, consume_rng=True, noise_tape=None):
         """`consume_rng` (extension, default True like the reference): draw the per-step randn_like the reference's ddim_sample
         draws even at eta = 0 (gaussian_diffusion.py:781), so that the torch generator stands where it would after the reference's
         loop (e.g. the next window's start noise); False skips those S small launches."""
@@ -152,7 +152,7 @@ class SpacedDiffusion(_sch.Tables):
         if const_noise is True:
             raise NotImplementedError()          # gaussian_diffusion.py:914-915
         return self._run(_lib.ST_MODE_DDIM, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, eta,
-                         skip_timesteps, init_image, randomize_class, cond_fn_with_grad, False, consume_rng)
+                         skip_timesteps, init_image, randomize_class, cond_fn_with_grad, False, consume_rng, noise_tape)
 
     def training_losses(self, *a, **k):
         raise NotImplementedError("training is out of scope for syntalker_b200 (SURVEY.md §8)")

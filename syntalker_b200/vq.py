@@ -70,6 +70,11 @@ class RVQVAE:
             raise _lib.StError("RVQVAE has no weights: call load_state_dict() first")
         return self._h
 
+    def set_engine(self, name):
+        """GEMM engine of THIS decoder ('simt', 'tc', or None = the process default)."""
+        _lib.check(_lib.lib().st_vq_set_engine(self.handle, {"simt": _lib.ST_ENGINE_SIMT, "tc": _lib.ST_ENGINE_TC, None: -1}[name]))
+        return self
+
     def latent2origin(self, x, return_indices=False):
         """x [B,T/4,512] fp32 on the GPU (already x vqvae_latent_scale) -> (rec [B,T,D], None, None).
         Like the reference (residual_vq.py:146) the call leaves the final residual in `x` when x is a

@@ -24,7 +24,18 @@ for _ in range(3):
     win.run_device(d["audio"], d["word"], d["seed"], d["noise"], y=y)
 torch.cuda.synchronize()
 buf = torch.zeros(120000, dtype=torch.int64, device="cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if os.environ.get("ST_FLUSH") else None
+# event time of the same call without stamps, like bench.py takes it (ST_FLUSH=1: a 256 MiB write before it, as bench.py does)
+for _ in range(2):
+    if flush is not None:
+        flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); win.run_device(d["audio"], d["word"], d["seed"], d["noise"], y=y); e1.record()
+    torch.cuda.synchronize()
+    print(f"window batch by events ({'L2 flushed' if flush is not None else 'warm L2'}): {e0.elapsed_time(e1):.3f} ms")
 _lib.check(L.st_debug_trace(buf.data_ptr()))
+if flush is not None:
+    flush.zero_()
 win.run_device(d["audio"], d["word"], d["seed"], d["noise"], y=y)
 torch.cuda.synchronize()
 _lib.check(L.st_debug_trace(None))
