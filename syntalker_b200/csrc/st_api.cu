@@ -246,7 +246,7 @@ static bool g_zrec_fc2 = true;     // st_debug_probe bit 1024: the last block's 
 namespace st { extern int g_tc_probe; extern bool g_tc_fast; extern bool g_tc_taps; }
 extern "C" int st_debug_probe(int flags) {
   st::g_tc_taps = !(flags & 8192);
-  st::g_tc_probe = flags & 15;
+  st::g_tc_probe = (flags & 15) | ((flags & (16384 | 32768 | 65536)) >> 10);   // bits 16384.. reach the kernels as probe bits 16, 32, 64 (experiments)
   st::g_tc_fast = !(flags & 16);
   g_fused_attn = !(flags & 32);
   g_rank_simt = (flags & 64) != 0;

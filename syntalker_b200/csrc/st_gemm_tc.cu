@@ -171,6 +171,80 @@ constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;   // bytes of one A plane tile (12
 constexpr int TAPS_ROWS = 152;                  // staged rows of a conv tile: 128 outputs + (taps - 1) * dilation <= 24 of halo
 constexpr int TAPS_SLOT = 2 * TAPS_ROWS * 128;  // hi + lo plane of one channel block, 38 912 B (a multiple of the 1024 B swizzle atom per plane)
 
+// ---- MMA issue loop of both tcgen05 kernels -------------------------------------------------------------------
+// The tensor pipe runs at most two MMAs behind the issuing thread (tests/umma_probe.cu: a delay of d cycles between two K
+// blocks costs d - 30 cycles at BN = 64, d - 215 at BN = 128), so whatever that thread does between the last MMA of a K block
+// and the first of the next is exposed.  As first written (blocking barrier wait, descriptors rebuilt from the stage index on
+// the vector datapath and moved to uniform registers with a dozen R2URs, probe / trace tests against constant memory: ~275
+// cycles) a 64-wide K block took 694 cycles against 454 of tensor time, a 128-wide one 833 against 776.  Here the loop is
+// unrolled over the ring (S compile-time), so every descriptor is loop-invariant and lives in a uniform register, and the NEXT
+// stage's barrier is tested (non-blocking) between the third and the fourth k-step, its answer read after the fourth: in the
+// steady state the thread goes from the last MMA of a block straight to the commit and the next block's first MMA.
+template <bool CAT>
+__device__ __forceinline__ void tc_issue_loop(uint64_t* full_bar, uint64_t* empty_bar, const uint32_t smem_base, const int stage_bytes,
+                                              const int w_plane, const int BN, const int STAGES, const uint32_t tmem_base, const int num_kb,
+                                              long long* dbg) {
+  constexpr uint64_t kDescHi = (64ull << 32) | (1ull << 46) | (2ull << 61);
+  uint32_t idesc_w = umma_idesc_f16(TC_BM, CAT ? 2 * BN : BN), idesc_n = umma_idesc_f16(TC_BM, BN);
+  uint32_t d_base = ((smem_base >> 4) & 0x3FFF) | (1u << 16);                  // low word of umma_desc_sw128(stage 0)
+  uint32_t d_stage = (uint32_t)stage_bytes >> 4, d_wlo = (uint32_t)w_plane >> 4;
+  uint32_t tm_main = tmem_base, tm_corr = tmem_base + BN;
+  uint32_t fb0 = smem_u32(full_bar), eb0 = smem_u32(empty_bar);
+  int stages = STAGES, nkb = num_kb;
+  // everything the loop needs is formed (and pinned: the empty asm statements are definition points) BEFORE the wait for the first
+  // operands, i.e. while the thread has nothing else to do; kernel parameters would otherwise be re-read from constant memory
+  // inside the loop
+  asm volatile("" : "+r"(idesc_w), "+r"(idesc_n), "+r"(d_base), "+r"(d_stage), "+r"(d_wlo), "+r"(tm_main), "+r"(tm_corr), "+r"(fb0), "+r"(eb0),
+               "+r"(stages), "+r"(nkb));
+  mbar_wait(full_bar, 0);
+  tc_fence_after();
+  trace_stamp(21, true);                             // first operands landed
+  uint32_t lo = d_base, ph = 0, eb = eb0;
+  int s = 0;
+  for (int kb = 0; kb < nkb; ++kb) {
+    if (dbg && kb < 16) dbg[24 + kb] = clock64();
+    // the k-step advance (+2 per 32 bytes) is applied to the low word: the high word stays a compile-time constant
+    const uint32_t ah = lo, al = ah + (TC_A_PLANE >> 4), wh = ah + (2 * TC_A_PLANE >> 4), wl = wh + d_wlo;
+    const uint32_t acc0 = kb != 0;
+    auto kstep = [&](int k) {
+      const uint64_t dah = kDescHi | (uint64_t)(ah + 2 * k), dal = kDescHi | (uint64_t)(al + 2 * k);
+      const uint64_t dwh = kDescHi | (uint64_t)(wh + 2 * k), dwl = kDescHi | (uint64_t)(wl + 2 * k);
+      if (CAT) {
+        // columns [0, BN) = a_hi.w_hi (main), [BN, 2BN) = a_hi.w_lo; then a_lo.w_hi joins the second half
+        umma_f16(tm_main, dah, dwh, idesc_w, k ? 1u : acc0);
+        umma_f16(tm_corr, dal, dwh, idesc_n, 1);
+      } else {
+        // hi.hi goes to the main accumulator; the two 2^-11-sized cross terms go to their own accumulator so that the
+        // tensor core's truncating fp32 adds see a 3x shorter chain on the large sum (measured: error / 3)
+        umma_f16(tm_main, dah, dwh, idesc_n, k ? 1u : acc0);
+        umma_f16(tm_corr, dah, dwl, idesc_n, k ? 1u : acc0);
+        umma_f16(tm_corr, dal, dwh, idesc_n, 1);
+      }
+    };
+    kstep(0);
+    kstep(1);
+    // the next block's stage, barrier addresses and descriptor base, formed while this block's MMAs are queued
+    const bool wrap = s + 1 == stages;
+    int sn = wrap ? 0 : s + 1;
+    uint32_t phn = wrap ? ph ^ 1 : ph;
+    uint32_t lo_n = wrap ? d_base : lo + d_stage;
+    uint32_t fbn = fb0 + 8 * sn, ebn = eb0 + 8 * sn;
+    asm volatile("" : "+r"(sn), "+r"(phn), "+r"(lo_n), "+r"(fbn), "+r"(ebn));
+    const bool more = kb + 1 < nkb;
+    kstep(2);
+    if (more) asm volatile("mbarrier.test_wait.parity.shared::cta.b64 st_pfull, [%0], %1;" ::"r"(fbn), "r"(phn) : "memory");
+    kstep(3);
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(eb) : "memory");
+    if (more) {
+      uint32_t ok;
+      asm volatile("selp.u32 %0, 1, 0, st_pfull;" : "=r"(ok));
+      if (!ok) mbar_wait(full_bar + sn, phn);
+      tc_fence_after();
+    }
+    s = sn; ph = phn; lo = lo_n; eb = ebn;
+  }
+}
+
 struct TcEpi {
   float* out;            // [M, ldo] fp32 or null
   const float* bias;     // [N] or null
@@ -385,8 +459,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (elect_one()) {
       // ===== MMA issuer =====
+      if (!(ep.probe & 13)) {
+        asm volatile(".reg .pred st_pfull;");
+        if (BN <= 128) tc_issue_loop<true>(full_bar, empty_bar, smem_u32(smem), STAGE_BYTES, W_PLANE, BN, STAGES, tmem_base, num_kb, dbg);
+        else tc_issue_loop<false>(full_bar, empty_bar, smem_u32(smem), STAGE_BYTES, W_PLANE, BN, STAGES, tmem_base, num_kb, dbg);
+      }
       const uint32_t idesc = umma_idesc_f16(TC_BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < ((ep.probe & 13) ? num_kb : 0); ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
@@ -815,7 +894,10 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
-  long long* dbg = (ep.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? ep.dbg : nullptr;
+  // timeline of one CTA: (0,0), which the launch puts on an idle SM ahead of time, or (probe bit 32) the LAST one, which like most
+  // CTAs of a layer starts when its SM's CTA of the previous layer has exited
+  const bool dbg_cta = (ep.probe & 32) ? (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1) : (blockIdx.x == 0 && blockIdx.y == 0);
+  long long* dbg = (ep.dbg && dbg_cta) ? ep.dbg : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   trace_stamp(20);                                   // CTA entry
 
@@ -851,6 +933,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);   // REDUX result lives in a uniform register
+  if (dbg && threadIdx.x == 0) dbg[32] = clock64();                       // set-up done
   pdl_launch();     // dependents may be scheduled; they still wait for this grid's completion before touching memory
   if (ep.attn) {
     // the attention epilogue writes into the peer CTA's shared memory: both CTAs of the cluster must be running before
@@ -862,44 +945,62 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     if (elect_one()) {
       // ===== TMA producer =====
-      // the weight halves of the first ring pass do not depend on the predecessor kernel: issue them before the wait
+      // The weight halves of the first ring pass do not depend on the predecessor kernel: they are issued before the wait.
+      // What runs between the wait's return and the first activation tile's request is on the critical path of every layer
+      // (timeline of a CTA that starts late, tests/layer_timeline.py with ST_PROBE=32768: 950 cycles when the generic loop -- a
+      // division for the conv modes, probe / trace tests against constant memory, cold instruction-cache lines -- came first),
+      // so everything is formed and pinned before the wait and the first pass of A tiles is one short loop behind it.
       const int pre = num_kb < STAGES ? num_kb : STAGES;
-      if (!(ep.probe & 2)) {
+      const bool no_tma = (ep.probe & 2) != 0;
+      if (!no_tma) {
         for (int kb = 0; kb < pre; ++kb) {
           mbar_expect_tx(&full_bar[kb], STAGE_BYTES);
           tma_load_3d(smem + kb * STAGE_BYTES + 2 * TC_A_PLANE, &tmW, &full_bar[kb], kb * TC_BK, n0, 0);
         }
       }
+      int mode = ep.mode, kb_split = ep.kb_split, kpt = ep.kb_per_tap, dil = ep.dil, pad = ep.pad;
+      int clip = mode ? m0 / ep.T : 0;
+      uint32_t a_dst = smem_u32(smem), a_bar = smem_u32(full_bar);
+      int row0 = m0, stage_b = STAGE_BYTES, npre = no_tma ? 0 : pre;
+      asm volatile("" : "+r"(mode), "+r"(kb_split), "+r"(kpt), "+r"(dil), "+r"(pad), "+r"(clip), "+r"(a_dst), "+r"(a_bar), "+r"(row0), "+r"(stage_b),
+                   "+r"(npre));
+      auto load_a = [&](int kb, uint32_t dst, uint32_t bar) {
+        if (mode == 0) {
+          if (kb < kb_split)
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(bar), "r"(kb * TC_BK), "r"(row0), "r"(0) : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmA2)), "r"(bar), "r"((kb - kb_split) * TC_BK), "r"(row0), "r"(0) : "memory");
+        } else {
+          const int j = kb / kpt, cb = kb - j * kpt;
+          asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(bar), "r"(cb * TC_BK), "r"(j * dil - pad), "r"(clip), "r"(0) : "memory");
+        }
+      };
       pdl_wait();
+      for (int kb = 0; kb < npre; ++kb) load_a(kb, a_dst + kb * stage_b, a_bar + 8 * kb);
       trace_stamp(1, true);
-      if (dbg) dbg[1] = clock64();
-      int s = 0;
-      uint32_t ph = 0;                       // ring pass parity
-      for (int kb = 0; kb < num_kb; ++kb) {
-        uint8_t* st = smem + s * STAGE_BYTES;
-        if (ep.probe & 2) {
-          if (kb >= pre) mbar_wait(&empty_bar[s], ph ^ 1);
+      if (dbg) { const long long now = clock64(); dbg[1] = now; dbg[8] = now; }
+      // the residual tile is only needed by the epilogue: it is requested behind the first ring pass of operands, not in front
+      // of it (all 128 CTAs start at once, and the first K block's arrival is what the tensor pipe waits for)
+      if (ep.has_res) {
+        mbar_expect_tx(res_bar, NCH * FAST_BOX_F32);
+        for (int c = 0; c < NCH; ++c) tma_load_2d(res_tile + c * FAST_BOX_F32, &tmO, res_bar, n0 + c * 32, m0);
+      }
+      if (no_tma)
+        for (int kb = 0; kb < pre; ++kb) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[kb])) : "memory");
+      int s = pre == STAGES ? 0 : pre;
+      uint32_t ph = pre == STAGES ? 1 : 0;                       // ring pass parity
+      for (int kb = pre; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (no_tma) {
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
         } else {
-          if (kb >= pre) {
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-            tma_load_3d(st + 2 * TC_A_PLANE, &tmW, &full_bar[s], kb * TC_BK, n0, 0);
-          }
-          if (ep.mode == 0) {
-            if (kb < ep.kb_split) tma_load_3d(st, &tmA, &full_bar[s], kb * TC_BK, m0, 0);
-            else tma_load_3d(st, &tmA2, &full_bar[s], (kb - ep.kb_split) * TC_BK, m0, 0);
-          } else {
-            const int j = kb / ep.kb_per_tap, cb = kb - j * ep.kb_per_tap;
-            tma_load_4d(st, &tmA, &full_bar[s], cb * TC_BK, j * ep.dil - ep.pad, m0 / ep.T, 0);
-          }
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_3d(smem + s * STAGE_BYTES + 2 * TC_A_PLANE, &tmW, &full_bar[s], kb * TC_BK, n0, 0);
+          load_a(kb, a_dst + s * stage_b, a_bar + 8 * s);
           if (dbg && kb < 16) dbg[8 + kb] = clock64();
-        }
-        // the residual tile is only needed by the epilogue: it is requested behind the first ring pass of operands, not
-        // in front of it (all 128 CTAs start at once, and the first K block's arrival is what the tensor pipe waits for)
-        if (ep.has_res && kb == pre - 1) {
-          mbar_expect_tx(res_bar, NCH * FAST_BOX_F32);
-          for (int c = 0; c < NCH; ++c) tma_load_2d(res_tile + c * FAST_BOX_F32, &tmO, res_bar, n0 + c * 32, m0);
         }
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
@@ -907,44 +1008,49 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     if (elect_one()) {
       // ===== MMA issuer =====
-      const bool cat = BN <= 128;
-      const uint32_t idesc_w = umma_idesc_f16(TC_BM, cat ? 2 * BN : BN);
-      const uint32_t idesc_n = umma_idesc_f16(TC_BM, BN);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        if (kb == 0) trace_stamp(21, true);          // first operands landed
-        if (dbg && kb < 16) dbg[24 + kb] = clock64();
-        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t a_lo = a_hi + TC_A_PLANE;
-        const uint32_t w_hi = a_hi + 2 * TC_A_PLANE;
-        const uint32_t w_lo = w_hi + W_PLANE;
-        if (!(ep.probe & 1)) {
-          if (cat) {
+      asm volatile(".reg .pred st_pfull;");          // answer of the early barrier test (a predicate cannot cross asm statements otherwise)
+      const uint32_t sb = smem_u32(smem);
+      if (ep.probe & 1) {                            // timing probe: no MMAs, the ring is only drained
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (kb == 0) trace_stamp(21, true);
+          if (dbg && kb < 16) dbg[24 + kb] = clock64();
+          umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      } else if (ep.probe & 16) {
+        // the loop as first written (A/B reference, st_debug_probe bit 16384): blocking wait, descriptors rebuilt per K block
+        const bool cat = BN <= 128;
+        const uint32_t idesc_w = umma_idesc_f16(TC_BM, cat ? 2 * BN : BN), idesc_n = umma_idesc_f16(TC_BM, BN);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (kb == 0) trace_stamp(21, true);
+          if (dbg && kb < 16) dbg[24 + kb] = clock64();
+          const uint32_t a_hi = sb + s * STAGE_BYTES, a_lo = a_hi + TC_A_PLANE, w_hi = a_hi + 2 * TC_A_PLANE, w_lo = w_hi + W_PLANE;
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint64_t dah = umma_desc_sw128(a_hi) + 2 * k, dal = umma_desc_sw128(a_lo) + 2 * k;
-              const uint64_t dwh = umma_desc_sw128(w_hi) + 2 * k;
-              // columns [0, BN) = a_hi.w_hi (main), [BN, 2BN) = a_hi.w_lo; then a_lo.w_hi joins the second half
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t dah = umma_desc_sw128(a_hi) + 2 * k, dal = umma_desc_sw128(a_lo) + 2 * k;
+            const uint64_t dwh = umma_desc_sw128(w_hi) + 2 * k, dwl = umma_desc_sw128(w_lo) + 2 * k;
+            if (cat) {
               umma_f16(tmem_base, dah, dwh, idesc_w, (kb | k) != 0);
               umma_f16(tmem_base + BN, dal, dwh, idesc_n, 1);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint64_t dah = umma_desc_sw128(a_hi) + 2 * k, dal = umma_desc_sw128(a_lo) + 2 * k;
-              const uint64_t dwh = umma_desc_sw128(w_hi) + 2 * k, dwl = umma_desc_sw128(w_lo) + 2 * k;
+            } else {
               umma_f16(tmem_base, dah, dwh, idesc_n, (kb | k) != 0);
               umma_f16(tmem_base + BN, dah, dwl, idesc_n, (kb | k) != 0);
               umma_f16(tmem_base + BN, dal, dwh, idesc_n, 1);
             }
           }
+          umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&empty_bar[s]);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-      }
+      } else if (BN <= 128) tc_issue_loop<true>(full_bar, empty_bar, sb, STAGE_BYTES, W_PLANE, BN, STAGES, tmem_base, num_kb, dbg);
+      else tc_issue_loop<false>(full_bar, empty_bar, sb, STAGE_BYTES, W_PLANE, BN, STAGES, tmem_base, num_kb, dbg);
       umma_commit(acc_bar);
       if (dbg) dbg[2] = clock64();
     }

@@ -17,6 +17,8 @@ B = 32
 torch.set_grad_enabled(False)
 L = _lib.lib()
 dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
+if os.environ.get("ST_PROBE"):          # 32768: the timeline of the LAST CTA of the grid instead of CTA (0,0)
+    _lib.check(L.st_debug_probe(int(os.environ["ST_PROBE"])))
 _lib.check(L.st_debug_timeline_select(N, K))
 _lib.check(L.st_debug_timeline(dbg.data_ptr()))          # before the step graph is captured: the captured launches carry the pointer
 model = MDM(None).load_state_dict(synth.mdm_state_dict("beatx_motionclip", seed=0))
@@ -30,5 +32,5 @@ for _ in range(4):
 torch.cuda.synchronize()
 t = dbg.cpu().tolist(); t0 = t[0]
 nkb = K // 64
-print(f"N={N} K={K}: dependency resolved {t[1]-t0}, first operands {t[24]-t0}, last K block ready {t[24+min(nkb,16)-1]-t0}, "
+print(f"N={N} K={K}: set-up done {t[32]-t0}, dependency resolved {t[1]-t0}, first TMA issued {t[8]-t0}, first operands {t[24]-t0}, last K block ready {t[24+min(nkb,16)-1]-t0}, "
       f"accumulator ready {t[3]-t0}, staged {t[6]-t0}, stores read {t[4]-t0}, CTA end {t[5]-t0}")

@@ -8,12 +8,13 @@ from syntalker_b200 import _lib
 L = _lib.lib()
 L.st_debug_probe.argtypes = [C.c_int]
 dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
+EXTRA = int(os.environ.get('ST_PROBE_EXTRA', '0'))
 names = {0: "product", 1: "TMA only", 2: "MMA only", 6: "MMA only grouped", 10: "MMA only 1 acc", 4: "grouped", 8: "1 acc"}
 for (M, N, K) in [(128, 512, 512), (2048, 512, 512), (2048, 1024, 512), (2048, 1536, 512), (2048, 512, 1024)]:
     A = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda") / K ** 0.5; b = torch.randn(N, device="cuda")
     out = torch.empty(M, N, device="cuda")
-    for probe in (0, 1, 2, 6, 10, 4, 8):
-        _lib.check(L.st_debug_probe(probe))
+    for probe in ((0, 1, 2) if os.environ.get('ST_PROBE_SHORT') else (0, 1, 2, 6, 10, 4, 8)):
+        _lib.check(L.st_debug_probe(probe | EXTRA))
         ms = C.c_double(0)
         _lib.check(L.st_bench_gemm(M, N, K, 1, 200, A.data_ptr(), W.data_ptr(), b.data_ptr(), out.data_ptr(), C.byref(ms)))
         call = lambda e: _lib.check(L.st_selftest_gemm(M, N, K, e, A.data_ptr(), W.data_ptr(), b.data_ptr(), out.data_ptr(), _lib.stream_ptr()))
