@@ -85,6 +85,7 @@ int st_set_pdl(int on);
 int st_debug_timeline(long long* dev_buf);
 /* Debug: only trunk-kernel launches with this N and K record the timeline (0, 0 = every launch). */
 int st_debug_timeline_select(int N, int K);
+int st_debug_timeline_select2(int N, int K);   /* a second shape, recorded 1024 slots behind the first (tests/boundary_probe.py) */
 /* Debug: device buffer of 120000 uint64; every kernel's first thread appends (%globaltimer ns, kernel id); slot 0 = count. NULL = off. */
 int st_debug_trace(unsigned long long* dev_buf);
 /* debug / A-B switches.  bits 0-3: timing-only variants of the tcgen05 main loop (results are garbage); 16: trunk kernel off

@@ -20,7 +20,7 @@ ST_COEF_STRIDE = 5
 
 # every symbol include/syntalker_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "st_last_error", "st_abi_version", "st_launch_count", "st_set_engine", "st_get_engine", "st_model_set_engine", "st_vq_set_engine", "st_set_graphs", "st_set_pdl", "st_debug_timeline", "st_debug_timeline_select", "st_debug_trace", "st_debug_probe", "st_debug_cond_taps",
+    "st_last_error", "st_abi_version", "st_launch_count", "st_set_engine", "st_get_engine", "st_model_set_engine", "st_vq_set_engine", "st_set_graphs", "st_set_pdl", "st_debug_timeline", "st_debug_timeline_select", "st_debug_timeline_select2", "st_debug_trace", "st_debug_probe", "st_debug_cond_taps",
     "st_model_create", "st_model_destroy", "st_vq_create", "st_vq_destroy", "st_vq_out_dim",
     "st_schedule_create", "st_schedule_destroy", "st_cond_encode", "st_denoise", "st_sample", "st_sample_chunk", "st_sample_begin", "st_sample_run", "st_sample_end",
     "st_rvq_decode", "st_pose_assemble_330", "st_pose_assemble_623", "st_sample_to_tokens", "st_pose_330_to_aa165", "st_moments_accumulate", "st_l1div_accumulate",
@@ -75,6 +75,7 @@ def lib():
     L.st_set_pdl.argtypes = [i32]
     L.st_debug_timeline.argtypes = [vp]
     L.st_debug_timeline_select.argtypes = [i32, i32]
+    L.st_debug_timeline_select2.argtypes = [i32, i32]
     L.st_debug_trace.argtypes = [vp]
     L.st_debug_cond_taps.argtypes = [vp, vp, vp, i32, vp]
     L.st_model_create.argtypes = [C.POINTER(StTensor), i32, i32, C.POINTER(vp)]

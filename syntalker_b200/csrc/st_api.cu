@@ -86,6 +86,7 @@ static double g_prof_flops = 0.0;
 
 static int gemm_dispatch(const GemmP& p, cudaStream_t s) {
   if (cur_engine() == ST_ENGINE_TC && tc_supported(p)) return gemm_tc(p, s);
+  ST_TRY(fast_chain_flush());      // an open layer chain leaves before anything else is launched
   return gemm_simt(p, s);
 }
 
@@ -95,6 +96,13 @@ int gemm(const GemmP& p, cudaStream_t s) {
     g_prof_flops += 2.0 * (double)p.M * (double)p.N * (double)p.K;
   }
   return gemm_dispatch(p, s);
+}
+// the replay of profile_end() chains what the recorded pass chained: markers (M = -1 begin, -2 end) in the launch list
+static void profile_mark(int what) {
+  if (!g_prof) return;
+  GemmP m;
+  m.M = what;
+  g_prof_list.push_back(m);
 }
 
 bool profiling() { return g_prof; }
@@ -109,7 +117,7 @@ int profile_end(double* ms, double* flops, int64_t* n) {
   g_prof = false;
   ST_CHECK_CUDA(cudaDeviceSynchronize());
   if (flops) *flops = g_prof_flops;
-  if (n) *n = (int64_t)g_prof_list.size();
+  if (n) { *n = 0; for (const GemmP& p : g_prof_list) *n += p.M >= 0; }
   if (ms) *ms = 0.0;
   if (g_prof_list.empty()) return ST_OK;
   cudaStream_t s = nullptr;
@@ -120,11 +128,15 @@ int profile_end(double* ms, double* flops, int64_t* n) {
   // the replay stream's split scratch is sized for the largest fp32 operand before the capture starts
   size_t need = 0;
   for (const GemmP& p : g_prof_list)
-    if (cur_engine() == ST_ENGINE_TC && tc_supported(p)) need = std::max(need, tc_scratch_need(p));
+    if (p.M >= 0 && cur_engine() == ST_ENGINE_TC && tc_supported(p)) need = std::max(need, tc_scratch_need(p));
   if (need) ST_TRY(tc_scratch_reserve(s, need));
   ST_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
   int r = ST_OK;
-  for (const GemmP& p : g_prof_list) { r = gemm_dispatch(p, s); if (r != ST_OK) break; }
+  for (const GemmP& p : g_prof_list) {
+    r = p.M == -1 ? fast_chain_begin(s) : p.M == -2 ? fast_chain_end() : gemm_dispatch(p, s);
+    if (r != ST_OK) break;
+  }
+  if (r != ST_OK) fast_chain_end();
   cudaError_t ce = cudaStreamEndCapture(s, &graph);
   g_launches = l0;
   if (r != ST_OK) { if (graph) cudaGraphDestroy(graph); tc_scratch_release(s); cudaStreamDestroy(s); (void)cudaGetLastError(); return r; }
@@ -243,9 +255,10 @@ static bool g_zrec = true;         // st_debug_probe bit 512 turns the z recursi
 static bool g_dual_chain = false;  // st_debug_probe bit 4096 (experiment): the evaluations of a step as two chains on two streams
 static bool g_zrec_fc2 = true;     // st_debug_probe bit 1024: the last block's fc2 stays a layer of its own inside the z recursion
 
-namespace st { extern int g_tc_probe; extern bool g_tc_fast; extern bool g_tc_taps; }
+namespace st { extern int g_tc_probe; extern bool g_tc_fast; extern bool g_tc_taps; extern bool g_tc_chain; }
 extern "C" int st_debug_probe(int flags) {
   st::g_tc_taps = !(flags & 8192);
+  st::g_tc_chain = (flags & 131072) != 0;
   st::g_tc_probe = (flags & 15) | ((flags & (16384 | 32768 | 65536)) >> 10);   // bits 16384.. reach the kernels as probe bits 16, 32, 64 (experiments)
   st::g_tc_fast = !(flags & 16);
   g_fused_attn = !(flags & 32);
@@ -292,6 +305,8 @@ extern "C" int st_debug_probe(int flags);
 namespace st { extern int g_tc_dbg_n, g_tc_dbg_k; }
 extern "C" int st_debug_timeline(long long* dev_buf) { st::g_tc_dbg = dev_buf; return ST_OK; }
 extern "C" int st_debug_timeline_select(int N, int K) { st::g_tc_dbg_n = N; st::g_tc_dbg_k = K; return ST_OK; }
+namespace st { extern int g_tc_dbg_n2, g_tc_dbg_k2; }
+extern "C" int st_debug_timeline_select2(int N, int K) { st::g_tc_dbg_n2 = N; st::g_tc_dbg_k2 = K; return ST_OK; }
 extern "C" int st_debug_trace(unsigned long long* dev_buf) {
   ST_TRY(st::set_trace_kernels(dev_buf));
   return st::set_trace_tc(dev_buf);
@@ -759,7 +774,7 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   // block.  LayerNorm never runs as a kernel: the GEMM that consumes it reads the raw residual planes and applies (mean, 1/sigma)
   // in its epilogue from the row statistics its producer left.  Evaluations are stacked along the rows, so a subset is a row range
   // of every buffer (the plane stride stays that of the whole stack).
-  auto chain_tc = [&](int e0, int ne, cudaStream_t cs) -> int {
+  auto chain_layers = [&](int e0, int ne, cudaStream_t cs) -> int {
     const int Rc = ne * rows;
     const size_t r0 = (size_t)e0 * rows;
     float* X = m->X + r0 * 512; float* P = m->H + r0 * 512; float* stats = m->ln_stats + r0 * 32;
@@ -776,6 +791,7 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
         GemmP pq = linear(X, Rc, 512, b.qkv_wg, nullptr, m->QKV + r0 * 1536, 1536);
         pq.a_planes = X_p; pq.a_plane_stride = ps512; pq.ln_stats = stats; pq.ln_s = b.qkv_s; pq.ln_c = b.qkv_c;
         ST_TRY(gemm(pq, cs));
+        ST_TRY(fast_chain_flush());
         ST_TRY(attention32(m->QKV + r0 * 1536, nullptr, ATT_p, ne * B, cs, ps512));
       }
       GemmP pp = linear(nullptr, Rc, 512, b.projw, b.projb, X, 512);
@@ -807,6 +823,15 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
     GemmP po = linear(X, Rc, 512, m->out_w, m->out_b, m->O + r0 * 1536, 1536);
     po.a_planes = X_p; po.a_plane_stride = ps512;
     return gemm(po, cs);
+  };
+  // every trunk layer only reads rows of its own 128-row tile, so the layers leave as chains: one cluster launch per run
+  auto chain_tc = [&](int e0, int ne, cudaStream_t cs) -> int {
+    ST_TRY(fast_chain_begin(cs));
+    profile_mark(-1);
+    const int r = chain_layers(e0, ne, cs);
+    const int r2 = fast_chain_end();
+    profile_mark(-2);
+    return r != ST_OK ? r : r2;
   };
   if (tc) {
     if (g_dual_chain && pl.nE >= 2 && loop) {

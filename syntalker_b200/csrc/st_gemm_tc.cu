@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -782,9 +783,10 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
 }
 // the CTA only has to keep its staging memory alive until the TMA engine has read it; the writes themselves are
 // performed before the grid counts as complete, which is what the dependent kernel's griddepcontrol.wait observes
-__device__ __forceinline__ void tma_store_commit_wait() {
+__device__ __forceinline__ void tma_store_commit_wait(bool complete = false) {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (complete) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the writes themselves (a consumer in the same grid follows)
+  else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -869,10 +871,26 @@ constexpr float kPScale = 1024.0f;               // softmax probabilities are sp
 constexpr int FAST_BOX_F32 = 128 * 32 * 4;       // one fp32 staging box: 128 rows x 32 columns, 128B rows
 constexpr int FAST_BOX_PL = 2 * TC_A_PLANE;      // one plane staging box: 2 planes x 128 rows x 64 halfs
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, const FastEpi ep,
-                    const int num_kb, const int BN, const int STAGES, const __grid_constant__ CUtensorMap tmA2) {
+// LEGACY = true keeps what the product no longer runs -- the packed-fp32 FMA attention epilogue (attn == 1) and the MMA issue loop as
+// first written -- as a second instantiation for A/B measurements and the test that holds the tensor-core attention against it
+// (st_debug_probe bits 2048 / 16384); the product's instantiation is a third shorter, which its instruction fetch feels (-0.4 %).
+//
+// CHAIN = true is the body of gemm_tc_chain_kernel: the CTA runs layer after layer of a list (li of nl) as one CTA of a cluster
+// of 8 = the 8 column tiles of one 128-row tile.  Every dependency between consecutive trunk layers stays inside a row tile (a
+// Linear layer and the 32-token attention only read their own rows), so a cluster barrier after the layer's stores have completed
+// replaces the kernel boundary: no CTA launch (0.9 us after the previous CTA's exit), no set-up, no grid-completion latency
+// (tests/boundary_probe.py: the dependent's wait returns 1.3 - 2.1 us after the last CTA has exited).  TMEM is allocated once; the
+// barriers of layer li + 1 are initialised (second barrier set) while layer li runs.
+struct FastLayer {
+  CUtensorMap tmA, tmW, tmO, tmP, tmA2;
+  FastEpi ep;
+  int num_kb, BN, STAGES, pad_;
+};
+constexpr int FAST_TAIL = 4096;                  // CHAIN: bias / column sums / barriers of two consecutive layers at the end of shared memory
+template <bool LEGACY, bool CHAIN>
+__device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const CUtensorMap& tmP,
+                                           const FastEpi& ep, const int num_kb, const int BN, const int STAGES, const CUtensorMap& tmA2,
+                                           const int li, const int nl, uint32_t& tmem_keep, const FastLayer* next, const int prev_stages) {
   const int W_PLANE = BN * TC_BK * 2;
   const int STAGE_BYTES = 2 * TC_A_PLANE + 2 * W_PLANE;
   const int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
@@ -880,7 +898,13 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res_tile = smem + STAGES * STAGE_BYTES;                              // NCH boxes (only when has_res)
-  float* bias_s = reinterpret_cast<float*>(res_tile + (ep.attn ? ATT_SX_BYTES : ep.has_res ? NCH * FAST_BOX_F32 : 0));
+  uint32_t dyn_smem;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_smem));
+  // CHAIN: the small per-layer state sits at a fixed place (two sets, layer parity), so that the next layer's set can be prepared
+  // while this layer runs; otherwise it follows the ring
+  uint8_t* tail_set = smem_raw + dyn_smem - FAST_TAIL;
+  float* bias_s = CHAIN ? reinterpret_cast<float*>(tail_set + (li & 1) * 2048)
+                        : reinterpret_cast<float*>(res_tile + (ep.attn ? ATT_SX_BYTES : ep.has_res ? NCH * FAST_BOX_F32 : 0));
   float* lns_s = bias_s + 192;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(lns_s + 192);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -890,7 +914,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // ready (256 arrivals), P V complete (commit)
   // [4]: the peer CTA's partial scores have landed in this CTA's score buffer (st.async complete_tx, 16 KB)
   uint64_t* att_bar = res_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(att_bar + 5);
+  uint32_t* tmem_slot = CHAIN ? reinterpret_cast<uint32_t*>(tail_set + 2048 - 16) : reinterpret_cast<uint32_t*>(att_bar + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
@@ -899,9 +923,18 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const bool dbg_cta = (ep.probe & 32) ? (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1) : (blockIdx.x == 0 && blockIdx.y == 0);
   long long* dbg = (ep.dbg && dbg_cta) ? ep.dbg : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  // boundary records (probe bit 64): every CTA of the selected launch leaves {globaltimer at entry, SM id, globaltimer after the
+  // dependency wait, globaltimer at exit} behind the 64 timeline slots (tests/boundary_probe.py)
+  long long* brec = (ep.dbg && (ep.probe & 64)) ? ep.dbg + 64 + 4 * (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (brec && threadIdx.x == 0) {
+    unsigned long long gt; uint32_t smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    brec[0] = (long long)gt; brec[1] = smid;
+  }
   trace_stamp(20);                                   // CTA entry
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && lane == 0 && (!CHAIN || li == 0)) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     if (ep.has_out || ep.has_res) tma_prefetch_desc(&tmO);
@@ -909,16 +942,27 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (ep.kb_split < num_kb) tma_prefetch_desc(&tmA2);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(acc_bar, 1);
-    mbar_init(res_bar, 1);
-    mbar_init(&att_bar[0], 256); mbar_init(&att_bar[1], 1); mbar_init(&att_bar[2], 256); mbar_init(&att_bar[3], 1);
-    mbar_init(&att_bar[4], 1);
-    fence_barrier_init();
-    if (ep.attn == 2) mbar_expect_tx(&att_bar[4], ATT_SX_TX);      // the one arrival; the phase completes when the peer's 16 KB are in
+    auto init_set = [](uint64_t* fb, int stages, int attn, int old_stages) {
+      uint64_t* eb = fb + stages;
+      uint64_t* ab = eb + stages;                    // acc_bar, res_bar, att_bar[0..4]
+      // the set held the barriers of the layer before this one's predecessor (all phases complete, nobody waiting): an mbarrier
+      // object is invalidated before its memory becomes another one
+      for (int i = 0; i < 2 * old_stages + 7 && old_stages > 0; ++i)
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(fb + i)) : "memory");
+      for (int i = 0; i < stages; ++i) { mbar_init(&fb[i], 1); mbar_init(&eb[i], 1); }
+      mbar_init(ab, 1);
+      mbar_init(ab + 1, 1);
+      mbar_init(ab + 2, 256); mbar_init(ab + 3, 1); mbar_init(ab + 4, 256); mbar_init(ab + 5, 1);
+      mbar_init(ab + 6, 1);
+      fence_barrier_init();
+      if (attn == 2) mbar_expect_tx(ab + 6, ATT_SX_TX);            // the one arrival; the phase completes when the peer's 16 KB are in
+    };
+    if (!CHAIN || li == 0) init_set(full_bar, STAGES, ep.attn, 0);
+    if (CHAIN && next)
+      init_set(reinterpret_cast<uint64_t*>(tail_set + ((li + 1) & 1) * 2048 + 2 * 192 * 4), next->STAGES, next->ep.attn, li > 0 ? prev_stages : 0);
   }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2 && (!CHAIN || li == 0)) {
+    tmem_alloc(tmem_slot, CHAIN ? 512 : TMEM_COLS);
     tmem_relinquish();
   }
   // bias and LayerNorm column sums are weights: safe to read before the predecessor has finished.  The loads are issued
@@ -929,13 +973,16 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (ep.bias) bias_r = __ldg(ep.bias + n0 + et);
     if (ep.ln_s) lns_r = __ldg(ep.ln_s + n0 + et);
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);   // REDUX result lives in a uniform register
+  if (!CHAIN || li == 0) {
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tmem_keep = *tmem_slot;
+  }
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, tmem_keep);    // REDUX result lives in a uniform register
   if (dbg && threadIdx.x == 0) dbg[32] = clock64();                       // set-up done
-  pdl_launch();     // dependents may be scheduled; they still wait for this grid's completion before touching memory
-  if (ep.attn) {
+  if (!CHAIN || li == 0) pdl_launch();     // dependents may be scheduled; they still wait for this grid's completion before touching memory
+  if (ep.attn && (!CHAIN || li == 0)) {
     // the attention epilogue writes into the peer CTA's shared memory: both CTAs of the cluster must be running before
     // either does (co-scheduling guarantees residency, not that the peer has started)
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -952,12 +999,19 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // so everything is formed and pinned before the wait and the first pass of A tiles is one short loop behind it.
       const int pre = num_kb < STAGES ? num_kb : STAGES;
       const bool no_tma = (ep.probe & 2) != 0;
+      // inside a chain the cluster barrier that ended the previous layer ordered the peers' stores before this thread; the proxy
+      // fence orders them before its TMA loads.  It comes FIRST: behind the weight loads it waited for them to land (timeline:
+      // 3 157 cycles from the layer's start to the first activation tile's request, 6 087 with the 128-wide weight tiles)
+      if (dbg) dbg[33] = clock64();
+      if (CHAIN && li > 0) asm volatile("fence.proxy.async;" ::: "memory");
+      if (dbg) dbg[34] = clock64();
       if (!no_tma) {
         for (int kb = 0; kb < pre; ++kb) {
           mbar_expect_tx(&full_bar[kb], STAGE_BYTES);
           tma_load_3d(smem + kb * STAGE_BYTES + 2 * TC_A_PLANE, &tmW, &full_bar[kb], kb * TC_BK, n0, 0);
         }
       }
+      if (dbg) dbg[35] = clock64();
       int mode = ep.mode, kb_split = ep.kb_split, kpt = ep.kb_per_tap, dil = ep.dil, pad = ep.pad;
       int clip = mode ? m0 / ep.T : 0;
       uint32_t a_dst = smem_u32(smem), a_bar = smem_u32(full_bar);
@@ -978,10 +1032,15 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(bar), "r"(cb * TC_BK), "r"(j * dil - pad), "r"(clip), "r"(0) : "memory");
         }
       };
-      pdl_wait();
+      if (!CHAIN || li == 0) pdl_wait();
       for (int kb = 0; kb < npre; ++kb) load_a(kb, a_dst + kb * stage_b, a_bar + 8 * kb);
+      if (CHAIN && next) {            // the next layer's descriptors, off its critical path
+        tma_prefetch_desc(&next->tmA); tma_prefetch_desc(&next->tmW); tma_prefetch_desc(&next->tmO); tma_prefetch_desc(&next->tmP);
+        tma_prefetch_desc(&next->tmA2);
+      }
       trace_stamp(1, true);
       if (dbg) { const long long now = clock64(); dbg[1] = now; dbg[8] = now; }
+      if (brec) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); brec[2] = (long long)gt; }
       // the residual tile is only needed by the epilogue: it is requested behind the first ring pass of operands, not in front
       // of it (all 128 CTAs start at once, and the first K block's arrival is what the tensor pipe waits for)
       if (ep.has_res) {
@@ -1021,7 +1080,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-      } else if (ep.probe & 16) {
+      } else if (LEGACY && (ep.probe & 16)) {
         // the loop as first written (A/B reference, st_debug_probe bit 16384): blocking wait, descriptors rebuilt per K block
         const bool cat = BN <= 128;
         const uint32_t idesc_w = umma_idesc_f16(TC_BM, cat ? 2 * BN : BN), idesc_n = umma_idesc_f16(TC_BM, BN);
@@ -1097,7 +1156,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ===== epilogue: warps 2..9; TMEM lane group = warp % 4 (rows), the two warps of a group alternate 32-column chunks =====
-    pdl_wait();
+    if (!CHAIN || li == 0) pdl_wait();
     const int lg = warp & 3, cpart = (warp - 2) >> 2;
     const int r = lg * 32 + lane, grow = m0 + r;
     const bool row_ok = grow < ep.M;
@@ -1111,7 +1170,7 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float mj[16], qj[16];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float4 t = st4[i];
+        const float4 t = __ldcg(st4 + i);            // written by other SMs a layer ago: never from this SM's L1
         mj[2 * i] = t.x; qj[2 * i] = t.y; mj[2 * i + 1] = t.z; qj[2 * i + 1] = t.w;
       }
       float mu = 0.f, m2 = 0.f;
@@ -1149,9 +1208,12 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       //  6. thread (row, dim half): 32 dims of O -> plane staging (over the dead Q tiles) -> one TMA store
       const uint32_t sx = smem_u32(res_tile);
       uint32_t sx_peer;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(sx_peer) : "r"(sx), "r"((uint32_t)((blockIdx.x & 1) ^ 1)));
+      uint32_t peer_rank;                            // the other dim half of this head: the neighbour in the cluster (of 2, or of 8 in a chain)
+      asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(peer_rank));
+      peer_rank ^= 1u;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(sx_peer) : "r"(sx), "r"(peer_rank));
       uint32_t sxbar_peer;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(sxbar_peer) : "r"(smem_u32(&att_bar[4])), "r"((uint32_t)((blockIdx.x & 1) ^ 1)));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(sxbar_peer) : "r"(smem_u32(&att_bar[4])), "r"(peer_rank));
       const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < 3; ++cc) {
@@ -1286,10 +1348,10 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (warp == 2 && elect_one()) {
         tma_store_3d(&tmP, stage0 + ATT2_O, blockIdx.x * 64, m0, 0);
-        tma_store_commit_wait();
+        tma_store_commit_wait(CHAIN);
       }
       if (dbg && threadIdx.x == 64) { dbg[47] = clock64(); dbg[4] = dbg[47]; }
-    } else if (ep.attn) {
+    } else if (LEGACY && ep.attn) {
       // ---- fused attention (transformer.py:83-104).  This CTA holds, for 4 sequences x 32 tokens (TMEM lane group = one
       // sequence, lane = token), 64 of the 128 dims of q, k and v of one head; its cluster peer holds the other 64.
       // q, k, v go to shared memory (fp32); the two warps of a lane group then take 16 query rows each and work in
@@ -1546,24 +1608,71 @@ gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_before();
     if (dbg && threadIdx.x == 64) dbg[6] = clock64();
     // the staging memory must outlive the TMA engine's reads: each issuing thread waits for its own bulk groups
-    if (lg == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (lg == 0 && lane == 0) {
+      if (CHAIN) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (dbg && warp == 4) dbg[36] = clock64();
+    }
     if (dbg && threadIdx.x == 64) dbg[4] = clock64();
     }
   }
-  if (ep.attn == 1 && warp < 2) {
+  if (LEGACY && ep.attn == 1 && warp < 2) {
     // the producer and MMA warps take part in the cluster barrier of the FMA attention epilogue (the tensor-core one exchanges
     // its scores through st.async + an mbarrier instead)
     __syncwarp();
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
+  tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[37] = clock64();
   trace_stamp(23);                                   // epilogue and stores done
-  if (warp == 2) {
+  if (CHAIN && li + 1 < nl) {
+    // layer boundary inside the chain: this CTA's stores are complete (the issuing threads waited for the writes, the row
+    // statistics are ordinary stores), release them to the 7 peers of the row tile and acquire theirs
+    // (one warp releases for the CTA -- the CTA barrier above made the other warps' writes its own, release is cumulative --
+    // the rest arrive relaxed: 320 releasing threads per CTA took 3 200 cycles from the last store to the next layer's start)
+    if (warp == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    } else {
+      asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+  } else if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, CHAIN ? 512 : TMEM_COLS);
   }
   if (dbg && threadIdx.x == 0) dbg[5] = clock64();
+  if (brec && threadIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); brec[3] = (long long)gt; }
+}
+
+template <bool LEGACY>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, const FastEpi ep,
+                    const int num_kb, const int BN, const int STAGES, const __grid_constant__ CUtensorMap tmA2) {
+  uint32_t keep = 0;
+  fast_layer<LEGACY, false>(tmA, tmW, tmO, tmP, ep, num_kb, BN, STAGES, tmA2, 0, 1, keep, nullptr, 0);
+}
+
+// The trunk layers of one evaluation stack as ONE launch: clusters of 8 CTAs (grid.x = 8 column tiles of every layer), one cluster
+// per 128-row tile, every CTA walking the layer list (see fast_layer<., true>).
+constexpr int FAST_CHAIN_MAX = 32;
+struct FastChain {
+  int nl, pad_[15];
+  FastLayer ly[FAST_CHAIN_MAX];
+};
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_chain_kernel(const __grid_constant__ FastChain P) {
+  uint32_t keep = 0;
+  const int nl = P.nl;
+#pragma unroll 1
+  for (int li = 0; li < nl; ++li) {
+    const FastLayer& L = P.ly[li];
+    fast_layer<false, true>(L.tmA, L.tmW, L.tmO, L.tmP, L.ep, L.num_kb, L.BN, L.STAGES, L.tmA2, li, nl, keep, li + 1 < nl ? &P.ly[li + 1] : nullptr,
+                            li > 0 ? P.ly[li - 1].STAGES : 0);
+  }
 }
 
 // fp32 [M,K] (row stride lda) -> fp16 planes [2][M][Kp], value * scale split into hi + lo
@@ -1687,6 +1796,7 @@ static std::unordered_map<const float*, WPlanes> g_wplanes;
 static std::mutex g_w_mu;
 long long* g_tc_dbg = nullptr;  // set by st_debug_timeline
 int g_tc_probe = 0;             // set by st_debug_probe
+int g_tc_dbg_n2 = -1, g_tc_dbg_k2 = -1;   // st_debug_timeline_select2: a second shape, recorded 1024 slots further on
 int g_tc_dbg_n = 0, g_tc_dbg_k = 0;   // st_debug_timeline_select: only launches with this N, K record the timeline (0 = all)
 bool g_tc_fast = true;          // trunk kernel for the shapes it takes (st_debug_probe bit 16 turns it off)
 bool g_tc_taps = true;          // staged-taps conv mode of the generic kernel (st_debug_probe bit 8192 turns it off)
@@ -1923,6 +2033,83 @@ static bool tc_fast_supported(const GemmP& p) {
   return stages >= 2 && staging <= stages * stage && (BN % 64 == 0 || !p.o_planes);
 }
 
+// ---- layer chains (gemm_tc_chain_kernel).  Between fast_chain_begin and fast_chain_end the trunk launches of one stream are collected
+// instead of launched; a run of layers that all have 8 column tiles and the same number of row tiles leaves as one cluster launch.
+// Anything else that is launched in between flushes the run first, so the stream order of the caller's calls is kept.
+struct ChainState {
+  bool open = false;
+  cudaStream_t s = nullptr;
+  unsigned grid_y = 0;
+  int seen = 0;                 // trunk layers since fast_chain_begin (ST_CHAIN_SKIP: the first ones stay single launches; for bisecting)
+  std::vector<FastLayer> ly;
+  std::vector<int> smem;        // single-launch shared memory of each pending layer (used when a run of one is flushed)
+};
+static thread_local ChainState g_chain;
+bool g_tc_chain = false;       // st_debug_probe bit 131072 turns layer chaining ON (measured slower than one launch per layer: DESIGN.md)
+
+static int launch_fast_single(const FastLayer& L, unsigned grid_y, int smem, bool legacy, cudaStream_t s) {
+  static DeviceOnce attr;
+  if (attr.first()) {
+    ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  }
+  dim3 grid((L.ep.N + L.BN - 1) / L.BN, grid_y);
+  if (L.ep.attn) launch_k_cluster(legacy ? gemm_tc_fast_kernel<true> : gemm_tc_fast_kernel<false>, grid, dim3(TC_THREADS), (size_t)smem, s, 2, L.tmA, L.tmW, L.tmO, L.tmP, L.ep, L.num_kb, L.BN, L.STAGES, L.tmA2);
+  else launch_k(legacy ? gemm_tc_fast_kernel<true> : gemm_tc_fast_kernel<false>, grid, dim3(TC_THREADS), (size_t)smem, s, L.tmA, L.tmW, L.tmO, L.tmP, L.ep, L.num_kb, L.BN, L.STAGES, L.tmA2);
+  ST_CHECK_LAUNCH();
+  return ST_OK;
+}
+
+int fast_chain_flush() {
+  ChainState& c = g_chain;
+  if (c.ly.empty()) return ST_OK;
+  int r = ST_OK;
+  if (c.ly.size() == 1) {
+    r = launch_fast_single(c.ly[0], c.grid_y, c.smem[0], false, c.s);
+  } else {
+    static DeviceOnce attr;
+    if (attr.first()) ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    if (getenv("ST_CHAIN_DEBUG")) {
+      for (int cs = 2; cs <= 8; cs *= 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(8, c.grid_y); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = 232448;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = -1;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gemm_tc_chain_kernel, &cfg);
+        fprintf(stderr, "chain kernel: cluster size %d -> max active clusters %d (%s)\n", cs, n, cudaGetErrorString(e));
+      }
+    }
+    static thread_local FastChain P;               // 25 KB: passed by value, kept off the stack
+    P.nl = (int)c.ly.size();
+    for (int i = 0; i < P.nl; ++i) P.ly[i] = c.ly[i];
+    launch_k_cluster(gemm_tc_chain_kernel, dim3(8, c.grid_y), dim3(TC_THREADS), (size_t)232448, c.s, 8, P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("gemm_tc_chain_kernel launch (%d layers): %s", P.nl, cudaGetErrorString(e));
+      r = ST_ECUDA;
+    } else {
+      st::g_launches++;
+    }
+  }
+  c.ly.clear();
+  c.smem.clear();
+  return r;
+}
+int fast_chain_begin(cudaStream_t s) {
+  ST_TRY(fast_chain_flush());
+  g_chain.open = g_tc_chain;
+  g_chain.s = s;
+  g_chain.seen = 0;
+  return ST_OK;
+}
+int fast_chain_end() {
+  const int r = fast_chain_flush();
+  g_chain.open = false;
+  return r;
+}
+
 static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long long pstride, cudaStream_t s) {
   const int BN = fast_bn(p);
   const int stage = 2 * TC_A_PLANE + 2 * BN * TC_BK * 2;
@@ -1948,17 +2135,36 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   ep.ln_stats = p.ln_stats; ep.stats_out = p.stats_out;
   ep.scale = w->inv_scale / kActScale;
   ep.act = p.act; ep.has_res = p.res ? 1 : 0; ep.has_out = p.out ? 1 : 0; ep.has_planes = p.o_planes ? 1 : 0;
-  ep.M = p.M; ep.N = p.N; ep.dbg = (g_tc_dbg_n == 0 || (g_tc_dbg_n == p.N && g_tc_dbg_k == p.K)) ? g_tc_dbg : nullptr; ep.probe = g_tc_probe; ep.attn = p.attn;
+  ep.M = p.M; ep.N = p.N; ep.dbg = (g_tc_dbg_n == 0 || (g_tc_dbg_n == p.N && g_tc_dbg_k == p.K)) ? g_tc_dbg : (g_tc_dbg && g_tc_dbg_n2 == p.N && g_tc_dbg_k2 == p.K) ? g_tc_dbg + 1024 : nullptr; ep.probe = g_tc_probe; ep.attn = p.attn;
   ep.mode = cmode; ep.T = p.Lout; ep.kb_per_tap = cmode == 0 ? 1 : p.C / TC_BK; ep.dil = p.dil; ep.pad = p.pad;
   ep.planes_relu = p.o_planes_relu;
   ep.kb_split = p.a2_planes ? (p.K - p.a2_K) / TC_BK : 0x7fffffff;
-  static DeviceOnce attr;
-  if (attr.first()) ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  const bool legacy = p.attn == 1 || (ep.probe & 16);
   dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM);
-  if (p.attn) launch_k_cluster(gemm_tc_fast_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, 2, *tmA, *tmW, *tmO, *tmP, ep, w->Kp / TC_BK, BN, stages, *tmA2);
-  else launch_k(gemm_tc_fast_kernel, grid, dim3(TC_THREADS), (size_t)smem, s, *tmA, *tmW, *tmO, *tmP, ep, w->Kp / TC_BK, BN, stages, *tmA2);
-  ST_CHECK_LAUNCH();
-  return ST_OK;
+  FastLayer L;
+  L.tmA = *tmA; L.tmW = *tmW; L.tmO = *tmO; L.tmP = *tmP; L.tmA2 = *tmA2;
+  L.ep = ep; L.num_kb = w->Kp / TC_BK; L.BN = BN; L.STAGES = stages; L.pad_ = 0;
+  ChainState& c = g_chain;
+  // a chain layer: 8 column tiles (= the cluster), full row tiles, plain rows, and room for the fixed tail block behind ring + residual
+  static const int chain_skip = [] { const char* e = getenv("ST_CHAIN_SKIP"); return e ? atoi(e) : 0; }();
+  const bool chainable = c.open && c.seen++ >= chain_skip && s == c.s && !legacy && grid.x == 8 && cmode == 0 && (p.M % TC_BM) == 0 &&
+                         stages * stage + (p.attn ? ATT_SX_BYTES : res) + 1024 + FAST_TAIL <= 232448;
+  if (chainable && (c.ly.empty() || c.grid_y == grid.y)) {
+    c.grid_y = grid.y;
+    c.ly.push_back(L);
+    c.smem.push_back(smem);
+    static const int chain_max = [] { const char* e = getenv("ST_CHAIN_MAX"); const int v = e ? atoi(e) : FAST_CHAIN_MAX; return v < 1 ? 1 : v > FAST_CHAIN_MAX ? FAST_CHAIN_MAX : v; }();
+    if ((int)c.ly.size() >= chain_max) return fast_chain_flush();   // (ST_CHAIN_MAX: shorter chains, for bisecting)
+    return ST_OK;
+  }
+  ST_TRY(fast_chain_flush());
+  if (chainable) {                                   // a run with a different number of row tiles starts
+    c.grid_y = grid.y;
+    c.ly.push_back(L);
+    c.smem.push_back(smem);
+    return ST_OK;
+  }
+  return launch_fast_single(L, grid.y, smem, legacy, s);
 }
 
 // bytes of split scratch a GEMM needs (0: its operand already arrives as planes)
@@ -2010,11 +2216,13 @@ int gemm_tc(const GemmP& p, cudaStream_t s) {
     ST_TRY(tc_scratch_reserve(s, tc_scratch_need(p), &sc));
     __half* sp = reinterpret_cast<__half*>(sc->base);
     const long long n4 = rows * (Ka >> 2);
-launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, s, p.A, p.lda, (int)rows, Ka, Ka, kActScale, p.a_relu, sp, pstride);
+    ST_TRY(fast_chain_flush());
+    launch_k(split_planes_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, s, p.A, p.lda, (int)rows, Ka, Ka, kActScale, p.a_relu, sp, pstride);
     ST_CHECK_LAUNCH();
     planes = sp;
   }
   if ((g_tc_fast || p.attn) && tc_fast_supported(p)) return gemm_tc_fast(p, w, planes, pstride, s);
+  ST_TRY(fast_chain_flush());
   if (p.a2_planes) { set_error("gemm_tc: a two-tensor operand is served by the trunk kernel only"); return ST_EUNSUPPORTED; }
   if (p.attn) { set_error("gemm_tc: fused attention needs the 1536 x 512 qkv layout"); return ST_EUNSUPPORTED; }
   if (p.ln_stats || p.stats_out) { set_error("gemm_tc: folded LayerNorm is served by the trunk kernel only"); return ST_EUNSUPPORTED; }

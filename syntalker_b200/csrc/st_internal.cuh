@@ -173,6 +173,9 @@ int gemm_tc(const GemmP& p, cudaStream_t s);
 bool profiling();
 int set_trace_kernels(unsigned long long* p);
 int set_trace_tc(unsigned long long* p);
+int fast_chain_begin(cudaStream_t s);   // collect the trunk launches of stream s into layer chains (gemm_tc_chain_kernel) ...
+int fast_chain_end();                   // ... and launch what is pending
+int fast_chain_flush();
 int profile_begin();
 int profile_end(double* ms, double* flops, int64_t* n);
 

@@ -13,7 +13,7 @@ from syntalker_b200.cfg_sampler import ClassifierFreeSampleModel
 from syntalker_b200.denoiser import MDM
 from syntalker_b200.diffusion import create_gaussian_diffusion
 N, K = int(sys.argv[1]), int(sys.argv[2])
-B = 32
+B = int(os.environ.get("ST_B", "32"))
 torch.set_grad_enabled(False)
 L = _lib.lib()
 dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
@@ -33,4 +33,5 @@ torch.cuda.synchronize()
 t = dbg.cpu().tolist(); t0 = t[0]
 nkb = K // 64
 print(f"N={N} K={K}: set-up done {t[32]-t0}, dependency resolved {t[1]-t0}, first TMA issued {t[8]-t0}, first operands {t[24]-t0}, last K block ready {t[24+min(nkb,16)-1]-t0}, "
-      f"accumulator ready {t[3]-t0}, staged {t[6]-t0}, stores read {t[4]-t0}, CTA end {t[5]-t0}")
+      f"accumulator ready {t[3]-t0}, staged {t[6]-t0}, stores read {t[4]-t0}, CTA end {t[5]-t0}"
+      f" | producer: at its branch {t[33]-t0}, proxy fence done {t[34]-t0}, weight tiles requested {t[35]-t0}; stores waited for {t[36]-t0}, CTA barrier passed {t[37]-t0}")

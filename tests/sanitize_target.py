@@ -10,8 +10,8 @@ from syntalker_b200.diffusion import create_gaussian_diffusion
 from syntalker_b200.pipeline import Window330, LongClip330
 from syntalker_b200.vq import RVQVAE
 torch.set_grad_enabled(False)
-_lib.check(_lib.lib().st_set_graphs(0))
-B = 3
+_lib.check(_lib.lib().st_set_graphs(int(os.environ.get("ST_GRAPHS", "0"))))
+B = int(os.environ.get("ST_B", "3"))
 model = MDM(None).load_state_dict(synth.mdm_state_dict("beatx_motionclip", seed=0))
 w = ClassifierFreeSampleModel(model)
 vqs = [RVQVAE(None, d).load_state_dict(synth.rvq_state_dict(d, seed=0)) for d in synth.PART_DIMS_BEATX]

@@ -337,6 +337,34 @@ def test_attention_on_tensor_cores_equals_the_fma_attention(W, models):
     assert maxabs(got[:2], oref) < 1e-4
 
 
+def test_layer_chains_equal_one_launch_per_layer(models):
+    """st_debug_probe bit 131072: the trunk layers of an evaluation stack as ONE cluster launch (gemm_tc_chain_kernel: clusters of 8 CTAs =
+    the column tiles of a 128-row tile, a cluster barrier instead of the kernel boundary between layers; measured slower than one launch
+    per layer and off by default).  Same kernels' arithmetic, so single evaluations must agree bit for bit; B = 4 with
+    two evaluations stacked is two row tiles, B = 6 is three (the chain needs whole 128-row tiles; other batches fall back)."""
+    L = _lib.lib()
+    _lib.set_engine("tc")
+    m = ClassifierFreeSampleModel(models["beatx_motionclip"])
+    for B in (4, 6, 3):
+        inp = synth.make_inputs(B, seed=31 + B, variant="beatx_motionclip")
+        t = torch.tensor([980, 700, 400, 100, 20, 0][:B]).cuda()
+        y = y_of(inp); y["scale"] = torch.ones(1) * 2.0
+        ref = m(inp["noise"].cuda(), t, y)
+        n0 = _lib.launch_count()
+        m(inp["noise"].cuda(), t, y)
+        n_ref = _lib.launch_count() - n0
+        try:
+            _lib.check(L.st_debug_probe(131072))
+            n0 = _lib.launch_count()
+            got = m(inp["noise"].cuda(), t, y)
+            n_chain = _lib.launch_count() - n0
+        finally:
+            _lib.check(L.st_debug_probe(0))
+        print(f"layer chains B={B}: launches per evaluation {n_ref} -> {n_chain}, max-abs difference {maxabs(got, ref):.1e}")
+        assert torch.equal(got, ref)
+        assert (n_chain < n_ref) == ((B * 64) % 128 == 0)
+
+
 def test_ddim50_cfg_vs_oracle(W, models, engine):
     """BASELINE config 2 at reduced batch: motionclip model, CFG 2.0, full DDIM-50, against the oracle."""
     inp = synth.make_inputs(2, seed=21, variant="beatx_motionclip")
