@@ -33,25 +33,25 @@ E_COND, E_TRUNK, E_DEC = 4.677e9, 1.2342e9 + 0.0336e9, 3.899e9
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, averaged over the launches of the
-    committed `ncu --set full` capture (profiles/r1c_ncu_gemm_tc_fast_full.csv, else the r1b one; cold-cache replays).
-    None if absent."""
+    """(dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, file it was read from): the mean over the
+    launches of the newest committed `ncu --set full` capture of the trunk kernel under profiles/ (cold-cache replays of the kernel inside
+    the sampling loop; tests/gpu_evidence.sh writes it).  (None, None) if absent."""
     import csv
-    for name in ("r1c_ncu_gemm_tc_fast_full.csv", "r1b_ncu_gemm_tc_fast_full.csv"):
+    for name in ("r2b_ncu_step_fast.csv", "r2_ncu_step_fast.csv", "r1c_ncu_gemm_tc_fast_full.csv", "r1b_ncu_gemm_tc_fast_full.csv"):
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
             break
     else:
-        return None
+        return None, None
     rows = list(csv.reader(open(p)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot = 0.0
     for r in data:
-        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            i = hdr.index(name)
+        for col in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(col)
             tot += float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
-    return tot / max(len(data), 1)
+    return tot / max(len(data), 1), "profiles/" + name
 
 
 def peaks():
@@ -399,7 +399,7 @@ def main():
     achieved = g_flops / (g_ms / 1000) / 1e12 if g_ms > 0 else 0.0
     alg = B * (E_COND + S_STEPS * 2 * E_TRUNK + E_DEC)
     step_ms = tot_ms / args.steps
-    roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": ncu_traffic(),
+    roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1],
             "kernel": "gemm_tc_fast_kernel / gemm_tc_kernel (tcgen05 split-fp16; the qkv launches carry the fused attention)" if args.engine == "tc" else "gemm_simt_kernel (exact fp32 FMA)",
             "launches_profiled": g_n, "kernel_ms_per_step": g_ms, "kernel_share_of_step": g_ms / step_ms if step_ms else None,
             "executed_flops_per_step": g_flops, "algorithmic_flops_per_step": alg,

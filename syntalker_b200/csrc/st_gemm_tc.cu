@@ -922,7 +922,8 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
   // CTAs of a layer starts when its SM's CTA of the previous layer has exited
   const bool dbg_cta = (ep.probe & 32) ? (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1) : (blockIdx.x == 0 && blockIdx.y == 0);
   long long* dbg = (ep.dbg && dbg_cta) ? ep.dbg : nullptr;
-  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  const long long t_entry = dbg ? clock64() : 0;     // every thread's own copy: a stamp that is relative to the entry does not read another thread's store
+  if (dbg && threadIdx.x == 0) dbg[0] = t_entry;
   // boundary records (probe bit 64): every CTA of the selected launch leaves {globaltimer at entry, SM id, globaltimer after the
   // dependency wait, globaltimer at exit} behind the 64 timeline slots (tests/boundary_probe.py)
   long long* brec = (ep.dbg && (ep.probe & 64)) ? ep.dbg + 64 + 4 * (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
@@ -1260,7 +1261,7 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
         for (int q = 0; q < 8; ++q) sts128u(oth + (((uint32_t)q ^ sw) << 4), z4);
       }
       tc_fence_before();                                 // this thread's reads of the v accumulators precede the P V MMAs (att_bar[2])
-      if (dbg && threadIdx.x == 64) { dbg[40] = dbg[0]; dbg[41] = dbg[3]; dbg[42] = clock64(); }
+      if (dbg && threadIdx.x == 64) { dbg[40] = t_entry; dbg[41] = dbg[3]; dbg[42] = clock64(); }
       // partial scores of this row over the 64 local dims: keys [16 cpart, +16) of the sequence's diagonal block
       float sv[16];
       const uint32_t srow = (uint32_t)(r * ATT_LDS + cpart * 16) * 4;
@@ -1384,7 +1385,7 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
       }
       tc_fence_before();
       asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory");     // q, k, v of this sequence are in place
-      if (dbg && threadIdx.x == 64) { dbg[40] = dbg[0]; dbg[41] = dbg[3]; dbg[42] = clock64(); }
+      if (dbg && threadIdx.x == 64) { dbg[40] = t_entry; dbg[41] = dbg[3]; dbg[42] = clock64(); }
       // phase B: thread (rq, kq) of warp (lg, cpart): query rows 16*cpart + rq + 4a, keys kq + 8b  (a, b = 0..3)
       const int rq = lane >> 3, kq = lane & 7;
       const int row0 = lg * 32 + cpart * 16 + rq;                     // tile row of a = 0

@@ -5,7 +5,8 @@ WANT = ["ID", "Kernel Name", "Grid Size", "Block Size", "launch__cluster_size", 
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_bytes.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
+        "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__inst_executed.sum", "sm__icc_request_hit_rate.pct", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"]
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units, data = rows[0], rows[1], rows[2:]
 idx = [hdr.index(w) for w in WANT if w in hdr]

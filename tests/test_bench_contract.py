@@ -38,7 +38,8 @@ def test_metric_is_baselines_metric():
 
 
 def test_roofline_inputs_exist():
-    assert bench.ncu_traffic() > 1e6                            # bytes per launch from the committed ncu capture
+    traffic, src = bench.ncu_traffic()                          # bytes per launch from the newest committed ncu capture
+    assert traffic > 1e6 and os.path.exists(os.path.join(ROOT, src))
     pk = bench.peaks()
     assert pk["tflops"] > 100 and pk["hbm"] > 1000
     # algorithmic FLOPs of config 2: 32 * (4.677 + 50 * 2 * 1.2678 + 3.899) G = 4.33 TFLOP

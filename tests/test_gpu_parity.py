@@ -250,6 +250,34 @@ def test_ddpm_draws_noise_like_the_reference(models):
     assert not torch.equal(a, c)
 
 
+def test_p_sample_loop_const_noise_repeats_the_first_clips_draw(models):
+    """const_noise=True (gaussian_diffusion.py:543-544): every step draws randn_like(x) and then gives ALL clips the first clip's noise.
+    The drawn path must equal the tape path fed with the same draws (same seed, same order, row 0 repeated), and two clips that start
+    from the same state and conditioning must then stay identical."""
+    m = models["beatx"]
+    B = 2
+    inp = synth.make_inputs(B, seed=12)
+    y = y_of(inp)
+    for k in ("audio", "word", "seed"):
+        y[k] = y[k][[0]].repeat(B, *([1] * (y[k].dim() - 1))).contiguous()
+    x0 = inp["noise"][[0]].repeat(B, 1, 1, 1).cuda()
+    d = create_gaussian_diffusion(timestep_respacing=[20])
+    torch.manual_seed(1234)
+    torch.cuda.manual_seed(1234)
+    got = d.p_sample_loop(m, (B, 1536, 1, 32), noise=x0, clip_denoised=False, model_kwargs={"y": y}, const_noise=True)
+    torch.manual_seed(1234)
+    torch.cuda.manual_seed(1234)
+    tape = torch.empty(20, B, 1536, 1, 32, device="cuda")
+    for k in range(20):
+        tape[k].normal_()
+        tape[k] = tape[k][[0]].repeat(B, 1, 1, 1)
+    ref = d.p_sample_loop(m, (B, 1536, 1, 32), noise=x0, clip_denoised=False, model_kwargs={"y": y}, noise_tape=tape)
+    assert torch.equal(got, ref)
+    assert maxabs(got[0], got[1]) < 1e-5                      # (rows of one GEMM tile: identical inputs, identical results)
+    free = d.p_sample_loop(m, (B, 1536, 1, 32), noise=x0, clip_denoised=False, model_kwargs={"y": y})
+    assert maxabs(free[0], free[1]) > 1e-2                    # without const_noise the two clips draw different noise
+
+
 def test_ddim_last_step_returns_x0_and_python_loop_agrees(models):
     """At k=0 alpha_bar_prev = 1 so x <- x0 exactly; and the native loop equals a Python loop over st_denoise
     with the reference's update formula (gaussian_diffusion.py:772-790)."""
