@@ -217,6 +217,8 @@ struct st_model {
   // fp16 hi/lo operand planes for the tcgen05 engine
   __half *H_p = nullptr, *ATT_p = nullptr, *G_p = nullptr, *X_p = nullptr, *xs_p = nullptr;
   float* ln_stats = nullptr;   // [nE*B*32][16][2] partial (mean, M2) over 32 columns each of the residual rows
+  unsigned* sig = nullptr;     // row-tile signals of the trunk layers of one evaluation pass: [kSigLayers][sig_rt] counters, zeroed by the token prologue
+  int sig_rt = 0;
   // sampling-loop state on the device + one captured step graph per (plan, mode, engine)
   LoopState* loop = nullptr;
   int32_t* t_model_dev = nullptr;
@@ -254,11 +256,13 @@ static bool g_attn_tc = true;      // QK^T and PV of the fused attention as tcge
 static bool g_zrec = true;         // st_debug_probe bit 512 turns the z recursion of deterministic DDIM off (state kept in x space)
 static bool g_dual_chain = false;  // st_debug_probe bit 4096 (experiment): the evaluations of a step as two chains on two streams
 static bool g_zrec_fc2 = true;     // st_debug_probe bit 1024: the last block's fc2 stays a layer of its own inside the z recursion
+static bool g_row_sig = true;      // st_debug_probe bit 262144: trunk layers wait for the whole predecessor grid instead of row-tile signals
 
 namespace st { extern int g_tc_probe; extern bool g_tc_fast; extern bool g_tc_taps; extern bool g_tc_chain; }
 extern "C" int st_debug_probe(int flags) {
   st::g_tc_taps = !(flags & 8192);
   st::g_tc_chain = (flags & 131072) != 0;
+  g_row_sig = !(flags & 262144);
   st::g_tc_probe = (flags & 15) | ((flags & (16384 | 32768 | 65536)) >> 10);   // bits 16384.. reach the kernels as probe bits 16, 32, 64 (experiments)
   st::g_tc_fast = !(flags & 16);
   g_fused_attn = !(flags & 32);
@@ -415,6 +419,7 @@ extern "C" void st_model_destroy(st_model* m) {
   delete m;
 }
 
+constexpr size_t kSigLayers = 40;     // >= trunk launches of one evaluation pass (8 blocks x 4 + the GEMM that ends it)
 static int model_workspace(st_model* m, int B) {
   if (B <= m->ws_B) return ST_OK;
   const size_t rows = (size_t)B * 32, nE = ST_MAX_EVALS;
@@ -428,6 +433,8 @@ static int model_workspace(st_model* m, int B) {
   f += 2 * (size_t)B + 64;
   f += nE * rows * (512 * 3 + 1024) + rows * 1536;             // fp16 hi+lo planes H_p, ATT_p, X_p, G_p, xs_p (2 halves = 1 float each)
   f += 1000 * (1 + ST_COEF_STRIDE) + 64 + nE * rows * 32;
+  const size_t sig_rt = (nE * rows + 127) / 128;
+  f += kSigLayers * sig_rt;
   size_t bytes = f * sizeof(float) + (size_t)B * sizeof(int64_t) + 64 * 256;
   for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);  // captured pointers die with the old block
   m->graphs.clear(); m->warmed.clear(); m->graph_nodes.clear();
@@ -458,6 +465,9 @@ static int model_workspace(st_model* m, int B) {
   m->G_p = a.take<__half>(2 * nE * rows * 1024);
   m->xs_p = a.take<__half>(2 * rows * 1536);
   m->ln_stats = a.take<float>(nE * rows * 32);
+  m->sig = a.take<unsigned>(kSigLayers * sig_rt);
+  m->sig_rt = (int)sig_rt;
+  ST_CHECK_CUDA(cudaMemsetAsync(m->sig, 0, kSigLayers * sig_rt * sizeof(unsigned), nullptr));
   m->loop = a.take<LoopState>(1);
   m->t_model_dev = a.take<int32_t>(1000);
   m->coef_dev = a.take<float>(1000 * ST_COEF_STRIDE);
@@ -753,6 +763,11 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   tp.ls = loop ? m->loop : nullptr; tp.t_model_dev = m->t_model_dev;
   tp.rope_cos = m->rope_cos; tp.rope_sin = m->rope_sin; tp.x = m->X; tp.B = B; tp.nE = pl.nE;
   tp.x_planes = tc ? m->X_p : nullptr; tp.stats = tc ? m->ln_stats : nullptr;
+  // row-tile signals between the trunk layers (tcgen05 engine, fused attention, one launch per layer, one chain of evaluations): the token
+  // prologue zeroes the counters -- it has waited for everything before it and every layer after it waits for it
+  const bool row_sig = tc && g_row_sig && g_fused_attn && !st::g_tc_chain && !(g_dual_chain && pl.nE >= 2 && loop) && m->sig != nullptr &&
+                       (R + 127) / 128 <= m->sig_rt;
+  if (row_sig) { tp.sig_zero = m->sig; tp.sig_n = (int)(kSigLayers * (size_t)m->sig_rt); }
   for (int e = 0; e < ST_MAX_EVALS; ++e) { tp.cst[e] = m->cst_real; tp.cst_bcast[e] = 0; tp.sv[e] = nullptr; tp.sv_bcast[e] = 0; }
   for (int e = 0; e < pl.nE; ++e) {
     if (pl.ev[e].cst_null) { tp.cst[e] = m->cst_null; tp.cst_bcast[e] = 1; }
@@ -777,6 +792,20 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   auto chain_layers = [&](int e0, int ne, cudaStream_t cs) -> int {
     const int Rc = ne * rows;
     const size_t r0 = (size_t)e0 * rows;
+    // layer j signals counters [j][row tile]; layer j + 1 waits for the column CTAs of layer j on its own row tile
+    int sig_j = 0, sig_prev_cols = 0;
+    auto gemm = [&](GemmP& p, cudaStream_t st_) -> int {
+      if (row_sig && sig_j + 1 < (int)kSigLayers) {
+        const int cols = tc_fast_grid_x(p);
+        if (cols > 0) {
+          if (sig_prev_cols > 0) { p.sig_in = m->sig + (size_t)(sig_j - 1) * m->sig_rt; p.sig_expect = sig_prev_cols; }
+          p.sig_out = m->sig + (size_t)sig_j * m->sig_rt;
+          ++sig_j;
+        }
+        sig_prev_cols = cols;            // a layer outside the trunk kernel breaks the chain: its successor waits for the grid
+      }
+      return st::gemm(p, st_);
+    };
     float* X = m->X + r0 * 512; float* P = m->H + r0 * 512; float* stats = m->ln_stats + r0 * 32;
     __half* X_p = m->X_p + r0 * 512; __half* ATT_p = m->ATT_p + r0 * 512; __half* G_p = m->G_p + r0 * 1024;
     for (int i = 0; i < 8; ++i) {

@@ -763,6 +763,9 @@ struct FastEpi {
   int mode, T, kb_per_tap, dil, pad;
   int planes_relu;         // the planes carry max(result, 0)
   int kb_split;            // mode 0: K blocks >= kb_split come from the second operand tensor (tmA2), counted from its column 0
+  const unsigned* sig_in;  // row-tile signals (GemmP): wait for sig_in[blockIdx.y] >= sig_expect instead of the grid dependency ...
+  int sig_expect;
+  unsigned* sig_out;       // ... and add 1 to sig_out[blockIdx.y] when this CTA's results are in memory
   long long* dbg;
   int probe;
 };
@@ -787,6 +790,22 @@ __device__ __forceinline__ void tma_store_commit_wait(bool complete = false) {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   if (complete) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the writes themselves (a consumer in the same grid follows)
   else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// Dependency of a trunk layer: the whole predecessor grid (griddepcontrol.wait), or -- row-tile signals -- the column CTAs of the producer
+// layer that wrote this CTA's 128 input rows.  The producers belong to an EARLIER launch, all of whose CTAs were resident before this launch
+// became eligible (programmatic launch: every CTA of the primary has passed launch_dependents), so the wait cannot starve them.  Bounded
+// like mbar_wait: a protocol bug ends in a trap.
+__device__ __forceinline__ void tc_wait_dep(const unsigned* sig, int expect, int row_tile) {
+  if (!sig) { pdl_wait(); return; }
+  const unsigned* p = sig + row_tile;
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  if ((int)v >= expect) return;
+  const long long t0 = clock64();
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (clock64() - t0 > 4000000000LL) __trap();
+  } while ((int)v < expect);
 }
 __device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -942,7 +961,11 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
     if (ep.has_planes) tma_prefetch_desc(&tmP);
     if (ep.kb_split < num_kb) tma_prefetch_desc(&tmA2);
   }
-  if (warp == 1 && lane == 0) {
+  // The producer warp initialises the barriers itself and goes straight to its loads: what lies between a CTA's entry and the request
+  // for its first activation tile is on the critical path of every layer (the CTA that replaces the last-finishing CTA of the previous
+  // layer enters 0.9 us after that exit), and the CTA barrier of the set-up -- TMEM allocation, bias loads -- was 0.45 us of it.  The
+  // other nine warps meet at a named barrier the producer warp only ARRIVES at.
+  if (warp == 0 && lane == 0) {
     auto init_set = [](uint64_t* fb, int stages, int attn, int old_stages) {
       uint64_t* eb = fb + stages;
       uint64_t* ab = eb + stages;                    // acc_bar, res_bar, att_bar[0..4]
@@ -975,19 +998,25 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
     if (ep.ln_s) lns_r = __ldg(ep.ln_s + n0 + et);
   }
   if (!CHAIN || li == 0) {
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    tmem_keep = *tmem_slot;
+    if (warp == 0) {
+      __syncwarp();
+      asm volatile("bar.arrive 8, 320;" ::: "memory");       // barriers initialised (lane 0 above); does not wait for the others
+    } else {
+      tc_fence_before();
+      asm volatile("bar.sync 8, 320;" ::: "memory");
+      tc_fence_after();
+      tmem_keep = *tmem_slot;
+    }
   }
   const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, tmem_keep);    // REDUX result lives in a uniform register
   if (dbg && threadIdx.x == 0) dbg[32] = clock64();                       // set-up done
   if (!CHAIN || li == 0) pdl_launch();     // dependents may be scheduled; they still wait for this grid's completion before touching memory
   if (ep.attn && (!CHAIN || li == 0)) {
     // the attention epilogue writes into the peer CTA's shared memory: both CTAs of the cluster must be running before
-    // either does (co-scheduling guarantees residency, not that the peer has started)
+    // either does (co-scheduling guarantees residency, not that the peer has started).  Everybody arrives here; the epilogue warps
+    // wait before their first work, the producer and MMA warps after theirs (nothing of theirs touches the peer)
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp >= 2) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
 
   if (warp == 0) {
@@ -1033,7 +1062,7 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
                        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(bar), "r"(cb * TC_BK), "r"(j * dil - pad), "r"(clip), "r"(0) : "memory");
         }
       };
-      if (!CHAIN || li == 0) pdl_wait();
+      if (!CHAIN || li == 0) tc_wait_dep(ep.sig_in, ep.sig_expect, blockIdx.y);
       for (int kb = 0; kb < npre; ++kb) load_a(kb, a_dst + kb * stage_b, a_bar + 8 * kb);
       if (CHAIN && next) {            // the next layer's descriptors, off its critical path
         tma_prefetch_desc(&next->tmA); tma_prefetch_desc(&next->tmW); tma_prefetch_desc(&next->tmO); tma_prefetch_desc(&next->tmP);
@@ -1157,7 +1186,7 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
     }
   } else {
     // ===== epilogue: warps 2..9; TMEM lane group = warp % 4 (rows), the two warps of a group alternate 32-column chunks =====
-    if (!CHAIN || li == 0) pdl_wait();
+    if (!CHAIN || li == 0) tc_wait_dep(ep.sig_in, ep.sig_expect, blockIdx.y);
     const int lg = warp & 3, cpart = (warp - 2) >> 2;
     const int r = lg * 32 + lane, grow = m0 + r;
     const bool row_ok = grow < ep.M;
@@ -1349,7 +1378,7 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (warp == 2 && elect_one()) {
         tma_store_3d(&tmP, stage0 + ATT2_O, blockIdx.x * 64, m0, 0);
-        tma_store_commit_wait(CHAIN);
+        tma_store_commit_wait(CHAIN || ep.sig_out != nullptr);
       }
       if (dbg && threadIdx.x == 64) { dbg[47] = clock64(); dbg[4] = dbg[47]; }
     } else if (LEGACY && ep.attn) {
@@ -1519,7 +1548,7 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (warp == 2 && elect_one()) {
         tma_store_3d(&tmP, stage0 + ATT_PL_OFF, blockIdx.x * 64, m0, 0);
-        tma_store_commit_wait();
+        tma_store_commit_wait(CHAIN || ep.sig_out != nullptr);
       }
       if (dbg && threadIdx.x == 64) dbg[47] = clock64();
       if (dbg && threadIdx.x == 64) dbg[4] = clock64();
@@ -1610,12 +1639,17 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
     if (dbg && threadIdx.x == 64) dbg[6] = clock64();
     // the staging memory must outlive the TMA engine's reads: each issuing thread waits for its own bulk groups
     if (lg == 0 && lane == 0) {
-      if (CHAIN) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (CHAIN || ep.sig_out) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       if (dbg && warp == 4) dbg[36] = clock64();
     }
+
     if (dbg && threadIdx.x == 64) dbg[4] = clock64();
     }
+  }
+  if (ep.attn && (!CHAIN || li == 0) && warp < 2) {
+    __syncwarp();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // pairs with the arrive of the set-up
   }
   if (LEGACY && ep.attn == 1 && warp < 2) {
     // the producer and MMA warps take part in the cluster barrier of the FMA attention epilogue (the tensor-core one exchanges
@@ -1627,6 +1661,13 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
   tc_fence_before();
   __syncthreads();
   if (dbg && threadIdx.x == 0) dbg[37] = clock64();
+  if (ep.sig_out && threadIdx.x == 0 && (!CHAIN || li + 1 == nl)) {
+    // The TMA stores were waited for by their issuers (cp.async.bulk.wait_group 0: the writes are performed) before the CTA barrier above.
+    // Ordinary global stores -- the row statistics -- need the releasing form, whose gpu-scope fence keeps the CTA alive ~1 300 cycles
+    // longer (timeline): layers without them count relaxed.
+    if (ep.stats_out) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ep.sig_out + blockIdx.y) : "memory");
+    else asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ep.sig_out + blockIdx.y) : "memory");
+  }
   trace_stamp(23);                                   // epilogue and stores done
   if (CHAIN && li + 1 < nl) {
     // layer boundary inside the chain: this CTA's stores are complete (the issuing threads waited for the writes, the row
@@ -2111,6 +2152,12 @@ int fast_chain_end() {
   return r;
 }
 
+int tc_fast_grid_x(const GemmP& p) {
+  if (!(g_tc_fast || p.attn) || !tc_supported(p) || !tc_fast_supported(p)) return 0;
+  const int BN = fast_bn(p);
+  return (p.N + BN - 1) / BN;
+}
+
 static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long long pstride, cudaStream_t s) {
   const int BN = fast_bn(p);
   const int stage = 2 * TC_A_PLANE + 2 * BN * TC_BK * 2;
@@ -2140,6 +2187,7 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   ep.mode = cmode; ep.T = p.Lout; ep.kb_per_tap = cmode == 0 ? 1 : p.C / TC_BK; ep.dil = p.dil; ep.pad = p.pad;
   ep.planes_relu = p.o_planes_relu;
   ep.kb_split = p.a2_planes ? (p.K - p.a2_K) / TC_BK : 0x7fffffff;
+  ep.sig_in = p.sig_in; ep.sig_expect = p.sig_expect; ep.sig_out = p.sig_out;
   const bool legacy = p.attn == 1 || (ep.probe & 16);
   dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM);
   FastLayer L;

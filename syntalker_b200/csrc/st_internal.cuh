@@ -152,7 +152,14 @@ struct GemmP {
   // Fused attention (tcgen05 engine): W is the qkv weight with rows permuted to [head][half][q 64 | k 64 | v 64], so that
   // CTA n owns 64 dims of q, k, v of one head; the epilogue runs the 32-token attention and writes o_planes [M, 512].
   int attn = 0;
+  // trunk kernel only, row-tile signals: instead of waiting for the whole predecessor grid (griddepcontrol.wait) a
+  // CTA of this launch waits until sig_in[its 128-row tile] has reached sig_expect (= the column CTAs of the producer layer), and when its
+  // own results are in memory it adds 1 to sig_out[its row tile].  Every access of the layer must stay inside the row tile.
+  const unsigned* sig_in = nullptr;
+  int sig_expect = 0;
+  unsigned* sig_out = nullptr;
 };
+int tc_fast_grid_x(const GemmP& p);       // column CTAs the trunk kernel would launch for p (0: not a trunk-kernel problem)
 
 constexpr float kActScale = 16.0f;   // activations are stored in fp16 planes as (v * 16): |v| < 4e3 representable, lo normal for |v| > 2^-6
 
@@ -212,6 +219,8 @@ struct TokensInP {
   __half* x_planes;          // optional: fp16 hi/lo planes of x (* kActScale), [2][nE*B*32][512]
   float* stats;              // optional: LayerNorm row statistics of x as 16 combinable partials, [nE*B*32][16][2]
   int B, nE;
+  unsigned* sig_zero = nullptr;   // optional: row-tile signals of the trunk layers that follow, zeroed by block 0 ...
+  int sig_n = 0;                  // ... (the launch has waited for everything before it, and everything after it waits for the launch)
 };
 int tokens_in(const TokensInP& p, cudaStream_t s);
 

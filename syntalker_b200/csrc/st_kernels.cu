@@ -501,6 +501,8 @@ __global__ void __launch_bounds__(256) tokens_in_kernel(TokensInP p) {
   pdl_wait();
   trace_stamp(3);
   pdl_launch();
+  if (p.sig_zero && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < p.sig_n; i += 256) p.sig_zero[i] = 0u;
   // one warp per (evaluation, row); lane l owns the rotary pairs (g*64 + l, g*64 + l + 32), g = 0..7
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -576,6 +578,8 @@ __global__ void __launch_bounds__(256) tokens_step_kernel(TokensStepP q) {
   trace_stamp(3);
   pdl_launch();
   const TokensInP& p = q.t;
+  if (p.sig_zero && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < p.sig_n; i += 256) p.sig_zero[i] = 0u;
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const long long rows_e = (long long)p.B * 32;
