@@ -901,14 +901,15 @@ constexpr int FAST_BOX_PL = 2 * TC_A_PLANE;      // one plane staging box: 2 pla
 // (tests/boundary_probe.py: the dependent's wait returns 1.3 - 2.1 us after the last CTA has exited).  TMEM is allocated once; the
 // barriers of layer li + 1 are initialised (second barrier set) while layer li runs.
 struct FastLayer {
-  CUtensorMap tmA, tmW, tmO, tmP, tmA2;
+  CUtensorMap tmA, tmW, tmO, tmP, tmA2, tmS;
   FastEpi ep;
   int num_kb, BN, STAGES, pad_;
 };
-constexpr int FAST_TAIL = 4096;                  // CHAIN: bias / column sums / barriers of two consecutive layers at the end of shared memory
+constexpr int FAST_TAIL = 8192;                  // CHAIN: bias / column sums / barriers of two consecutive layers + the statistics staging at the end of shared memory
+constexpr int FAST_STATS = 4096;                 // staging of the row statistics a producer of a folded LayerNorm leaves: 128 rows x <= 4 chunks x (mean, M2)
 template <bool LEGACY, bool CHAIN>
 __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const CUtensorMap& tmP,
-                                           const FastEpi& ep, const int num_kb, const int BN, const int STAGES, const CUtensorMap& tmA2,
+                                           const FastEpi& ep, const int num_kb, const int BN, const int STAGES, const CUtensorMap& tmA2, const CUtensorMap& tmS,
                                            const int li, const int nl, uint32_t& tmem_keep, const FastLayer* next, const int prev_stages) {
   const int W_PLANE = BN * TC_BK * 2;
   const int STAGE_BYTES = 2 * TC_A_PLANE + 2 * W_PLANE;
@@ -934,6 +935,9 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
   // [4]: the peer CTA's partial scores have landed in this CTA's score buffer (st.async complete_tx, 16 KB)
   uint64_t* att_bar = res_bar + 1;
   uint32_t* tmem_slot = CHAIN ? reinterpret_cast<uint32_t*>(tail_set + 2048 - 16) : reinterpret_cast<uint32_t*>(att_bar + 5);
+  // row statistics leave through a TMA store like every other result (no ordinary global store is left in the epilogue, so the
+  // row-tile signal needs no gpu-scope fence): [128 rows][NCH] (mean, M2) pairs
+  uint8_t* stats_s = CHAIN ? tail_set + 4096 : reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot) + 16 + 127) & ~uintptr_t(127));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
@@ -1598,7 +1602,7 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
         float qd = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) { const float dd = x[j] - mj; qd += dd * dd; }
-        if (row_ok) *reinterpret_cast<float2*>(ep.stats_out + ((long long)grow * 16 + blockIdx.x * NCH + c) * 2) = make_float2(mj, qd);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(smem_u32(stats_s) + (uint32_t)((r * NCH + c) * 8)), "f"(mj), "f"(qd) : "memory");
       }
       // Results leave as soon as a staging box is complete, not at the end of the epilogue: the TMA store of a box drains
       // (all 128 CTAs write 4-12 MB at once) while the planes of the same chunk / the next chunk are still being computed.
@@ -1631,6 +1635,8 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
         asm volatile("bar.sync 1, 256;" ::: "memory");                // both column halves of plane box c / 2 (all eight warps)
         if (warp == 4 && lane == 0) {
           tma_store_3d(&tmP, pl_base + (c >> 1) * FAST_BOX_PL, n0 + (c >> 1) * 64, m0, 0);
+          // the statistics of all chunks are staged once the last plane box is (the barrier above had all eight warps)
+          if (ep.stats_out && c + 2 >= NCH) tma_store_2d(&tmS, smem_u32(stats_s), blockIdx.x * NCH * 2, m0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -1662,11 +1668,10 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
   __syncthreads();
   if (dbg && threadIdx.x == 0) dbg[37] = clock64();
   if (ep.sig_out && threadIdx.x == 0 && (!CHAIN || li + 1 == nl)) {
-    // The TMA stores were waited for by their issuers (cp.async.bulk.wait_group 0: the writes are performed) before the CTA barrier above.
-    // Ordinary global stores -- the row statistics -- need the releasing form, whose gpu-scope fence keeps the CTA alive ~1 300 cycles
-    // longer (timeline): layers without them count relaxed.
-    if (ep.stats_out) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ep.sig_out + blockIdx.y) : "memory");
-    else asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ep.sig_out + blockIdx.y) : "memory");
+    // Every result of the layer -- the row statistics too -- left through TMA stores that their issuers waited for
+    // (cp.async.bulk.wait_group 0: the writes are performed) before the CTA barrier above, so the count needs no fence: a releasing
+    // count (gpu-scope fence) kept the CTA alive ~1 300 cycles longer (timeline), and the next layer's CTA on this SM starts that much later.
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ep.sig_out + blockIdx.y) : "memory");
   }
   trace_stamp(23);                                   // epilogue and stores done
   if (CHAIN && li + 1 < nl) {
@@ -1694,9 +1699,10 @@ template <bool LEGACY>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_fast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, const FastEpi ep,
-                    const int num_kb, const int BN, const int STAGES, const __grid_constant__ CUtensorMap tmA2) {
+                    const int num_kb, const int BN, const int STAGES, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmS) {
   uint32_t keep = 0;
-  fast_layer<LEGACY, false>(tmA, tmW, tmO, tmP, ep, num_kb, BN, STAGES, tmA2, 0, 1, keep, nullptr, 0);
+  fast_layer<LEGACY, false>(tmA, tmW, tmO, tmP, ep, num_kb, BN, STAGES, tmA2, tmS, 0, 1, keep, nullptr, 0);
 }
 
 // The trunk layers of one evaluation stack as ONE launch: clusters of 8 CTAs (grid.x = 8 column tiles of every layer), one cluster
@@ -1712,7 +1718,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_chain_kernel(const __gr
 #pragma unroll 1
   for (int li = 0; li < nl; ++li) {
     const FastLayer& L = P.ly[li];
-    fast_layer<false, true>(L.tmA, L.tmW, L.tmO, L.tmP, L.ep, L.num_kb, L.BN, L.STAGES, L.tmA2, li, nl, keep, li + 1 < nl ? &P.ly[li + 1] : nullptr,
+    fast_layer<false, true>(L.tmA, L.tmW, L.tmO, L.tmP, L.ep, L.num_kb, L.BN, L.STAGES, L.tmA2, L.tmS, li, nl, keep, li + 1 < nl ? &P.ly[li + 1] : nullptr,
                             li > 0 ? P.ly[li - 1].STAGES : 0);
   }
 }
@@ -2009,6 +2015,26 @@ static int get_map_long(const CUtensorMap** out, const __half* base, long long p
 
 // fp32 [rows, ld] row-major -> 2-D map {cols, rows}, box {32, 128}, 128B swizzle (residual prefetch and result store of
 // the trunk kernel)
+// row statistics [rows][16][2] fp32 (128 B per row): box = the 2 * nch floats a CTA with nch 32-column chunks owns x 128 rows, no swizzle
+static int get_map_stats(const CUtensorMap** out, const float* base, int rows, int nch) {
+  MapKey key{base, (long long)32, nch, rows, -10, 32};
+  std::lock_guard<std::mutex> lk(g_tc_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = &it->second; return ST_OK; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return ST_ECUDA; }
+  cuuint64_t gdim[2] = {32, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {128};
+  cuuint32_t box[2] = {(cuuint32_t)(2 * nch), TC_BM};
+  cuuint32_t est[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(row statistics rows=%d nch=%d) failed: %d", rows, nch, (int)r); return ST_ECUDA; }
+  *out = &(g_maps[key] = m);
+  return ST_OK;
+}
+
 static int get_map_2d_f32(const CUtensorMap** out, const float* base, int rows, int cols, int ld) {
   MapKey key{base, (long long)ld, cols, rows, -9, 32};
   std::lock_guard<std::mutex> lk(g_tc_mu);
@@ -2096,8 +2122,8 @@ static int launch_fast_single(const FastLayer& L, unsigned grid_y, int smem, boo
     ST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   }
   dim3 grid((L.ep.N + L.BN - 1) / L.BN, grid_y);
-  if (L.ep.attn) launch_k_cluster(legacy ? gemm_tc_fast_kernel<true> : gemm_tc_fast_kernel<false>, grid, dim3(TC_THREADS), (size_t)smem, s, 2, L.tmA, L.tmW, L.tmO, L.tmP, L.ep, L.num_kb, L.BN, L.STAGES, L.tmA2);
-  else launch_k(legacy ? gemm_tc_fast_kernel<true> : gemm_tc_fast_kernel<false>, grid, dim3(TC_THREADS), (size_t)smem, s, L.tmA, L.tmW, L.tmO, L.tmP, L.ep, L.num_kb, L.BN, L.STAGES, L.tmA2);
+  if (L.ep.attn) launch_k_cluster(legacy ? gemm_tc_fast_kernel<true> : gemm_tc_fast_kernel<false>, grid, dim3(TC_THREADS), (size_t)smem, s, 2, L.tmA, L.tmW, L.tmO, L.tmP, L.ep, L.num_kb, L.BN, L.STAGES, L.tmA2, L.tmS);
+  else launch_k(legacy ? gemm_tc_fast_kernel<true> : gemm_tc_fast_kernel<false>, grid, dim3(TC_THREADS), (size_t)smem, s, L.tmA, L.tmW, L.tmO, L.tmP, L.ep, L.num_kb, L.BN, L.STAGES, L.tmA2, L.tmS);
   ST_CHECK_LAUNCH();
   return ST_OK;
 }
@@ -2165,7 +2191,8 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   int stages = (232448 - 4096 - res) / stage;
   if (stages > 4) stages = 4;
   if (p.attn) { stages = 2; }
-  const int smem = stages * stage + (p.attn ? ATT_SX_BYTES : res) + 2 * 192 * 4 + (2 * stages + 2 + 5) * 8 + 16 + 1024;
+  const int smem = stages * stage + (p.attn ? ATT_SX_BYTES : res) + 2 * 192 * 4 + (2 * stages + 2 + 5) * 8 + 16 + 1024 + (p.stats_out ? FAST_STATS + 128 : 0);
+  if (smem > 232448) { set_error("gemm_tc_fast: %d bytes of shared memory (BN=%d stages=%d)", smem, BN, stages); return ST_EINVAL; }
   const CUtensorMap *tmA = nullptr, *tmW = nullptr, *tmO = nullptr, *tmP = nullptr;
   const int cmode = conv_mode(p);
   const CUtensorMap* tmA2 = nullptr;
@@ -2191,7 +2218,9 @@ static int gemm_tc_fast(const GemmP& p, WPlanes* w, const __half* planes, long l
   const bool legacy = p.attn == 1 || (ep.probe & 16);
   dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM);
   FastLayer L;
-  L.tmA = *tmA; L.tmW = *tmW; L.tmO = *tmO; L.tmP = *tmP; L.tmA2 = *tmA2;
+  const CUtensorMap* tmS = tmA;
+  if (p.stats_out) ST_TRY(get_map_stats(&tmS, p.stats_out, p.M, BN / 32));
+  L.tmA = *tmA; L.tmW = *tmW; L.tmO = *tmO; L.tmP = *tmP; L.tmA2 = *tmA2; L.tmS = *tmS;
   L.ep = ep; L.num_kb = w->Kp / TC_BK; L.BN = BN; L.STAGES = stages; L.pad_ = 0;
   ChainState& c = g_chain;
   // a chain layer: 8 column tiles (= the cluster), full row tiles, plain rows, and room for the fixed tail block behind ring + residual

@@ -365,6 +365,29 @@ def test_attention_on_tensor_cores_equals_the_fma_attention(W, models):
     assert maxabs(got[:2], oref) < 1e-4
 
 
+def test_row_tile_signals_equal_the_grid_dependency(models):
+    """The trunk layers wait for the column CTAs of the producer layer on their own 128-row tile (a counter per row tile, DESIGN.md
+    section 4) instead of for the whole predecessor grid; st_debug_probe bit 262144 restores griddepcontrol.wait.  Same arithmetic, so
+    evaluations must agree bit for bit -- at the bench's 16 row tiles (B = 32, two stacked evaluations), at a batch that leaves the last
+    row tile partial, and repeatedly (a consumer that started before its producers' stores had landed would read stale rows)."""
+    L = _lib.lib()
+    _lib.set_engine("tc")
+    m = ClassifierFreeSampleModel(models["beatx_motionclip"])
+    for B in (32, 5):
+        inp = synth.make_inputs(B, seed=41 + B, variant="beatx_motionclip")
+        t = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(B)).cuda()
+        y = y_of(inp); y["scale"] = torch.ones(1) * 2.0
+        x = inp["noise"].cuda()
+        try:
+            _lib.check(L.st_debug_probe(262144))
+            ref = m(x, t, y)
+        finally:
+            _lib.check(L.st_debug_probe(0))
+        for rep in range(6):
+            got = m(x, t, y)
+            assert torch.equal(got, ref), f"B={B} repetition {rep}: max-abs {maxabs(got, ref):.2e}"
+
+
 def test_layer_chains_equal_one_launch_per_layer(models):
     """st_debug_probe bit 131072: the trunk layers of an evaluation stack as ONE cluster launch (gemm_tc_chain_kernel: clusters of 8 CTAs =
     the column tiles of a 128-row tile, a cluster barrier instead of the kernel boundary between layers; measured slower than one launch
