@@ -92,7 +92,11 @@ int st_debug_trace(unsigned long long* dev_buf);
  * (generic tcgen05 kernel); 32: separate attention kernel; 64: RVQ code ranking on the SIMT engine; 128: WavEncoder with fp32
  * activations; 256: body parts decode one after the other; 512: the sampling loop keeps its state in x space (no z recursion);
  * 1024: the last block's fc2 stays a layer of its own inside the z recursion; 2048: packed-fp32 FMA attention epilogue instead of
- * the tcgen05 Q K^T / P V. */
+ * the tcgen05 Q K^T / P V; 4096: the two CFG evaluations as two chains on two streams (experiment); 8192: conv taps fetched per tap
+ * instead of staged once; 16384: the MMA issue loop as first written; 32768: timelines record the LAST CTA of a grid instead of
+ * CTA (0,0); 65536: per-CTA boundary records behind the timeline slots (tests/boundary_probe.py); 131072: the trunk layers of an
+ * evaluation stack as one cluster launch (layer chains; slower, off by default); 262144: trunk layers wait for the whole predecessor
+ * grid (griddepcontrol.wait) instead of the row-tile signals. */
 int st_debug_probe(int flags);
 /* Parity-test taps of the last st_cond_encode: atcat_out [B,128,512] = [WavEncoder output | word features]
  * per frame (models/denoiser.py:151-155, B <= 32), cst_out [B*32,512] = the hoisted conditioning constant.  Either may be NULL. */

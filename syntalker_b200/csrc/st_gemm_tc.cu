@@ -788,8 +788,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
 // performed before the grid counts as complete, which is what the dependent kernel's griddepcontrol.wait observes
 __device__ __forceinline__ void tma_store_commit_wait(bool complete = false) {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  if (complete) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the writes themselves (a consumer in the same grid follows)
-  else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (complete) {                                  // the writes themselves: a consumer that is not ordered by a kernel boundary follows
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+  } else {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
 }
 // Dependency of a trunk layer: the whole predecessor grid (griddepcontrol.wait), or -- row-tile signals -- the column CTAs of the producer
 // layer that wrote this CTA's 128 input rows.  The producers belong to an EARLIER launch, all of whose CTAs were resident before this launch
@@ -1067,6 +1071,10 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
         }
       };
       if (!CHAIN || li == 0) tc_wait_dep(ep.sig_in, ep.sig_expect, blockIdx.y);
+      // (the activation tiles were written through the async proxy, completed and fenced by their writers, and are read through the async
+      // proxy by requests initiated after the acquire: no proxy fence on this side.  Probe bit 8 adds one: +400 cycles per layer, it waits
+      // for the weight tiles in flight)
+      if (ep.probe & 8) asm volatile("fence.proxy.async.global;" ::: "memory");
       for (int kb = 0; kb < npre; ++kb) load_a(kb, a_dst + kb * stage_b, a_bar + 8 * kb);
       if (CHAIN && next) {            // the next layer's descriptors, off its critical path
         tma_prefetch_desc(&next->tmA); tma_prefetch_desc(&next->tmW); tma_prefetch_desc(&next->tmO); tma_prefetch_desc(&next->tmP);
@@ -1647,6 +1655,7 @@ __device__ __forceinline__ void fast_layer(const CUtensorMap& tmA, const CUtenso
     if (lg == 0 && lane == 0) {
       if (CHAIN || ep.sig_out) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (ep.sig_out) asm volatile("fence.proxy.async.global;" ::: "memory");   // the completed async-proxy writes, before the generic-proxy count (free here: nothing in flight)
       if (dbg && warp == 4) dbg[36] = clock64();
     }
 
