@@ -37,7 +37,7 @@ def ncu_traffic():
     launches of the newest committed `ncu --set full` capture of the trunk kernel under profiles/ (cold-cache replays of the kernel inside
     the sampling loop; tests/gpu_evidence.sh writes it).  (None, None) if absent."""
     import csv
-    for name in ("r2b_ncu_step_fast.csv", "r2_ncu_step_fast.csv", "r1c_ncu_gemm_tc_fast_full.csv", "r1b_ncu_gemm_tc_fast_full.csv"):
+    for name in ("r2c_ncu_step_fast.csv", "r2b_ncu_step_fast.csv", "r2_ncu_step_fast.csv", "r1c_ncu_gemm_tc_fast_full.csv", "r1b_ncu_gemm_tc_fast_full.csv"):
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
             break
