@@ -97,12 +97,21 @@ int gemm(const GemmP& p, cudaStream_t s) {
   }
   return gemm_dispatch(p, s);
 }
-// the replay of profile_end() chains what the recorded pass chained: markers (M = -1 begin, -2 end) in the launch list
-static void profile_mark(int what) {
+// the replay of profile_end() chains what the recorded pass chained: markers (M = -1 begin, -2 end) in the launch list; and it zeroes
+// the row-tile signals where the recorded pass's token prologue did (M = -3: a one-block kernel that, like the prologue, waits for
+// everything before it) -- replayed without that, every consumer would find its counter already satisfied and run ahead of its producers
+static void profile_mark(int what, unsigned* sig = nullptr, int sig_n = 0) {
   if (!g_prof) return;
   GemmP m;
   m.M = what;
+  m.sig_out = sig;
+  m.N = sig_n;
   g_prof_list.push_back(m);
+}
+__global__ void zero_u32_kernel(unsigned* p, int n) {
+  pdl_wait();
+  pdl_launch();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0u;
 }
 
 bool profiling() { return g_prof; }
@@ -133,6 +142,7 @@ int profile_end(double* ms, double* flops, int64_t* n) {
   ST_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
   int r = ST_OK;
   for (const GemmP& p : g_prof_list) {
+    if (p.M == -3) { launch_k(zero_u32_kernel, dim3(1), dim3(256), 0, s, p.sig_out, p.N); continue; }
     r = p.M == -1 ? fast_chain_begin(s) : p.M == -2 ? fast_chain_end() : gemm_dispatch(p, s);
     if (r != ST_OK) break;
   }
@@ -767,7 +777,10 @@ static int run_trunk(st_model* m, const Plan& pl, int B, const int64_t* t_dev, i
   // prologue zeroes the counters -- it has waited for everything before it and every layer after it waits for it
   const bool row_sig = tc && g_row_sig && g_fused_attn && !st::g_tc_chain && !(g_dual_chain && pl.nE >= 2 && loop) && m->sig != nullptr &&
                        (R + 127) / 128 <= m->sig_rt;
-  if (row_sig) { tp.sig_zero = m->sig; tp.sig_n = (int)(kSigLayers * (size_t)m->sig_rt); }
+  if (row_sig) {
+    tp.sig_zero = m->sig; tp.sig_n = (int)(kSigLayers * (size_t)m->sig_rt);
+    profile_mark(-3, tp.sig_zero, tp.sig_n);
+  }
   for (int e = 0; e < ST_MAX_EVALS; ++e) { tp.cst[e] = m->cst_real; tp.cst_bcast[e] = 0; tp.sv[e] = nullptr; tp.sv_bcast[e] = 0; }
   for (int e = 0; e < pl.nE; ++e) {
     if (pl.ev[e].cst_null) { tp.cst[e] = m->cst_null; tp.cst_bcast[e] = 1; }
