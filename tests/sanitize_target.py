@@ -11,6 +11,8 @@ from syntalker_b200.pipeline import Window330, LongClip330
 from syntalker_b200.vq import RVQVAE
 torch.set_grad_enabled(False)
 _lib.check(_lib.lib().st_set_graphs(int(os.environ.get("ST_GRAPHS", "0"))))
+if os.environ.get("ST_PROBE"):
+    _lib.check(_lib.lib().st_debug_probe(int(os.environ["ST_PROBE"])))
 B = int(os.environ.get("ST_B", "3"))
 model = MDM(None).load_state_dict(synth.mdm_state_dict("beatx_motionclip", seed=0))
 w = ClassifierFreeSampleModel(model)
